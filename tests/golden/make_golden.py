@@ -1,0 +1,136 @@
+"""Generate the golden fixtures in this directory from the REFERENCE's own nn.Module classes.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+The reference ships no tests or golden vectors, so these fixtures -- outputs of the
+unmodified reference modules + the step body restated from vae-gan.py:404-424 around them -- are
+what pins ``oracle/``.  Weights come from ``oracle.step.deterministic_state`` (a pure function of
+the state_dict keys), inputs from ``oracle.step.synthetic_batch``; both are re-derived by the tests,
+so only outputs are stored (a few hundred KB in total).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+from torch.nn.utils import clip_grad_norm_
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_loader  # noqa: E402
+from oracle.step import LossWeights, deterministic_state, synthetic_batch  # noqa: E402
+
+CASES = {
+    # name: (family, H, W, batch, z)
+    "base_32x32_b4": ("base", 32, 32, 4, 128),
+    "base_64x64_b16": ("base", 64, 64, 16, 128),       # BASELINE.json configs[0]
+    "v2_32x64_b2": ("v2", 32, 64, 2, 128),
+    "v2_32x32_b3_z32": ("v2", 32, 32, 3, 32),
+    "unet_32x32_b2": ("unet", 32, 32, 2, 128),
+}
+
+
+def summarize(t: torch.Tensor, n: int = 6) -> torch.Tensor:
+    """[l2 norm, sum, first n values] -- small but position- and scale-sensitive."""
+    f = t.detach().double().flatten()
+    head = torch.zeros(n, dtype=torch.float64)
+    head[:min(n, f.numel())] = f[:n]
+    return torch.cat([torch.stack([f.norm(), f.sum()]), head])
+
+
+def unet_repaired_forward(G, image, mask, texts):
+    """the reference's own submodules, composed with the two-line repair."""
+    enc, dec = G.style_vae_encoder_module, G.image_vae_decoder_module
+    x = torch.cat([image, mask], 1)
+    pooled = []
+    for i in (1, 2, 3, 4):
+        x = getattr(enc, f"pool{i}")(getattr(enc, f"e_conv{i}")(x))
+        pooled.append(x)
+    b = enc.bottleneck_conv(x)
+    mu, logvar = enc.mu_head(b), enc.logvar_head(b)
+    z = G.reparameterize(mu, logvar)
+    t = G.char_text_encoder_module(texts)
+    y = dec.bottleneck_upsample(torch.cat([z, t.mean(dim=3, keepdim=True)], 1))
+    for i in (1, 2, 3, 4):
+        y = getattr(dec, f"d_upconv{i}")(torch.cat([y, pooled[4 - i]], 1))
+    return dec.output_activation_fn(dec.final_image_conv(y)), mu, logvar
+
+
+def run_case(name):
+    family, h, w, batch, z = CASES[name]
+    mod, G, D = ref_loader.build(family, h, w, z)
+    G.load_state_dict(deterministic_state(G, 1234), strict=True)
+    D.load_state_dict(deterministic_state(D, 4321), strict=True)
+    G.train(); D.train()
+    wts = LossWeights.for_family(family)
+    opt_G = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.5, 0.999))   # vae-gan.py:541
+    opt_D = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.5, 0.999))   # vae-gan.py:542
+    gold = {"case": name, "family": family, "h": h, "w": w, "batch": batch, "z": z, "steps": []}
+
+    fwd = (lambda a, b, c: unet_repaired_forward(G, a, b, c)) if family == "unet" else G
+    if family == "unet":   # record that the shipped forward cannot run (row U)
+        ru, en, mask, texts = synthetic_batch(batch, h, w, step=0)
+        try:
+            copy.deepcopy(G)(ru, mask, texts)   # on a copy: the encoder half runs (and updates BN stats) before the error
+            gold["shipped_forward_error"] = None
+        except RuntimeError as e:
+            gold["shipped_forward_error"] = str(e)[:80]
+
+    for step in range(2):
+        ru, en, mask, texts = synthetic_batch(batch, h, w, step=step)
+        torch.manual_seed(10_000 + step)
+        # ---- step body, vae-gan.py:404-424 / vae-gan-v2.py:707-740 (perceptual weight 0) ----
+        fake, mu, logvar = fwd(ru, mask, texts)
+        opt_D.zero_grad()
+        real_preds = D(en)
+        loss_d_real = mod.hinge_loss(real_preds, 1)
+        loss_d_fake = mod.hinge_loss(D(fake.detach()), 0)
+        loss_d = (loss_d_real + loss_d_fake) * 0.5
+        loss_d.backward()
+        d_grads = {k: summarize(p.grad) for k, p in D.named_parameters()}
+        opt_D.step()
+        opt_G.zero_grad()
+        fake_preds = D(fake)
+        recon = F.l1_loss(fake, en)
+        kl = torch.mean(-0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp(), dim=[1, 2, 3]))
+        gan = mod.hinge_loss(fake_preds, None)
+        loss_g = wts.recon * recon + wts.kl * kl + wts.gan * gan
+        loss_g.backward()
+        g_grads = {k: summarize(p.grad) for k, p in G.named_parameters() if p.grad is not None}
+        gn = clip_grad_norm_(G.parameters(), max_norm=1.0)
+        opt_G.step()
+        # ------------------------------------------------------------------------------------
+        rec = {
+            "losses": {"loss_G": float(loss_g), "loss_D": float(loss_d), "recon": float(recon), "kl": float(kl),
+                       "gan": float(gan), "d_real": float(loss_d_real), "d_fake": float(loss_d_fake)},
+            "grad_norm": float(gn),
+            "mu": mu.detach().clone(), "logvar": logvar.detach().clone(),
+            "recon_img": fake.detach().clone() if fake.numel() <= 40_000 else None,
+            "recon_sum": summarize(fake, 16), "real_preds": real_preds.detach().clone(),
+            "fake_preds": fake_preds.detach().clone(),
+            "d_grads": d_grads, "g_grads": g_grads,
+            "G_state": {k: summarize(v.float()) for k, v in G.state_dict().items()},
+            "D_state": {k: summarize(v.float()) for k, v in D.state_dict().items()},
+        }
+        gold["steps"].append(rec)
+
+    # eval-mode forward (BN running stats, no spectral-norm power iteration; noise still sampled)
+    G.eval(); D.eval()
+    ru, en, mask, texts = synthetic_batch(batch, h, w, step=7)
+    with torch.no_grad():
+        torch.manual_seed(77)
+        fake, mu, logvar = fwd(ru, mask, texts)
+        gold["eval"] = {"recon_sum": summarize(fake, 16), "mu": mu.clone(), "d_out": D(en).clone()}
+    torch.save(gold, os.path.join(HERE, name + ".pt"))
+    print(name, {k: round(v, 6) for k, v in gold["steps"][0]["losses"].items()},
+          os.path.getsize(os.path.join(HERE, name + ".pt")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    assert ref_loader.available(), "needs /root/reference"
+    torch.set_num_threads(8)
+    for n in (sys.argv[1:] or CASES):
+        run_case(n)
