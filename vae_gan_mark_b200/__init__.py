@@ -1,0 +1,6 @@
+"""B200-native VAE-GAN training step (drop-in for Andrey1408/vae-gan-mark's nn.Module surface).
+
+Hand-written sm_100a CUDA kernels (csrc/) behind a C ABI (include/vaegan_b200.h), called from
+PyTorch host code.  No CPU fallback: the ops raise if libvaegan_b200.so is missing.
+"""
+__version__ = "0.1.0"

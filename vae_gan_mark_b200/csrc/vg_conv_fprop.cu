@@ -1,0 +1,336 @@
+// Implicit-GEMM convolution forward ("fprop") on tcgen05 tensor cores, sm_100a.
+//
+//   D[m, n] = sum_{tap, c} A[pixel(m) shifted by tap, c] * W[n, tap*Cin + c]
+//
+// * A (activations, NHWC bf16) is never materialised as an im2col matrix: each K step is one TMA
+//   box {64 channels, TW, 1, TH, TN} of a 5-D view (s*ld, W/s, s, H/s, N) of the tensor, shifted by the
+//   tap; TMA zero-fills out-of-bounds pixels, which implements the padding.  The stride-2 view
+//   (s = 2) folds the column parity into the channel coordinate and the row parity into dim 2, so a
+//   stride-2 conv (and the adjoint of a stride-2 ConvTranspose) is the same kernel.
+// * W (bf16, [n_gemm][taps*Cin], K contiguous) is a 2-D TMA box {64, BN}.
+// * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered fp32 TMEM
+//   accumulator; 4 epilogue warps drain TMEM with tcgen05.ld, add bias / activation, and store bf16 or
+//   fp32 NHWC rows (optionally scattered as a pixel shuffle for ConvTranspose, optionally into a channel
+//   slice of a wider buffer = fused concat, optionally fp32 atomics for split-K).
+// * Persistent: grid = min(tiles, #SMs); warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM
+//   allocator, 4..7 = epilogue.
+//
+// This one kernel serves Conv2d fprop, Conv2d dgrad (flipped weights), ConvTranspose2d fprop/dgrad and the
+// GEMM-shaped layers (1x1 convs, full-kernel heads, bottleneck ConvT) of the reference models
+// (vae-gan.py:52-60,76-81,153-157; vae-gan-v2.py:123-127,168-176,199-241).
+#include "vg_common.cuh"
+#include "../../include/vaegan_b200.h"
+
+namespace vg {
+
+constexpr int kBM = 128;          // GEMM M tile (pixels) == TMEM lanes
+constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kFpropThreads = 256;
+constexpr int kMaxTaps = VG_MAX_TAPS;
+
+struct FpropParams {
+  int m_n, m_h, m_w;            // output pixel grid
+  int tn, th, tw;               // pixel tile, tn*th*tw == 128
+  int tiles_n, tiles_h, tiles_w;
+  int cin, num_taps, n_gemm, bn, n_tiles;
+  int ksteps, ksplit, stages;
+  // epilogue
+  void* out;
+  int out_kind;                 // 0 bf16, 1 fp32, 2 fp32 atomic add
+  int out_h, out_w, out_ld, out_coff;
+  int su_h, su_w, sub_h0, sub_w0, cout_per_sub;
+  const float* bias;
+  int act;                      // 0 none, 1 relu, 2 leaky relu 0.2
+  int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
+};
+
+__global__ void __launch_bounds__(kFpropThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ FpropParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB][B bn*128 B] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = p.bn * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tmem_full = bars + 2 * p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      int rest = tile / p.n_tiles;
+      const int m_t = rest % m_tiles;
+      const int split = rest / m_tiles;
+      const int tw_i = m_t % p.tiles_w;
+      const int th_i = (m_t / p.tiles_w) % p.tiles_h;
+      const int tn_i = m_t / (p.tiles_w * p.tiles_h);
+      const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
+      const int k_begin = static_cast<int>((static_cast<long long>(p.ksteps) * split) / p.ksplit);
+      const int k_end = static_cast<int>((static_cast<long long>(p.ksteps) * (split + 1)) / p.ksplit);
+      const int cchunks = p.cin / kBK;
+      int tap = k_begin / cchunks;
+      int cc = k_begin % cchunks;
+      for (int k = k_begin; k < k_end; ++k) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        const int4 t = p.taps[tap];
+        tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
+        tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + cc * kBK, n_t * p.bn);
+        if (++cc == cchunks) { cc = 0; ++tap; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (tile / p.n_tiles) / m_tiles;
+      const int k_begin = static_cast<int>((static_cast<long long>(p.ksteps) * split) / p.ksplit);
+      const int k_end = static_cast<int>((static_cast<long long>(p.ksteps) * (split + 1)) / p.ksplit);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+      for (int k = k_begin; k < k_end; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int j = 0; j < kBK / kUmmaK; ++j) {
+          const uint64_t da = umma_smem_desc_sw128(sa + j * kUmmaK * 2, 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sb + j * kUmmaK * 2, 16, 1024);
+          umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // GEMM row inside the tile == pixel inside the tile
+    const int r_w = row % p.tw;
+    const int r_h = (row / p.tw) % p.th;
+    const int r_n = row / (p.tw * p.th);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      const int m_t = (tile / p.n_tiles) % m_tiles;
+      const int tw_i = m_t % p.tiles_w;
+      const int th_i = (m_t / p.tiles_w) % p.tiles_h;
+      const int tn_i = m_t / (p.tiles_w * p.tiles_h);
+      const int ow = tw_i * p.tw + r_w, oh = th_i * p.th + r_h, n = tn_i * p.tn + r_n;
+      const bool row_ok = (ow < p.m_w) && (oh < p.m_h) && (n < p.m_n);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      for (int c = 0; c < p.bn; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c, r);
+        tmem_ld_wait();
+        const int ng0 = n_t * p.bn + c;        // first GEMM column of this chunk
+        if (row_ok && ng0 < p.n_gemm) {
+          const int sub = ng0 / p.cout_per_sub;   // uniform over the chunk when cout_per_sub % 32 == 0
+          const int ch0 = ng0 - sub * p.cout_per_sub;
+          const int dh = p.sub_h0 + sub / p.su_w, dw = p.sub_w0 + sub % p.su_w;
+          const long long pix = (static_cast<long long>(n) * p.out_h + (oh * p.su_h + dh)) * p.out_w + (ow * p.su_w + dw);
+          const long long off = pix * p.out_ld + p.out_coff + ch0;
+          const int nvalid = min(32, p.n_gemm - ng0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + ch0 + j);
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+            v[j] = x;
+          }
+          if (p.out_kind == 0) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+            if (nvalid == 32 && ((off & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                bf16x8 pk;
+                pk.u[0] = pack_bf16x2(v[j], v[j + 1]);
+                pk.u[1] = pack_bf16x2(v[j + 2], v[j + 3]);
+                pk.u[2] = pack_bf16x2(v[j + 4], v[j + 5]);
+                pk.u[3] = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<bf16x8*>(o + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j]);
+            }
+          } else if (p.out_kind == 1) {
+            float* o = reinterpret_cast<float*>(p.out) + off;
+            if (nvalid == 32 && ((off & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < nvalid; ++j) o[j] = v[j];
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + off;
+            for (int j = 0; j < nvalid; ++j) atomicAdd(o + j, v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int pick_pixel_tile(int m_n, int m_h, int m_w, int total, int* tn, int* th, int* tw) {
+  // tw = largest power of two <= min(m_w rounded up to pow2, total); th likewise; tn = rest
+  int w = 1;
+  while (w < m_w && w < total) w <<= 1;
+  int h = 1;
+  while (h < m_h && w * h < total) h <<= 1;
+  int n = total / (w * h);
+  *tw = w; *th = h; *tn = n;
+  (void)m_n;
+  return 0;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(d != nullptr, -1, "vg_conv_fprop: null descriptor");
+  VG_CHECK(d->cin > 0 && d->cin % 64 == 0, -1, "vg_conv_fprop: cin (%d) must be a positive multiple of 64", d->cin);
+  VG_CHECK(d->num_taps >= 1 && d->num_taps <= kMaxTaps, -1, "vg_conv_fprop: num_taps %d out of range", d->num_taps);
+  VG_CHECK(d->x_stride == 1 || d->x_stride == 2, -1, "vg_conv_fprop: x_stride must be 1 or 2");
+  VG_CHECK(d->x_h % d->x_stride == 0 && d->x_w % d->x_stride == 0, -1, "vg_conv_fprop: H,W must divide by the stride");
+  VG_CHECK(d->x_ld % 8 == 0 && d->w_ld % 8 == 0, -1, "vg_conv_fprop: leading dims must be multiples of 8");
+  VG_CHECK(d->n_gemm >= 1, -1, "vg_conv_fprop: n_gemm");
+  VG_CHECK(d->su_h >= 1 && d->su_w >= 1 && d->cout_per_sub >= 1, -1, "vg_conv_fprop: bad scatter");
+  VG_CHECK(d->su_h * d->su_w == 1 || d->cout_per_sub % 32 == 0, -1,
+           "vg_conv_fprop: pixel-shuffle epilogue needs cout_per_sub %% 32 == 0");
+  VG_CHECK((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0, -1,
+           "vg_conv_fprop: operands must be 16-byte aligned");
+
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_n = d->m_n; p.m_h = d->m_h; p.m_w = d->m_w;
+  pick_pixel_tile(p.m_n, p.m_h, p.m_w, kBM, &p.tn, &p.th, &p.tw);
+  p.tiles_n = cdiv(p.m_n, p.tn); p.tiles_h = cdiv(p.m_h, p.th); p.tiles_w = cdiv(p.m_w, p.tw);
+  p.cin = d->cin; p.num_taps = d->num_taps; p.n_gemm = d->n_gemm;
+  const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int sms = num_sms();
+  // N tile: the widest that still leaves enough tiles to fill the machine
+  int bn = 256;
+  if (d->n_gemm <= 64) bn = 64;
+  else if (d->n_gemm <= 128) bn = 128;
+  else if (m_tiles * cdiv(d->n_gemm, 256) < sms && d->n_gemm % 256 != 0) bn = 128;
+  else if (m_tiles * cdiv(d->n_gemm, 256) < sms / 2) bn = 128;
+  if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 256) bn = d->force_bn;
+  p.bn = bn;
+  p.n_tiles = cdiv(d->n_gemm, bn);
+  p.ksteps = d->num_taps * (d->cin / kBK);
+  int ksplit = d->ksplit;
+  if (ksplit <= 0) {
+    ksplit = 1;
+    const int tiles = m_tiles * p.n_tiles;
+    if (d->out_kind == 2 && tiles < sms) ksplit = min(p.ksteps, max(1, sms / tiles));
+  }
+  VG_CHECK(ksplit == 1 || d->out_kind == 2, -1, "vg_conv_fprop: split-K needs the fp32 atomic output kind");
+  VG_CHECK(ksplit <= p.ksteps, -1, "vg_conv_fprop: ksplit %d > k steps %d", ksplit, p.ksteps);
+  p.ksplit = ksplit;
+  const int stage_bytes = kBM * kBK * 2 + bn * kBK * 2;
+  p.stages = min(8, (200 * 1024) / stage_bytes);
+  p.out = d->out; p.out_kind = d->out_kind;
+  p.out_h = d->out_h; p.out_w = d->out_w; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
+  p.su_h = d->su_h; p.su_w = d->su_w; p.sub_h0 = d->sub_h0; p.sub_w0 = d->sub_w0; p.cout_per_sub = d->cout_per_sub;
+  p.bias = d->bias; p.act = d->act;
+  for (int i = 0; i < d->num_taps; ++i) {
+    p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
+    VG_CHECK(d->taps[i][2] >= 0 && d->taps[i][2] < d->x_stride, -1, "vg_conv_fprop: tap %d row parity out of range", i);
+  }
+
+  const int s = d->x_stride;
+  CUtensorMap tmap_a, tmap_b;
+  {
+    const uint64_t ld = static_cast<uint64_t>(d->x_ld), W = d->x_w, H = d->x_h;
+    uint64_t dims[5] = {ld * s, W / s, static_cast<uint64_t>(s), H / s, static_cast<uint64_t>(d->x_n)};
+    uint64_t strides[5] = {1, ld * s, W * ld, W * ld * s, H * W * ld};
+    uint32_t box[5] = {kBK, static_cast<uint32_t>(p.tw), 1, static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.tn)};
+    int rc = encode_tmap_bf16(&tmap_a, d->x, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(d->num_taps) * d->cin, static_cast<uint64_t>(d->n_gemm)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(d->w_ld)};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    int rc = encode_tmap_bf16(&tmap_b, d->w, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
+  const int grid = min(total_tiles, sms);
+  conv_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tmap_a, tmap_b, p);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,273 @@
+// Implicit-GEMM convolution weight gradient ("wgrad") on tcgen05 tensor cores, sm_100a.
+//
+//   dW[co, tap*Cin + ci] = sum_{pixels p} dY[p, co] * X[p shifted by tap, ci]
+//
+// The reduction (GEMM K) runs over output pixels, which is the *strided* dimension of both NHWC
+// operands, so both tiles are MN-major: a TMA box {64 channels, TW, 1, TH, TN} (64 pixels per K step)
+// lands as [pixel][64 ch] rows of 128 swizzled bytes, which is exactly the canonical MN-major
+// SWIZZLE_128B layout (8-pixel groups 1024 B apart = SBO, 64-channel groups one box apart = LBO).
+// A = dY^T (128 output channels = 2 boxes), B = X^T at up to 4 (tap, 64-channel) blocks = N up to 256.
+// Split-K over pixel tiles fills the machine; partial tiles are combined with fp32 atomics.
+//
+// Serves Conv2d wgrad and (with the operand roles swapped by the caller) ConvTranspose2d wgrad of
+// the reference layers (vae-gan.py:52-60,76-81,153-157; vae-gan-v2.py:123-127,168-176,199-241).
+#include "vg_common.cuh"
+#include "../../include/vaegan_b200.h"
+
+namespace vg {
+
+constexpr int kWgBM = 128;        // output channels per tile
+constexpr int kWgPix = 64;        // pixels per K step
+constexpr int kWgThreads = 256;
+constexpr int kWgBoxBytes = 64 * kWgPix * 2;   // 8 KB: 64 px x 64 ch bf16
+
+struct WgradParams {
+  int m_n, m_h, m_w;              // output pixel grid (reduction space)
+  int tn, th, tw;                 // pixel tile, product == 64
+  int tiles_n, tiles_h, tiles_w;
+  int cout, cin, num_taps;
+  int g_coff;                     // channel offset of dY inside its buffer
+  int bn, nb;                     // N tile (64*nb)
+  int blocks_total;               // num_taps * cin/64
+  int m_tiles, n_tiles, ksplit, stages;
+  float* dw;                      // [cout][num_taps*cin] fp32
+  int dw_ld;
+  int atomic;
+  int4 taps[VG_MAX_TAPS];         // {c_base, dw, sh, dh}
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                  const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = 2 * kWgBoxBytes;
+  const uint32_t stage_bytes = a_bytes + p.nb * kWgBoxBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tmem_full = bars + 2 * p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_g);
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  const int cchunks = p.cin / 64;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      const int m_t = (tile / p.n_tiles) % p.m_tiles;
+      const int split = tile / (p.n_tiles * p.m_tiles);
+      const int k_begin = static_cast<int>((static_cast<long long>(pix_tiles) * split) / p.ksplit);
+      const int k_end = static_cast<int>((static_cast<long long>(pix_tiles) * (split + 1)) / p.ksplit);
+      const int nblk = min(p.nb, p.blocks_total - n_t * p.nb);
+      const int aboxes = min(2, (p.cout - m_t * kWgBM + 63) / 64);
+      for (int k = k_begin; k < k_end; ++k) {
+        const int tw_i = k % p.tiles_w;
+        const int th_i = (k / p.tiles_w) % p.tiles_h;
+        const int tn_i = k / (p.tiles_w * p.tiles_h);
+        const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], (aboxes + nblk) * kWgBoxBytes);
+        for (int i = 0; i < aboxes; ++i)
+          tma_load_5d(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], p.g_coff + m_t * kWgBM + i * 64, ow0, 0, oh0, n0);
+        for (int i = 0; i < nblk; ++i) {
+          const int b = n_t * p.nb + i;
+          const int4 t = p.taps[b / cchunks];
+          tma_load_5d(sb + i * kWgBoxBytes, &tmap_x, &full_bar[stage], t.x + (b % cchunks) * 64, ow0 + t.y, t.z,
+                      oh0 + t.w, n0);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(kWgBM, p.bn, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / (p.n_tiles * p.m_tiles);
+      const int k_begin = static_cast<int>((static_cast<long long>(pix_tiles) * split) / p.ksplit);
+      const int k_end = static_cast<int>((static_cast<long long>(pix_tiles) * (split + 1)) / p.ksplit);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+      for (int k = k_begin; k < k_end; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int j = 0; j < kWgPix / 16; ++j) {
+          // 16 pixels (= 2 groups of 8 rows, SBO apart) per MMA; 64-channel groups LBO (= one box) apart
+          const uint64_t da = umma_smem_desc_sw128(sa + j * 16 * 128, kWgBoxBytes, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sb + j * 16 * 128, kWgBoxBytes, 1024);
+          umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      const int m_t = (tile / p.n_tiles) % p.m_tiles;
+      const int co = m_t * kWgBM + row;
+      const int ncols = min(p.bn, p.blocks_total * 64 - n_t * p.bn);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      for (int c = 0; c < p.bn; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c, r);
+        tmem_ld_wait();
+        if (co < p.cout && c < ncols) {
+          float* o = p.dw + static_cast<long long>(co) * p.dw_ld + n_t * p.bn + c;
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(d != nullptr, -1, "vg_conv_wgrad: null descriptor");
+  VG_CHECK(d->cin > 0 && d->cin % 64 == 0, -1, "vg_conv_wgrad: cin (%d) must be a positive multiple of 64", d->cin);
+  VG_CHECK(d->cout >= 1, -1, "vg_conv_wgrad: cout");
+  VG_CHECK(d->num_taps >= 1 && d->num_taps <= VG_MAX_TAPS, -1, "vg_conv_wgrad: num_taps %d out of range", d->num_taps);
+  VG_CHECK(d->x_stride == 1 || d->x_stride == 2, -1, "vg_conv_wgrad: x_stride must be 1 or 2");
+  VG_CHECK(d->x_h % d->x_stride == 0 && d->x_w % d->x_stride == 0, -1, "vg_conv_wgrad: H,W must divide by the stride");
+  VG_CHECK(d->x_ld % 8 == 0 && d->g_ld % 8 == 0 && d->dw_ld % 4 == 0, -1, "vg_conv_wgrad: leading dims alignment");
+  VG_CHECK(d->dw_ld >= d->num_taps * d->cin, -1, "vg_conv_wgrad: dw_ld too small");
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_n = d->m_n; p.m_h = d->m_h; p.m_w = d->m_w;
+  {
+    int w = 1;
+    while (w < p.m_w && w < kWgPix) w <<= 1;
+    int h = 1;
+    while (h < p.m_h && w * h < kWgPix) h <<= 1;
+    p.tw = w; p.th = h; p.tn = kWgPix / (w * h);
+  }
+  p.tiles_n = cdiv(p.m_n, p.tn); p.tiles_h = cdiv(p.m_h, p.th); p.tiles_w = cdiv(p.m_w, p.tw);
+  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  p.cout = d->cout; p.cin = d->cin; p.num_taps = d->num_taps; p.g_coff = d->g_coff;
+  p.blocks_total = d->num_taps * (d->cin / 64);
+  p.m_tiles = cdiv(d->cout, kWgBM);
+  const int sms = num_sms();
+  int nb = min(4, p.blocks_total);
+  if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
+  p.nb = nb; p.bn = nb * 64;
+  p.n_tiles = cdiv(p.blocks_total, nb);
+  int ksplit = d->ksplit;
+  if (ksplit <= 0) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    ksplit = max(1, min(pix_tiles, (sms + tiles - 1) / tiles));
+    // keep at least ~8 K steps per split so the pipeline fills
+    ksplit = max(1, min(ksplit, pix_tiles / 8 > 0 ? pix_tiles / 8 : 1));
+  }
+  VG_CHECK(ksplit <= pix_tiles, -1, "vg_conv_wgrad: ksplit %d > pixel tiles %d", ksplit, pix_tiles);
+  p.ksplit = ksplit;
+  p.atomic = ksplit > 1 ? 1 : 0;
+  const int stage_bytes = (2 + nb) * kWgBoxBytes;
+  p.stages = min(8, (200 * 1024) / stage_bytes);
+  p.dw = d->dw; p.dw_ld = d->dw_ld;
+  for (int i = 0; i < d->num_taps; ++i) {
+    p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
+    VG_CHECK(d->taps[i][2] >= 0 && d->taps[i][2] < d->x_stride, -1, "vg_conv_wgrad: tap %d row parity out of range", i);
+  }
+  if (p.atomic)
+    VG_CUDA(cudaMemsetAsync(d->dw, 0, static_cast<size_t>(d->cout) * d->dw_ld * sizeof(float), stream));
+
+  CUtensorMap tmap_g, tmap_x;
+  const uint32_t box[5] = {64, static_cast<uint32_t>(p.tw), 1, static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.tn)};
+  {
+    const uint64_t ld = d->g_ld, W = d->m_w, H = d->m_h;
+    uint64_t dims[5] = {ld, W, 1, H, static_cast<uint64_t>(d->m_n)};
+    uint64_t strides[5] = {1, ld, W * ld, W * ld, H * W * ld};
+    int rc = encode_tmap_bf16(&tmap_g, d->g, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const int s = d->x_stride;
+    const uint64_t ld = d->x_ld, W = d->x_w, H = d->x_h;
+    uint64_t dims[5] = {ld * s, W / s, static_cast<uint64_t>(s), H / s, static_cast<uint64_t>(d->x_n)};
+    uint64_t strides[5] = {1, ld * s, W * ld, W * ld * s, H * W * ld};
+    int rc = encode_tmap_bf16(&tmap_x, d->x, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  conv_wgrad_kernel<<<min(total_tiles, sms), kWgThreads, smem, stream>>>(tmap_g, tmap_x, p);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
