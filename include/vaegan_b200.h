@@ -89,6 +89,113 @@ typedef struct VgConvWgrad {
 } VgConvWgrad;
 int vg_conv_wgrad(const VgConvWgrad* desc /*host*/, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation + activation (+ fused 2x2 max-pool).  groups = 1: BatchNorm2d (training) statistics over all
+ * rows; groups = N: InstanceNorm2d statistics per sample.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.2).
+ * Replaces nn.BatchNorm2d + nn.ReLU (+ nn.MaxPool2d) of the generator (vae-gan.py:52-55,76-81;
+ * vae-gan-v2.py:157-177,236-242) and nn.InstanceNorm2d + nn.LeakyReLU of D (vae-gan.py:154-156).
+ * ------------------------------------------------------------------------------------------- */
+/* sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 (fp32, zeroed internally) */
+int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c, float* sums,
+                  void* stream);
+/* mean_rstd[g][0][c] = mean, [g][1][c] = 1/sqrt(var+eps); when groups == 1 and running_mean != NULL also updates the
+ * running statistics (momentum, unbiased variance) and increments *num_batches_tracked (int64, nullable). */
+int vg_norm_finalize(const float* sums, int groups, long long rows_per_group, int c, float eps, float* mean_rstd,
+                     float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                     void* stream);
+typedef struct VgNormApply {
+  const void* x; int x_ld, x_coff;      /* raw conv output, bf16 NHWC */
+  int n, h, w, c;
+  const float* mean_rstd; int per_sample;
+  const float* gamma; const float* beta; /* nullable */
+  int act;
+  void* y; int y_ld, y_coff;            /* full-resolution output (may be a channel slice of a concat buffer) */
+  void* pool; int p_ld, p_coff;         /* optional 2x2 max-pooled output (NULL = none) */
+} VgNormApply;
+int vg_norm_apply(const VgNormApply* desc /*host*/, void* stream);
+typedef struct VgNormBackward {
+  const void* x; int x_ld, x_coff;      /* raw conv output saved by the forward */
+  const void* dy; int dy_ld, dy_coff;   /* grad wrt y (nullable) */
+  const void* dpool; int dp_ld, dp_coff;/* grad wrt the pooled output (nullable) */
+  int n, h, w, c;
+  const float* mean_rstd; int per_sample;
+  const float* gamma; const float* beta;
+  int act;
+  float* sums;                          /* scratch fp32 [groups][2][c] */
+  void* dx; int dx_ld, dx_coff;         /* grad wrt x, bf16 */
+  float* dgamma; float* dbeta;          /* fp32 [c], nullable */
+  int accumulate;                       /* add into dgamma/dbeta instead of overwriting */
+} VgNormBackward;
+int vg_norm_backward(const VgNormBackward* desc /*host*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data movement / elementwise
+ * ------------------------------------------------------------------------------------------- */
+/* out[sum k_d*out_strides[d]] (=|+=) scale * in[sum k_d*in_strides[d]] over a 5-D index space (dims, host arrays;
+ * dtype codes 0 = fp32, 1 = bf16; scale is an optional DEVICE scalar, inverted when scale_inverse).  Used for the
+ * fp32 OIHW <-> bf16 GEMM-layout weight/gradient re-layouts, NCHW fp32 <-> NHWC bf16 at the module boundary
+ * (torch.cat of image+mask vae-gan.py:139, z/text concat vae-gan-v2.py:249-251) and W/sigma of spectral norm. */
+int vg_strided_copy(const void* in, int in_dtype, void* out, int out_dtype, const long long* dims,
+                    const long long* in_strides, const long long* out_strides, const float* scale, int scale_inverse,
+                    int accumulate, void* stream);
+/* dx = dy * act'(y) for an activation that was fused into a conv epilogue (act 1 ReLU, 2 LeakyReLU(0.2)); bf16 rows */
+int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, void* dx, int dx_ld, long long rows, int c, int act,
+               void* stream);
+/* out[c] (=|+=) sum_r in[r*ld + c], fp32 (bias gradients of small matrices) */
+int vg_colsum_f32(const float* in, long long rows, int cols, int ld, float* out, int accumulate, void* stream);
+/* FiLM (vae-gan-v2.py:146-149): y = gb[:, :c] * x + gb[:, c:]; gb and y dense bf16 [rows][2c] / [rows][c] */
+int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, void* y, long long rows, int c, void* stream);
+int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx, int dx_ld,
+                int dx_coff, long long rows, int c, void* stream);
+/* F.interpolate(bilinear, align_corners=False) of a (1 x w0) map to (h x w) (vae-gan-v2.py:138-140) */
+int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c, void* y, int h, int w, void* stream);
+int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt /*fp32 [n][w0][c]*/, void* stream);
+/* im2col / col2im for few-channel images (first conv of the encoder vae-gan-v2.py:154 and of D vae-gan.py:153) */
+int vg_im2col(const void* src, int n, int h, int w, int ld, int c, int kh, int kw, int stride, int pad, void* col,
+              int kpad, void* stream);
+int vg_col2im(const void* dcol, int kpad, int n, int h, int w, int c, int kh, int kw, int stride, int pad,
+              float* dsrc_nchw, void* stream);
+/* direct stride-1 convs with <= 4 output channels; w fp32 [cout][kh][kw][cin]; out/dy fp32 NHWC [n][oh][ow][cout]
+ * (final_image_conv vae-gan-v2.py:232, decode.15 vae-gan.py:81, D's patch head vae-gan.py:157) */
+int vg_conv_smalln_fwd(const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, const float* wt,
+                       const float* bias, int cout, int kh, int kw, int pad, float* out, void* stream);
+int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int cin, const float* wt, int cout, int kh, int kw,
+                         int pad, void* dx, int dx_ld, int dx_coff, void* stream);
+int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, int cout,
+                         int kh, int kw, int pad, float* dw, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses, reparameterisation, spectral norm, optimiser (fp32)
+ * ------------------------------------------------------------------------------------------- */
+/* heads fp32 [b][2z] (mu | logvar before bias); writes mu, logvar, z = mu + eps*exp(logvar/2) and
+ * *kl_out = mean_b(-0.5 mean_c(1 + lv - mu^2 - e^lv))   (vae-gan.py:133-136, :420) */
+int vg_reparam_kl_fwd(const float* heads, const float* bias_mu, const float* bias_lv, const float* eps, int b, int z,
+                      float* mu, float* logvar, float* zout, float* kl_out, void* stream);
+/* dheads[b][2z] from dz, optional external dmu/dlogvar and the scalar dkl (device); optional bf16 copy (row stride bf_ld) */
+int vg_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, const float* dmu_ext,
+                      const float* dlv_ext, const float* dkl, int b, int z, float* dheads, void* dheads_bf16, int bf_ld,
+                      void* stream);
+int vg_sigmoid_fwd(const float* pre_nhwc, int n, int c, int hw, float* y_nchw, void* stream);      /* vae-gan.py:82 */
+int vg_sigmoid_bwd(const float* y_nchw, const float* dy_nchw, int n, int c, int hw, float* dpre_nhwc, void* stream);
+int vg_l1_fwd(const float* a, const float* b, long long n, float* out, void* stream);              /* vae-gan.py:419 */
+int vg_l1_bwd(const float* a, const float* b, long long n, const float* gout, float* da, int accumulate, void* stream);
+/* hinge_loss (vae-gan.py:313-320): mode 1 real, 0 fake, 2 generator */
+int vg_hinge_fwd(const float* p, long long n, int mode, float* out, void* stream);
+int vg_hinge_bwd(const float* p, long long n, int mode, const float* gout, float* dp, void* stream);
+/* spectral_norm (vae-gan.py:153-156): one power iteration in training mode (u, v updated in place), sigma = u.Wv;
+ * scratch fp32 [rows + cols + 2] */
+int vg_spectral_sigma(const float* w, int rows, int cols, float* u, float* v, int training, float eps, float* sigma,
+                      float* scratch, void* stream);
+/* dw_orig (=|+=) g/sigma - (<g, w_orig>/sigma^2) u v^T ; scratch fp32 [1] */
+int vg_spectral_bwd(const float* g, const float* w_orig, const float* u, const float* v, const float* sigma, int rows,
+                    int cols, float* dw, int accumulate, float* scratch, void* stream);
+/* clip_grad_norm_ + Adam over flat buffers (vae-gan.py:424, :541-542): *out (+)= sum g^2; the Adam pass scales g by
+ * min(1, max_norm/(sqrt(*gnorm_sq)+1e-6)) when gnorm_sq != NULL and max_norm > 0 */
+int vg_sumsq(const float* g, long long n, float* out, int zero_first, void* stream);
+int vg_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                 int step, const float* gnorm_sq, float max_norm, int write_back_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,29 @@ class VgConvWgrad(C.Structure):
     ]
 
 
+class VgNormApply(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ld", C.c_int), ("x_coff", C.c_int),
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+        ("mean_rstd", C.c_void_p), ("per_sample", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("act", C.c_int), ("y", C.c_void_p), ("y_ld", C.c_int), ("y_coff", C.c_int),
+        ("pool", C.c_void_p), ("p_ld", C.c_int), ("p_coff", C.c_int),
+    ]
+
+
+class VgNormBackward(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_ld", C.c_int), ("x_coff", C.c_int),
+        ("dy", C.c_void_p), ("dy_ld", C.c_int), ("dy_coff", C.c_int),
+        ("dpool", C.c_void_p), ("dp_ld", C.c_int), ("dp_coff", C.c_int),
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+        ("mean_rstd", C.c_void_p), ("per_sample", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("act", C.c_int), ("sums", C.c_void_p),
+        ("dx", C.c_void_p), ("dx_ld", C.c_int), ("dx_coff", C.c_int),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int),
+    ]
+
+
 _lib = None
 
 

@@ -1,0 +1,529 @@
+// HBM-bound data-movement and elementwise kernels around the tensor-core convolutions:
+//   * generic 5-D strided copy with dtype conversion / device-scalar scaling / accumulation (weight re-layouts
+//     fp32 OIHW -> bf16 GEMM layouts, gradient re-layouts back, NCHW fp32 <-> NHWC bf16 at the module boundary,
+//     z/text concat of vae-gan-v2.py:249-251, spectral-norm division by sigma);
+//   * FiLM modulation gamma*x+beta and its backward (vae-gan-v2.py:146-149);
+//   * bilinear upsampling of the (1 x W/16) text map and its backward (vae-gan-v2.py:138-140);
+//   * im2col / col2im for the 3- and 4-channel image-side layers (first conv of the encoder and of D);
+//   * direct convolutions with <= 4 output channels (final_image_conv vae-gan-v2.py:232, decode.15
+//     vae-gan.py:81, D's patch head vae-gan.py:157) -- HBM-bound GEMV-like work, kept off the tensor pipe.
+#include <algorithm>
+#include "vg_common.cuh"
+#include "../../include/vaegan_b200.h"
+
+namespace vg {
+
+static int ew_grid(long long items, int per_block = 256) {
+  long long b = (items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// strided copy
+// ---------------------------------------------------------------------------------------------
+struct CopyParams {
+  long long dims[5], is[5], os[5];
+};
+template <typename TI, typename TO>
+__global__ void strided_copy_kernel(const TI* __restrict__ in, TO* __restrict__ out, CopyParams p,
+                                    const float* __restrict__ scale, int scale_inverse, int accumulate) {
+  const long long total = p.dims[0] * p.dims[1] * p.dims[2] * p.dims[3] * p.dims[4];
+  float sc = 1.f;
+  if (scale != nullptr) sc = scale_inverse ? 1.f / *scale : *scale;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i, io = 0, oo = 0;
+#pragma unroll
+    for (int d = 4; d >= 0; --d) {
+      const long long k = r % p.dims[d];
+      r /= p.dims[d];
+      io += k * p.is[d];
+      oo += k * p.os[d];
+    }
+    float v = static_cast<float>(in[io]) * sc;
+    if (accumulate) v += static_cast<float>(out[oo]);
+    out[oo] = static_cast<TO>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FiLM
+// ---------------------------------------------------------------------------------------------
+__global__ void film_fwd_kernel(const __nv_bfloat16* __restrict__ gb, const __nv_bfloat16* __restrict__ x, int x_ld,
+                                int x_coff, __nv_bfloat16* __restrict__ y, long long rows, int c) {
+  const int cv = c / 8;
+  const long long total = rows * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cv;
+    const int ch = static_cast<int>(i % cv) * 8;
+    float g[8], b[8], xv[8], o[8];
+    load8(gb + r * 2 * c + ch, g);
+    load8(gb + r * 2 * c + c + ch, b);
+    load8(x + r * x_ld + x_coff + ch, xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(g[k], xv[k], b[k]);
+    store8(y + r * c + ch, o);
+  }
+}
+__global__ void film_bwd_kernel(const __nv_bfloat16* __restrict__ gb, const __nv_bfloat16* __restrict__ x, int x_ld,
+                                int x_coff, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dgb,
+                                __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff, long long rows, int c) {
+  const int cv = c / 8;
+  const long long total = rows * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cv;
+    const int ch = static_cast<int>(i % cv) * 8;
+    float g[8], xv[8], d[8], o1[8], o2[8];
+    load8(gb + r * 2 * c + ch, g);
+    load8(x + r * x_ld + x_coff + ch, xv);
+    load8(dy + r * c + ch, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { o1[k] = d[k] * xv[k]; o2[k] = d[k] * g[k]; }
+    store8(dgb + r * 2 * c + ch, o1);      // d gamma
+    store8(dgb + r * 2 * c + c + ch, d);   // d beta
+    store8(dx + r * dx_ld + dx_coff + ch, o2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear upsample of a (1 x w0) map to (h x w), align_corners = False; rows of the result are identical
+// ---------------------------------------------------------------------------------------------
+VG_DEVICE void lerp_src(int j, int w0, int w, int& j0, int& j1, float& lam) {
+  float src = (static_cast<float>(j) + 0.5f) * (static_cast<float>(w0) / static_cast<float>(w)) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  j0 = static_cast<int>(src);
+  if (j0 > w0 - 1) j0 = w0 - 1;
+  j1 = j0 + (j0 < w0 - 1 ? 1 : 0);
+  lam = src - static_cast<float>(j0);
+}
+__global__ void upsample_fwd_kernel(const __nv_bfloat16* __restrict__ t, int t_ld, int t_coff, int n, int w0, int c,
+                                    __nv_bfloat16* __restrict__ y, int h, int w) {
+  const int cv = c / 8;
+  const long long total = static_cast<long long>(n) * h * w * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    const int j = static_cast<int>(pix % w);
+    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    int j0, j1;
+    float lam;
+    lerp_src(j, w0, w, j0, j1, lam);
+    float a[8], bb[8], o[8];
+    load8(t + (static_cast<long long>(b) * w0 + j0) * t_ld + t_coff + ch, a);
+    load8(t + (static_cast<long long>(b) * w0 + j1) * t_ld + t_coff + ch, bb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (1.f - lam) * a[k] + lam * bb[k];
+    store8(y + pix * c + ch, o);
+  }
+}
+// dt[b][js][c] (fp32, accumulated) = sum_i sum_j weight(j -> js) dy[b][i][j][c]; one thread per (b, js, cvec, i-chunk)
+__global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int n, int h, int w, int c, int w0,
+                                    float* __restrict__ dt, int rows_per_thread) {
+  const int cv = c / 8;
+  const int ichunks = (h + rows_per_thread - 1) / rows_per_thread;
+  const long long total = static_cast<long long>(n) * w0 * cv * ichunks;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(idx % cv) * 8;
+    long long r = idx / cv;
+    const int js = static_cast<int>(r % w0);
+    r /= w0;
+    const int ic = static_cast<int>(r % ichunks);
+    const int b = static_cast<int>(r / ichunks);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // destination columns whose source interval touches js: a conservative window, filtered exactly below
+    const float ratio = static_cast<float>(w) / static_cast<float>(w0);
+    int jlo = static_cast<int>((static_cast<float>(js) - 1.f) * ratio) - 2;
+    int jhi = static_cast<int>((static_cast<float>(js) + 2.f) * ratio) + 2;
+    if (jlo < 0) jlo = 0;
+    if (jhi > w - 1) jhi = w - 1;
+    for (int j = jlo; j <= jhi; ++j) {
+      int j0, j1;
+      float lam;
+      lerp_src(j, w0, w, j0, j1, lam);
+      float wgt = 0.f;
+      if (j0 == js) wgt += 1.f - lam;
+      if (j1 == js) wgt += lam;
+      if (wgt == 0.f) continue;
+      const int i_end = min(h, (ic + 1) * rows_per_thread);
+      for (int i = ic * rows_per_thread; i < i_end; ++i) {
+        float d[8];
+        load8(dy + ((static_cast<long long>(b) * h + i) * w + j) * c + ch, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, d[k], acc[k]);
+      }
+    }
+    float* o = dt + (static_cast<long long>(b) * w0 + js) * c + ch;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(o + k, acc[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col / col2im for few-channel NHWC bf16 images: col[m][(r*kw+q)*c + ch], zero padded to kpad columns
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ src, int n, int h, int w, int ld, int c, int kh,
+                              int kw, int stride, int pad, int oh, int ow, __nv_bfloat16* __restrict__ col, int kpad) {
+  const long long total = static_cast<long long>(n) * oh * ow * kpad;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % kpad);
+    const long long m = i / kpad;
+    __nv_bfloat16 v = zero;
+    if (k < kh * kw * c) {
+      const int ch = k % c, tap = k / c;
+      const int q = tap % kw, r = tap / kw;
+      const int ox = static_cast<int>(m % ow), oy = static_cast<int>((m / ow) % oh);
+      const int b = static_cast<int>(m / (static_cast<long long>(ow) * oh));
+      const int iy = oy * stride + r - pad, ix = ox * stride + q - pad;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = src[((static_cast<long long>(b) * h + iy) * w + ix) * ld + ch];
+    }
+    col[i] = v;
+  }
+}
+// dsrc[b][c][iy][ix] (fp32 NCHW, overwritten) = sum over taps of dcol
+__global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dcol, int kpad, int n, int h, int w, int c, int kh,
+                              int kw, int stride, int pad, int oh, int ow, float* __restrict__ dsrc) {
+  const long long total = static_cast<long long>(n) * c * h * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ix = static_cast<int>(i % w), iy = static_cast<int>((i / w) % h);
+    const int ch = static_cast<int>((i / (static_cast<long long>(w) * h)) % c);
+    const int b = static_cast<int>(i / (static_cast<long long>(w) * h * c));
+    float acc = 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int ty = iy + pad - r;
+      if (ty < 0 || ty % stride != 0) continue;
+      const int oy = ty / stride;
+      if (oy >= oh) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int tx = ix + pad - q;
+        if (tx < 0 || tx % stride != 0) continue;
+        const int ox = tx / stride;
+        if (ox >= ow) continue;
+        acc += __bfloat162float(dcol[((static_cast<long long>(b) * oh + oy) * ow + ox) * kpad + (r * kw + q) * c + ch]);
+      }
+    }
+    dsrc[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// direct stride-1 convolutions with few (<= 4) output channels; weights fp32 [cout][kh][kw][cin]
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxSmallN = 4;
+// forward: a group of G lanes per output pixel, lanes stride over (tap, channel-vector)
+__global__ void smalln_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int n, int h, int w,
+                                  int cin, const float* __restrict__ wt, const float* __restrict__ bias, int cout,
+                                  int kh, int kw, int pad, int oh, int ow, float* __restrict__ out, int lanes_per_px) {
+  const int G = lanes_per_px;
+  const long long pixels = static_cast<long long>(n) * oh * ow;
+  const int cv = cin / 8;
+  const int kvecs = kh * kw * cv;
+  const int lane_in_g = threadIdx.x % G;
+  for (long long px = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+       px < ((pixels + (32 / G) - 1) / (32 / G)) * (32 / G);      // keep whole warps in the loop for the shuffles
+       px += static_cast<long long>(gridDim.x) * blockDim.x / G) {
+    float acc[kMaxSmallN] = {0.f, 0.f, 0.f, 0.f};
+    if (px < pixels) {
+      const int ox = static_cast<int>(px % ow), oy = static_cast<int>((px / ow) % oh);
+      const int b = static_cast<int>(px / (static_cast<long long>(ow) * oh));
+      for (int kv = lane_in_g; kv < kvecs; kv += G) {
+        const int tap = kv / cv, ch = (kv % cv) * 8;
+        const int iy = oy + tap / kw - pad, ix = ox + tap % kw - pad;
+        if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+        float f[8];
+        load8(x + ((static_cast<long long>(b) * h + iy) * w + ix) * x_ld + x_coff + ch, f);
+        for (int o = 0; o < cout; ++o) {
+          const float* wp = wt + (static_cast<long long>(o) * kh * kw + tap) * cin + ch;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o] = fmaf(f[k], __ldg(wp + k), acc[o]);
+        }
+      }
+    }
+    for (int o = 0; o < cout; ++o) {
+      float v = acc[o];
+      for (int s = G / 2; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane_in_g == 0 && px < pixels) out[px * cout + o] = v + (bias ? bias[o] : 0.f);
+    }
+  }
+}
+// data gradient: thread per (input pixel, channel vector)
+__global__ void smalln_dgrad_kernel(const float* __restrict__ dy, int n, int oh, int ow, int cout,
+                                    const float* __restrict__ wt, int kh, int kw, int pad, int h, int w, int cin,
+                                    __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff) {
+  const int cv = cin / 8;
+  const long long total = static_cast<long long>(n) * h * w * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    const int ix = static_cast<int>(pix % w), iy = static_cast<int>((pix / w) % h);
+    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int oy = iy + pad - r;
+      if (oy < 0 || oy >= oh) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int ox = ix + pad - q;
+        if (ox < 0 || ox >= ow) continue;
+        const float* g = dy + ((static_cast<long long>(b) * oh + oy) * ow + ox) * cout;
+        for (int o = 0; o < cout; ++o) {
+          const float gv = g[o];
+          const float* wp = wt + (static_cast<long long>(o) * kh * kw + r * kw + q) * cin + ch;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(gv, __ldg(wp + k), acc[k]);
+        }
+      }
+    }
+    store8(dx + pix * dx_ld + dx_coff + ch, acc);
+  }
+}
+// weight gradient: block = (tap, pixel chunk); thread = (channel vector, pixel lane); fp32 atomics per block
+__global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                           int x_ld, int x_coff, int n, int h, int w, int cin, int cout,
+                                                           int kh, int kw, int pad, int oh, int ow,
+                                                           float* __restrict__ dw, float* __restrict__ dbias) {
+  const int cv = cin / 8;
+  const int cvl = cv < 256 ? cv : 256;
+  const int ppar = 256 / cvl;
+  const int tap = blockIdx.y;
+  const int r = tap / kw, q = tap % kw;
+  const int tid = threadIdx.x;
+  const int pl = tid / cvl, cvi = tid % cvl;
+  const long long pixels = static_cast<long long>(n) * oh * ow;
+  __shared__ float red[256][8 * kMaxSmallN + 1];
+  for (int cv0 = 0; cv0 < cv; cv0 += cvl) {
+    const int cvec = cv0 + cvi;
+    const int ch = cvec * 8;
+    float acc[kMaxSmallN][8];
+    float bacc[kMaxSmallN];
+    for (int o = 0; o < kMaxSmallN; ++o) {
+      bacc[o] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
+    }
+    if (pl < ppar && cvec < cv) {
+      for (long long px = static_cast<long long>(blockIdx.x) * ppar + pl; px < pixels;
+           px += static_cast<long long>(gridDim.x) * ppar) {
+        const int ox = static_cast<int>(px % ow), oy = static_cast<int>((px / ow) % oh);
+        const int b = static_cast<int>(px / (static_cast<long long>(ow) * oh));
+        const float* g = dy + px * cout;
+        if (tap == 0 && cvec == 0)
+          for (int o = 0; o < cout; ++o) bacc[o] += g[o];
+        const int iy = oy + r - pad, ix = ox + q - pad;
+        if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+        float f[8];
+        load8(x + ((static_cast<long long>(b) * h + iy) * w + ix) * x_ld + x_coff + ch, f);
+        for (int o = 0; o < cout; ++o) {
+          const float gv = g[o];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o][k] = fmaf(gv, f[k], acc[o][k]);
+        }
+      }
+    }
+    for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[tid][o * 8 + k] = acc[o][k];
+    __syncthreads();
+    if (pl == 0 && cvec < cv) {
+      for (int o = 0; o < cout; ++o)
+        for (int k = 0; k < 8; ++k) {
+          float a = 0.f;
+          for (int p2 = 0; p2 < ppar; ++p2) a += red[p2 * cvl + cvi][o * 8 + k];
+          atomicAdd(dw + (static_cast<long long>(o) * kh * kw + tap) * cin + ch + k, a);
+        }
+    }
+    __syncthreads();
+    if (dbias != nullptr && tap == 0 && cv0 == 0 && cvi == 0 && pl < ppar)
+      for (int o = 0; o < cout; ++o)
+        if (bacc[o] != 0.f) atomicAdd(dbias + o, bacc[o]);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// plain activation backward (for activations fused into a conv epilogue): dx = dy * act'(y)
+// ---------------------------------------------------------------------------------------------
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy,
+                               int dy_ld, __nv_bfloat16* __restrict__ dx, int dx_ld, long long rows, int c, int act) {
+  const int cv = c / 8;
+  const long long total = rows * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cv;
+    const int ch = static_cast<int>(i % cv) * 8;
+    float yv[8], d[8], o[8];
+    load8(y + r * y_ld + ch, yv);
+    load8(dy + r * dy_ld + ch, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = d[k] * (yv[k] > 0.f ? 1.f : (act == 2 ? 0.2f : 0.f));
+    store8(dx + r * dx_ld + ch, o);
+  }
+}
+// out[c] (=|+=) sum_r in[r][c]   (fp32; small matrices: bias gradients of the heads)
+__global__ void colsum_f32_kernel(const float* __restrict__ in, long long rows, int cols, int ld, float* __restrict__ out,
+                                  int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (long long r = 0; r < rows; ++r) acc += in[r * ld + c];
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_strided_copy(const void* in, int in_dtype, void* out, int out_dtype, const long long* dims,
+                               const long long* in_strides, const long long* out_strides, const float* scale,
+                               int scale_inverse, int accumulate, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  CopyParams p;
+  long long total = 1;
+  for (int i = 0; i < 5; ++i) {
+    p.dims[i] = dims[i]; p.is[i] = in_strides[i]; p.os[i] = out_strides[i];
+    VG_CHECK(dims[i] >= 1, -1, "vg_strided_copy: dims must be >= 1");
+    total *= dims[i];
+  }
+  const int g = ew_grid(total);
+  if (in_dtype == 0 && out_dtype == 0)
+    strided_copy_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), p, scale, scale_inverse, accumulate);
+  else if (in_dtype == 0 && out_dtype == 1)
+    strided_copy_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), p, scale, scale_inverse, accumulate);
+  else if (in_dtype == 1 && out_dtype == 0)
+    strided_copy_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<float*>(out), p, scale, scale_inverse, accumulate);
+  else if (in_dtype == 1 && out_dtype == 1)
+    strided_copy_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), p, scale, scale_inverse, accumulate);
+  else
+    VG_CHECK(false, -1, "vg_strided_copy: dtype codes are 0 (fp32) and 1 (bf16)");
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, void* y, long long rows, int c,
+                           void* stream_) {
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_film_fwd: channels must be multiples of 8");
+  film_fwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+      static_cast<__nv_bfloat16*>(y), rows, c);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx,
+                           int dx_ld, int dx_coff, long long rows, int c, void* stream_) {
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && dx_ld % 8 == 0 && dx_coff % 8 == 0, -1,
+           "vg_film_bwd: channels must be multiples of 8");
+  film_bwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+      static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dgb), static_cast<__nv_bfloat16*>(dx), dx_ld,
+      dx_coff, rows, c);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c, void* y, int h, int w,
+                                 void* stream_) {
+  VG_CHECK(c % 8 == 0 && t_ld % 8 == 0 && t_coff % 8 == 0, -1, "vg_upsample_w_fwd: channels must be multiples of 8");
+  upsample_fwd_kernel<<<ew_grid(static_cast<long long>(n) * h * w * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(t), t_ld, t_coff, n, w0, c, static_cast<__nv_bfloat16*>(y), h, w);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(c % 8 == 0, -1, "vg_upsample_w_bwd: channels must be multiples of 8");
+  VG_CUDA(cudaMemsetAsync(dt, 0, sizeof(float) * static_cast<size_t>(n) * w0 * c, st));
+  const int rpt = 8;
+  const long long items = static_cast<long long>(n) * w0 * (c / 8) * ((h + rpt - 1) / rpt);
+  upsample_bwd_kernel<<<ew_grid(items), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, w0, dt, rpt);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vg_im2col(const void* src, int n, int h, int w, int ld, int c, int kh, int kw, int stride, int pad,
+                         void* col, int kpad, void* stream_) {
+  VG_CHECK(kh * kw * c <= kpad && kpad % 64 == 0, -1, "vg_im2col: kpad must be a multiple of 64 >= kh*kw*c");
+  const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
+  im2col_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * kpad), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(src), n, h, w, ld, c, kh, kw, stride, pad, oh, ow,
+      static_cast<__nv_bfloat16*>(col), kpad);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int vg_col2im(const void* dcol, int kpad, int n, int h, int w, int c, int kh, int kw, int stride, int pad,
+                         float* dsrc_nchw, void* stream_) {
+  const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
+  col2im_kernel<<<ew_grid(static_cast<long long>(n) * c * h * w), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(dcol), kpad, n, h, w, c, kh, kw, stride, pad, oh, ow, dsrc_nchw);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int smalln_lanes(int kvecs) {
+  int g = 1;
+  while (g < 32 && g < kvecs) g <<= 1;
+  return g;
+}
+extern "C" int vg_conv_smalln_fwd(const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, const float* wt,
+                                  const float* bias, int cout, int kh, int kw, int pad, float* out, void* stream_) {
+  VG_CHECK(cout >= 1 && cout <= kMaxSmallN && cin % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1,
+           "vg_conv_smalln_fwd: cout must be 1..4 and channels multiples of 8");
+  const int oh = h + 2 * pad - kh + 1, ow = w + 2 * pad - kw + 1;
+  const int G = smalln_lanes(kh * kw * (cin / 8));
+  smalln_fwd_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * G), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w, cin, wt, bias, cout, kh, kw, pad, oh, ow, out, G);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int cin, const float* wt, int cout, int kh,
+                                    int kw, int pad, void* dx, int dx_ld, int dx_coff, void* stream_) {
+  VG_CHECK(cout >= 1 && cout <= kMaxSmallN && cin % 8 == 0 && dx_ld % 8 == 0 && dx_coff % 8 == 0, -1,
+           "vg_conv_smalln_dgrad: cout must be 1..4 and channels multiples of 8");
+  const int oh = h + 2 * pad - kh + 1, ow = w + 2 * pad - kw + 1;
+  smalln_dgrad_kernel<<<ew_grid(static_cast<long long>(n) * h * w * (cin / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      dy, n, oh, ow, cout, wt, kh, kw, pad, h, w, cin, static_cast<__nv_bfloat16*>(dx), dx_ld, dx_coff);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, int x_coff, int n, int h, int w, int cin,
+                                    int cout, int kh, int kw, int pad, float* dw, float* dbias, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(cout >= 1 && cout <= kMaxSmallN && cin % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1,
+           "vg_conv_smalln_wgrad: cout must be 1..4 and channels multiples of 8");
+  const int oh = h + 2 * pad - kh + 1, ow = w + 2 * pad - kw + 1;
+  VG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * static_cast<size_t>(cout) * kh * kw * cin, st));
+  if (dbias) VG_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * cout, st));
+  const int cv = cin / 8, cvl = cv < 256 ? cv : 256, ppar = 256 / cvl;
+  const long long pixels = static_cast<long long>(n) * oh * ow;
+  int gx = static_cast<int>(std::min<long long>((pixels + ppar * 16 - 1) / (ppar * 16), std::max(1, num_sms() * 4 / (kh * kw))));
+  if (gx < 1) gx = 1;
+  smalln_wgrad_kernel<<<dim3(gx, kh * kw), 256, 0, st>>>(dy, static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w,
+                                                         cin, cout, kh, kw, pad, oh, ow, dw, dbias);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, void* dx, int dx_ld, long long rows, int c,
+                          int act, void* stream_) {
+  VG_CHECK(c % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, -1, "vg_act_bwd: channels must be multiples of 8");
+  act_bwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(y), y_ld, static_cast<const __nv_bfloat16*>(dy), dy_ld,
+      static_cast<__nv_bfloat16*>(dx), dx_ld, rows, c, act);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int vg_colsum_f32(const float* in, long long rows, int cols, int ld, float* out, int accumulate, void* stream_) {
+  colsum_f32_kernel<<<cdiv(cols, 128), 128, 0, static_cast<cudaStream_t>(stream_)>>>(in, rows, cols, ld, out, accumulate);
+  VG_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,561 @@
+"""Autograd-level building blocks: each ``torch.autograd.Function`` here runs hand-written CUDA kernels
+(ops.py / conv.py) in both directions.  Activations between them are NHWC bf16 views; parameters stay fp32 in
+PyTorch layouts so that state_dicts match the reference modules.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .conv import ConvLinear, fprop, new_act, wgrad
+from .ops import BF16, F32, round_up
+
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch() -> None:
+    """Invalidate cached bf16 weight re-layouts (call after updating parameters through raw pointers)."""
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
+class WeightCache:
+    """bf16 GEMM layouts of one fp32 parameter, rebuilt only when the parameter changed."""
+
+    def __init__(self):
+        self.key = None
+        self.store: Dict[str, object] = {}
+
+    def get(self, name: str, param, build):
+        params = param if isinstance(param, (tuple, list)) else (param,)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (_WEIGHT_EPOCH,)
+        if key != self.key:
+            self.key, self.store = key, {}
+        if name not in self.store:
+            self.store[name] = build()
+        return self.store[name]
+
+    def clear(self):
+        self.key, self.store = None, {}
+
+
+def grad_in(t: Optional[torch.Tensor], like: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Coerce an incoming autograd gradient to a valid NHWC bf16 view (copying only if it is not one already);
+    when the channel count is not a multiple of 64 the copy is padded so the tensor pipe can read it."""
+    if t is None:
+        return None
+    c = t.shape[3]
+    need_pad = c % 64 != 0 and t.stride(2) < round_up(c, 64)
+    if t.dtype == BF16 and ops.nhwc_ok(t) and not need_pad:
+        return t
+    out = new_act(t.shape[0], t.shape[1], t.shape[2], c, t.device)
+    ops.strided_copy(t, out)
+    return out
+
+
+def _write_param_grad(view_oihw: torch.Tensor) -> torch.Tensor:
+    """Materialise an fp32 gradient given as a permuted view into a fresh contiguous tensor in parameter layout."""
+    out = torch.empty(view_oihw.shape, dtype=F32, device=view_oihw.device)
+    ops.strided_copy(view_oihw, out)
+    return out
+
+
+def _bias_grad(dy: torch.Tensor) -> torch.Tensor:
+    """Per-channel sum of an NHWC bf16 gradient (fp32)."""
+    return ops.norm_stats(dy, per_sample=False)[0, 0].clone()
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions on the tensor pipe
+# ------------------------------------------------------------------------------------------------
+class Conv2dFn(Function):
+    """y = act(conv2d(x, w) + b).  Replaces nn.Conv2d forward/backward (cuDNN) of the reference layers."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_kind: int, sn):
+        scale = sn.sigma if sn is not None else None
+        wf = cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach(), scale)) if sn is None else op.prep_fwd(weight.detach(), scale)
+        y = op.forward(x, wf, bias.detach() if bias is not None else None, act, out, out_kind)
+        ctx.op, ctx.cache, ctx.act, ctx.sn, ctx.has_bias = op, cache, act, sn, bias is not None
+        ctx.in_hw = (x.shape[1], x.shape[2])
+        ctx.save_for_backward(x, weight, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        op: ConvLinear = ctx.op
+        dy = grad_in(dy)
+        if ctx.act:
+            g = new_act(*dy.shape, dy.device)
+            ops.act_bwd(y, dy, g, ctx.act)
+            dy = g
+        dx = dw = db = None
+        sn = ctx.sn
+        scale = sn.sigma if sn is not None else None
+        if ctx.needs_input_grad[0]:
+            wb = (ctx.cache.get("bwd", weight, lambda: op.prep_bwd(weight.detach(), scale)) if sn is None
+                  else op.prep_bwd(weight.detach(), scale))
+            dx = op.backward_data(dy, wb, ctx.in_hw)
+        if ctx.needs_input_grad[1]:
+            gview = op.backward_weight(dy, x)
+            dw = _write_param_grad(gview)
+            if sn is not None:
+                dw = sn.backward(dw, weight.detach())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _bias_grad(dy)
+        return dx, dw, db, None, None, None, None, None, None
+
+
+class ConvTranspose2dFn(Function):
+    """y = act(conv_transpose2d(x, w) + b), computed as the data-gradient primitive of the adjoint conv ``op``
+    (cin(op) = C_out of the transpose, cout(op) = C_in of the transpose; the IOHW weight is op's OIHW)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_hw):
+        wb = cache.get("bwd", weight, lambda: op.prep_bwd(weight.detach()))
+        y = op.backward_data(x, wb, out_hw, bias.detach() if bias is not None else None, act, out)
+        ctx.op, ctx.cache, ctx.act, ctx.has_bias = op, cache, act, bias is not None
+        ctx.save_for_backward(x, weight, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        op: ConvLinear = ctx.op
+        dy = grad_in(dy)
+        if ctx.act:
+            g = new_act(*dy.shape, dy.device)
+            ops.act_bwd(y, dy, g, ctx.act)
+            dy = g
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wf = ctx.cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach()))
+            dx = op.forward(dy, wf)
+        if ctx.needs_input_grad[1]:
+            dw = _write_param_grad(op.backward_weight(x, dy))     # operands swapped: [cout(op)=C_in][cin(op)=C_out]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _bias_grad(dy)
+        return dx, dw, db, None, None, None, None, None
+
+
+class HeadsFn(Function):
+    """mu_head and logvar_head (full-spatial-kernel Conv2d, vae-gan.py:59-60, vae-gan-v2.py:168-169) as ONE split-K
+    GEMM with N = 2z over the flattened (h, w, c) feature map; fp32 result [B,1,1,2z] WITHOUT bias (the bias is
+    added in the fused reparameterisation kernel)."""
+
+    @staticmethod
+    def forward(ctx, feat, w_mu, w_lv, op: ConvLinear, cache_f: WeightCache, cache_b: WeightCache):
+        z, c, kh, kw = w_mu.shape
+
+        def build():
+            wf = torch.empty((2 * z, kh, kw, c), dtype=BF16, device=feat.device)
+            ops.strided_copy(w_mu.detach().permute(0, 2, 3, 1), wf[:z])
+            ops.strided_copy(w_lv.detach().permute(0, 2, 3, 1), wf[z:])
+            return wf.view(2 * z, kh * kw * c)
+        wf = cache_f.get("fwd", (w_mu, w_lv), build)
+        if not feat.is_contiguous():
+            feat = ops.dense_nhwc(feat)
+        y = op.forward(feat, wf, None, 0, None, 2)
+        ctx.op, ctx.cache_b = op, cache_b
+        ctx.save_for_backward(feat, w_mu, w_lv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        feat, w_mu, w_lv = ctx.saved_tensors
+        op: ConvLinear = ctx.op
+        z, c, kh, kw = w_mu.shape
+        dy = grad_in(dy)
+        dx = dmu = dlv = None
+        if ctx.needs_input_grad[0]:
+            def build():
+                wd = (torch.zeros if op.cout_p != 2 * z else torch.empty)((kh, kw, c, op.cout_p), dtype=BF16, device=dy.device)
+                ops.strided_copy(w_mu.detach().permute(2, 3, 1, 0), wd[..., :z])
+                ops.strided_copy(w_lv.detach().permute(2, 3, 1, 0), wd[..., z:2 * z])
+                return {"shuffle": wd.view(kh * kw * c, op.cout_p)}
+            wb = ctx.cache_b.get("bwd", (w_mu, w_lv), build)
+            dx = op.backward_data(dy, wb, (feat.shape[1], feat.shape[2]))
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            g = op.backward_weight(dy, feat)                 # view [2z, c, kh, kw]
+            dmu, dlv = _write_param_grad(g[:z]), _write_param_grad(g[z:])
+        return dx, dmu, dlv, None, None, None
+
+
+class CopyIntoFn(Function):
+    """Copy an NHWC tensor into a channel slice of a concat buffer (only needed when the producer could not
+    write there directly)."""
+
+    @staticmethod
+    def forward(ctx, src, dst):
+        ops.strided_copy(src, dst)
+        return dst.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+# ------------------------------------------------------------------------------------------------
+# few-channel image-side conv (im2col + GEMM) and few-output-channel conv (CUDA cores)
+# ------------------------------------------------------------------------------------------------
+class ImageConvFn(Function):
+    """Conv2d whose input is a 3/4-channel NCHW fp32 image (or a channel-concatenation of several): the
+    encoder's first conv on cat(image, mask) (vae-gan-v2.py:318-319) and D's first conv (vae-gan.py:153).
+    im2col into a [pixels][64] bf16 matrix, then a plain tensor-core GEMM with bias/activation fused."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, geom, cache: WeightCache, act: int, sn, *images):
+        kh, kw, stride, pad = geom
+        n, _, h, w = images[0].shape
+        cin = sum(t.shape[1] for t in images)
+        cout = weight.shape[0]
+        kpad = round_up(kh * kw * cin, 64)
+        src = torch.empty((n, h, w, 8), dtype=BF16, device=weight.device)
+        c0 = 0
+        for t in images:
+            ops.strided_copy(t.detach().permute(0, 2, 3, 1), src[..., c0:c0 + t.shape[1]])
+            c0 += t.shape[1]
+        oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+        col = torch.empty((n, oh, ow, kpad), dtype=BF16, device=weight.device)
+        ops.im2col(src, cin, kh, kw, stride, pad, col)
+        scale = sn.sigma if sn is not None else None
+
+        def build():
+            wf = torch.zeros((cout, kpad), dtype=BF16, device=weight.device)
+            ops.strided_copy(weight.detach().permute(0, 2, 3, 1), wf[:, :kh * kw * cin].view(cout, kh, kw, cin), scale,
+                             scale_inverse=scale is not None)
+            return wf
+        wf = cache.get("fwd", weight, build) if sn is None else build()
+        y = new_act(n, oh, ow, cout, weight.device)
+        fprop(col, [(0, 0, 0, 0)], 1, kpad, wf, cout, (n, oh, ow), y, bias=bias.detach() if bias is not None else None,
+              act=act)
+        ctx.geom, ctx.act, ctx.sn, ctx.cin, ctx.kpad, ctx.has_bias = geom, act, sn, cin, kpad, bias is not None
+        ctx.img_shapes = [tuple(t.shape) for t in images]
+        ctx.save_for_backward(col, weight, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, weight, y = ctx.saved_tensors
+        kh, kw, stride, pad = ctx.geom
+        cout, cin, kpad = weight.shape[0], ctx.cin, ctx.kpad
+        dy = grad_in(dy)
+        if ctx.act:
+            g = new_act(*dy.shape, dy.device)
+            ops.act_bwd(y, dy, g, ctx.act)
+            dy = g
+        n, oh, ow, _ = dy.shape
+        dw = db = None
+        sn = ctx.sn
+        if ctx.needs_input_grad[0]:
+            dwm = torch.empty((cout, kpad), dtype=F32, device=dy.device)
+            wgrad(dy, cout, col, [(0, 0, 0, 0)], 1, kpad, (n, oh, ow), dwm)
+            dw = _write_param_grad(dwm[:, :kh * kw * cin].view(cout, kh, kw, cin).permute(0, 3, 1, 2))
+            if sn is not None:
+                dw = sn.backward(dw, weight.detach())
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            db = _bias_grad(dy)
+        dimgs = [None] * len(ctx.img_shapes)
+        if any(ctx.needs_input_grad[6:]):
+            scale = sn.sigma if sn is not None else None
+            cout_p = round_up(cout, 64)
+            wd = torch.zeros((kpad, cout_p), dtype=BF16, device=dy.device)      # [(r,q,ci)][co]
+            ops.strided_copy(weight.detach().permute(2, 3, 1, 0), wd[:kh * kw * cin, :cout].view(kh, kw, cin, cout), scale,
+                             scale_inverse=scale is not None)
+            dcol = torch.empty((n, oh, ow, kpad), dtype=BF16, device=dy.device)
+            from .conv import pad_channels
+            fprop(pad_channels(dy, cout_p), [(0, 0, 0, 0)], 1, cout_p, wd, kpad, (n, oh, ow), dcol)
+            n_, _, h, w = ctx.img_shapes[0]
+            dsrc = torch.empty((n_, cin, h, w), dtype=F32, device=dy.device)
+            ops.col2im(dcol, n_, h, w, cin, kh, kw, stride, pad, dsrc)
+            c0 = 0
+            for i, shp in enumerate(ctx.img_shapes):
+                if ctx.needs_input_grad[6 + i]:
+                    dimgs[i] = dsrc[:, c0:c0 + shp[1]]
+                c0 += shp[1]
+        return (dw, db, None, None, None, None, *dimgs)
+
+
+class SmallOutConvFn(Function):
+    """Stride-1 Conv2d with <= 4 output channels on CUDA cores (HBM-bound): final_image_conv
+    (vae-gan-v2.py:232), decode.15 (vae-gan.py:81), D's patch head (vae-gan.py:157).  Output fp32 NHWC."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad: int):
+        cout, cin, kh, kw = weight.shape
+        n, h, w, _ = x.shape
+        wt = torch.empty((cout, kh, kw, cin), dtype=F32, device=x.device)
+        ops.strided_copy(weight.detach().permute(0, 2, 3, 1), wt)
+        oh, ow = h + 2 * pad - kh + 1, w + 2 * pad - kw + 1
+        out = torch.empty((n, oh, ow, cout), dtype=F32, device=x.device)
+        ops.smalln_fwd(x, wt, bias.detach() if bias is not None else None, kh, kw, pad, out)
+        ctx.pad, ctx.has_bias = pad, bias is not None
+        ctx.save_for_backward(x, wt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wt = ctx.saved_tensors
+        cout, kh, kw, cin = wt.shape
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = new_act(x.shape[0], x.shape[1], x.shape[2], cin, x.device)
+            ops.smalln_dgrad(dy, wt, kh, kw, ctx.pad, dx)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dwt = torch.empty_like(wt)
+            db_ = torch.empty(cout, dtype=F32, device=x.device) if ctx.has_bias else None
+            ops.smalln_wgrad(dy, x, kh, kw, ctx.pad, dwt, db_)
+            dw = _write_param_grad(dwt.permute(0, 3, 1, 2))
+            db = db_
+        return dx, dw, db, None
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation + activation (+ pool)
+# ------------------------------------------------------------------------------------------------
+class NormActFn(Function):
+    """BatchNorm2d (training or eval) + ReLU [+ MaxPool2d(2)]  or  InstanceNorm2d(affine) + LeakyReLU(0.2).
+    Returns (y, pooled-or-None).  ``out`` lets the full-resolution result land in a slice of a concat buffer."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, per_sample: bool, act: int, pool: bool, out, eps: float, bn_state, pool_out=None):
+        n, h, w, c = x.shape
+        g, b = (gamma.detach() if gamma is not None else None), (beta.detach() if beta is not None else None)
+        if bn_state is not None and not bn_state["training"]:
+            mr = torch.stack([bn_state["running_mean"], torch.rsqrt(bn_state["running_var"] + eps)]).unsqueeze(0).contiguous()
+            ctx.eval_mode = True
+        else:
+            sums = ops.norm_stats(x, per_sample)
+            rows = h * w if per_sample else n * h * w
+            rm = rv = nbt = None
+            if bn_state is not None:
+                rm, rv, nbt = bn_state["running_mean"], bn_state["running_var"], bn_state["num_batches_tracked"]
+            mr = ops.norm_finalize(sums, rows, eps, 0.1, rm, rv, nbt)
+            ctx.eval_mode = False
+        y = out if out is not None else new_act(n, h, w, c, x.device)
+        pooled = None
+        if pool:
+            pooled = pool_out if pool_out is not None else new_act(n, h // 2, w // 2, c, x.device)
+        ops.norm_apply(x, mr, g, b, act, y, pooled)
+        ctx.per_sample, ctx.act, ctx.pool = per_sample, act, pool
+        ctx.save_for_backward(x, gamma, beta, mr)
+        y_ret = y.detach() if out is not None else y
+        p_ret = pooled.detach() if (pool and pool_out is not None) else pooled
+        return y_ret, p_ret
+
+    @staticmethod
+    def backward(ctx, dy, dpool):
+        x, gamma, beta, mr = ctx.saved_tensors
+        assert not ctx.eval_mode, "backward through eval-mode normalisation is not supported"
+        dy, dpool = grad_in(dy), grad_in(dpool)
+        n, h, w, c = x.shape
+        dx = new_act(n, h, w, c, x.device)
+        dgamma = torch.empty(c, dtype=F32, device=x.device) if gamma is not None else None
+        dbeta = torch.empty(c, dtype=F32, device=x.device) if beta is not None else None
+        ops.norm_backward(x, dy, dpool, mr, ctx.per_sample, gamma, beta, ctx.act, dx, dgamma, dbeta)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# FiLM, upsample, layout glue
+# ------------------------------------------------------------------------------------------------
+class FiLMFn(Function):
+    """y = gamma * x + beta with (gamma | beta) = gb[..., :C] | gb[..., C:]   (vae-gan-v2.py:146-149)."""
+
+    @staticmethod
+    def forward(ctx, gb, x):
+        n, h, w, c = x.shape
+        y = torch.empty((n, h, w, c), dtype=BF16, device=x.device)
+        ops.film_fwd(gb, x, y)
+        ctx.save_for_backward(gb, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        gb, x = ctx.saved_tensors
+        dy = grad_in(dy)
+        if not dy.is_contiguous():
+            dy = ops.dense_nhwc(dy)
+        dgb = torch.empty_like(gb)
+        dx = torch.empty(x.shape, dtype=BF16, device=x.device)
+        ops.film_bwd(gb, x, dy, dgb, dx)
+        return dgb, dx
+
+
+class UpsampleWFn(Function):
+    """F.interpolate(t, size=(h, w), mode='bilinear', align_corners=False) for a (1 x w0) map (vae-gan-v2.py:138-140)."""
+
+    @staticmethod
+    def forward(ctx, t, h: int, w: int):
+        n, _, w0, c = t.shape
+        y = torch.empty((n, h, w, c), dtype=BF16, device=t.device)
+        ops.upsample_w_fwd(t, y)
+        ctx.w0 = w0
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = grad_in(dy)
+        if not dy.is_contiguous():
+            dy = ops.dense_nhwc(dy)
+        n, h, w, c = dy.shape
+        dt = torch.empty((n, 1, ctx.w0, c), dtype=F32, device=dy.device)
+        ops.upsample_w_bwd(dy, dt)
+        out = torch.empty((n, 1, ctx.w0, c), dtype=BF16, device=dy.device)
+        ops.strided_copy(dt, out)
+        return out, None, None
+
+
+class ToNHWCFn(Function):
+    """NCHW fp32 -> NHWC bf16 (module boundary / stock-torch text encoder output)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        n, c, h, w = t.shape
+        out = new_act(n, h, w, c, t.device)
+        ops.strided_copy(t.permute(0, 2, 3, 1), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, h, w, c = dy.shape
+        out = torch.empty((n, c, h, w), dtype=F32, device=dy.device)
+        ops.strided_copy(dy.permute(0, 3, 1, 2), out)
+        return out
+
+
+class CatSlicesFn(Function):
+    """torch.cat([a, b], dim=C) where both already sit in adjacent channel slices of one buffer: no copy in
+    either direction (vae-gan-v2.py:251-274, vae-gan-unet.py:232-248)."""
+
+    @staticmethod
+    def forward(ctx, a, b, buf):
+        ca, cb = a.shape[3], b.shape[3]
+        assert a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf.data_ptr() + 2 * ca and buf.shape[3] == ca + cb
+        ctx.ca = ca
+        return buf.detach()
+
+    @staticmethod
+    def backward(ctx, d):
+        d = grad_in(d)
+        return d[..., :ctx.ca], d[..., ctx.ca:], None
+
+
+class ZTextCatFn(Function):
+    """cat([z.expand(-1,-1,1,w0), text], C) as an NHWC bf16 [B,1,w0,z+ct] tensor (vae-gan-v2.py:249-251; with w0 = 1
+    it is cat([z, spatial_broadcast(text)]) of vae-gan.py:143-145).  z: fp32 [B, zc]; text: NHWC bf16 [B,1,w0,ct]."""
+
+    @staticmethod
+    def forward(ctx, z, text):
+        b, zc = z.shape
+        _, _, w0, ct = text.shape
+        out = new_act(b, 1, w0, zc + ct, z.device)
+        ops.strided_copy(z.view(b, 1, 1, zc).expand(b, 1, w0, zc), out[..., :zc])
+        ops.strided_copy(text, out[..., zc:])
+        ctx.zc = zc
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = grad_in(d)
+        zc = ctx.zc
+        dz = ops.norm_stats(d[..., :zc], per_sample=True)[:, 0, :].contiguous()   # sum over the w0 columns, fp32
+        return dz, d[..., zc:]
+
+
+# ------------------------------------------------------------------------------------------------
+# reparameterisation + KL, output sigmoid, losses
+# ------------------------------------------------------------------------------------------------
+class ReparamKLFn(Function):
+    """(mu, logvar, z, kl) from the raw head GEMM result (vae-gan.py:133-136,420).  ``eps`` comes from
+    torch.randn_like on the host side so the RNG stream matches the reference."""
+
+    @staticmethod
+    def forward(ctx, heads, bias_mu, bias_lv, eps):
+        b = heads.shape[0]
+        h2 = heads.reshape(b, -1)
+        mu, lv, z, kl = ops.reparam_kl_fwd(h2, bias_mu.detach(), bias_lv.detach(), eps)
+        ctx.save_for_backward(mu, lv, eps)
+        ctx.heads_shape = heads.shape
+        return mu, lv, z, kl
+
+    @staticmethod
+    def backward(ctx, dmu, dlv, dz, dkl):
+        mu, lv, eps = ctx.saved_tensors
+        c = lambda t: t.contiguous() if t is not None else None
+        dheads = ops.reparam_kl_bwd(mu, lv, eps, c(dz), c(dmu), c(dlv), c(dkl))
+        z = mu.shape[1]
+        db_mu = torch.empty(z, dtype=F32, device=mu.device)
+        db_lv = torch.empty(z, dtype=F32, device=mu.device)
+        ops.colsum_f32(dheads[:, :z], db_mu)
+        ops.colsum_f32(dheads[:, z:], db_lv)
+        return dheads.view(ctx.heads_shape), db_mu, db_lv, None
+
+
+class SigmoidOutFn(Function):
+    """NHWC fp32 pre-activation -> NCHW fp32 sigmoid image (vae-gan.py:82)."""
+
+    @staticmethod
+    def forward(ctx, pre):
+        n, h, w, c = pre.shape
+        y = torch.empty((n, c, h, w), dtype=F32, device=pre.device)
+        ops.sigmoid_fwd(pre, y)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        n, c, h, w = y.shape
+        dpre = torch.empty((n, h, w, c), dtype=F32, device=y.device)
+        ops.sigmoid_bwd(y, dy.contiguous(), dpre)
+        return dpre
+
+
+class L1LossFn(Function):
+    """nn.L1Loss() (mean) -- vae-gan.py:419,537."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        return ops.l1_fwd(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a)
+        ops.l1_bwd(a, b, g.contiguous(), da)
+        return da, None
+
+
+class HingeLossFn(Function):
+    """hinge_loss(preds, target) -- vae-gan.py:313-320.  mode: 1 real, 0 fake, 2 generator (target None)."""
+
+    @staticmethod
+    def forward(ctx, p, mode: int):
+        p = p.contiguous()
+        ctx.save_for_backward(p)
+        ctx.mode = mode
+        return ops.hinge_fwd(p, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        dp = torch.empty_like(p)
+        ops.hinge_bwd(p, ctx.mode, g.contiguous(), dp)
+        return dp, None
+
+
+def l1_loss(a, b):
+    return L1LossFn.apply(a, b)
+
+
+def hinge_loss(preds, target):
+    """Same call convention as the reference's hinge_loss(preds, target) with target in {1, 0, None}."""
+    return HingeLossFn.apply(preds, 1 if target == 1 else (0 if target == 0 else 2))

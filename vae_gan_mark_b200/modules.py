@@ -1,0 +1,575 @@
+"""Drop-in nn.Modules with the reference's constructor signatures, attribute names and state_dict keys,
+whose forward/backward run on the hand-written sm_100a kernels (layers.py).
+
+The parameter containers are stock ``nn.Conv2d`` / ``nn.ConvTranspose2d`` / ``nn.BatchNorm2d`` /
+``nn.InstanceNorm2d`` / ``spectral_norm`` objects arranged exactly as in the reference, so ``state_dict()``,
+``parameters()`` order, ``.to()``, ``.train()/.eval()`` and checkpoint loading behave identically; they are
+never *called* -- the executors below read their tensors and launch our kernels.  Only the recurrent text
+encoder (``CharacterTokenEncoder``; <2% of the FLOPs) and the 384->64 text projection run as
+stock torch modules.
+
+Like the reference, constructors read the module-level ``PATCH_SHAPE`` = (W, H) unless ``patch_shape`` is given.
+
+Reference: vae-gan.py:47-159, vae-gan-v2.py:65-349, vae-gan-unet.py:124-317.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+from torch.nn.utils import spectral_norm
+
+from . import layers as L
+from . import ops
+from .conv import ConvLinear, new_act
+from .ops import BF16, F32
+
+PATCH_SHAPE = (448, 64)   # (W, H), vae-gan.py:31
+Z_CH = 128
+TEXT_CH = 64
+ALPHABET_STR = (" !\"#$%&'()*+,-./0123456789:;<=>?@ABCDEFGHIJKLMNOPQRSTUVWXYZ[\\]^_`"
+                "abcdefghijklmnopqrstuvwxyz{|}~")                       # vae-gan-v2.py:33
+_RU_LOWER = "".join(chr(c) for c in range(0x430, 0x436)) + "ё" + "".join(chr(c) for c in range(0x436, 0x450))
+_RU_UPPER = "".join(chr(c) for c in range(0x410, 0x416)) + "Ё" + "".join(chr(c) for c in range(0x416, 0x430))
+ALPHABET_STR_UNET = ALPHABET_STR + _RU_LOWER + _RU_UPPER                # vae-gan-unet.py:33
+CHAR_EMB_DIM, CHAR_RNN_HIDDEN_DIM, CHAR_RNN_LAYERS = 128, 256, 2
+RELU, LRELU = 1, 2
+
+
+def _hw(patch_shape) -> Tuple[int, int]:
+    w, h = patch_shape if patch_shape is not None else PATCH_SHAPE
+    return h, w
+
+
+def _require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("vae_gan_mark_b200 modules run only on CUDA (sm_100a); there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# executors over stock parameter containers
+# ------------------------------------------------------------------------------------------------
+def _state(mod: nn.Module, make):
+    st = mod.__dict__.get("_vg_state")
+    if st is None:
+        st = make()
+        mod.__dict__["_vg_state"] = st
+    return st
+
+
+def _bn_state(bn: nn.BatchNorm2d):
+    return {"training": bn.training, "running_mean": bn.running_mean, "running_var": bn.running_var,
+            "num_batches_tracked": bn.num_batches_tracked}
+
+
+def run_conv(conv: nn.Conv2d, x, act=0, out=None, in_hw=None, sn=None, weight=None):
+    """nn.Conv2d on the tensor pipe; ``x`` NHWC bf16."""
+    w = conv.weight if weight is None else weight
+    st = _state(conv, lambda: (ConvLinear(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.kernel_size[1],
+                                          conv.stride[0], tuple(conv.padding), in_hw), L.WeightCache()))
+    return L.Conv2dFn.apply(x, w, conv.bias, st[0], st[1], act, out, 0, sn)
+
+
+def run_convT(ct: nn.ConvTranspose2d, x, out_hw, act=0, out=None):
+    """nn.ConvTranspose2d as the data-gradient of its adjoint conv; ``x`` NHWC bf16."""
+    st = _state(ct, lambda: (ConvLinear(ct.out_channels, ct.in_channels, ct.kernel_size[0], ct.kernel_size[1],
+                                        ct.stride[0], tuple(ct.padding), tuple(out_hw)), L.WeightCache()))
+    return L.ConvTranspose2dFn.apply(x, ct.weight, ct.bias, st[0], st[1], act, out, tuple(out_hw))
+
+
+def run_bn_relu(bn: nn.BatchNorm2d, x, pool=False, out=None, pool_out=None):
+    return L.NormActFn.apply(x, bn.weight, bn.bias, False, RELU, pool, out, bn.eps, _bn_state(bn), pool_out)
+
+
+def run_image_conv(conv: nn.Conv2d, images: Sequence[torch.Tensor], act=0, sn=None, weight=None):
+    w = conv.weight if weight is None else weight
+    st = _state(conv, lambda: L.WeightCache())
+    geom = (conv.kernel_size[0], conv.kernel_size[1], conv.stride[0], conv.padding[0])
+    return L.ImageConvFn.apply(w, conv.bias, geom, st, act, sn, *images)
+
+
+def run_double_conv(seq: nn.Sequential, x, images=None, pool=False, out=None, pool_out=None):
+    """[Conv3x3 -> BN -> ReLU] x2 (+ fused MaxPool2d(2)); the first conv may take raw NCHW images."""
+    raw = run_image_conv(seq[0], images) if images is not None else run_conv(seq[0], x)
+    y, _ = run_bn_relu(seq[1], raw)
+    raw = run_conv(seq[3], y)
+    return run_bn_relu(seq[4], raw, pool=pool, out=out, pool_out=pool_out)
+
+
+class _SNCall:
+    """Spectral-norm state of ONE forward call (sigma, u, v snapshots) -- D runs three times per step and each call's
+    backward must see the sigma/u/v of its own forward (torch.nn.utils.spectral_norm semantics)."""
+
+    def __init__(self, conv: nn.Module, training: bool):
+        w = conv.weight_orig.detach()
+        self.rows, self.cols = w.shape[0], w[0].numel()
+        u, v = conv.weight_u, conv.weight_v
+        self.sigma = ops.spectral_sigma(w.view(self.rows, self.cols), u, v, training)
+        self.u, self.v = (u.clone(), v.clone()) if training else (u, v)
+
+    def backward(self, g: torch.Tensor, w_orig: torch.Tensor) -> torch.Tensor:
+        dw = torch.empty_like(g)
+        ops.spectral_bwd(g.view(self.rows, self.cols), w_orig.view(self.rows, self.cols), self.u, self.v, self.sigma,
+                         dw.view(self.rows, self.cols))
+        return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# text encoders (stock torch)
+# ------------------------------------------------------------------------------------------------
+class CharacterTokenEncoder(nn.Module):
+    """vae-gan-v2.py:65-114.  Stock Embedding + biGRU + adaptive pool; output (B, 2*hid, 1, W/16) fp32."""
+
+    def __init__(self, alphabet_str, emb_dim, rnn_hidden_dim, rnn_layers, target_feature_width):
+        super().__init__()
+        self.alphabet = alphabet_str
+        self.vocab_size = len(alphabet_str) + 1
+        self.char_to_idx = {ch: i + 1 for i, ch in enumerate(alphabet_str)}
+        self.pad_idx = 0
+        self.embedding = nn.Embedding(self.vocab_size, emb_dim, padding_idx=self.pad_idx)
+        self.rnn = nn.GRU(emb_dim, rnn_hidden_dim, num_layers=rnn_layers, batch_first=True, bidirectional=True,
+                          dropout=0.1 if rnn_layers > 1 else 0)
+        self.rnn_output_dim = rnn_hidden_dim * 2
+        self.target_feature_width = target_feature_width
+        self.adaptive_pool = nn.AdaptiveAvgPool1d(target_feature_width)
+
+    def tokens_to_indices(self, text_list, max_len_chars):
+        idx = torch.zeros(len(text_list), max_len_chars, dtype=torch.long)
+        for r, text in enumerate(text_list):
+            ids = [self.char_to_idx.get(ch, self.pad_idx) for ch in text][:max_len_chars]
+            if ids:
+                idx[r, :len(ids)] = torch.tensor(ids, dtype=torch.long)
+        return idx
+
+    def forward(self, texts_batch, max_len_chars_for_tokenization=60):
+        idx = self.tokens_to_indices(texts_batch, max_len_chars_for_tokenization).to(self.embedding.weight.device)
+        out, _ = self.rnn(self.embedding(idx))
+        return self.adaptive_pool(out.permute(0, 2, 1)).unsqueeze(2)
+
+
+class TransformerTextEncoder(nn.Module):
+    """vae-gan.py:86-116.  The SBERT model is an external dependency (no grad flows into it); pass ``embedder``
+    (texts -> (B, 384) tensor) to inject it, otherwise sentence_transformers is imported lazily."""
+
+    def __init__(self, model_name="sentence-transformers/paraphrase-multilingual-MiniLM-L12-v2", out_dim=TEXT_CH,
+                 embedder: Optional[Callable] = None, embedding_dim: int = 384):
+        super().__init__()
+        self._embedder = embedder
+        self._model_name = model_name
+        self.fc = nn.Linear(embedding_dim, out_dim)
+        self.out_dim = out_dim
+
+    def _embed(self, texts):
+        if self._embedder is None:
+            from sentence_transformers import SentenceTransformer   # noqa: deferred, optional dependency
+            model = SentenceTransformer(self._model_name, device=str(self.fc.weight.device))
+            self._embedder = lambda t: model.encode(t, convert_to_tensor=True)
+        return self._embedder(texts)
+
+    def forward(self, texts):
+        with torch.no_grad():
+            e = self._embed(texts).to(self.fc.weight)
+        return self.fc(e)
+
+
+# ------------------------------------------------------------------------------------------------
+# shared tail: heads + reparameterisation
+# ------------------------------------------------------------------------------------------------
+def run_heads(mu_head: nn.Conv2d, logvar_head: nn.Conv2d, feat: torch.Tensor, owner: nn.Module):
+    """Both full-kernel heads as ONE split-K GEMM with N = 2z, then bias + reparameterisation + KL in one kernel.
+    Returns mu, logvar (B,z,1,1 fp32), z (B,z fp32) and the KL scalar.  eps is drawn with torch.randn on the
+    host-visible generator, at the same point in the RNG stream as the reference (vae-gan.py:135)."""
+    b, h, w, c = feat.shape
+    z = mu_head.out_channels
+    st = _state(mu_head, lambda: (ConvLinear(c, 2 * z, h, w, 1, (0, 0), (h, w)), L.WeightCache(), L.WeightCache()))
+    heads = L.HeadsFn.apply(feat, mu_head.weight, logvar_head.weight, st[0], st[1], st[2])
+    eps_fn = owner.__dict__.get("eps_fn")          # test hook: draw eps from another generator (e.g. the CPU one)
+    eps = (eps_fn((b, z, 1, 1)).to(feat.device, F32) if eps_fn is not None
+           else torch.randn((b, z, 1, 1), dtype=F32, device=feat.device)).reshape(b, z).contiguous()
+    mu, lv, zz, kl = L.ReparamKLFn.apply(heads, mu_head.bias, logvar_head.bias, eps)
+    owner.__dict__["_last_kl"] = kl
+    return mu.view(b, z, 1, 1), lv.view(b, z, 1, 1), zz, kl
+
+
+# ------------------------------------------------------------------------------------------------
+# base conv VAE-GAN (vae-gan.py)
+# ------------------------------------------------------------------------------------------------
+class VAEEncoder(nn.Module):
+    """vae-gan.py:47-66."""
+
+    def __init__(self, in_ch=4, z_ch=Z_CH, patch_shape=None):
+        super().__init__()
+        layers, c = [], in_ch
+        for wdt in (128, 256, 512, 1024):
+            layers += [nn.Conv2d(c, wdt, 3, 2, 1), nn.BatchNorm2d(wdt), nn.ReLU(True)]
+            c = wdt
+        self.feat = nn.Sequential(*layers)
+        h, w = _hw(patch_shape)
+        self.mu_head = nn.Conv2d(1024, z_ch, kernel_size=(h // 16, w // 16))
+        self.logvar_head = nn.Conv2d(1024, z_ch, kernel_size=(h // 16, w // 16))
+
+    def features(self, images: Sequence[torch.Tensor]):
+        x = run_image_conv(self.feat[0], images)
+        x, _ = run_bn_relu(self.feat[1], x)
+        for i in (3, 6, 9):
+            x = run_conv(self.feat[i], x)
+            x, _ = run_bn_relu(self.feat[i + 1], x)
+        return x
+
+    def encode(self, images):
+        return run_heads(self.mu_head, self.logvar_head, self.features(images), self)
+
+    def forward(self, x):
+        _require_cuda(x)
+        mu, lv, _, _ = self.encode([x])
+        return mu, lv
+
+
+class VAEDecoder(nn.Module):
+    """vae-gan.py:68-84."""
+
+    def __init__(self, z_ch=Z_CH, text_ch=TEXT_CH, out_ch=3, patch_shape=None):
+        super().__init__()
+        h, w = _hw(patch_shape)
+        self.start_hw = (h // 16, w // 16)
+        wd = (1024, 512, 256, 128, 64)
+        layers: List[nn.Module] = [nn.ConvTranspose2d(z_ch + text_ch, wd[0], kernel_size=self.start_hw, stride=1, padding=0),
+                                   nn.BatchNorm2d(wd[0]), nn.ReLU(True)]
+        for a, b in zip(wd[:-1], wd[1:]):
+            layers += [nn.ConvTranspose2d(a, b, kernel_size=4, stride=2, padding=1), nn.BatchNorm2d(b), nn.ReLU(True)]
+        layers += [nn.Conv2d(wd[-1], out_ch, kernel_size=3, stride=1, padding=1), nn.Sigmoid()]
+        self.decode = nn.Sequential(*layers)
+
+    def decode_nhwc(self, zc: torch.Tensor):
+        """zc: NHWC bf16 [B,1,1,z+text]."""
+        d = self.decode
+        hw = self.start_hw
+        x = run_convT(d[0], zc, hw)
+        x, _ = run_bn_relu(d[1], x)
+        for i in (3, 6, 9, 12):
+            hw = (hw[0] * 2, hw[1] * 2)
+            x = run_convT(d[i], x, hw)
+            x, _ = run_bn_relu(d[i + 1], x)
+        pre = L.SmallOutConvFn.apply(x, d[15].weight, d[15].bias, 1)
+        return L.SigmoidOutFn.apply(pre)
+
+    def forward(self, z):
+        _require_cuda(z)
+        return self.decode_nhwc(L.ToNHWCFn.apply(z))
+
+
+class VAEGAN(nn.Module):
+    """vae-gan.py:124-146."""
+
+    def __init__(self, in_ch=4, z_ch=Z_CH, text_ch=TEXT_CH, out_ch=3, patch_shape=None, text_embedder=None):
+        super().__init__()
+        self.encoder = VAEEncoder(in_ch=in_ch, z_ch=z_ch, patch_shape=patch_shape)
+        self.text_encoder = TransformerTextEncoder(out_dim=text_ch, embedder=text_embedder)
+        self.decoder = VAEDecoder(z_ch=z_ch, text_ch=text_ch, out_ch=out_ch, patch_shape=patch_shape)
+
+    def reparameterize(self, mu, logvar):
+        std = torch.exp(0.5 * logvar)
+        return mu + torch.randn_like(std) * std
+
+    def forward(self, image, mask, texts):
+        _require_cuda(image)
+        mu, logvar, z, kl = self.encoder.encode([image, mask])
+        self.__dict__["_last_kl"] = kl
+        text = self.text_encoder(texts)                                   # (B, text_ch) fp32, stock Linear
+        t_nhwc = L.ToNHWCFn.apply(text.view(text.shape[0], text.shape[1], 1, 1))
+        zc = L.ZTextCatFn.apply(z, t_nhwc)
+        return self.decoder.decode_nhwc(zc), mu, logvar
+
+
+class Discriminator(nn.Module):
+    """vae-gan.py:148-159: SN-Conv4x4 s2 + LReLU; 3x [SN-Conv4x4 s2 -> InstanceNorm(affine) -> LReLU]; Conv4x4 s1 p1."""
+
+    def __init__(self, in_ch=3):
+        super().__init__()
+        body: List[nn.Module] = []
+        c = in_ch
+        for i, wdt in enumerate((64, 128, 256, 512)):
+            body.append(spectral_norm(nn.Conv2d(c, wdt, kernel_size=4, stride=2, padding=1)))
+            if i:
+                body.append(nn.InstanceNorm2d(wdt, affine=True))
+            body.append(nn.LeakyReLU(0.2, inplace=True))
+            c = wdt
+        body.append(nn.Conv2d(c, 1, kernel_size=4, stride=1, padding=1))
+        self.body = nn.Sequential(*body)
+
+    def forward(self, x):
+        _require_cuda(x)
+        b = self.body
+        sn = _SNCall(b[0], self.training)
+        y = run_image_conv(b[0], [x], act=LRELU, sn=sn, weight=b[0].weight_orig)
+        for i in (2, 5, 8):
+            sn = _SNCall(b[i], self.training)
+            raw = run_conv(b[i], y, sn=sn, weight=b[i].weight_orig)
+            inorm = b[i + 1]
+            y, _ = L.NormActFn.apply(raw, inorm.weight, inorm.bias, True, LRELU, False, None, inorm.eps, None, None)
+        out = L.SmallOutConvFn.apply(y, b[11].weight, b[11].bias, 1)       # NHWC fp32 [B,h',w',1]
+        return out.permute(0, 3, 1, 2)                                     # (B,1,h',w') view, as the reference returns
+
+
+# ------------------------------------------------------------------------------------------------
+# U-Net families (vae-gan-v2.py, vae-gan-unet.py)
+# ------------------------------------------------------------------------------------------------
+def _double_conv(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+                         nn.Conv2d(cout, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class VAEEncoderWithSkips(nn.Module):
+    """vae-gan-v2.py:152-187 == vae-gan-unet.py:124-176."""
+
+    def __init__(self, in_ch=4, z_ch=Z_CH, patch_shape=None):
+        super().__init__()
+        self.e_conv1 = _double_conv(in_ch, 64)
+        self.pool1 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.e_conv2 = _double_conv(64, 128)
+        self.pool2 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.e_conv3 = _double_conv(128, 256)
+        self.pool3 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.e_conv4 = _double_conv(256, 512)
+        self.pool4 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.bottleneck_conv = _double_conv(512, 1024)
+        h, w = _hw(patch_shape)
+        self.feature_map_h, self.feature_map_w = h // 16, w // 16
+        self.mu_head = nn.Conv2d(1024, z_ch, kernel_size=(self.feature_map_h, self.feature_map_w))
+        self.logvar_head = nn.Conv2d(1024, z_ch, kernel_size=(self.feature_map_h, self.feature_map_w))
+
+    def encode(self, images, skip_dests=None, pool_dests=None):
+        """Returns (mu, logvar, z, kl, skips, pooled).  ``skip_dests[i]`` / ``pool_dests[i]`` are optional NHWC views
+        (channel slices of the decoder's concat buffers) that receive the skip / pooled map directly."""
+        skips, pooled = [], []
+        x = None
+        for i in range(4):
+            s, p = run_double_conv(getattr(self, f"e_conv{i + 1}"), x, images=images if i == 0 else None, pool=True,
+                                   out=skip_dests[i] if skip_dests else None,
+                                   pool_out=pool_dests[i] if pool_dests else None)
+            skips.append(s)
+            pooled.append(p)
+            x = p
+        feat, _ = run_double_conv(self.bottleneck_conv, x)
+        mu, lv, z, kl = run_heads(self.mu_head, self.logvar_head, feat, self)
+        return mu, lv, z, kl, skips, pooled
+
+    def forward(self, x):
+        _require_cuda(x)
+        mu, lv, _, _, skips, _ = self.encode([x])
+        return mu, lv, skips        # skips are NHWC bf16 here (internal layout of this package)
+
+
+class SpatialFiLMLayer(nn.Module):
+    """vae-gan-v2.py:117-149."""
+
+    def __init__(self, text_channels_in, num_features_main):
+        super().__init__()
+        t = text_channels_in
+        self.param_predictor = nn.Sequential(nn.Conv2d(t, t, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(t),
+                                             nn.ReLU(inplace=True), nn.Conv2d(t, num_features_main * 2, kernel_size=1))
+        self.num_features_main = num_features_main
+
+    def forward(self, x_main, text_base_nhwc):
+        """x_main: NHWC bf16 [B,h,w,C]; text_base_nhwc: NHWC bf16 [B,1,w0,T]."""
+        _, h, w, _ = x_main.shape
+        pp = self.param_predictor
+        t = L.UpsampleWFn.apply(text_base_nhwc, h, w)
+        raw = run_conv(pp[0], t)
+        y, _ = run_bn_relu(pp[1], raw)
+        gb = run_conv(pp[3], y)
+        return L.FiLMFn.apply(gb, x_main)
+
+
+class VAEDecoderWithSpatialFiLM(nn.Module):
+    """vae-gan-v2.py:191-280."""
+
+    SKIP_CH = (512, 256, 128, 64)
+
+    def __init__(self, z_ch, text_channels_in, out_ch_image, patch_h, patch_w):
+        super().__init__()
+        self.initial_h, self.initial_w = patch_h // 16, patch_w // 16
+        self.bottleneck_proc = nn.Sequential(
+            nn.ConvTranspose2d(z_ch + text_channels_in, 1024, kernel_size=(self.initial_h, 1), stride=1, padding=0),
+            nn.BatchNorm2d(1024), nn.ReLU(inplace=True))
+        c = 1024
+        for i, skip in enumerate(self.SKIP_CH, start=1):
+            setattr(self, f"up_tconv{i}", nn.ConvTranspose2d(c, c // 2, kernel_size=2, stride=2))
+            setattr(self, f"spatial_film{i}", SpatialFiLMLayer(text_channels_in, c // 2 + skip))
+            setattr(self, f"conv_block{i}", _double_conv(c // 2 + skip, c // 2))
+            c //= 2
+        self.final_image_conv = nn.Conv2d(64, out_ch_image, kernel_size=1)
+        self.output_activation_fn = nn.Sigmoid()
+
+    def concat_buffers(self, batch: int, device):
+        """Pre-allocated [B, h, w, up + skip] buffers; the encoder writes skip i into the upper channel slice."""
+        bufs, h, w = [], self.initial_h * 2, self.initial_w * 2
+        for skip in self.SKIP_CH:
+            bufs.append(torch.empty((batch, h, w, 2 * skip), dtype=BF16, device=device))
+            h, w = h * 2, w * 2
+        return bufs   # stage 1 (deepest) first
+
+    def decode(self, z, text_nhwc, skips, bufs=None):
+        """z: fp32 [B,zc]; text_nhwc: NHWC bf16 [B,1,w0,T]; skips: [s1..s4] NHWC (ideally views into ``bufs``)."""
+        b = z.shape[0]
+        if bufs is None:
+            bufs = self.concat_buffers(b, z.device)
+        zc = L.ZTextCatFn.apply(z, text_nhwc)
+        x = run_convT(self.bottleneck_proc[0], zc, (self.initial_h, self.initial_w))
+        x, _ = run_bn_relu(self.bottleneck_proc[1], x)
+        h, w = self.initial_h, self.initial_w
+        for i in (1, 2, 3, 4):
+            h, w = h * 2, w * 2
+            buf, skip = bufs[i - 1], skips[4 - i]
+            cu = skip.shape[3]
+            if skip.data_ptr() != buf.data_ptr() + 2 * cu:      # skip produced elsewhere: copy into the slice
+                skip = L.CopyIntoFn.apply(skip, buf[..., cu:])
+            up = run_convT(getattr(self, f"up_tconv{i}"), x, (h, w), out=buf[..., :cu])
+            xc = L.CatSlicesFn.apply(up, skip, buf)
+            xm = getattr(self, f"spatial_film{i}")(xc, text_nhwc)
+            x, _ = run_double_conv(getattr(self, f"conv_block{i}"), xm)
+        pre = L.SmallOutConvFn.apply(x, self.final_image_conv.weight, self.final_image_conv.bias, 0)
+        return L.SigmoidOutFn.apply(pre)
+
+    def forward(self, z_latents, spatial_text_features_base, skips_list):
+        _require_cuda(z_latents)
+        t = L.ToNHWCFn.apply(spatial_text_features_base)
+        return self.decode(z_latents.reshape(z_latents.shape[0], -1), t, skips_list)
+
+
+class VAEGAN_UNet_SpatialFiLM(nn.Module):
+    """vae-gan-v2.py:283-327."""
+
+    def __init__(self, in_ch_style=4, z_ch_style=Z_CH, out_ch_img=3, alphabet_str_text=ALPHABET_STR,
+                 char_emb_dim_text=CHAR_EMB_DIM, char_rnn_hidden_dim_text=CHAR_RNN_HIDDEN_DIM,
+                 char_rnn_layers_text=CHAR_RNN_LAYERS, patch_shape=None):
+        super().__init__()
+        h, w = _hw(patch_shape)
+        self.text_feature_base_width = w // 16
+        self.char_text_encoder_module = CharacterTokenEncoder(alphabet_str_text, char_emb_dim_text,
+                                                              char_rnn_hidden_dim_text, char_rnn_layers_text,
+                                                              self.text_feature_base_width)
+        self.style_vae_encoder_module = VAEEncoderWithSkips(in_ch=in_ch_style, z_ch=z_ch_style, patch_shape=(w, h))
+        self.image_vae_decoder_module = VAEDecoderWithSpatialFiLM(
+            z_ch=z_ch_style, text_channels_in=self.char_text_encoder_module.rnn_output_dim, out_ch_image=out_ch_img,
+            patch_h=h, patch_w=w)
+
+    def reparameterize(self, mu, logvar):
+        std = torch.exp(0.5 * logvar)
+        return mu + torch.randn_like(std) * std
+
+    def forward(self, image_for_style_in, mask_for_style_in, texts_batch_list_in):
+        _require_cuda(image_for_style_in)
+        dec = self.image_vae_decoder_module
+        b = image_for_style_in.shape[0]
+        bufs = dec.concat_buffers(b, image_for_style_in.device)
+        dests = [bufs[3 - i][..., bufs[3 - i].shape[3] // 2:] for i in range(4)]      # s1..s4 -> stage 4..1
+        mu, logvar, z, kl, skips, _ = self.style_vae_encoder_module.encode(
+            [image_for_style_in, mask_for_style_in], skip_dests=dests)
+        self.__dict__["_last_kl"] = kl
+        text = self.char_text_encoder_module(texts_batch_list_in)          # RNG order: eps before GRU dropout (:320-322)
+        t = L.ToNHWCFn.apply(text)
+        return dec.decode(z, t, skips, bufs), mu, logvar
+
+
+def _up_block(cin, cout):
+    return nn.Sequential(nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+                         nn.Conv2d(cout, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+                         nn.Conv2d(cout, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class VAEDecoderWithSkips(nn.Module):
+    """vae-gan-unet.py:179-254, executed in the shape-consistent "row U" repair: the bottleneck ConvT is
+    fed a 1x1 input (text map mean-pooled over width) and the pooled encoder maps are the skips.  The shipped
+    forward cannot run for any PATCH_SHAPE (it raises in the reference too); ``forward`` raises the same way."""
+
+    SKIP_CH = (512, 256, 128, 64)
+
+    def __init__(self, z_ch=Z_CH, text_feat_channels=CHAR_RNN_HIDDEN_DIM * 2, out_ch_image=3, patch_shape=None):
+        super().__init__()
+        h, w = _hw(patch_shape)
+        self.initial_h, self.initial_w = h // 16, w // 16
+        self.bottleneck_upsample = nn.Sequential(
+            nn.ConvTranspose2d(z_ch + text_feat_channels, 1024, kernel_size=(self.initial_h, self.initial_w), stride=1,
+                               padding=0), nn.BatchNorm2d(1024), nn.ReLU(inplace=True))
+        c = 1024
+        for i, skip in enumerate(self.SKIP_CH, start=1):
+            setattr(self, f"d_upconv{i}", _up_block(c + skip, c // 2))
+            c //= 2
+        self.final_image_conv = nn.Conv2d(64, out_ch_image, kernel_size=1)
+        self.output_activation_fn = nn.Sigmoid()
+
+    def concat_buffers(self, batch, device):
+        bufs, h, w, c = [], self.initial_h, self.initial_w, 1024
+        for skip in self.SKIP_CH:
+            bufs.append(torch.empty((batch, h, w, c + skip), dtype=BF16, device=device))
+            h, w, c = h * 2, w * 2, c // 2
+        return bufs
+
+    def decode_repaired(self, z, text_nhwc_1x1, pooled, bufs=None):
+        b = z.shape[0]
+        if bufs is None:
+            bufs = self.concat_buffers(b, z.device)
+        zc = L.ZTextCatFn.apply(z, text_nhwc_1x1)
+        h, w, c = self.initial_h, self.initial_w, 1024
+        raw = run_convT(self.bottleneck_upsample[0], zc, (h, w))
+        x, _ = run_bn_relu(self.bottleneck_upsample[1], raw, out=bufs[0][..., :c])
+        for i in (1, 2, 3, 4):
+            buf, skip = bufs[i - 1], pooled[4 - i]
+            if skip.data_ptr() != buf.data_ptr() + 2 * c:
+                skip = L.CopyIntoFn.apply(skip, buf[..., c:])
+            xc = L.CatSlicesFn.apply(x, skip, buf)
+            blk = getattr(self, f"d_upconv{i}")
+            h, w, c = h * 2, w * 2, c // 2
+            raw = run_convT(blk[0], xc, (h, w))
+            y, _ = run_bn_relu(blk[1], raw)
+            raw = run_conv(blk[3], y)
+            y, _ = run_bn_relu(blk[4], raw)
+            raw = run_conv(blk[6], y)
+            x, _ = run_bn_relu(blk[7], raw, out=bufs[i][..., :c] if i < 4 else None)
+        pre = L.SmallOutConvFn.apply(x, self.final_image_conv.weight, self.final_image_conv.bias, 0)
+        return L.SigmoidOutFn.apply(pre)
+
+    def forward(self, z_latents, text_features_input, skips_list):
+        raise RuntimeError("VAEDecoderWithSkips.forward is shape-inconsistent as shipped in the reference "
+                           "(vae-gan-unet.py:193-199,230-240: Sizes of tensors must match); use decode_repaired")
+
+
+class VAEGAN_UNet_CharEmb(nn.Module):
+    """vae-gan-unet.py:257-297 (repaired composition, see VAEDecoderWithSkips)."""
+
+    def __init__(self, in_ch_for_style_encoder=4, z_ch_for_style=Z_CH, out_ch_for_image=3,
+                 alphabet_str_for_text=ALPHABET_STR_UNET, char_emb_dim_for_text=CHAR_EMB_DIM,
+                 char_rnn_hidden_dim_for_text=CHAR_RNN_HIDDEN_DIM, char_rnn_layers_for_text=CHAR_RNN_LAYERS,
+                 patch_shape=None):
+        super().__init__()
+        h, w = _hw(patch_shape)
+        self.text_feature_target_spatial_width = w // 16
+        self.char_text_encoder_module = CharacterTokenEncoder(alphabet_str_for_text, char_emb_dim_for_text,
+                                                              char_rnn_hidden_dim_for_text, char_rnn_layers_for_text,
+                                                              self.text_feature_target_spatial_width)
+        self.style_vae_encoder_module = VAEEncoderWithSkips(in_ch=in_ch_for_style_encoder, z_ch=z_ch_for_style,
+                                                            patch_shape=(w, h))
+        self.image_vae_decoder_module = VAEDecoderWithSkips(
+            z_ch=z_ch_for_style, text_feat_channels=self.char_text_encoder_module.rnn_output_dim,
+            out_ch_image=out_ch_for_image, patch_shape=(w, h))
+
+    def reparameterize(self, mu, logvar):
+        std = torch.exp(0.5 * logvar)
+        return mu + torch.randn_like(std) * std
+
+    def forward(self, image_for_style_input, mask_for_style_input, texts_batch_list_input):
+        _require_cuda(image_for_style_input)
+        dec = self.image_vae_decoder_module
+        b = image_for_style_input.shape[0]
+        bufs = dec.concat_buffers(b, image_for_style_input.device)
+        # pooled p1..p4 feed stages 4..1: bufs[3-i][..., C_main:]
+        mains = (1024, 512, 256, 128)
+        pdests = [bufs[3 - i][..., mains[3 - i]:] for i in range(4)]
+        mu, logvar, z, kl, _, pooled = self.style_vae_encoder_module.encode(
+            [image_for_style_input, mask_for_style_input], pool_dests=pdests)
+        self.__dict__["_last_kl"] = kl
+        text = self.char_text_encoder_module(texts_batch_list_input)
+        t = L.ToNHWCFn.apply(text.mean(dim=3, keepdim=True))
+        return dec.decode_repaired(z, t, pooled, bufs), mu, logvar

@@ -1,0 +1,274 @@
+"""Thin Python wrappers over the C ABI (include/vaegan_b200.h): tensors in, kernel launches out.
+
+Everything here enqueues hand-written CUDA kernels on the current torch stream; torch is used only for
+memory (allocation, views).  NHWC bf16 activations are plain torch tensors of shape [N, H, W, C] whose last
+stride is 1 and whose pixel stride ``ld = stride(2)`` may exceed C (a channel slice of a wider buffer).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+_LL5 = C.c_longlong * 5
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def nhwc_ok(t: torch.Tensor) -> bool:
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    return (t.dim() == 4 and t.stride(3) == 1 and ld >= c and (h == 1 or t.stride(1) == w * ld) and
+            (n == 1 or t.stride(0) == h * w * ld) and t.data_ptr() % 16 == 0 and ld % 8 == 0)
+
+
+def as_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Return ``t`` if it already is a valid (possibly channel-sliced) NHWC view, else a dense copy."""
+    if t.dtype == BF16 and nhwc_ok(t):
+        return t
+    return dense_nhwc(t)
+
+
+def dense_nhwc(t: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(t.shape, dtype=BF16, device=t.device)
+    strided_copy(t, out)
+    return out
+
+
+def ld_of(t: torch.Tensor) -> int:
+    return t.stride(2)
+
+
+# ----------------------------------------------------------------------------------------------
+# data movement
+# ----------------------------------------------------------------------------------------------
+def strided_copy(src: torch.Tensor, dst: torch.Tensor, scale: Optional[torch.Tensor] = None,
+                 scale_inverse: bool = False, accumulate: bool = False) -> None:
+    """dst[...] (=|+=) scale * src[...] for two tensors of equal shape (<= 5 dims), any strides, fp32/bf16."""
+    assert src.shape == dst.shape and src.dim() <= 5, (src.shape, dst.shape)
+    if src.numel() == 0:
+        return
+    pad = 5 - src.dim()
+    dims = [1] * pad + list(src.shape)
+    iss = [0] * pad + list(src.stride())
+    oss = [0] * pad + list(dst.stride())
+    code = {F32: 0, BF16: 1}
+    _lib.call("vg_strided_copy", _p(src), code[src.dtype], _p(dst), code[dst.dtype], _LL5(*dims), _LL5(*iss), _LL5(*oss),
+              _p(scale), int(scale_inverse), int(accumulate), stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# normalisation + activation (+ pool)
+# ----------------------------------------------------------------------------------------------
+def norm_stats(x: torch.Tensor, per_sample: bool) -> torch.Tensor:
+    n, h, w, c = x.shape
+    groups = n if per_sample else 1
+    rows = h * w if per_sample else n * h * w
+    sums = torch.empty(groups, 2, c, dtype=F32, device=x.device)
+    _lib.call("vg_norm_stats", _p(x), ld_of(x), 0, groups, C.c_longlong(rows), c, _p(sums), stream())
+    return sums
+
+
+def norm_finalize(sums: torch.Tensor, rows: int, eps: float, momentum: float = 0.1,
+                  running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None,
+                  num_batches_tracked: Optional[torch.Tensor] = None) -> torch.Tensor:
+    groups, _, c = sums.shape
+    mr = torch.empty_like(sums)
+    _lib.call("vg_norm_finalize", _p(sums), groups, C.c_longlong(rows), c, C.c_float(eps), _p(mr), C.c_float(momentum),
+              _p(running_mean), _p(running_var), _p(num_batches_tracked), stream())
+    return mr
+
+
+def norm_apply(x: torch.Tensor, mean_rstd: torch.Tensor, gamma, beta, act: int, y: torch.Tensor,
+               pool: Optional[torch.Tensor] = None) -> None:
+    n, h, w, c = x.shape
+    d = _lib.VgNormApply()
+    d.x, d.x_ld, d.x_coff = x.data_ptr(), ld_of(x), 0
+    d.n, d.h, d.w, d.c = n, h, w, c
+    d.mean_rstd, d.per_sample = mean_rstd.data_ptr(), int(mean_rstd.shape[0] > 1 or False)
+    d.gamma = gamma.data_ptr() if gamma is not None else None
+    d.beta = beta.data_ptr() if beta is not None else None
+    d.act = act
+    d.y, d.y_ld, d.y_coff = y.data_ptr(), ld_of(y), 0
+    if pool is not None:
+        d.pool, d.p_ld, d.p_coff = pool.data_ptr(), ld_of(pool), 0
+    _lib.call("vg_norm_apply", C.byref(d), stream())
+
+
+def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dgamma, dbeta, accumulate=False):
+    n, h, w, c = x.shape
+    groups = n if per_sample else 1
+    sums = torch.empty(groups, 2, c, dtype=F32, device=x.device)
+    d = _lib.VgNormBackward()
+    d.x, d.x_ld, d.x_coff = x.data_ptr(), ld_of(x), 0
+    if dy is not None:
+        d.dy, d.dy_ld, d.dy_coff = dy.data_ptr(), ld_of(dy), 0
+    if dpool is not None:
+        d.dpool, d.dp_ld, d.dp_coff = dpool.data_ptr(), ld_of(dpool), 0
+    d.n, d.h, d.w, d.c = n, h, w, c
+    d.mean_rstd, d.per_sample = mean_rstd.data_ptr(), int(per_sample)
+    d.gamma = gamma.data_ptr() if gamma is not None else None
+    d.beta = beta.data_ptr() if beta is not None else None
+    d.act = act
+    d.sums = sums.data_ptr()
+    d.dx, d.dx_ld, d.dx_coff = dx.data_ptr(), ld_of(dx), 0
+    d.dgamma = dgamma.data_ptr() if dgamma is not None else None
+    d.dbeta = dbeta.data_ptr() if dbeta is not None else None
+    d.accumulate = int(accumulate)
+    _lib.call("vg_norm_backward", C.byref(d), stream())
+
+
+def act_bwd(y, dy, dx, act):
+    n, h, w, c = y.shape
+    _lib.call("vg_act_bwd", _p(y), ld_of(y), _p(dy), ld_of(dy), _p(dx), ld_of(dx), C.c_longlong(n * h * w), c, act,
+              stream())
+
+
+def colsum_f32(t2d, out, accumulate=False):
+    rows, cols = t2d.shape
+    _lib.call("vg_colsum_f32", _p(t2d), C.c_longlong(rows), cols, t2d.stride(0), _p(out), int(accumulate), stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# FiLM / upsample / im2col / small-N convs
+# ----------------------------------------------------------------------------------------------
+def film_fwd(gb, x, y):
+    n, h, w, c = x.shape
+    _lib.call("vg_film_fwd", _p(gb), _p(x), ld_of(x), 0, _p(y), C.c_longlong(n * h * w), c, stream())
+
+
+def film_bwd(gb, x, dy, dgb, dx):
+    n, h, w, c = x.shape
+    _lib.call("vg_film_bwd", _p(gb), _p(x), ld_of(x), 0, _p(dy), _p(dgb), _p(dx), ld_of(dx), 0,
+              C.c_longlong(n * h * w), c, stream())
+
+
+def upsample_w_fwd(t, y):
+    n, _, w0, c = t.shape
+    _, h, w, _ = y.shape
+    _lib.call("vg_upsample_w_fwd", _p(t), ld_of(t), 0, n, w0, c, _p(y), h, w, stream())
+
+
+def upsample_w_bwd(dy, dt):
+    n, h, w, c = dy.shape
+    w0 = dt.shape[2]
+    _lib.call("vg_upsample_w_bwd", _p(dy), n, h, w, c, w0, _p(dt), stream())
+
+
+def im2col(src, c, kh, kw, stride, pad, col):
+    n, h, w, _ = src.shape
+    _lib.call("vg_im2col", _p(src), n, h, w, ld_of(src), c, kh, kw, stride, pad, _p(col), col.shape[-1], stream())
+
+
+def col2im(dcol, n, h, w, c, kh, kw, stride, pad, dsrc_nchw):
+    _lib.call("vg_col2im", _p(dcol), dcol.shape[-1], n, h, w, c, kh, kw, stride, pad, _p(dsrc_nchw), stream())
+
+
+def smalln_fwd(x, wt, bias, kh, kw, pad, out):
+    n, h, w, cin = x.shape
+    _lib.call("vg_conv_smalln_fwd", _p(x), ld_of(x), 0, n, h, w, cin, _p(wt), _p(bias), wt.shape[0], kh, kw, pad,
+              _p(out), stream())
+
+
+def smalln_dgrad(dy, wt, kh, kw, pad, dx):
+    n, h, w, cin = dx.shape
+    _lib.call("vg_conv_smalln_dgrad", _p(dy), n, h, w, cin, _p(wt), wt.shape[0], kh, kw, pad, _p(dx), ld_of(dx), 0,
+              stream())
+
+
+def smalln_wgrad(dy, x, kh, kw, pad, dw, dbias):
+    n, h, w, cin = x.shape
+    _lib.call("vg_conv_smalln_wgrad", _p(dy), _p(x), ld_of(x), 0, n, h, w, cin, dw.shape[0], kh, kw, pad, _p(dw),
+              _p(dbias), stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# losses / reparam / spectral norm / optimiser
+# ----------------------------------------------------------------------------------------------
+def reparam_kl_fwd(heads, bias_mu, bias_lv, eps):
+    b, z2 = heads.shape
+    z = z2 // 2
+    mu, lv, zo = (torch.empty(b, z, dtype=F32, device=heads.device) for _ in range(3))
+    kl = torch.empty((), dtype=F32, device=heads.device)
+    _lib.call("vg_reparam_kl_fwd", _p(heads), _p(bias_mu), _p(bias_lv), _p(eps), b, z, _p(mu), _p(lv), _p(zo), _p(kl),
+              stream())
+    return mu, lv, zo, kl
+
+
+def reparam_kl_bwd(mu, lv, eps, dz, dmu, dlv, dkl, dheads_bf16=None):
+    b, z = mu.shape
+    dheads = torch.empty(b, 2 * z, dtype=F32, device=mu.device)
+    _lib.call("vg_reparam_kl_bwd", _p(mu), _p(lv), _p(eps), _p(dz), _p(dmu), _p(dlv), _p(dkl), b, z, _p(dheads),
+              _p(dheads_bf16), dheads_bf16.stride(0) if dheads_bf16 is not None else 0, stream())
+    return dheads
+
+
+def sigmoid_fwd(pre_nhwc, y_nchw):
+    n, c, h, w = y_nchw.shape
+    _lib.call("vg_sigmoid_fwd", _p(pre_nhwc), n, c, h * w, _p(y_nchw), stream())
+
+
+def sigmoid_bwd(y_nchw, dy_nchw, dpre_nhwc):
+    n, c, h, w = y_nchw.shape
+    _lib.call("vg_sigmoid_bwd", _p(y_nchw), _p(dy_nchw), n, c, h * w, _p(dpre_nhwc), stream())
+
+
+def l1_fwd(a, b):
+    out = torch.empty((), dtype=F32, device=a.device)
+    _lib.call("vg_l1_fwd", _p(a), _p(b), C.c_longlong(a.numel()), _p(out), stream())
+    return out
+
+
+def l1_bwd(a, b, gout, da, accumulate=False):
+    _lib.call("vg_l1_bwd", _p(a), _p(b), C.c_longlong(a.numel()), _p(gout), _p(da), int(accumulate), stream())
+
+
+def hinge_fwd(p, mode):
+    out = torch.empty((), dtype=F32, device=p.device)
+    _lib.call("vg_hinge_fwd", _p(p), C.c_longlong(p.numel()), mode, _p(out), stream())
+    return out
+
+
+def hinge_bwd(p, mode, gout, dp):
+    _lib.call("vg_hinge_bwd", _p(p), C.c_longlong(p.numel()), mode, _p(gout), _p(dp), stream())
+
+
+def spectral_sigma(w2d, u, v, training, eps=1e-12):
+    rows, cols = w2d.shape
+    sigma = torch.empty((), dtype=F32, device=w2d.device)
+    scratch = torch.empty(rows + cols + 2, dtype=F32, device=w2d.device)
+    _lib.call("vg_spectral_sigma", _p(w2d), rows, cols, _p(u), _p(v), int(training), C.c_float(eps), _p(sigma),
+              _p(scratch), stream())
+    return sigma
+
+
+def spectral_bwd(g2d, w2d, u, v, sigma, dw, accumulate=False):
+    rows, cols = w2d.shape
+    scratch = torch.empty(1, dtype=F32, device=w2d.device)
+    _lib.call("vg_spectral_bwd", _p(g2d), _p(w2d), _p(u), _p(v), _p(sigma), rows, cols, _p(dw), int(accumulate),
+              _p(scratch), stream())
+
+
+def sumsq(g, out, zero_first=True):
+    _lib.call("vg_sumsq", _p(g), C.c_longlong(g.numel()), _p(out), int(zero_first), stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, gnorm_sq=None, max_norm=0.0, write_back_grad=False):
+    _lib.call("vg_adam_step", _p(p), _p(g), _p(m), _p(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
+              C.c_float(beta2), C.c_float(eps), int(step), _p(gnorm_sq), C.c_float(max_norm), int(write_back_grad),
+              stream())
