@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the VAE-GAN training step (BASELINE.json metric: train images/s; conv tensor-pipe fraction).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPUs
+
+A "step" is one full training iteration (G forward, D step, G step, clip, both Adam updates) on one batch of
+synthetic images.  Workload at N=1: BASELINE.json configs[1] -- vae-gan-v2.py U-Net+FiLM generator + PatchGAN
+discriminator at 128x128, batch 64 per GPU, bf16 tensor-core math with fp32 accumulation and fp32 master weights.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic conv GFLOP per image of one train step (SURVEY.md section 8a / BASELINE.md section 2)
+STEP_GFLOP_PER_IMG = {"v2_128": 411.4, "base_64": 6.34, "unet_256": 265.3}
+WORKLOADS = {
+    "v2_128": dict(family="v2", h=128, w=128, batch=64, z=128, name="vae-gan-v2 128x128 b64/GPU"),
+    "base_64": dict(family="base", h=64, w=64, batch=16, z=128, name="vae-gan base 64x64 b16"),
+    "unet_256": dict(family="unet", h=256, w=256, batch=32, z=128, name="vae-gan-unet (repaired) 256x256 b32/GPU"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tf": p["bf16_tflops_sustained"], "tf_burst": p["bf16_tflops"], "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tf": 1400.0, "tf_burst": 1590.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's step on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(wl, sample_batch: int, steps: int, warmup: int):
+    """images/s of the reference algorithm (oracle port, fp32, torch CPU kernels) on a bounded sample."""
+    import torch
+    from oracle import models as om
+    from oracle.step import LossWeights, deterministic_state, make_optimizers, synthetic_batch, train_step
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fam, h, w, z = wl["family"], wl["h"], wl["w"], wl["z"]
+    if fam == "base":
+        G = om.VAEGAN(4, z, 64, 3, patch_hw=(h, w))
+    elif fam == "v2":
+        G = om.VAEGAN_UNet_SpatialFiLM(4, z, patch_hw=(h, w))
+    else:
+        G = om.VAEGAN_UNet_CharEmb(4, z, patch_hw=(h, w), repaired=True)
+    D = om.Discriminator(3)
+    G.load_state_dict(deterministic_state(G, 1234)); D.load_state_dict(deterministic_state(D, 4321))
+    og, od = make_optimizers(G, D)
+    wts = LossWeights.for_family(fam)
+    times = []
+    for i in range(warmup + steps):
+        batch = synthetic_batch(sample_batch, h, w, step=i)
+        t0 = time.perf_counter()
+        train_step(G, D, og, od, batch, wts, seed=10_000 + i, keep_grads=False)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return sample_batch / sec, sec, cores, torch.get_num_threads()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = max(1, min(wl["batch"], 4 if wl["h"] >= 128 else wl["batch"]))
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, sec, cores, threads = cpu_reference_rate(wl, sample, steps, warmup)
+    sample_txt = (f"{wl['name']}: oracle port of the reference step (fp32, torch CPU), batch {sample} per step "
+                  f"(bounded sample of the batch-{wl['batch']} workload), {steps} timed steps, {threads} threads")
+    line = {"impl": "reference", "metric": "train_images_per_sec", "value": rate, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "per_gpu_batch": wl["batch"], "sample_batch": sample},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample_txt},
+            "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def build_models(wl, device):
+    import torch
+    from vae_gan_mark_b200 import modules as M
+    fam, h, w, z = wl["family"], wl["h"], wl["w"], wl["z"]
+    torch.manual_seed(1234)
+    if fam == "base":
+        G = M.VAEGAN(4, z, 64, 3, patch_shape=(w, h), text_embedder=lambda t: torch.randn(len(t), 384))
+    elif fam == "v2":
+        G = M.VAEGAN_UNet_SpatialFiLM(4, z, patch_shape=(w, h))
+    else:
+        G = M.VAEGAN_UNet_CharEmb(4, z, patch_shape=(w, h))
+    D = M.Discriminator(3)
+    return G.to(device).train(), D.to(device).train()
+
+
+TEXTS = ["SALE", "New arrivals 2024", "Buy 1 get 1 FREE!", "50% off", "Limited time offer - today",
+         "Free shipping on orders over $25", "Best price", "Hello, world", "Summer collection", "Subscribe & save",
+         "Open 24/7", "Click here", "Black Friday deals start now", "Top rated", "Only 3 left in stock", "Thank you"]
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from vae_gan_mark_b200 import _lib, conv
+    from vae_gan_mark_b200.parallel import DataParallelReducer
+    from vae_gan_mark_b200.train import LossWeights, VAEGANTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, h, w = wl["batch"], wl["h"], wl["w"]
+    G, D = build_models(wl, dev)
+    reducer = DataParallelReducer(world) if world > 1 else None
+    if reducer is not None:
+        reducer.broadcast_parameters(list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()))
+    wts = LossWeights.for_family(wl["family"])
+    trainer = VAEGANTrainer(G, D, wts, grad_hook=reducer.hook if reducer else None)
+
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    pool = 2
+    data = [(torch.rand(B, 3, h, w, device=dev, generator=gen), torch.rand(B, 3, h, w, device=dev, generator=gen),
+             (torch.rand(B, 1, h, w, device=dev, generator=gen) > 0.5).float()) for _ in range(pool)]
+    texts = [TEXTS[i % len(TEXTS)] for i in range(B)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        ru, en, mask = data[i % pool]
+        return trainer.step(ru, en, mask, texts)
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.lib().vg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = one_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib().vg_launch_count() - launches0
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end-to-end: pinned host inputs, H2D inside the timed region, D2H of the loss scalars ----
+    host = [tuple(x.cpu().pin_memory() for x in d) for d in data]
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        ru, en, mask = (x.to(dev, non_blocking=True) for x in host[i % pool])
+        o = trainer.step(ru, en, mask, texts)
+        scal = torch.stack([o["loss_G"], o["loss_D"], o["recon"], o["kl"], o["gan"]]).cpu()   # 5 floats D2H (syncs)
+    e3.record()
+    barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t2) / 1e3)
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+
+    # ---- dominant kernel, timed live with CUDA events on the launching stream ----
+    conv.PROFILE = []
+    prof_steps = 2
+    for i in range(prof_steps):
+        one_step(i)
+    torch.cuda.synchronize()
+    recs, conv.PROFILE = conv.PROFILE, None
+    by = {}
+    for kind, key, flops, a, b in recs:
+        k = (kind, key)
+        d = by.setdefault(k, [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b); d[1] += flops; d[2] += 1
+    top = max(by.items(), key=lambda kv: kv[1][0])
+    (tkind, tkey), (tms, tflops, tcnt) = top
+    conv_ms = sum(v[0] for v in by.values()) / prof_steps
+    conv_flops = sum(v[1] for v in by.values()) / prof_steps
+    pk = peaks()
+    achieved = tflops / (tms / 1e3) / 1e12
+    step_ms = ms / args.steps
+    alg_tflop_step = STEP_GFLOP_PER_IMG[args.workload] * B / 1e3
+
+    if rank == 0:
+        sys.path.insert(0, ROOT)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 4 if h >= 128 else B
+            rate, sec, cores, threads = cpu_reference_rate(wl, sample, 2 if h >= 128 else 5, 1)
+            cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"oracle port of the reference step (fp32 torch CPU), batch {sample} of the {wl['name']} "
+                             f"workload, {sec:.2f} s/step, host has {cores} logical cores"}
+        line = {
+            "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "image": [h, w],
+                       "parallelism": f"dp{world}", "precision": "bf16 storage + tcgen05 bf16 MMA, fp32 accumulate, fp32 master weights",
+                       "l2": "per-step working set (activations >> 1 GB) far exceeds the 126 MB L2; 2 input batches cycled",
+                       "perceptual_term": "excluded (weights unavailable offline)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tf"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16 GEMM)",
+                         "kernel": f"conv_{tkind}_kernel", "shape": str(tkey), "launches_per_step": tcnt / prof_steps,
+                         "kernel_ms_per_step": tms / prof_steps,
+                         "all_conv_ms_per_step": conv_ms, "all_conv_tflops": conv_flops / (conv_ms / 1e3) / 1e12,
+                         "conv_share_of_step": conv_ms / step_ms,
+                         "step_algorithmic_tflops": alg_tflop_step / (step_ms / 1e3),
+                         "step_frac_of_peak": alg_tflop_step / (step_ms / 1e3) / pk["tf"]},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="v2_128", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ extern "C" {
 const char* vg_last_error(void);
 int vg_version(void);
 int vg_device_info(int* sm_count, int* cc_major, int* cc_minor);   /* host pointers */
+unsigned long long vg_launch_count(void);   /* kernels this library has launched so far in this process */
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core implicit GEMMs (tcgen05 / TMEM / TMA)

@@ -1,0 +1,108 @@
+"""CPU-side checks of the C ABI boundary: the shared library builds, loads, and exports every symbol that
+include/vaegan_b200.h declares; error paths return codes instead of aborting.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vae_gan_mark_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "vaegan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+char\s*\*|unsigned\s+long\s+long|int)\s+(vg_\w+)\s*\(", src, flags=re.M)
+    assert len(names) >= 30
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_version_and_error_string(lib):
+    assert lib.vg_version() == 1
+    lib.vg_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.vg_last_error(), bytes)
+
+
+def test_bad_descriptor_returns_error_code_not_abort(lib):
+    from vae_gan_mark_b200 import _lib
+    d = _lib.VgConvFprop()
+    d.cin = 48          # not a multiple of 64: must be rejected on the host before any launch
+    d.num_taps = 1
+    rc = lib.vg_conv_fprop(ctypes.byref(d), None)
+    assert rc < 0
+    assert b"cin" in lib.vg_last_error()
+    w = _lib.VgConvWgrad()
+    w.cin, w.cout, w.num_taps = 64, 64, 99
+    assert lib.vg_conv_wgrad(ctypes.byref(w), None) < 0
+    assert b"num_taps" in lib.vg_last_error()
+    with pytest.raises(_lib.VgError):
+        _lib.call("vg_hinge_fwd", None, ctypes.c_longlong(4), 7, None, None)
+
+
+def test_struct_layout_matches_header(lib):
+    """ctypes mirrors of the descriptor structs must have the C sizes (compiled probe)."""
+    import subprocess, tempfile, textwrap
+    from vae_gan_mark_b200 import _lib
+    code = textwrap.dedent('''
+        #include <stdio.h>
+        #include "vaegan_b200.h"
+        int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(VgConvFprop), sizeof(VgConvWgrad), sizeof(VgNormApply), sizeof(VgNormBackward)); return 0; }
+    ''')
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "p.c"), os.path.join(td, "p")
+        open(src, "w").write(code)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.VgConvFprop), ctypes.sizeof(_lib.VgConvWgrad),
+                     ctypes.sizeof(_lib.VgNormApply), ctypes.sizeof(_lib.VgNormBackward)]
+
+
+def test_modules_refuse_cpu_tensors():
+    """No CPU fallback: the drop-in modules raise on CPU inputs instead of silently running eager torch."""
+    import torch
+    from vae_gan_mark_b200 import modules as M
+    d = M.Discriminator(3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d(torch.zeros(1, 3, 32, 32))
+
+
+def test_state_dict_contract_matches_oracle():
+    """Same keys, shapes and parameter order as the (reference-pinned) oracle modules for every family."""
+    import torch
+    from oracle import models as om
+    from vae_gan_mark_b200 import modules as M
+    pairs = [
+        (M.VAEGAN(patch_shape=(32, 32), text_embedder=lambda t: torch.zeros(len(t), 384)), om.VAEGAN(patch_hw=(32, 32))),
+        (M.Discriminator(), om.Discriminator()),
+        (M.VAEGAN_UNet_SpatialFiLM(patch_shape=(64, 32)), om.VAEGAN_UNet_SpatialFiLM(patch_hw=(32, 64))),
+        (M.VAEGAN_UNet_CharEmb(patch_shape=(32, 32)), om.VAEGAN_UNet_CharEmb(patch_hw=(32, 32))),
+    ]
+    for mine, ora in pairs:
+        a, b = mine.state_dict(), ora.state_dict()
+        assert list(a) == list(b)
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+        assert [n for n, _ in mine.named_parameters()] == [n for n, _ in ora.named_parameters()]
+
+
+def test_conv_tap_geometry():
+    """Tap tables: stride-2 taps decompose input coordinate 2*o + r - p into (view coordinate, parity)."""
+    from vae_gan_mark_b200.conv import ConvLinear, conv_taps
+    ld = 128
+    for k, p in ((4, 1), (3, 1), (2, 0)):
+        taps = conv_taps(k, k, 2, p, p, ld)
+        for (cb, dw, sh, dh), (r, q) in zip(taps, [(r, q) for r in range(k) for q in range(k)]):
+            assert 2 * dh + sh == r - p and 2 * dw + cb // ld == q - p and cb % ld == 0
+    op = ConvLinear(64, 128, 4, 4, 2, (1, 1))
+    assert op.out_hw(64, 448) == (32, 224)

@@ -41,7 +41,7 @@ def build_pair(family, h, w, z):
     for g in (og, mg):
         g.train()
         if hasattr(g, "char_text_encoder_module"):
-            g.char_text_encoder_module.eval()      # GRU dropout draws from different RNGs on CPU and CUDA
+            g.char_text_encoder_module.rnn.dropout = 0.0   # GRU dropout draws from different RNGs on CPU and CUDA
     od.train(); md.train()
     return og, od, mg.cuda(), md.cuda()
 
@@ -84,7 +84,7 @@ def test_train_step_matches_oracle(family, h, w, batch, z):
     for (name, p), g in zip(mg.named_parameters(), grads["G"]):
         if name in ref.g_grads and g is not None:
             gerr["G." + name] = rel(g, ref.g_grads[name])
-    worst = sorted(gerr.items(), key=lambda kv: -kv[1])[:8]
+    worst = sorted(((k, v) for k, v in gerr.items() if not ref_is_noise(k, ref)), key=lambda kv: -kv[1])[:14]
     print("worst grads:", [(k, f"{v:.2e}") for k, v in worst])
     assert set(n for n, p in mg.named_parameters() if p.grad is not None) >= set(ref.g_grads), "missing G gradients"
     for k, v in report.items():

@@ -21,6 +21,26 @@ from .ops import BF16, F32, round_up
 
 Tap = Tuple[int, int, int, int]   # (c_base, dw, sh, dh)
 
+# When set to a list, every tensor-core launch appends (kind, shape-key, flops, start_event, end_event): bench.py
+# uses it to time the dominant kernel live on the launching stream.
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(e0, kind, key, flops):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append((kind, key, flops, e0, e1))
+
 
 def conv_taps(kh: int, kw: int, stride: int, ph: int, pw: int, ld: int) -> List[Tap]:
     """Taps of a (kh x kw, stride, pad) convolution reading its input through the stride view."""
@@ -65,7 +85,9 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
     d.cout_per_sub = cout_per_sub or n_gemm
     d.bias = bias.data_ptr() if bias is not None else None
     d.act, d.ksplit, d.force_bn = act, ksplit, force_bn
+    e0 = _prof_begin()
     _lib.call("vg_conv_fprop", C.byref(d), ops.stream())
+    _prof_end(e0, "fprop", (m, n_gemm, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * n_gemm * len(taps) * cin)
 
 
 def wgrad(g: torch.Tensor, cout: int, x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int,
@@ -82,7 +104,9 @@ def wgrad(g: torch.Tensor, cout: int, x: torch.Tensor, taps: Sequence[Tap], x_st
     _fill_taps(d.taps, taps)
     d.dw, d.dw_ld = dw.data_ptr(), dw.stride(0)
     d.ksplit, d.force_bn = ksplit, force_bn
+    e0 = _prof_begin()
     _lib.call("vg_conv_wgrad", C.byref(d), ops.stream())
+    _prof_end(e0, "wgrad", (m, cout, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * cout * len(taps) * cin)
 
 
 def pad_channels(t: torch.Tensor, c_pad: int) -> torch.Tensor:
@@ -188,15 +212,10 @@ class ConvLinear:
             out = new_act(n, h, w, self.cin, dy.device)
         g = pad_channels(dy, self.cout_p)
         if "shuffle" in wb:
-            if self.flat:      # out viewed as one pixel with kh*kw*cin channels
-                assert out.is_contiguous()
-                fprop(g, [(0, 0, 0, 0)], 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, 1, 1),
-                      out.view(n, 1, 1, h * w * self.cin), bias=None, act=act)
-                assert bias is None
-            else:              # pixel shuffle: column kernel (kh x 1) or 2x2 stride 2
-                su = (self.kh, self.kw)
-                fprop(g, [(0, 0, 0, 0)], 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, oh, ow), out,
-                      su=su, cout_per_sub=self.cin, bias=bias, act=act)
+            # pixel shuffle: GEMM column (r, q, ci) of input pixel (oh, ow) lands at output pixel (oh*kh + r, ow*kw + q).
+            # Covers the full-kernel case (1x1 input), the column kernel (kh x 1) and 2x2 stride 2.
+            fprop(g, [(0, 0, 0, 0)], 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, oh, ow), out,
+                  su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act)
             return out
         if "s1" in wb:
             taps = [(0, self.pw - q, 0, self.ph - r) for r in range(self.kh) for q in range(self.kw)]

@@ -32,6 +32,14 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
+// every kernel launch site is followed by VG_LAUNCH_OK(): counts the launch (vg_launch_count) and checks it
+extern unsigned long long g_launches;
+#define VG_LAUNCH_OK()                 \
+  do {                                 \
+    ++vg::g_launches;                  \
+    VG_CUDA(cudaGetLastError());       \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------
 // shared-memory address / mbarrier
 // ------------------------------------------------------------------------------------------

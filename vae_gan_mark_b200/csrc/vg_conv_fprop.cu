@@ -331,6 +331,6 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
   const int grid = min(total_tiles, sms);
   conv_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tmap_a, tmap_b, p);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }

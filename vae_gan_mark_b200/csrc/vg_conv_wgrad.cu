@@ -225,10 +225,17 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   p.n_tiles = cdiv(p.blocks_total, nb);
   int ksplit = d->ksplit;
   if (ksplit <= 0) {
+    // fill one wave: the largest split with tiles*ksplit <= #SMs (a second, partial wave costs a full tile time)
     const int tiles = p.m_tiles * p.n_tiles;
-    ksplit = max(1, min(pix_tiles, (sms + tiles - 1) / tiles));
-    // keep at least ~8 K steps per split so the pipeline fills
-    ksplit = max(1, min(ksplit, pix_tiles / 8 > 0 ? pix_tiles / 8 : 1));
+    // choose the split that wastes the least of the last wave; keep >= ~8 K steps per split so the pipeline fills
+    const int max_split = max(1, min(64, pix_tiles / 8));
+    double best = -1.0;
+    ksplit = 1;
+    for (int s = 1; s <= max_split; ++s) {
+      const long long work = static_cast<long long>(tiles) * s;
+      const double eff = static_cast<double>(work) / (static_cast<double>((work + sms - 1) / sms) * sms);
+      if (eff > best + 1e-9) { best = eff; ksplit = s; }
+    }
   }
   VG_CHECK(ksplit <= pix_tiles, -1, "vg_conv_wgrad: ksplit %d > pixel tiles %d", ksplit, pix_tiles);
   p.ksplit = ksplit;
@@ -268,6 +275,6 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   }
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   conv_wgrad_kernel<<<min(total_tiles, sms), kWgThreads, smem, stream>>>(tmap_g, tmap_x, p);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }

@@ -406,7 +406,7 @@ extern "C" int vg_strided_copy(const void* in, int in_dtype, void* out, int out_
     strided_copy_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), p, scale, scale_inverse, accumulate);
   else
     VG_CHECK(false, -1, "vg_strided_copy: dtype codes are 0 (fp32) and 1 (bf16)");
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -416,7 +416,7 @@ extern "C" int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, 
   film_fwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
       static_cast<__nv_bfloat16*>(y), rows, c);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx,
@@ -427,7 +427,7 @@ extern "C" int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, 
       static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
       static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dgb), static_cast<__nv_bfloat16*>(dx), dx_ld,
       dx_coff, rows, c);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -436,7 +436,7 @@ extern "C" int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int
   VG_CHECK(c % 8 == 0 && t_ld % 8 == 0 && t_coff % 8 == 0, -1, "vg_upsample_w_fwd: channels must be multiples of 8");
   upsample_fwd_kernel<<<ew_grid(static_cast<long long>(n) * h * w * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(t), t_ld, t_coff, n, w0, c, static_cast<__nv_bfloat16*>(y), h, w);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt, void* stream_) {
@@ -446,7 +446,7 @@ extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int
   const int rpt = 8;
   const long long items = static_cast<long long>(n) * w0 * (c / 8) * ((h + rpt - 1) / rpt);
   upsample_bwd_kernel<<<ew_grid(items), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, w0, dt, rpt);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -457,7 +457,7 @@ extern "C" int vg_im2col(const void* src, int n, int h, int w, int ld, int c, in
   im2col_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * kpad), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(src), n, h, w, ld, c, kh, kw, stride, pad, oh, ow,
       static_cast<__nv_bfloat16*>(col), kpad);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_col2im(const void* dcol, int kpad, int n, int h, int w, int c, int kh, int kw, int stride, int pad,
@@ -465,7 +465,7 @@ extern "C" int vg_col2im(const void* dcol, int kpad, int n, int h, int w, int c,
   const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
   col2im_kernel<<<ew_grid(static_cast<long long>(n) * c * h * w), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(dcol), kpad, n, h, w, c, kh, kw, stride, pad, oh, ow, dsrc_nchw);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -482,7 +482,7 @@ extern "C" int vg_conv_smalln_fwd(const void* x, int x_ld, int x_coff, int n, in
   const int G = smalln_lanes(kh * kw * (cin / 8));
   smalln_fwd_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * G), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w, cin, wt, bias, cout, kh, kw, pad, oh, ow, out, G);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int cin, const float* wt, int cout, int kh,
@@ -492,7 +492,7 @@ extern "C" int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int ci
   const int oh = h + 2 * pad - kh + 1, ow = w + 2 * pad - kw + 1;
   smalln_dgrad_kernel<<<ew_grid(static_cast<long long>(n) * h * w * (cin / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       dy, n, oh, ow, cout, wt, kh, kw, pad, h, w, cin, static_cast<__nv_bfloat16*>(dx), dx_ld, dx_coff);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, int x_coff, int n, int h, int w, int cin,
@@ -509,7 +509,7 @@ extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, in
   if (gx < 1) gx = 1;
   smalln_wgrad_kernel<<<dim3(gx, kh * kw), 256, 0, st>>>(dy, static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w,
                                                          cin, cout, kh, kw, pad, oh, ow, dw, dbias);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -519,11 +519,11 @@ extern "C" int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, vo
   act_bwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(y), y_ld, static_cast<const __nv_bfloat16*>(dy), dy_ld,
       static_cast<__nv_bfloat16*>(dx), dx_ld, rows, c, act);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_colsum_f32(const float* in, long long rows, int cols, int ld, float* out, int accumulate, void* stream_) {
   colsum_f32_kernel<<<cdiv(cols, 128), 128, 0, static_cast<cudaStream_t>(stream_)>>>(in, rows, cols, ld, out, accumulate);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }

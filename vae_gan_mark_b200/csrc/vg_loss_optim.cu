@@ -263,7 +263,7 @@ extern "C" int vg_reparam_kl_fwd(const float* heads, const float* bias_mu, const
   VG_CUDA(cudaMemsetAsync(kl_out, 0, sizeof(float), ST));
   reparam_fwd_kernel<<<lo_grid(static_cast<long long>(b) * z), 256, 0, ST>>>(heads, bias_mu, bias_lv, eps, b, z, mu, logvar,
                                                                              zout, kl_out);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* dz,
@@ -271,43 +271,43 @@ extern "C" int vg_reparam_kl_bwd(const float* mu, const float* logvar, const flo
                                  float* dheads, void* dheads_bf16, int bf_ld, void* stream_) {
   reparam_bwd_kernel<<<lo_grid(static_cast<long long>(b) * z), 256, 0, ST>>>(
       mu, logvar, eps, dz, dmu_ext, dlv_ext, dkl, b, z, dheads, static_cast<__nv_bfloat16*>(dheads_bf16), bf_ld);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_sigmoid_fwd(const float* pre_nhwc, int n, int c, int hw, float* y_nchw, void* stream_) {
   sigmoid_nhwc_to_nchw_kernel<<<lo_grid(static_cast<long long>(n) * c * hw), 256, 0, ST>>>(pre_nhwc, n, c, hw, y_nchw);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_sigmoid_bwd(const float* y_nchw, const float* dy_nchw, int n, int c, int hw, float* dpre_nhwc,
                               void* stream_) {
   sigmoid_bwd_kernel<<<lo_grid(static_cast<long long>(n) * c * hw), 256, 0, ST>>>(y_nchw, dy_nchw, n, c, hw, dpre_nhwc);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_l1_fwd(const float* a, const float* b, long long n, float* out, void* stream_) {
   VG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST));
   l1_fwd_kernel<<<lo_grid(n, 1024), 256, 0, ST>>>(a, b, n, out);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_l1_bwd(const float* a, const float* b, long long n, const float* gout, float* da, int accumulate,
                          void* stream_) {
   l1_bwd_kernel<<<lo_grid(n), 256, 0, ST>>>(a, b, n, gout, da, accumulate);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_hinge_fwd(const float* p, long long n, int mode, float* out, void* stream_) {
   VG_CHECK(mode >= 0 && mode <= 2, -1, "vg_hinge_fwd: mode must be 0 (fake), 1 (real) or 2 (generator)");
   VG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST));
   hinge_fwd_kernel<<<lo_grid(n, 1024), 256, 0, ST>>>(p, n, mode, out);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_hinge_bwd(const float* p, long long n, int mode, const float* gout, float* dp, void* stream_) {
   VG_CHECK(mode >= 0 && mode <= 2, -1, "vg_hinge_bwd: mode must be 0 (fake), 1 (real) or 2 (generator)");
   hinge_bwd_kernel<<<lo_grid(n), 256, 0, ST>>>(p, n, mode, gout, dp);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -320,14 +320,14 @@ extern "C" int vg_spectral_sigma(const float* w, int rows, int cols, float* u, f
   VG_CUDA(cudaMemsetAsync(nrm, 0, 2 * sizeof(float), ST));
   if (training) {
     sn_wtu_kernel<<<cdiv(cols, 256), 256, 0, ST>>>(w, u, rows, cols, t, nrm);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCH_OK();
     sn_wv_kernel<<<rows, 256, 0, ST>>>(w, t, nrm, eps, rows, cols, s, nrm + 1);
   } else {
     sn_wv_kernel<<<rows, 256, 0, ST>>>(w, v, nullptr, eps, rows, cols, s, nrm + 1);
   }
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   sn_finish_kernel<<<cdiv(std::max(rows, cols), 256), 256, 0, ST>>>(t, s, nrm, eps, rows, cols, training, u, v, sigma);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 // scratch: fp32 [1]
@@ -336,9 +336,9 @@ extern "C" int vg_spectral_bwd(const float* g, const float* w_orig, const float*
   const long long n = static_cast<long long>(rows) * cols;
   VG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), ST));
   dot_kernel<<<lo_grid(n, 1024), 256, 0, ST>>>(g, w_orig, n, scratch);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   sn_bwd_kernel<<<lo_grid(n), 256, 0, ST>>>(g, u, v, sigma, scratch, rows, cols, dw, accumulate);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -346,7 +346,7 @@ extern "C" int vg_sumsq(const float* g, long long n, float* out, int zero_first,
   VG_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, -1, "vg_sumsq: buffer must be 16-byte aligned");
   if (zero_first) VG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST));
   sumsq_kernel<<<lo_grid(n, 2048), 256, 0, ST>>>(g, n, out);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
@@ -357,6 +357,6 @@ extern "C" int vg_adam_step(float* p, float* g, float* m, float* v, long long n,
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), step));
   adam_kernel<<<lo_grid(n, 1024), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), gnorm_sq, max_norm,
                                                 write_back_grad);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }

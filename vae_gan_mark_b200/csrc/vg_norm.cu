@@ -338,7 +338,7 @@ extern "C" int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, lo
   if (groups > 1) gx = max(1, min(gx, (num_sms() * 8) / groups));
   stats_kernel<<<dim3(gx, groups), kNT, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, c, rows_per_group,
                                                  sums);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -348,7 +348,7 @@ extern "C" int vg_norm_finalize(const float* sums, int groups, long long rows_pe
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   finalize_kernel<<<cdiv(groups * c, 128), 128, 0, st>>>(sums, groups, c, rows_per_group, eps, mean_rstd, momentum,
                                                          running_mean, running_var, num_batches_tracked);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -366,7 +366,7 @@ extern "C" int vg_norm_apply(const VgNormApply* d, void* stream_) {
   p.pool = static_cast<__nv_bfloat16*>(d->pool); p.p_ld = d->p_ld; p.p_coff = d->p_coff;
   const long long cells = static_cast<long long>(d->n) * (d->pool ? d->h / 2 : d->h) * (d->pool ? d->w / 2 : d->w);
   apply_kernel<<<grid_for(cells * (d->c / 8), kNT), kNT, 0, st>>>(p);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   return 0;
 }
 
@@ -392,12 +392,12 @@ extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
   int gx = grid_for(cells, m.rows_par * 4);
   if (groups > 1) gx = max(1, min(gx, (num_sms() * 8) / groups));
   bwd_kernel<false><<<dim3(gx, groups), kNT, 0, st>>>(p);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   bwd_kernel<true><<<dim3(gx, groups), kNT, 0, st>>>(p);
-  VG_CUDA(cudaGetLastError());
+  VG_LAUNCH_OK();
   if (d->dgamma != nullptr || d->dbeta != nullptr) {
     affine_grad_kernel<<<cdiv(d->c, 128), 128, 0, st>>>(d->sums, groups, d->c, d->dgamma, d->dbeta, d->accumulate);
-    VG_CUDA(cudaGetLastError());
+    VG_LAUNCH_OK();
   }
   return 0;
 }

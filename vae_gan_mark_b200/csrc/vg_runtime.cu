@@ -9,6 +9,7 @@
 namespace vg {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -77,6 +78,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 extern "C" const char* vg_last_error(void) { return vg::g_err; }
 
 extern "C" int vg_version(void) { return VG_API_VERSION; }
+
+extern "C" unsigned long long vg_launch_count(void) { return vg::g_launches; }
 
 extern "C" int vg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
