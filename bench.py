@@ -179,9 +179,15 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i):
-        ru, en, mask = data[i % pool]
-        return trainer.step(ru, en, mask, texts)
+    use_graph = not args.no_graph and (world == 1 or args.graph_dp)
+    if use_graph:
+        trainer.capture(data[0][0], data[0][1], data[0][2], texts)
+
+    def one_step(i, src=None):
+        ru, en, mask = (src or data)[i % pool]
+        if use_graph:
+            return trainer.replay(ru, en, mask)      # device->device (or pinned host->device) copies + one graph launch
+        return trainer.step(ru.to(dev, non_blocking=True), en.to(dev, non_blocking=True), mask.to(dev, non_blocking=True), texts)
 
     for i in range(args.warmup):
         one_step(i)
@@ -199,6 +205,8 @@ def run_ours(args, wl):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.lib().vg_launch_count() - launches0
+    if use_graph:      # the launches were recorded once at capture time and are replayed by the graph every step
+        launches = trainer.launches_per_step * args.steps
     if sampler:
         sampler.stop_flag.set()
         sampler.join()
@@ -214,8 +222,7 @@ def run_ours(args, wl):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
-        ru, en, mask = (x.to(dev, non_blocking=True) for x in host[i % pool])
-        o = trainer.step(ru, en, mask, texts)
+        o = one_step(i, host)
         scal = torch.stack([o["loss_G"], o["loss_D"], o["recon"], o["kl"], o["gan"]]).cpu()   # 5 floats D2H (syncs)
     e3.record()
     barrier()
@@ -229,7 +236,7 @@ def run_ours(args, wl):
     conv.PROFILE = []
     prof_steps = 2
     for i in range(prof_steps):
-        one_step(i)
+        trainer.step(*data[i % pool], texts)      # eager path: per-launch CUDA events cannot be recorded inside a graph
     torch.cuda.synchronize()
     recs, conv.PROFILE = conv.PROFILE, None
     by = {}
@@ -237,6 +244,12 @@ def run_ours(args, wl):
         k = (kind, key)
         d = by.setdefault(k, [0.0, 0.0, 0])
         d[0] += a.elapsed_time(b); d[1] += flops; d[2] += 1
+    if args.dump_convs and rank == 0:
+        rows = [{"kind": k[0], "m": list(k[1][0]), "n": k[1][1], "k": k[1][2], "launches_per_step": v[2] / prof_steps,
+                 "ms_per_step": v[0] / prof_steps, "tflops": v[1] / (v[0] / 1e3) / 1e12}
+                for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])]
+        with open(args.dump_convs, "w") as f:
+            json.dump(rows, f, indent=1)
     top = max(by.items(), key=lambda kv: kv[1][0])
     (tkind, tkey), (tms, tflops, tcnt) = top
     conv_ms = sum(v[0] for v in by.values()) / prof_steps
@@ -260,7 +273,7 @@ def run_ours(args, wl):
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "image": [h, w],
-                       "parallelism": f"dp{world}", "precision": "bf16 storage + tcgen05 bf16 MMA, fp32 accumulate, fp32 master weights",
+                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "precision": "bf16 storage + tcgen05 bf16 MMA, fp32 accumulate, fp32 master weights",
                        "l2": "per-step working set (activations >> 1 GB) far exceeds the 126 MB L2; 2 input batches cycled",
                        "perceptual_term": "excluded (weights unavailable offline)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20},
@@ -290,6 +303,9 @@ def main():
     ap.add_argument("--workload", default="v2_128", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-convs", default="", help="write the per-shape tensor-core kernel timing table to this file")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--graph-dp", action="store_true", help="also capture the NCCL all-reduces (multi-GPU) in the graph")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:

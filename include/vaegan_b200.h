@@ -194,6 +194,14 @@ int vg_spectral_bwd(const float* g, const float* w_orig, const float* u, const f
 /* clip_grad_norm_ + Adam over flat buffers (vae-gan.py:424, :541-542): *out (+)= sum g^2; the Adam pass scales g by
  * min(1, max_norm/(sqrt(*gnorm_sq)+1e-6)) when gnorm_sq != NULL and max_norm > 0 */
 int vg_sumsq(const float* g, long long n, float* out, int zero_first, void* stream);
+/* multi-tensor forms: `table` is a DEVICE array of `count` entries (g == NULL entries are skipped); `state` is a
+ * device float[4] {step, 1-beta1^step, sqrt(1-beta2^step), -} advanced by vg_adam_prepare, so a captured CUDA graph of
+ * the step replays with the right bias corrections */
+typedef struct VgAdamTensor { float* p; float* g; float* m; float* v; long long n; } VgAdamTensor;
+int vg_adam_prepare(float* state, float beta1, float beta2, void* stream);
+int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, void* stream);
+int vg_multi_adam(const VgAdamTensor* table, int count, float lr, float beta1, float beta2, float eps,
+                  const float* state, const float* gnorm_sq, float max_norm, int write_back_grad, void* stream);
 int vg_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                  int step, const float* gnorm_sq, float max_norm, int write_back_grad, void* stream);
 

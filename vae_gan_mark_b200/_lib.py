@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.vg_last_error.restype = C.c_char_p
         _lib.vg_version.restype = C.c_int
+        _lib.vg_launch_count.restype = C.c_ulonglong
     return _lib
 
 

@@ -253,6 +253,63 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
+// ---- multi-tensor variants: one launch for a whole parameter list (table of VgAdamTensor on the device) ----
+// state[0] = step count, state[1] = 1 - beta1^step, state[2] = sqrt(1 - beta2^step); advanced on the device so
+// that a captured CUDA graph replays correctly.
+__global__ void adam_prepare_kernel(float* state, float b1, float b2) {
+  const double step = static_cast<double>(state[0]) + 1.0;
+  state[0] = static_cast<float>(step);
+  state[1] = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));
+  state[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), step)));
+}
+__global__ void multi_sumsq_kernel(const VgAdamTensor* __restrict__ tab, int count, float* out) {
+  float acc = 0.f;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int t = 0; t < count; ++t) {
+    const float* g = tab[t].g;
+    const long long n = tab[t].n;
+    if (g == nullptr) continue;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+      const long long n4 = n / 4;
+      const float4* g4 = reinterpret_cast<const float4*>(g);
+      for (long long i = tid; i < n4; i += nth) {
+        const float4 v = g4[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      for (long long i = n4 * 4 + tid; i < n; i += nth) acc += g[i] * g[i];
+    } else {
+      for (long long i = tid; i < n; i += nth) acc += g[i] * g[i];
+    }
+  }
+  const float s = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+__global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int count, float lr, float b1, float b2,
+                                  float eps, const float* __restrict__ state, const float* __restrict__ gnorm_sq,
+                                  float max_norm, int write_back_grad) {
+  float clip = 1.f;
+  if (gnorm_sq != nullptr && max_norm > 0.f) clip = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
+  const float step = lr / state[1];
+  const float bc2_sqrt = state[2];
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int t = 0; t < count; ++t) {
+    float* p = tab[t].p; float* g = tab[t].g; float* m = tab[t].m; float* v = tab[t].v;
+    const long long n = tab[t].n;
+    if (g == nullptr) continue;
+    for (long long i = tid; i < n; i += nth) {
+      const float gi = g[i] * clip;
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+      if (write_back_grad) g[i] = gi;
+    }
+  }
+}
+
 }  // namespace vg
 
 using namespace vg;
@@ -357,6 +414,26 @@ extern "C" int vg_adam_step(float* p, float* g, float* m, float* v, long long n,
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), step));
   adam_kernel<<<lo_grid(n, 1024), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), gnorm_sq, max_norm,
                                                 write_back_grad);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_adam_prepare(float* state, float beta1, float beta2, void* stream_) {
+  adam_prepare_kernel<<<1, 1, 0, ST>>>(state, beta1, beta2);
+  VG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, void* stream_) {
+  VG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST));
+  multi_sumsq_kernel<<<num_sms() * 4, 256, 0, ST>>>(table, count, out);
+  VG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int vg_multi_adam(const VgAdamTensor* table, int count, float lr, float beta1, float beta2, float eps,
+                             const float* state, const float* gnorm_sq, float max_norm, int write_back_grad,
+                             void* stream_) {
+  multi_adam_kernel<<<num_sms() * 4, 256, 0, ST>>>(table, count, lr, beta1, beta2, eps, state, gnorm_sq, max_norm,
+                                                   write_back_grad);
   VG_LAUNCH_OK();
   return 0;
 }

@@ -9,8 +9,11 @@
 // activation (the U-Net skip, possibly into a channel slice of the decoder's concat buffer) and the pooled
 // tensor in one sweep; its backward routes the pooled gradient to the first maximum of each window.
 //
-// All kernels are HBM-bound: 16-byte (8 x bf16) vector accesses, one channel-vector per thread, fp32 math,
-// block-level partial sums in shared memory, one fp32 atomic per (block, channel).
+// All kernels are HBM-bound.  Layout of the work: a thread owns ONE 8-channel vector (16-byte accesses) for its
+// whole lifetime, so the per-channel constants (scale, shift, mean, rstd, ...) are loaded once into registers,
+// and it walks rows with several independent loads in flight.  Reductions: registers -> shared memory across
+// the rows of a block -> one fp32 atomic per (block, channel); grids are kept small (<= 2 blocks per SM per
+// group) so that the atomics on one address do not serialise.
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
 
@@ -40,6 +43,36 @@ VG_DEVICE float act_grad(float pre, int act) {
   return 1.f;
 }
 VG_DEVICE float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+VG_DEVICE bf16x8 ldv(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+VG_DEVICE void unpack8(const bf16x8& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16x2(v.u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// block-level reduction of 16 per-thread partials over the row lanes, then one atomic per channel
+VG_DEVICE void reduce_rows_atomic(float (&red)[kNT][17], const float (&s)[8], const float (&q)[8], const RowMap& m,
+                                  int rl, int cvi, int cvec, float* dst0, float* dst1) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[tid][i] = s[i]; red[tid][8 + i] = q[i]; }
+  __syncthreads();
+  // all 256 threads cooperate: thread t reduces partial (t % 16) of channel vector (t / 16) when it exists
+  for (int item = tid; item < m.cvl * 16; item += kNT) {
+    const int v = item >> 4, k = item & 15;
+    if (cvec - cvi + v < m.cv) {
+      float a = 0.f;
+      for (int r = 0; r < m.rows_par; ++r) a += red[r * m.cvl + v][k];
+      float* dst = (k < 8 ? dst0 : dst1) + (cvec - cvi + v) * 8 + (k & 7);
+      atomicAdd(dst, a);
+    }
+  }
+  __syncthreads();
+  (void)rl;
+}
 
 // ---------------------------------------------------------------------------------------------
 // statistics: sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 over the rows of group g
@@ -58,26 +91,29 @@ __global__ void __launch_bounds__(kNT) stats_kernel(const __nv_bfloat16* __restr
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     if (rl < m.rows_par && cvec < m.cv) {
       const __nv_bfloat16* base = x + static_cast<long long>(g) * rows_per_group * ld + coff + cvec * 8;
-      for (long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl; r < rows_per_group;
-           r += static_cast<long long>(gridDim.x) * m.rows_par) {
+      const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
+      long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
+      for (; r + 3 * stride < rows_per_group; r += 4 * stride) {
+        bf16x8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldv(base + (r + u * stride) * ld);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+        }
+      }
+      for (; r < rows_per_group; r += stride) {
         float f[8];
-        load8(base + r * ld, f);
+        unpack8(ldv(base + r * ld), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { red[tid][i] = s[i]; red[tid][8 + i] = q[i]; }
-    __syncthreads();
-    if (rl == 0 && cvec < m.cv) {
-      for (int k = 0; k < 16; ++k) {
-        float a = 0.f;
-        for (int r = 0; r < m.rows_par; ++r) a += red[r * m.cvl + cvi][k];
-        const int ch = cvec * 8 + (k & 7);
-        atomicAdd(sums + (static_cast<long long>(g) * 2 + (k >> 3)) * c + ch, a);
-      }
-    }
-    __syncthreads();
+    float* dst = sums + static_cast<long long>(g) * 2 * c;
+    reduce_rows_atomic(red, s, q, m, rl, cvi, cvec, dst, dst + c);
   }
 }
 
@@ -104,6 +140,7 @@ __global__ void finalize_kernel(const float* __restrict__ sums, int groups, int 
 
 // ---------------------------------------------------------------------------------------------
 // apply: y = act(gamma * (x - mean) * rstd + beta), optional fused 2x2 max-pool output
+// blockIdx.y = sample when per_sample (so the constants are block-uniform per channel), else 0
 // ---------------------------------------------------------------------------------------------
 struct ApplyParams {
   const __nv_bfloat16* x; int x_ld, x_coff;
@@ -115,21 +152,21 @@ struct ApplyParams {
   __nv_bfloat16* pool; int p_ld, p_coff;
 };
 
+template <bool kPool>
 __global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
-  const int cv = p.c / 8;
-  const bool pooled = p.pool != nullptr;
-  const int ph = pooled ? p.h / 2 : p.h, pw = pooled ? p.w / 2 : p.w;
-  const long long cells = static_cast<long long>(p.n) * ph * pw;
-  const long long total = cells * cv;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cvec = static_cast<int>(idx % cv);
-    const long long cell = idx / cv;
-    const int pj = static_cast<int>(cell % pw);
-    const int pi = static_cast<int>((cell / pw) % ph);
-    const int n = static_cast<int>(cell / (static_cast<long long>(pw) * ph));
+  const RowMap m = row_map(p.c);
+  const int tid = threadIdx.x;
+  const int rl = tid / m.cvl, cvi = tid % m.cvl;
+  const int grp = blockIdx.y;
+  const int n_count = p.per_sample ? 1 : p.n;
+  const int ph = kPool ? p.h / 2 : p.h, pw = kPool ? p.w / 2 : p.w;
+  const long long cells = static_cast<long long>(n_count) * ph * pw;
+  const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
+  for (int cv0 = 0; cv0 < m.cv; cv0 += m.cvl) {
+    const int cvec = cv0 + cvi;
+    if (rl >= m.rows_par || cvec >= m.cv) continue;
     const int ch = cvec * 8;
-    const float* mr = p.mean_rstd + static_cast<long long>(p.per_sample ? n : 0) * 2 * p.c;
+    const float* mr = p.mean_rstd + static_cast<long long>(p.per_sample ? grp : 0) * 2 * p.c;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -138,33 +175,66 @@ __global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
       sc[i] = g * rstd;
       sh[i] = b - mr[ch + i] * g * rstd;
     }
-    const int reps = pooled ? 2 : 1;
-    float mx[8];
+    const __nv_bfloat16* xb = p.x + p.x_coff + ch;
+    __nv_bfloat16* yb = p.y + p.y_coff + ch;
+    const long long pix0 = static_cast<long long>(p.per_sample ? grp : 0) * p.h * p.w;
+    if (!kPool) {
+      long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
+      for (; r + 3 * stride < cells; r += 4 * stride) {
+        bf16x8 v[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
-    for (int a = 0; a < reps; ++a)
-      for (int b = 0; b < reps; ++b) {
-        const int i_h = pooled ? 2 * pi + a : pi, i_w = pooled ? 2 * pj + b : pj;
-        const long long pix = (static_cast<long long>(n) * p.h + i_h) * p.w + i_w;
-        float f[8], o[8];
-        load8(p.x + pix * p.x_ld + p.x_coff + ch, f);
+        for (int u = 0; u < 4; ++u) v[u] = ldv(xb + (pix0 + r + u * stride) * p.x_ld);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
-          mx[i] = fmaxf(mx[i], bf16_round(o[i]));
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
+          store8(yb + (pix0 + r + u * stride) * p.y_ld, f);
         }
-        store8(p.y + pix * p.y_ld + p.y_coff + ch, o);
       }
-    if (pooled) {
-      const long long ppix = (static_cast<long long>(n) * ph + pi) * pw + pj;
-      store8(p.pool + ppix * p.p_ld + p.p_coff + ch, mx);
+      for (; r < cells; r += stride) {
+        float f[8];
+        unpack8(ldv(xb + (pix0 + r) * p.x_ld), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
+        store8(yb + (pix0 + r) * p.y_ld, f);
+      }
+    } else {
+      for (long long cell = static_cast<long long>(blockIdx.x) * m.rows_par + rl; cell < cells; cell += stride) {
+        const int pj = static_cast<int>(cell % pw);
+        const int pi = static_cast<int>((cell / pw) % ph);
+        const long long nn = (p.per_sample ? grp : cell / (static_cast<long long>(pw) * ph));
+        const long long row0 = (nn * p.h + 2 * pi) * p.w + 2 * pj;
+        bf16x8 v[4];
+        v[0] = ldv(xb + row0 * p.x_ld);
+        v[1] = ldv(xb + (row0 + 1) * p.x_ld);
+        v[2] = ldv(xb + (row0 + p.w) * p.x_ld);
+        v[3] = ldv(xb + (row0 + p.w + 1) * p.x_ld);
+        float mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
+            mx[i] = fmaxf(mx[i], bf16_round(f[i]));
+          }
+          store8(yb + (row0 + (u >> 1) * p.w + (u & 1)) * p.y_ld, f);
+        }
+        const long long ppix = (nn * ph + pi) * pw + pj;
+        store8(p.pool + ppix * p.p_ld + p.p_coff + ch, mx);
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward.  g = (dy + routed pooled grad) * act'(pre);  pass 1 reduces sum g and sum g*xhat,
-// pass 2 writes dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)).
+// backward.  g = (dy + routed pooled grad) * act'(pre);  pass 1 (kApply = false) reduces sum g and sum g*xhat,
+// pass 2 (kApply = true) writes dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)).
 // ---------------------------------------------------------------------------------------------
 struct BwdParams {
   const __nv_bfloat16* x; int x_ld, x_coff;           // raw (pre-normalisation) conv output
@@ -178,129 +248,128 @@ struct BwdParams {
   __nv_bfloat16* dx; int dx_ld, dx_coff;
 };
 
-// computes g[8] for the 1 or 4 pixels of a cell; returns through arrays indexed [pixel][i]
-VG_DEVICE void cell_grads(const BwdParams& p, int n, int pi, int pj, int ch, const float* mr, bool pooled,
-                          float (&xh)[4][8], float (&g)[4][8]) {
-  float sc[8], sh[8], mean[8], rstd[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float ga = p.gamma ? p.gamma[ch + i] : 1.f, be = p.beta ? p.beta[ch + i] : 0.f;
-    mean[i] = mr[ch + i];
-    rstd[i] = mr[p.c + ch + i];
-    sc[i] = ga * rstd[i];
-    sh[i] = be - mean[i] * ga * rstd[i];
-  }
-  const int reps = pooled ? 2 : 1;
-  float pre[4][8], yv[4][8];
-  for (int a = 0; a < reps; ++a)
-    for (int b = 0; b < reps; ++b) {
-      const int k = a * 2 + b;
-      const int i_h = pooled ? 2 * pi + a : pi, i_w = pooled ? 2 * pj + b : pj;
-      const long long pix = (static_cast<long long>(n) * p.h + i_h) * p.w + i_w;
-      float f[8];
-      load8(p.x + pix * p.x_ld + p.x_coff + ch, f);
-      float d[8];
-      if (p.dy != nullptr) load8(p.dy + pix * p.dy_ld + p.dy_coff + ch, d);
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        xh[k][i] = (f[i] - mean[i]) * rstd[i];
-        pre[k][i] = fmaf(f[i], sc[i], sh[i]);
-        yv[k][i] = bf16_round(act_fwd(pre[k][i], p.act));
-        g[k][i] = d[i];
-      }
-    }
-  if (pooled && p.dpool != nullptr) {
-    const int ph = p.h / 2, pw = p.w / 2;
-    const long long ppix = (static_cast<long long>(n) * ph + pi) * pw + pj;
-    float dp[8];
-    load8(p.dpool + ppix * p.dp_ld + p.dp_coff + ch, dp);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int best = 0;
-      float bv = yv[0][i];
-#pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (yv[k][i] > bv) { bv = yv[k][i]; best = k; }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k == best) g[k][i] += dp[i];
-    }
-  }
-  const int npx = pooled ? 4 : 1;
-  for (int k = 0; k < npx; ++k)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[k][i] *= act_grad(pre[k][i], p.act);
-}
-
-template <bool kApply>
+template <bool kApply, bool kPool>
 __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams p) {
-  const bool pooled = p.dpool != nullptr;
-  const int ph = pooled ? p.h / 2 : p.h, pw = pooled ? p.w / 2 : p.w;
   const RowMap m = row_map(p.c);
   const int tid = threadIdx.x;
   const int rl = tid / m.cvl, cvi = tid % m.cvl;
   const int grp = blockIdx.y;                       // sample index when per_sample, else 0
-  const int n_begin = p.per_sample ? grp : 0, n_count = p.per_sample ? 1 : p.n;
+  const int n_count = p.per_sample ? 1 : p.n;
+  const int ph = kPool ? p.h / 2 : p.h, pw = kPool ? p.w / 2 : p.w;
   const long long cells = static_cast<long long>(n_count) * ph * pw;
+  const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
   const float inv_rows = 1.f / (static_cast<float>(n_count) * p.h * p.w);
+  const long long pix0 = static_cast<long long>(p.per_sample ? grp : 0) * p.h * p.w;
   __shared__ float red[kApply ? 1 : kNT][17];
   for (int cv0 = 0; cv0 < m.cv; cv0 += m.cvl) {
     const int cvec = cv0 + cvi;
     const int ch = cvec * 8;
     const bool active = rl < m.rows_par && cvec < m.cv;
-    const float* mr = p.mean_rstd + static_cast<long long>(grp) * 2 * p.c;
-    float s[8], q[8], k1[8], k2[8], sc[8];
+    float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-    if (kApply && active) {
-      const float* sm = p.sums + static_cast<long long>(grp) * 2 * p.c;
+    if (active) {
+      const float* mr = p.mean_rstd + static_cast<long long>(grp) * 2 * p.c;
+      float mean[8], rstd[8], sc[8], sh[8], k1[8], k2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        k1[i] = sm[ch + i] * inv_rows;
-        k2[i] = sm[p.c + ch + i] * inv_rows;
-        sc[i] = (p.gamma ? p.gamma[ch + i] : 1.f) * mr[p.c + ch + i];
+        const float ga = p.gamma ? p.gamma[ch + i] : 1.f, be = p.beta ? p.beta[ch + i] : 0.f;
+        mean[i] = mr[ch + i];
+        rstd[i] = mr[p.c + ch + i];
+        sc[i] = ga * rstd[i];
+        sh[i] = be - mean[i] * sc[i];
+        if (kApply) {
+          const float* sm = p.sums + static_cast<long long>(grp) * 2 * p.c;
+          k1[i] = sm[ch + i] * inv_rows;
+          k2[i] = sm[p.c + ch + i] * inv_rows;
+        }
       }
-    }
-    if (active) {
-      for (long long cell = static_cast<long long>(blockIdx.x) * m.rows_par + rl; cell < cells;
-           cell += static_cast<long long>(gridDim.x) * m.rows_par) {
-        const int pj = static_cast<int>(cell % pw);
-        const int pi = static_cast<int>((cell / pw) % ph);
-        const int n = n_begin + static_cast<int>(cell / (static_cast<long long>(pw) * ph));
-        float xh[4][8], g[4][8];
-        cell_grads(p, n, pi, pj, ch, mr, pooled, xh, g);
-        const int npx = pooled ? 4 : 1;
-        for (int k = 0; k < npx; ++k) {
-          if (kApply) {
-            const int i_h = pooled ? 2 * pi + (k >> 1) : pi, i_w = pooled ? 2 * pj + (k & 1) : pj;
-            const long long pix = (static_cast<long long>(n) * p.h + i_h) * p.w + i_w;
-            float o[8];
+      const __nv_bfloat16* xb = p.x + p.x_coff + ch;
+      const __nv_bfloat16* gb = p.dy ? p.dy + p.dy_coff + ch : nullptr;
+      __nv_bfloat16* ob = kApply ? p.dx + p.dx_coff + ch : nullptr;
+
+      // one pixel: g = dyv * act'(pre); accumulate or emit dx
+      auto pixel = [&](const bf16x8& xv, const float (&dyv)[8], long long pix) {
+        float f[8], o[8];
+        unpack8(xv, f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = sc[i] * (g[k][i] - k1[i] - xh[k][i] * k2[i]);
-            store8(p.dx + pix * p.dx_ld + p.dx_coff + ch, o);
-          } else {
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (f[i] - mean[i]) * rstd[i];
+          const float g = dyv[i] * act_grad(fmaf(f[i], sc[i], sh[i]), p.act);
+          if (kApply) o[i] = sc[i] * (g - k1[i] - xh * k2[i]);
+          else { s[i] += g; q[i] = fmaf(g, xh, q[i]); }
+        }
+        if (kApply) store8(ob + pix * p.dx_ld, o);
+      };
+
+      if (!kPool) {
+        long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
+        for (; r + stride < cells; r += 2 * stride) {
+          const long long pa = pix0 + r, pb = pix0 + r + stride;
+          const bf16x8 xa = ldv(xb + pa * p.x_ld), xc = ldv(xb + pb * p.x_ld);
+          const bf16x8 da = ldv(gb + pa * p.dy_ld), dc = ldv(gb + pb * p.dy_ld);
+          float d[8];
+          unpack8(da, d);
+          pixel(xa, d, pa);
+          unpack8(dc, d);
+          pixel(xc, d, pb);
+        }
+        for (; r < cells; r += stride) {
+          const long long pa = pix0 + r;
+          float d[8];
+          unpack8(ldv(gb + pa * p.dy_ld), d);
+          pixel(ldv(xb + pa * p.x_ld), d, pa);
+        }
+      } else {
+        for (long long cell = static_cast<long long>(blockIdx.x) * m.rows_par + rl; cell < cells; cell += stride) {
+          const int pj = static_cast<int>(cell % pw);
+          const int pi = static_cast<int>((cell / pw) % ph);
+          const long long nn = (p.per_sample ? grp : cell / (static_cast<long long>(pw) * ph));
+          const long long row0 = (nn * p.h + 2 * pi) * p.w + 2 * pj;
+          long long pix[4] = {row0, row0 + 1, row0 + p.w, row0 + p.w + 1};
+          bf16x8 xv[4], dv[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += g[k][i]; q[i] += g[k][i] * xh[k][i]; }
+          for (int u = 0; u < 4; ++u) xv[u] = ldv(xb + pix[u] * p.x_ld);
+          if (gb != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dv[u] = ldv(gb + pix[u] * p.dy_ld);
+          }
+          const long long ppix = (nn * ph + pi) * pw + pj;
+          float dp[8];
+          unpack8(ldv(p.dpool + ppix * p.dp_ld + p.dp_coff + ch), dp);
+          // first maximum of the (bf16-rounded) activations of the window, per channel
+          int best[8];
+          float bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { best[i] = 0; bv[i] = -INFINITY; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(xv[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float yv = bf16_round(act_fwd(fmaf(f[i], sc[i], sh[i]), p.act));
+              if (yv > bv[i]) { bv[i] = yv; best[i] = u; }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float d[8];
+            if (gb != nullptr) unpack8(dv[u], d);
+            else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] += (best[i] == u) ? dp[i] : 0.f;
+            pixel(xv[u], d, pix[u]);
           }
         }
       }
     }
-    if (!kApply) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { red[tid][i] = s[i]; red[tid][8 + i] = q[i]; }
-      __syncthreads();
-      if (rl == 0 && cvec < m.cv) {
-        for (int k = 0; k < 16; ++k) {
-          float a = 0.f;
-          for (int r = 0; r < m.rows_par; ++r) a += red[r * m.cvl + cvi][k];
-          atomicAdd(p.sums + (static_cast<long long>(grp) * 2 + (k >> 3)) * p.c + cvec * 8 + (k & 7), a);
-        }
-      }
-      __syncthreads();
+    if constexpr (!kApply) {
+      float* dst = p.sums + static_cast<long long>(grp) * 2 * p.c;
+      reduce_rows_atomic(red, s, q, m, rl, cvi, cvec, dst, dst + p.c);
     }
   }
 }
@@ -316,9 +385,12 @@ __global__ void affine_grad_kernel(const float* __restrict__ sums, int groups, i
   if (dbeta) dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + b;
 }
 
-static int grid_for(long long work_items, int per_block) {
-  long long blocks = (work_items + per_block - 1) / per_block;
-  const long long cap = static_cast<long long>(num_sms()) * 8;
+// grid.x for a row-walking kernel: enough blocks to cover the rows, at most `per_sm` blocks per SM (per group)
+static int row_grid(long long rows, int rows_par, int groups, int per_sm, int rows_per_thread) {
+  long long blocks = (rows + static_cast<long long>(rows_par) * rows_per_thread - 1) /
+                     (static_cast<long long>(rows_par) * rows_per_thread);
+  long long cap = static_cast<long long>(num_sms()) * per_sm / (groups > 0 ? groups : 1);
+  if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
@@ -334,8 +406,7 @@ extern "C" int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, lo
   VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_norm_stats: channels must be multiples of 8");
   VG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * c, st));
   const RowMap m = row_map(c);
-  int gx = grid_for(rows_per_group, m.rows_par * 8);
-  if (groups > 1) gx = max(1, min(gx, (num_sms() * 8) / groups));
+  const int gx = row_grid(rows_per_group, m.rows_par, groups, 4, 8);
   stats_kernel<<<dim3(gx, groups), kNT, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, c, rows_per_group,
                                                  sums);
   VG_LAUNCH_OK();
@@ -364,8 +435,15 @@ extern "C" int vg_norm_apply(const VgNormApply* d, void* stream_) {
   p.mean_rstd = d->mean_rstd; p.per_sample = d->per_sample; p.gamma = d->gamma; p.beta = d->beta; p.act = d->act;
   p.y = static_cast<__nv_bfloat16*>(d->y); p.y_ld = d->y_ld; p.y_coff = d->y_coff;
   p.pool = static_cast<__nv_bfloat16*>(d->pool); p.p_ld = d->p_ld; p.p_coff = d->p_coff;
-  const long long cells = static_cast<long long>(d->n) * (d->pool ? d->h / 2 : d->h) * (d->pool ? d->w / 2 : d->w);
-  apply_kernel<<<grid_for(cells * (d->c / 8), kNT), kNT, 0, st>>>(p);
+  const int groups = d->per_sample ? d->n : 1;
+  const RowMap m = row_map(d->c);
+  const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (d->pool ? d->h / 2 : d->h) *
+                          (d->pool ? d->w / 2 : d->w);
+  if (d->pool) {
+    apply_kernel<true><<<dim3(row_grid(cells, m.rows_par, groups, 8, 2), groups), kNT, 0, st>>>(p);
+  } else {
+    apply_kernel<false><<<dim3(row_grid(cells, m.rows_par, groups, 8, 8), groups), kNT, 0, st>>>(p);
+  }
   VG_LAUNCH_OK();
   return 0;
 }
@@ -387,13 +465,20 @@ extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
   const int groups = d->per_sample ? d->n : 1;
   VG_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(float) * 2 * groups * d->c, st));
   const RowMap m = row_map(d->c);
-  const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (d->dpool ? d->h / 2 : d->h) *
-                          (d->dpool ? d->w / 2 : d->w);
-  int gx = grid_for(cells, m.rows_par * 4);
-  if (groups > 1) gx = max(1, min(gx, (num_sms() * 8) / groups));
-  bwd_kernel<false><<<dim3(gx, groups), kNT, 0, st>>>(p);
-  VG_LAUNCH_OK();
-  bwd_kernel<true><<<dim3(gx, groups), kNT, 0, st>>>(p);
+  const bool pool = d->dpool != nullptr;
+  const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (pool ? d->h / 2 : d->h) *
+                          (pool ? d->w / 2 : d->w);
+  const dim3 g_red(row_grid(cells, m.rows_par, groups, 4, pool ? 2 : 8), groups);
+  const dim3 g_app(row_grid(cells, m.rows_par, groups, 8, pool ? 2 : 8), groups);
+  if (pool) {
+    bwd_kernel<false, true><<<g_red, kNT, 0, st>>>(p);
+    VG_LAUNCH_OK();
+    bwd_kernel<true, true><<<g_app, kNT, 0, st>>>(p);
+  } else {
+    bwd_kernel<false, false><<<g_red, kNT, 0, st>>>(p);
+    VG_LAUNCH_OK();
+    bwd_kernel<true, false><<<g_app, kNT, 0, st>>>(p);
+  }
   VG_LAUNCH_OK();
   if (d->dgamma != nullptr || d->dbeta != nullptr) {
     affine_grad_kernel<<<cdiv(d->c, 128), 128, 0, st>>>(d->sums, groups, d->c, d->dgamma, d->dbeta, d->accumulate);

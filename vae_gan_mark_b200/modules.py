@@ -143,7 +143,10 @@ class CharacterTokenEncoder(nn.Module):
         return idx
 
     def forward(self, texts_batch, max_len_chars_for_tokenization=60):
-        idx = self.tokens_to_indices(texts_batch, max_len_chars_for_tokenization).to(self.embedding.weight.device)
+        if torch.is_tensor(texts_batch):      # already tokenised (B, max_len) indices, e.g. a CUDA-graph static input
+            idx = texts_batch
+        else:
+            idx = self.tokens_to_indices(texts_batch, max_len_chars_for_tokenization).to(self.embedding.weight.device)
         out, _ = self.rnn(self.embedding(idx))
         return self.adaptive_pool(out.permute(0, 2, 1)).unsqueeze(2)
 
@@ -168,6 +171,8 @@ class TransformerTextEncoder(nn.Module):
         return self._embedder(texts)
 
     def forward(self, texts):
+        if torch.is_tensor(texts):            # precomputed (B, 384) sentence embeddings
+            return self.fc(texts.to(self.fc.weight))
         with torch.no_grad():
             e = self._embed(texts).to(self.fc.weight)
         return self.fc(e)
