@@ -28,12 +28,12 @@ def rnd(*shape, scale=1.0):
 def case_gemm(cin=64, cout=128, n=2, h=16, w=16, bn=0):
     import torch
     from vae_gan_mark_b200 import conv
-    x = conv.Act(rnd(n, h, w, cin), cin)
+    x = rnd(n, h, w, cin)
     wt = rnd(cout, cin, scale=cin ** -0.5)
     out = torch.zeros(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
-    conv.fprop(x, [(0, 0, 0, 0)], 1, cin, wt, cout, (n, h, w), out, (h, w), cout, force_bn=bn)
+    conv.fprop(x, [(0, 0, 0, 0)], 1, cin, wt, cout, (n, h, w), out, force_bn=bn)
     torch.cuda.synchronize()
-    ref = x.buf.float() @ wt.float().t()
+    ref = x.float() @ wt.float().t()
     return rel_err(out.float(), ref)
 
 
@@ -41,17 +41,17 @@ def case_conv(cin=64, cout=64, n=2, h=16, w=16, k=3, s=1, p=1, bn=0, bias=False,
     import torch
     import torch.nn.functional as F
     from vae_gan_mark_b200 import conv
-    x = conv.Act(rnd(n, h, w, cin), cin)
+    x = rnd(n, h, w, cin)
     wt = rnd(cout, k, k, cin, scale=(cin * k * k) ** -0.5)   # [co][r][q][ci]
     b = torch.randn(cout, device="cuda") if bias else None
     oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     dt = torch.bfloat16 if kind == 0 else torch.float32
     out = torch.zeros(n, oh, ow, cout, dtype=dt, device="cuda")
-    taps = conv.conv_taps(k, k, s, p, p, x.ld, 0)
-    conv.fprop(x, taps, s, cin, wt.view(cout, -1), cout, (n, oh, ow), out, (oh, ow), cout, bias=b, act=act,
+    taps = conv.conv_taps(k, k, s, p, p, x.stride(2))
+    conv.fprop(x, taps, s, cin, wt.view(cout, -1), cout, (n, oh, ow), out, bias=b, act=act,
                out_kind=kind, ksplit=ksplit, force_bn=bn)
     torch.cuda.synchronize()
-    ref = F.conv2d(x.buf.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), b, stride=s, padding=p)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), b, stride=s, padding=p)
     if act == 1:
         ref = ref.relu()
     elif act == 2:
@@ -64,15 +64,14 @@ def case_shuffle(cin=128, cout=64, n=2, h=8, w=8):
     import torch
     import torch.nn.functional as F
     from vae_gan_mark_b200 import conv
-    x = conv.Act(rnd(n, h, w, cin), cin)
+    x = rnd(n, h, w, cin)
     wt = rnd(cin, cout, 2, 2, scale=cin ** -0.5)             # IOHW
     b = torch.randn(cout, device="cuda")
     wf = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous()   # [(a,b,co)][ci]
     out = torch.zeros(n, 2 * h, 2 * w, 2 * cout, dtype=torch.bfloat16, device="cuda")
-    conv.fprop(x, [(0, 0, 0, 0)], 1, cin, wf, 4 * cout, (n, h, w), out, (2 * h, 2 * w), 2 * cout, out_coff=cout,
-               su=(2, 2), cout_per_sub=cout, bias=b)
+    conv.fprop(x, [(0, 0, 0, 0)], 1, cin, wf, 4 * cout, (n, h, w), out[..., cout:], su=(2, 2), cout_per_sub=cout, bias=b)
     torch.cuda.synchronize()
-    ref = F.conv_transpose2d(x.buf.float().permute(0, 3, 1, 2), wt.float(), b, stride=2).permute(0, 2, 3, 1)
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2).permute(0, 2, 3, 1)
     e = rel_err(out[..., cout:].float(), ref)
     assert float(out[..., :cout].float().abs().max()) == 0.0, "wrote outside the channel slice"
     return e
@@ -81,17 +80,17 @@ def case_shuffle(cin=128, cout=64, n=2, h=8, w=8):
 def case_wgrad(cin=64, cout=64, n=2, h=16, w=16, k=3, s=1, p=1, bn=0, ksplit=0):
     import torch
     from vae_gan_mark_b200 import conv
-    x = conv.Act(rnd(n, h, w, cin), cin)
+    x = rnd(n, h, w, cin)
     oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
-    g = conv.Act(rnd(n, oh, ow, cout), cout)
+    g = rnd(n, oh, ow, cout)
     dw = torch.full((cout, k * k * cin), 7.0, dtype=torch.float32, device="cuda")
-    taps = conv.conv_taps(k, k, s, p, p, x.ld, 0)
+    taps = conv.conv_taps(k, k, s, p, p, x.stride(2))
     conv.wgrad(g, cout, x, taps, s, cin, (n, oh, ow), dw, ksplit=ksplit, force_bn=bn)
     torch.cuda.synchronize()
-    xin = x.buf.float().permute(0, 3, 1, 2).requires_grad_(False)
+    xin = x.float().permute(0, 3, 1, 2).requires_grad_(False)
     wref = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
     y = torch.nn.functional.conv2d(xin, wref, None, stride=s, padding=p)
-    y.backward(g.buf.float().permute(0, 3, 1, 2))
+    y.backward(g.float().permute(0, 3, 1, 2))
     ref = wref.grad.permute(0, 2, 3, 1).reshape(cout, -1)     # [co][(r,q,ci)]
     return rel_err(dw, ref)
 
@@ -99,14 +98,14 @@ def case_wgrad(cin=64, cout=64, n=2, h=16, w=16, k=3, s=1, p=1, bn=0, ksplit=0):
 def case_perf(kind="fprop", cin=512, cout=512, n=8, h=128, w=128, k=3, iters=5):
     import torch
     from vae_gan_mark_b200 import conv
-    x = conv.Act(rnd(n, h, w, cin), cin)
-    taps = conv.conv_taps(k, k, 1, k // 2, k // 2, x.ld, 0)
+    x = rnd(n, h, w, cin)
+    taps = conv.conv_taps(k, k, 1, k // 2, k // 2, x.stride(2))
     if kind == "fprop":
         wt = rnd(cout, k * k * cin, scale=0.02)
         out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
-        fn = lambda: conv.fprop(x, taps, 1, cin, wt, cout, (n, h, w), out, (h, w), cout)
+        fn = lambda: conv.fprop(x, taps, 1, cin, wt, cout, (n, h, w), out)
     else:
-        g = conv.Act(rnd(n, h, w, cout), cout)
+        g = rnd(n, h, w, cout)
         dw = torch.empty(cout, k * k * cin, dtype=torch.float32, device="cuda")
         fn = lambda: conv.wgrad(g, cout, x, taps, 1, cin, (n, h, w), dw)
     for _ in range(3):

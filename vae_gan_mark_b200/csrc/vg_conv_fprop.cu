@@ -29,6 +29,8 @@ constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle
 constexpr int kUmmaK = 16;
 constexpr int kFpropThreads = 256;
 constexpr int kMaxTaps = VG_MAX_TAPS;
+constexpr int kEpiPitch = 144;      // bytes per staged row: 128 data + 16 pad (bank spread)
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch + 4 * 32 * 8;   // 4 warps x (32-row staging tile + 32 row offsets)
 
 struct FpropParams {
   int m_n, m_h, m_w;            // output pixel grid
@@ -43,6 +45,7 @@ struct FpropParams {
   int su_h, su_w, sub_h0, sub_w0, cout_per_sub;
   const float* bias;
   int act;                      // 0 none, 1 relu, 2 leaky relu 0.2
+  int vec_ok;                   // destination allows 16-byte vector stores
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
 };
 
@@ -61,6 +64,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_full = bars + 2 * p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,11 +157,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers (thread = one pixel row, 32 columns at a time) -> bias/activation -> per-warp staging tile in
+    // shared memory -> coalesced 16-byte global stores (8 lanes cover 128 contiguous bytes of one output row).
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // GEMM row inside the tile == pixel inside the tile
     const int r_w = row % p.tw;
     const int r_h = (row / p.tw) % p.th;
     const int r_n = row / (p.tw * p.th);
+    uint8_t* stg = epi_smem + quad * (32 * kEpiPitch);
+    long long* rbase = reinterpret_cast<long long*>(epi_smem + 4 * 32 * kEpiPitch) + quad * 32;
+    const int esz = p.out_kind == 0 ? 2 : 4;
+    const int chunk_cols = p.out_kind == 0 ? 64 : 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -168,57 +178,96 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int tn_i = m_t / (p.tiles_w * p.tiles_h);
       const int ow = tw_i * p.tw + r_w, oh = th_i * p.th + r_h, n = tn_i * p.tn + r_n;
       const bool row_ok = (ow < p.m_w) && (oh < p.m_h) && (n < p.m_n);
+      const long long my_base =
+          ((static_cast<long long>(n) * p.out_h + oh * p.su_h) * p.out_w + ow * p.su_w) * p.out_ld;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
-      for (int c = 0; c < p.bn; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c, r);
-        tmem_ld_wait();
-        const int ng0 = n_t * p.bn + c;        // first GEMM column of this chunk
-        if (row_ok && ng0 < p.n_gemm) {
-          const int sub = ng0 / p.cout_per_sub;   // uniform over the chunk when cout_per_sub % 32 == 0
-          const int ch0 = ng0 - sub * p.cout_per_sub;
-          const int dh = p.sub_h0 + sub / p.su_w, dw = p.sub_w0 + sub % p.su_w;
-          const long long pix = (static_cast<long long>(n) * p.out_h + (oh * p.su_h + dh)) * p.out_w + (ow * p.su_w + dw);
-          const long long off = pix * p.out_ld + p.out_coff + ch0;
-          const int nvalid = min(32, p.n_gemm - ng0);
-          float v[32];
+      if (p.vec_ok && p.out_kind != 2) {
+        rbase[lane] = row_ok ? my_base : -1;
+        __syncwarp();
+        for (int c = 0; c < p.bn; c += chunk_cols) {
+          const int ng0 = n_t * p.bn + c;        // first GEMM column of this chunk
+          if (ng0 >= p.n_gemm) break;
+          for (int hh = 0; hh < chunk_cols / 32; ++hh) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c + hh * 32, r);
+            tmem_ld_wait();
+            const int ngh = ng0 + hh * 32;
+            const int ch0 = ngh % p.cout_per_sub;
+            const int nvalid = min(32, p.n_gemm - ngh);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + ch0 + j);
-            if (p.act == 1) x = fmaxf(x, 0.f);
-            else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
-            v[j] = x;
-          }
-          if (p.out_kind == 0) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-            if (nvalid == 32 && ((off & 7) == 0)) {
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + ch0 + j);
+              if (p.act == 1) x = fmaxf(x, 0.f);
+              else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+              r[j] = __float_as_uint(x);
+            }
+            uint8_t* dst = stg + lane * kEpiPitch + (esz == 2 ? hh * 64 : 0);
+            if (esz == 2) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                bf16x8 pk;
-                pk.u[0] = pack_bf16x2(v[j], v[j + 1]);
-                pk.u[1] = pack_bf16x2(v[j + 2], v[j + 3]);
-                pk.u[2] = pack_bf16x2(v[j + 4], v[j + 5]);
-                pk.u[3] = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<bf16x8*>(o + j) = pk;
+                uint4 pk;
+                pk.x = pack_bf16x2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                pk.y = pack_bf16x2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                pk.z = pack_bf16x2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+                pk.w = pack_bf16x2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+                *reinterpret_cast<uint4*>(dst + j * 2) = pk;
               }
             } else {
-              for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j]);
-            }
-          } else if (p.out_kind == 1) {
-            float* o = reinterpret_cast<float*>(p.out) + off;
-            if (nvalid == 32 && ((off & 3) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < nvalid; ++j) o[j] = v[j];
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
             }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + off;
-            for (int j = 0; j < nvalid; ++j) atomicAdd(o + j, v[j]);
+          }
+          __syncwarp();
+          const int seg = lane & 7, rsub = lane >> 3;
+          const int half = esz == 2 ? (seg >> 2) : 0;
+          const int ngh = ng0 + half * 32;
+          const int valid_bytes = min(128, (p.n_gemm - ng0) * esz);
+          if (seg * 16 < valid_bytes) {
+            const int sub = ngh / p.cout_per_sub;
+            const int ch0 = ngh - sub * p.cout_per_sub;
+            const long long delta =
+                (static_cast<long long>(p.sub_h0 + sub / p.su_w) * p.out_w + (p.sub_w0 + sub % p.su_w)) * p.out_ld +
+                p.out_coff + ch0 + (esz == 2 ? (seg & 3) * 8 : seg * 4);
+            uint8_t* gout = reinterpret_cast<uint8_t*>(p.out);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              const long long base = rbase[rr];
+              if (base >= 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kEpiPitch + seg * 16);
+                *reinterpret_cast<uint4*>(gout + (base + delta) * esz) = v;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // generic path (odd alignments, split-K atomics): each thread stores its own row
+        for (int c = 0; c < p.bn; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c, r);
+          tmem_ld_wait();
+          const int ng0 = n_t * p.bn + c;
+          if (row_ok && ng0 < p.n_gemm) {
+            const int sub = ng0 / p.cout_per_sub;   // uniform over the chunk when cout_per_sub % 32 == 0
+            const int ch0 = ng0 - sub * p.cout_per_sub;
+            const int dh = p.sub_h0 + sub / p.su_w, dw = p.sub_w0 + sub % p.su_w;
+            const long long off = my_base + (static_cast<long long>(dh) * p.out_w + dw) * p.out_ld + p.out_coff + ch0;
+            const int nvalid = min(32, p.n_gemm - ng0);
+            for (int j = 0; j < nvalid; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (p.bias != nullptr) x += __ldg(p.bias + ch0 + j);
+              if (p.act == 1) x = fmaxf(x, 0.f);
+              else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+              if (p.out_kind == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16(x);
+              else if (p.out_kind == 1) reinterpret_cast<float*>(p.out)[off + j] = x;
+              else atomicAdd(reinterpret_cast<float*>(p.out) + off + j, x);
+            }
           }
         }
       }
@@ -295,11 +344,17 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   VG_CHECK(ksplit <= p.ksteps, -1, "vg_conv_fprop: ksplit %d > k steps %d", ksplit, p.ksteps);
   p.ksplit = ksplit;
   const int stage_bytes = kBM * kBK * 2 + bn * kBK * 2;
-  p.stages = min(8, (200 * 1024) / stage_bytes);
+  p.stages = min(8, (227 * 1024 - 1024 - 256 - kEpiBytes) / stage_bytes);
   p.out = d->out; p.out_kind = d->out_kind;
   p.out_h = d->out_h; p.out_w = d->out_w; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.su_h = d->su_h; p.su_w = d->su_w; p.sub_h0 = d->sub_h0; p.sub_w0 = d->sub_w0; p.cout_per_sub = d->cout_per_sub;
   p.bias = d->bias; p.act = d->act;
+  {
+    const int esz = d->out_kind == 0 ? 2 : 4;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((static_cast<long long>(d->out_ld) * esz) % 16 == 0) &&
+               ((d->out_coff * esz) % 16 == 0) && ((d->cout_per_sub * esz) % 16 == 0) && (d->n_gemm % 8 == 0) &&
+               (d->su_h * d->su_w == 1 || d->cout_per_sub % 32 == 0);
+  }
   for (int i = 0; i < d->num_taps; ++i) {
     p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
     VG_CHECK(d->taps[i][2] >= 0 && d->taps[i][2] < d->x_stride, -1, "vg_conv_fprop: tap %d row parity out of range", i);
@@ -322,7 +377,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     int rc = encode_tmap_bf16(&tmap_b, d->w, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiBytes;
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

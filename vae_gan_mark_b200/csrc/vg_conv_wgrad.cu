@@ -20,6 +20,8 @@ constexpr int kWgBM = 128;        // output channels per tile
 constexpr int kWgPix = 64;        // pixels per K step
 constexpr int kWgThreads = 256;
 constexpr int kWgBoxBytes = 64 * kWgPix * 2;   // 8 KB: 64 px x 64 ch bf16
+constexpr int kWgEpiPitch = 144;               // staged row: 32 fp32 + 16 B pad
+constexpr int kWgEpiBytes = 4 * 32 * kWgEpiPitch;
 
 struct WgradParams {
   int m_n, m_h, m_w;              // output pixel grid (reduction space)
@@ -49,6 +51,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   uint64_t* tmem_full = bars + 2 * p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,8 +82,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   const int cchunks = p.cin / 64;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ===================== TMA producer =====================
+    // One lane per TMA box (2 dY boxes + up to 4 X boxes per stage): the coordinate arithmetic and the issue of the
+    // six copies run in parallel lanes instead of serially in one thread, which otherwise starves the tensor pipe.
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -91,23 +96,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
       const int k_end = static_cast<int>((static_cast<long long>(pix_tiles) * (split + 1)) / p.ksplit);
       const int nblk = min(p.nb, p.blocks_total - n_t * p.nb);
       const int aboxes = min(2, (p.cout - m_t * kWgBM + 63) / 64);
+      // this lane's box: lanes [0, aboxes) load dY, lanes [2, 2 + nblk) load X
+      const bool is_a = lane < aboxes;
+      const bool is_b = lane >= 2 && lane < 2 + nblk;
+      int c0 = 0, dwv = 0, shv = 0, dhv = 0;
+      if (is_a) c0 = p.g_coff + m_t * kWgBM + lane * 64;
+      if (is_b) {
+        const int b = n_t * p.nb + (lane - 2);
+        const int4 t = p.taps[b / cchunks];
+        c0 = t.x + (b % cchunks) * 64; dwv = t.y; shv = t.z; dhv = t.w;
+      }
+      int tw_i = k_begin % p.tiles_w;
+      int th_i = (k_begin / p.tiles_w) % p.tiles_h;
+      int tn_i = k_begin / (p.tiles_w * p.tiles_h);
       for (int k = k_begin; k < k_end; ++k) {
-        const int tw_i = k % p.tiles_w;
-        const int th_i = (k / p.tiles_w) % p.tiles_h;
-        const int tn_i = k / (p.tiles_w * p.tiles_h);
-        const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (aboxes + nblk) * kWgBoxBytes);
-        for (int i = 0; i < aboxes; ++i)
-          tma_load_5d(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], p.g_coff + m_t * kWgBM + i * 64, ow0, 0, oh0, n0);
-        for (int i = 0; i < nblk; ++i) {
-          const int b = n_t * p.nb + i;
-          const int4 t = p.taps[b / cchunks];
-          tma_load_5d(sb + i * kWgBoxBytes, &tmap_x, &full_bar[stage], t.x + (b % cchunks) * 64, ow0 + t.y, t.z,
-                      oh0 + t.w, n0);
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], (aboxes + nblk) * kWgBoxBytes);
         }
+        __syncwarp();
+        uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+        const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
+        if (is_a) tma_load_5d(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0, ow0, 0, oh0, n0);
+        if (is_b) tma_load_5d(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0, ow0 + dwv, shv,
+                              oh0 + dhv, n0);
+        if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -145,39 +158,51 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // TMEM -> registers (thread = one output-channel row, 32 fp32 columns at a time) -> per-warp staging tile in
+    // shared memory -> coalesced 16-byte stores / vector reductions (8 lanes cover 128 contiguous bytes of a dW row).
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    uint8_t* stg = epi_smem + quad * (32 * kWgEpiPitch);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile % p.n_tiles;
       const int m_t = (tile / p.n_tiles) % p.m_tiles;
-      const int co = m_t * kWgBM + row;
+      const int co_warp = m_t * kWgBM + quad * 32;           // first output channel handled by this warp
       const int ncols = min(p.bn, p.blocks_total * 64 - n_t * p.bn);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
-      for (int c = 0; c < p.bn; c += 32) {
+      for (int c = 0; c < ncols; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + c, r);
         tmem_ld_wait();
-        if (co < p.cout && c < ncols) {
-          float* o = p.dw + static_cast<long long>(co) * p.dw_ld + n_t * p.bn + c;
-          if (p.atomic) {
+        uint8_t* dst = stg + lane * kWgEpiPitch;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(r[j]));
-          } else {
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        const int seg = lane & 7, rsub = lane >> 3;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub;
+          if (co_warp + rr < p.cout) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * kWgEpiPitch + seg * 16);
+            float* o = p.dw + static_cast<long long>(co_warp + rr) * p.dw_ld + n_t * p.bn + c + seg * 4;
+            if (p.atomic) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                           : "memory");
+            } else {
+              *reinterpret_cast<float4*>(o) = v;
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    (void)row;
   }
 
   tc_fence_before();
@@ -241,7 +266,7 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   p.ksplit = ksplit;
   p.atomic = ksplit > 1 ? 1 : 0;
   const int stage_bytes = (2 + nb) * kWgBoxBytes;
-  p.stages = min(8, (200 * 1024) / stage_bytes);
+  p.stages = min(8, (227 * 1024 - 1024 - 256 - kWgEpiBytes) / stage_bytes);
   p.dw = d->dw; p.dw_ld = d->dw_ld;
   for (int i = 0; i < d->num_taps; ++i) {
     p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
@@ -267,7 +292,7 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
     int rc = encode_tmap_bf16(&tmap_x, d->x, 5, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + 256 + kWgEpiBytes;
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
