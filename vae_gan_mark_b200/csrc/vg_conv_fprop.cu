@@ -27,10 +27,9 @@ namespace vg {
 constexpr int kBM = 128;          // GEMM M tile (pixels) == TMEM lanes
 constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kFpropThreads = 256;
+constexpr int kFpropThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int kMaxTaps = VG_MAX_TAPS;
-constexpr int kEpiPitch = 144;      // bytes per staged row: 128 data + 16 pad (bank spread)
-constexpr int kEpiBytes = 4 * 32 * kEpiPitch + 4 * 32 * 8;   // 4 warps x (32-row staging tile + 32 row offsets)
+constexpr int kEpiBytes = 8 * 32 * 128;   // 8 epilogue warps x (32 rows x 128 B XOR-swizzled staging tile)
 
 struct FpropParams {
   int m_n, m_h, m_w;            // output pixel grid
@@ -78,7 +77,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -156,18 +155,21 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    // TMEM -> registers (thread = one pixel row, 32 columns at a time) -> bias/activation -> per-warp staging tile in
-    // shared memory -> coalesced 16-byte global stores (8 lanes cover 128 contiguous bytes of one output row).
+    // ===================== epilogue (8 warps) =====================
+    // TMEM -> registers (thread = one pixel row, 64 bf16 / 32 fp32 columns = 128 bytes per round) -> bias/activation
+    // -> XOR-swizzled per-warp staging tile in shared memory -> coalesced 16-byte global stores (8 lanes cover 128
+    // contiguous bytes of one output row).  Two warps share each TMEM lane quadrant and split the column chunks, so
+    // every SM sub-partition has two epilogue warps to hide each other's latencies.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int colhalf = (warp - 4) >> 2;       // which alternate column chunks this warp drains
     const int row = quad * 32 + lane;          // GEMM row inside the tile == pixel inside the tile
     const int r_w = row % p.tw;
     const int r_h = (row / p.tw) % p.th;
     const int r_n = row / (p.tw * p.th);
-    uint8_t* stg = epi_smem + quad * (32 * kEpiPitch);
-    long long* rbase = reinterpret_cast<long long*>(epi_smem + 4 * 32 * kEpiPitch) + quad * 32;
+    uint8_t* stg = epi_smem + (warp - 4) * (32 * 128);
     const int esz = p.out_kind == 0 ? 2 : 4;
     const int chunk_cols = p.out_kind == 0 ? 64 : 32;
+    const bool plain = (p.bias == nullptr) && (p.act == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -179,74 +181,78 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int ow = tw_i * p.tw + r_w, oh = th_i * p.th + r_h, n = tn_i * p.tn + r_n;
       const bool row_ok = (ow < p.m_w) && (oh < p.m_h) && (n < p.m_n);
       const long long my_base =
-          ((static_cast<long long>(n) * p.out_h + oh * p.su_h) * p.out_w + ow * p.su_w) * p.out_ld;
+          row_ok ? ((static_cast<long long>(n) * p.out_h + oh * p.su_h) * p.out_w + ow * p.su_w) * p.out_ld : -1;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
       if (p.vec_ok && p.out_kind != 2) {
-        rbase[lane] = row_ok ? my_base : -1;
-        __syncwarp();
-        for (int c = 0; c < p.bn; c += chunk_cols) {
+        for (int c = colhalf * chunk_cols; c < p.bn; c += 2 * chunk_cols) {
           const int ng0 = n_t * p.bn + c;        // first GEMM column of this chunk
           if (ng0 >= p.n_gemm) break;
-          for (int hh = 0; hh < chunk_cols / 32; ++hh) {
-            uint32_t r[32];
-            tmem_ld_32x32(t_row + c + hh * 32, r);
-            tmem_ld_wait();
-            const int ngh = ng0 + hh * 32;
-            const int ch0 = ngh % p.cout_per_sub;
-            const int nvalid = min(32, p.n_gemm - ngh);
+          uint32_t r[64];
+          tmem_ld_32x32(t_row + c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          if (esz == 2) tmem_ld_32x32(t_row + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+          tmem_ld_wait();
+          if (!plain) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]);
-              if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + ch0 + j);
-              if (p.act == 1) x = fmaxf(x, 0.f);
-              else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
-              r[j] = __float_as_uint(x);
-            }
-            uint8_t* dst = stg + lane * kEpiPitch + (esz == 2 ? hh * 64 : 0);
-            if (esz == 2) {
+            for (int hh = 0; hh < 2; ++hh) {
+              if (hh == 1 && esz != 2) break;
+              const int ngh = ng0 + hh * 32;
+              const int ch0 = ngh % p.cout_per_sub;
+              const int nvalid = min(32, p.n_gemm - ngh);
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                pk.x = pack_bf16x2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-                pk.y = pack_bf16x2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                pk.z = pack_bf16x2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-                pk.w = pack_bf16x2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-                *reinterpret_cast<uint4*>(dst + j * 2) = pk;
+              for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(r[hh * 32 + j]);
+                if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + ch0 + j);
+                if (p.act == 1) x = fmaxf(x, 0.f);
+                else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+                r[hh * 32 + j] = __float_as_uint(x);
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
             }
+          }
+          // stage: 16-byte segment s of row `lane` goes to slot (s ^ (lane & 7)) -> conflict-free both ways
+          uint8_t* dst = stg + lane * 128;
+          if (esz == 2) {
+#pragma unroll
+            for (int sgm = 0; sgm < 8; ++sgm) {
+              uint4 pk;
+              pk.x = pack_bf16x2(__uint_as_float(r[sgm * 8 + 0]), __uint_as_float(r[sgm * 8 + 1]));
+              pk.y = pack_bf16x2(__uint_as_float(r[sgm * 8 + 2]), __uint_as_float(r[sgm * 8 + 3]));
+              pk.z = pack_bf16x2(__uint_as_float(r[sgm * 8 + 4]), __uint_as_float(r[sgm * 8 + 5]));
+              pk.w = pack_bf16x2(__uint_as_float(r[sgm * 8 + 6]), __uint_as_float(r[sgm * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + ((sgm ^ (lane & 7)) << 4)) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int sgm = 0; sgm < 8; ++sgm)
+              *reinterpret_cast<uint4*>(dst + ((sgm ^ (lane & 7)) << 4)) =
+                  make_uint4(r[sgm * 4], r[sgm * 4 + 1], r[sgm * 4 + 2], r[sgm * 4 + 3]);
           }
           __syncwarp();
           const int seg = lane & 7, rsub = lane >> 3;
           const int half = esz == 2 ? (seg >> 2) : 0;
           const int ngh = ng0 + half * 32;
           const int valid_bytes = min(128, (p.n_gemm - ng0) * esz);
-          if (seg * 16 < valid_bytes) {
-            const int sub = ngh / p.cout_per_sub;
-            const int ch0 = ngh - sub * p.cout_per_sub;
-            const long long delta =
-                (static_cast<long long>(p.sub_h0 + sub / p.su_w) * p.out_w + (p.sub_w0 + sub % p.su_w)) * p.out_ld +
-                p.out_coff + ch0 + (esz == 2 ? (seg & 3) * 8 : seg * 4);
-            uint8_t* gout = reinterpret_cast<uint8_t*>(p.out);
+          const int sub = ngh / p.cout_per_sub;
+          const int ch0 = ngh - sub * p.cout_per_sub;
+          const long long delta =
+              (static_cast<long long>(p.sub_h0 + sub / p.su_w) * p.out_w + (p.sub_w0 + sub % p.su_w)) * p.out_ld +
+              p.out_coff + ch0 + (esz == 2 ? (seg & 3) * 8 : seg * 4);
+          uint8_t* gout = reinterpret_cast<uint8_t*>(p.out) + delta * esz;
+          const bool seg_ok = seg * 16 < valid_bytes;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rsub;
-              const long long base = rbase[rr];
-              if (base >= 0) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kEpiPitch + seg * 16);
-                *reinterpret_cast<uint4*>(gout + (base + delta) * esz) = v;
-              }
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const long long base = __shfl_sync(0xffffffffu, my_base, rr);
+            if (seg_ok && base >= 0) {
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4));
+              *reinterpret_cast<uint4*>(gout + base * esz) = v;
             }
           }
           __syncwarp();
         }
-      } else {
+      } else if (colhalf == 0) {
         // generic path (odd alignments, split-K atomics): each thread stores its own row
         for (int c = 0; c < p.bn; c += 32) {
           uint32_t r[32];
@@ -259,14 +265,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int dh = p.sub_h0 + sub / p.su_w, dw = p.sub_w0 + sub % p.su_w;
             const long long off = my_base + (static_cast<long long>(dh) * p.out_w + dw) * p.out_ld + p.out_coff + ch0;
             const int nvalid = min(32, p.n_gemm - ng0);
-            for (int j = 0; j < nvalid; ++j) {
-              float x = __uint_as_float(r[j]);
-              if (p.bias != nullptr) x += __ldg(p.bias + ch0 + j);
-              if (p.act == 1) x = fmaxf(x, 0.f);
-              else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
-              if (p.out_kind == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16(x);
-              else if (p.out_kind == 1) reinterpret_cast<float*>(p.out)[off + j] = x;
-              else atomicAdd(reinterpret_cast<float*>(p.out) + off + j, x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                float x = __uint_as_float(r[j]);
+                if (p.bias != nullptr) x += __ldg(p.bias + ch0 + j);
+                if (p.act == 1) x = fmaxf(x, 0.f);
+                else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+                if (p.out_kind == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16(x);
+                else if (p.out_kind == 1) reinterpret_cast<float*>(p.out)[off + j] = x;
+                else atomicAdd(reinterpret_cast<float*>(p.out) + off + j, x);
+              }
             }
           }
         }
