@@ -259,6 +259,13 @@ def run_ours(args, wl):
     step_ms = ms / args.steps
     alg_tflop_step = STEP_GFLOP_PER_IMG[args.workload] * B / 1e3
 
+    in_sync = None
+    if world > 1:      # replicas must hold identical parameters after the timed steps
+        chk = torch.stack([p.detach().double().sum() for p in list(G.parameters()) + list(D.parameters())]).sum()
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(abs(float(hi) - float(lo)) <= 1e-9 * max(1.0, abs(float(hi))))
     if rank == 0:
         sys.path.insert(0, ROOT)
         cpu = None
@@ -289,6 +296,8 @@ def run_ours(args, wl):
                          "step_frac_of_peak": alg_tflop_step / (step_ms / 1e3) / pk["tf"]},
             "cpu_baseline": cpu,
         }
+        if in_sync is not None:
+            line["dp_params_in_sync"] = in_sync
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
