@@ -179,7 +179,7 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = not args.no_graph and (world == 1 or args.graph_dp)
+    use_graph = not args.no_graph      # the NCCL all-reduces of the DP path are captured in the graph as well
     if use_graph:
         trainer.capture(data[0][0], data[0][1], data[0][2], texts)
 
@@ -266,6 +266,17 @@ def run_ours(args, wl):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         in_sync = bool(abs(float(hi) - float(lo)) <= 1e-9 * max(1.0, abs(float(hi))))
+        if not in_sync:      # say which tensors differ (diagnostic)
+            named = [("G." + k, v) for k, v in G.named_parameters()] + [("D." + k, v) for k, v in D.named_parameters()]
+            sums = torch.stack([v.detach().double().sum() for _, v in named])
+            absum = torch.stack([v.detach().double().abs().sum() for _, v in named])
+            mx, mn = sums.clone(), sums.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                d = ((mx - mn) / absum.clamp_min(1e-30)).cpu()
+                bad = [(named[i][0], float(d[i])) for i in torch.argsort(d, descending=True)[:8] if d[i] > 0]
+                print("DP out of sync:", int((d > 0).sum()), "of", len(named), "tensors differ; worst:", bad, file=sys.stderr)
     if rank == 0:
         sys.path.insert(0, ROOT)
         cpu = None
@@ -300,7 +311,12 @@ def run_ours(args, wl):
             line["dp_params_in_sync"] = in_sync
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A process group whose collectives were captured in a CUDA graph can hang in destroy_process_group();
+        # everything is printed and synchronised by now, so leave without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -314,7 +330,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-convs", default="", help="write the per-shape tensor-core kernel timing table to this file")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
-    ap.add_argument("--graph-dp", action="store_true", help="also capture the NCCL all-reduces (multi-GPU) in the graph")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:

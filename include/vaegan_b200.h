@@ -199,7 +199,8 @@ int vg_sumsq(const float* g, long long n, float* out, int zero_first, void* stre
  * the step replays with the right bias corrections */
 typedef struct VgAdamTensor { float* p; float* g; float* m; float* v; long long n; } VgAdamTensor;
 int vg_adam_prepare(float* state, float beta1, float beta2, void* stream);
-int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, void* stream);
+/* deterministic (fixed-order) reduction; scratch: device float[scratch_len], scratch_len >= 1 (use >= 4 x #SMs) */
+int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, float* scratch, int scratch_len, void* stream);
 int vg_multi_adam(const VgAdamTensor* table, int count, float lr, float beta1, float beta2, float eps,
                   const float* state, const float* gnorm_sq, float max_norm, int write_back_grad, void* stream);
 int vg_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,

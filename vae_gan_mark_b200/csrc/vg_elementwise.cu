@@ -170,22 +170,31 @@ __global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int n,
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ src, int n, int h, int w, int ld, int c, int kh,
                               int kw, int stride, int pad, int oh, int ow, __nv_bfloat16* __restrict__ col, int kpad) {
-  const long long total = static_cast<long long>(n) * oh * ow * kpad;
-  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  // one thread = 8 consecutive columns of one output pixel row (one 16-byte store)
+  const int kv = kpad / 8;
+  const long long total = static_cast<long long>(n) * oh * ow * kv;
+  const int kvalid = kh * kw * c;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % kpad);
-    const long long m = i / kpad;
-    __nv_bfloat16 v = zero;
-    if (k < kh * kw * c) {
-      const int ch = k % c, tap = k / c;
-      const int q = tap % kw, r = tap / kw;
-      const int ox = static_cast<int>(m % ow), oy = static_cast<int>((m / ow) % oh);
-      const int b = static_cast<int>(m / (static_cast<long long>(ow) * oh));
-      const int iy = oy * stride + r - pad, ix = ox * stride + q - pad;
-      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = src[((static_cast<long long>(b) * h + iy) * w + ix) * ld + ch];
+    const int k0 = static_cast<int>(i % kv) * 8;
+    const long long m = i / kv;
+    const int ox = static_cast<int>(m % ow), oy = static_cast<int>((m / ow) % oh);
+    const int b = static_cast<int>(m / (static_cast<long long>(ow) * oh));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      float v = 0.f;
+      if (k < kvalid) {
+        const int ch = k % c, tap = k / c;
+        const int q = tap % kw, r = tap / kw;
+        const int iy = oy * stride + r - pad, ix = ox * stride + q - pad;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+          v = __bfloat162float(src[((static_cast<long long>(b) * h + iy) * w + ix) * ld + ch]);
+      }
+      f[j] = v;
     }
-    col[i] = v;
+    store8(col + m * kpad + k0, f);
   }
 }
 // dsrc[b][c][iy][ix] (fp32 NCHW, overwritten) = sum over taps of dcol
@@ -454,7 +463,7 @@ extern "C" int vg_im2col(const void* src, int n, int h, int w, int ld, int c, in
                          void* col, int kpad, void* stream_) {
   VG_CHECK(kh * kw * c <= kpad && kpad % 64 == 0, -1, "vg_im2col: kpad must be a multiple of 64 >= kh*kw*c");
   const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
-  im2col_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * kpad), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  im2col_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * (kpad / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(src), n, h, w, ld, c, kh, kw, stride, pad, oh, ow,
       static_cast<__nv_bfloat16*>(col), kpad);
   VG_LAUNCH_OK();

@@ -262,6 +262,20 @@ __global__ void adam_prepare_kernel(float* state, float b1, float b2) {
   state[1] = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));
   state[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), step)));
 }
+// deterministic: per-block partials (fixed grid) + a single-block ordered final sum, so that data-parallel replicas
+// holding identical gradients compute bit-identical norms (and therefore bit-identical clipped updates)
+__global__ void final_sum_kernel(const float* __restrict__ partials, int n, float* out) {
+  __shared__ double sm[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += static_cast<double>(partials[i]);
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = static_cast<float>(sm[0]);
+}
 __global__ void multi_sumsq_kernel(const VgAdamTensor* __restrict__ tab, int count, float* out) {
   float acc = 0.f;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -283,7 +297,7 @@ __global__ void multi_sumsq_kernel(const VgAdamTensor* __restrict__ tab, int cou
     }
   }
   const float s = block_sum(acc);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;      // out = per-block partials
 }
 __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int count, float lr, float b1, float b2,
                                   float eps, const float* __restrict__ state, const float* __restrict__ gnorm_sq,
@@ -298,7 +312,29 @@ __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int coun
     float* p = tab[t].p; float* g = tab[t].g; float* m = tab[t].m; float* v = tab[t].v;
     const long long n = tab[t].n;
     if (g == nullptr) continue;
-    for (long long i = tid; i < n; i += nth) {
+    long long done = 0;
+    if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+          reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+      const long long n4 = n / 4;
+      float4* p4 = reinterpret_cast<float4*>(p); float4* g4 = reinterpret_cast<float4*>(g);
+      float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
+      for (long long i = tid; i < n4; i += nth) {
+        float4 pv = p4[i], gv = g4[i], mv = m4[i], vv = v4[i];
+        float* pp = &pv.x; float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float gi = gg[k] * clip;
+          mm[k] = b1 * mm[k] + (1.f - b1) * gi;
+          vq[k] = b2 * vq[k] + (1.f - b2) * gi * gi;
+          pp[k] -= step * mm[k] / (sqrtf(vq[k]) / bc2_sqrt + eps);
+          gg[k] = gi;
+        }
+        p4[i] = pv; m4[i] = mv; v4[i] = vv;
+        if (write_back_grad) g4[i] = gv;
+      }
+      done = n4 * 4;
+    }
+    for (long long i = done + tid; i < n; i += nth) {
       const float gi = g[i] * clip;
       const float mi = b1 * m[i] + (1.f - b1) * gi;
       const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -423,9 +459,13 @@ extern "C" int vg_adam_prepare(float* state, float beta1, float beta2, void* str
   VG_LAUNCH_OK();
   return 0;
 }
-extern "C" int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, void* stream_) {
-  VG_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST));
-  multi_sumsq_kernel<<<num_sms() * 4, 256, 0, ST>>>(table, count, out);
+extern "C" int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, float* scratch, int scratch_len,
+                              void* stream_) {
+  const int grid = std::min(num_sms() * 4, scratch_len);
+  VG_CHECK(grid >= 1, -1, "vg_multi_sumsq: scratch must hold at least one float");
+  multi_sumsq_kernel<<<grid, 256, 0, ST>>>(table, count, scratch);
+  VG_LAUNCH_OK();
+  final_sum_kernel<<<1, 256, 0, ST>>>(scratch, grid, out);
   VG_LAUNCH_OK();
   return 0;
 }

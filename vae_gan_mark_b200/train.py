@@ -55,8 +55,12 @@ class FusedAdam:
         dev = self.params[0].device
         self.norm_sq = torch.zeros((), dtype=F32, device=dev)
         self.state = torch.zeros(4, dtype=F32, device=dev)          # {step, 1-b1^t, sqrt(1-b2^t), -}
+        self._norm_scratch = torch.zeros(1024, dtype=F32, device=dev)
         self._table_host = torch.zeros((len(self.params), 5), dtype=torch.int64).pin_memory() if dev.type == "cuda" \
             else torch.zeros((len(self.params), 5), dtype=torch.int64)
+        self._table_host_graph = torch.zeros_like(self._table_host)
+        if dev.type == "cuda":
+            self._table_host_graph = self._table_host_graph.pin_memory()
         self._table = torch.zeros((len(self.params), 5), dtype=torch.int64, device=dev)
 
     @property
@@ -68,7 +72,15 @@ class FusedAdam:
             p.grad = None
 
     def _upload_table(self):
+        # the pinned staging table is read by an async H2D copy: do not rewrite it before the previous copy has run
+        ev = self.__dict__.get("_table_event")
+        if ev is not None and not torch.cuda.is_current_stream_capturing():
+            ev.synchronize()
         t = self._table_host
+        if torch.cuda.is_current_stream_capturing():
+            # a captured copy re-reads its host source on every replay: give the graph a table of its own that eager
+            # steps never overwrite
+            t = self._table_host_graph
         for i, (p, m, v) in enumerate(zip(self.params, self.exp_avg, self.exp_avg_sq)):
             g = p.grad
             if g is not None and not g.is_contiguous():
@@ -77,11 +89,15 @@ class FusedAdam:
             t[i, 0], t[i, 1] = p.data_ptr(), (g.data_ptr() if g is not None else 0)
             t[i, 2], t[i, 3], t[i, 4] = m.data_ptr(), v.data_ptr(), p.numel()
         self._table.copy_(t, non_blocking=True)
+        if not torch.cuda.is_current_stream_capturing():
+            self._table_event = torch.cuda.Event()
+            self._table_event.record()
 
     def grad_norm_sq(self) -> torch.Tensor:
         self._upload_table()
         _lib.call("vg_multi_sumsq", C.c_void_p(self._table.data_ptr()), len(self.params),
-                  C.c_void_p(self.norm_sq.data_ptr()), ops.stream())
+                  C.c_void_p(self.norm_sq.data_ptr()), C.c_void_p(self._norm_scratch.data_ptr()),
+                  self._norm_scratch.numel(), ops.stream())
         return self.norm_sq
 
     def step(self, max_norm: float = 0.0):
