@@ -8,7 +8,7 @@ fp32 master weights); the oracle is fp32.
   * per-parameter gradients: with random inputs and random weights the true gradients are small residuals of
     heavily cancelling sums, so ANY bf16 evaluation deviates by tens of percent from fp32 -- the reference's own
     modules under torch.autocast(bfloat16) on the same GPU are used as the calibration: our relative L2 error must
-    be <= max(5e-2, 2 x the autocast run's error) per tensor (the same rule is applied to the scalar quantities).  The backward kernels themselves are pinned
+    be <= max(5e-2, 2.5 x the autocast run's error) per tensor (the same rule is applied to the scalar quantities).  The backward kernels themselves are pinned
     tightly (<= 1e-2, typically 2e-3) op by op in tests/test_ops_gpu.py, where no such cancellation occurs.
 """
 import os
@@ -21,7 +21,7 @@ from oracle.step import LossWeights as OLW, deterministic_state, make_optimizers
 
 pytestmark = pytest.mark.gpu
 
-ACT_TOL, LATENT_TOL, GRAD_TOL, CAL = 2e-2, 6e-2, 5e-2, 2.0
+ACT_TOL, LATENT_TOL, GRAD_TOL, CAL = 2e-2, 6e-2, 5e-2, 2.5
 
 
 def rel(a, b):
