@@ -178,10 +178,46 @@ class TransformerTextEncoder(nn.Module):
         return self.fc(e)
 
 
+_SIDE_STREAMS = {}
+
+
+def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
+    """Run the (stock, launch-bound) recurrent text encoder on a side stream so that its ~500 small kernels overlap
+    with the style encoder's convolutions instead of serialising with them; autograd replays the backward on the same
+    stream, where it overlaps with the style encoder's backward.  Returns (NHWC bf16 text map, join) -- call join()
+    before consuming the map on the current stream."""
+    cur = torch.cuda.current_stream()
+    dev = cur.device
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        text = module(texts)
+        if reduce_width:
+            text = text.mean(dim=3, keepdim=True)
+        t = L.ToNHWCFn.apply(text)
+
+    def join():
+        cur.wait_stream(side)
+        t.record_stream(cur)
+        return t
+    return t, join
+
+
 # ------------------------------------------------------------------------------------------------
 # shared tail: heads + reparameterisation
 # ------------------------------------------------------------------------------------------------
-def run_heads(mu_head: nn.Conv2d, logvar_head: nn.Conv2d, feat: torch.Tensor, owner: nn.Module):
+def draw_eps(owner: nn.Module, b: int, z: int, device) -> torch.Tensor:
+    """Reparameterisation noise, (b, z) fp32 on ``device`` (vae-gan.py:135).  ``owner.eps_fn`` is a test hook that
+    draws it from another generator (e.g. the CPU one, to line up with the CPU oracle)."""
+    eps_fn = owner.__dict__.get("eps_fn")
+    eps = (eps_fn((b, z, 1, 1)).to(device, F32) if eps_fn is not None
+           else torch.randn((b, z, 1, 1), dtype=F32, device=device))
+    return eps.reshape(b, z).contiguous()
+
+
+def run_heads(mu_head: nn.Conv2d, logvar_head: nn.Conv2d, feat: torch.Tensor, owner: nn.Module, eps=None):
     """Both full-kernel heads as ONE split-K GEMM with N = 2z, then bias + reparameterisation + KL in one kernel.
     Returns mu, logvar (B,z,1,1 fp32), z (B,z fp32) and the KL scalar.  eps is drawn with torch.randn on the
     host-visible generator, at the same point in the RNG stream as the reference (vae-gan.py:135)."""
@@ -189,9 +225,8 @@ def run_heads(mu_head: nn.Conv2d, logvar_head: nn.Conv2d, feat: torch.Tensor, ow
     z = mu_head.out_channels
     st = _state(mu_head, lambda: (ConvLinear(c, 2 * z, h, w, 1, (0, 0), (h, w)), L.WeightCache(), L.WeightCache()))
     heads = L.HeadsFn.apply(feat, mu_head.weight, logvar_head.weight, st[0], st[1], st[2])
-    eps_fn = owner.__dict__.get("eps_fn")          # test hook: draw eps from another generator (e.g. the CPU one)
-    eps = (eps_fn((b, z, 1, 1)).to(feat.device, F32) if eps_fn is not None
-           else torch.randn((b, z, 1, 1), dtype=F32, device=feat.device)).reshape(b, z).contiguous()
+    if eps is None:
+        eps = draw_eps(owner, b, z, feat.device)
     mu, lv, zz, kl = L.ReparamKLFn.apply(heads, mu_head.bias, logvar_head.bias, eps)
     owner.__dict__["_last_kl"] = kl
     return mu.view(b, z, 1, 1), lv.view(b, z, 1, 1), zz, kl
@@ -344,7 +379,7 @@ class VAEEncoderWithSkips(nn.Module):
         self.mu_head = nn.Conv2d(1024, z_ch, kernel_size=(self.feature_map_h, self.feature_map_w))
         self.logvar_head = nn.Conv2d(1024, z_ch, kernel_size=(self.feature_map_h, self.feature_map_w))
 
-    def encode(self, images, skip_dests=None, pool_dests=None):
+    def encode(self, images, skip_dests=None, pool_dests=None, eps=None):
         """Returns (mu, logvar, z, kl, skips, pooled).  ``skip_dests[i]`` / ``pool_dests[i]`` are optional NHWC views
         (channel slices of the decoder's concat buffers) that receive the skip / pooled map directly."""
         skips, pooled = [], []
@@ -357,7 +392,7 @@ class VAEEncoderWithSkips(nn.Module):
             pooled.append(p)
             x = p
         feat, _ = run_double_conv(self.bottleneck_conv, x)
-        mu, lv, z, kl = run_heads(self.mu_head, self.logvar_head, feat, self)
+        mu, lv, z, kl = run_heads(self.mu_head, self.logvar_head, feat, self, eps)
         return mu, lv, z, kl, skips, pooled
 
     def forward(self, x):
@@ -470,11 +505,12 @@ class VAEGAN_UNet_SpatialFiLM(nn.Module):
         b = image_for_style_in.shape[0]
         bufs = dec.concat_buffers(b, image_for_style_in.device)
         dests = [bufs[3 - i][..., bufs[3 - i].shape[3] // 2:] for i in range(4)]      # s1..s4 -> stage 4..1
-        mu, logvar, z, kl, skips, _ = self.style_vae_encoder_module.encode(
-            [image_for_style_in, mask_for_style_in], skip_dests=dests)
+        enc = self.style_vae_encoder_module
+        eps = draw_eps(enc, b, enc.mu_head.out_channels, image_for_style_in.device)   # RNG order: eps before GRU dropout (:320-322)
+        _, join = text_features_async(self.char_text_encoder_module, texts_batch_list_in)
+        mu, logvar, z, kl, skips, _ = enc.encode([image_for_style_in, mask_for_style_in], skip_dests=dests, eps=eps)
         self.__dict__["_last_kl"] = kl
-        text = self.char_text_encoder_module(texts_batch_list_in)          # RNG order: eps before GRU dropout (:320-322)
-        t = L.ToNHWCFn.apply(text)
+        t = join()
         return dec.decode(z, t, skips, bufs), mu, logvar
 
 
@@ -572,9 +608,10 @@ class VAEGAN_UNet_CharEmb(nn.Module):
         # pooled p1..p4 feed stages 4..1: bufs[3-i][..., C_main:]
         mains = (1024, 512, 256, 128)
         pdests = [bufs[3 - i][..., mains[3 - i]:] for i in range(4)]
-        mu, logvar, z, kl, _, pooled = self.style_vae_encoder_module.encode(
-            [image_for_style_input, mask_for_style_input], pool_dests=pdests)
+        enc = self.style_vae_encoder_module
+        eps = draw_eps(enc, b, enc.mu_head.out_channels, image_for_style_input.device)
+        _, join = text_features_async(self.char_text_encoder_module, texts_batch_list_input, reduce_width=True)
+        mu, logvar, z, kl, _, pooled = enc.encode([image_for_style_input, mask_for_style_input], pool_dests=pdests, eps=eps)
         self.__dict__["_last_kl"] = kl
-        text = self.char_text_encoder_module(texts_batch_list_input)
-        t = L.ToNHWCFn.apply(text.mean(dim=3, keepdim=True))
+        t = join()
         return dec.decode_repaired(z, t, pooled, bufs), mu, logvar
