@@ -26,7 +26,8 @@ extern "C" {
 #endif
 
 #define VG_API_VERSION 1
-#define VG_MAX_TAPS 16
+#define VG_MAX_TAPS 16          /* kernel positions of one convolution */
+#define VG_MAX_FPROP_TAPS 96    /* fprop K-loop entries: taps x split-precision operand combinations */
 
 const char* vg_last_error(void);
 int vg_version(void);
@@ -53,8 +54,10 @@ typedef struct VgConvFprop {
   int x_stride;             /* view stride s: 1 or 2 */
   int m_n, m_h, m_w;        /* output pixel grid (GEMM M = m_n*m_h*m_w) */
   int cin;                  /* channels per tap, multiple of 64 */
-  int num_taps;             /* 1..VG_MAX_TAPS */
-  int taps[VG_MAX_TAPS][4]; /* {c_base, dw, sh, dh} */
+  int num_taps;             /* 1..VG_MAX_FPROP_TAPS */
+  int taps[VG_MAX_FPROP_TAPS][4]; /* {c_base, dw, sh, dh} */
+  int use_wk;               /* 0: tap i reads weight columns [i*cin, (i+1)*cin); 1: columns [wk[i], wk[i]+cin) */
+  int wk[VG_MAX_FPROP_TAPS];
   const void* w;            /* bf16 [n_gemm][w_ld], K = tap-major then channel */
   int w_ld;
   int n_gemm;               /* GEMM N */
@@ -83,6 +86,8 @@ typedef struct VgConvWgrad {
   int m_n, m_h, m_w;
   int cin, num_taps;
   int taps[VG_MAX_TAPS][4];
+  int num_combos;           /* 0/1: plain; >1: split-precision operand pairs accumulated into the same dw */
+  int combo_g[8], combo_x[8]; /* channel offsets added to the g / x channel coordinates for each pair */
   float* dw;                /* fp32 [cout][dw_ld]; overwritten (zeroed internally when split) */
   int dw_ld;
   int ksplit;               /* 0 = auto */
@@ -99,7 +104,7 @@ int vg_conv_wgrad(const VgConvWgrad* desc /*host*/, void* stream);
  * ------------------------------------------------------------------------------------------- */
 /* sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 (fp32, zeroed internally) */
 int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c, float* sums,
-                  void* stream);
+                  int dtype /*0 bf16, 1 fp32 activations*/, void* stream);
 /* mean_rstd[g][0][c] = mean, [g][1][c] = 1/sqrt(var+eps); when groups == 1 and running_mean != NULL also updates the
  * running statistics (momentum, unbiased variance) and increments *num_batches_tracked (int64, nullable). */
 int vg_norm_finalize(const float* sums, int groups, long long rows_per_group, int c, float eps, float* mean_rstd,
@@ -113,6 +118,7 @@ typedef struct VgNormApply {
   int act;
   void* y; int y_ld, y_coff;            /* full-resolution output (may be a channel slice of a concat buffer) */
   void* pool; int p_ld, p_coff;         /* optional 2x2 max-pooled output (NULL = none) */
+  int dtype;                            /* activation storage: 0 bf16, 1 fp32 (high-accuracy mode) */
 } VgNormApply;
 int vg_norm_apply(const VgNormApply* desc /*host*/, void* stream);
 typedef struct VgNormBackward {
@@ -127,6 +133,7 @@ typedef struct VgNormBackward {
   void* dx; int dx_ld, dx_coff;         /* grad wrt x, bf16 */
   float* dgamma; float* dbeta;          /* fp32 [c], nullable */
   int accumulate;                       /* add into dgamma/dbeta instead of overwriting */
+  int dtype;                            /* activation storage: 0 bf16, 1 fp32 */
 } VgNormBackward;
 int vg_norm_backward(const VgNormBackward* desc /*host*/, void* stream);
 
@@ -142,29 +149,38 @@ int vg_strided_copy(const void* in, int in_dtype, void* out, int out_dtype, cons
                     int accumulate, void* stream);
 /* dx = dy * act'(y) for an activation that was fused into a conv epilogue (act 1 ReLU, 2 LeakyReLU(0.2)); bf16 rows */
 int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, void* dx, int dx_ld, long long rows, int c, int act,
-               void* stream);
+               int dtype, void* stream);
+/* y = act(y) in place (where the activation cannot be fused into the producing epilogue: split-K launches) */
+int vg_act_fwd(void* y, int y_ld, long long rows, int c, int act, int dtype, void* stream);
 /* out[c] (=|+=) sum_r in[r*ld + c], fp32 (bias gradients of small matrices) */
 int vg_colsum_f32(const float* in, long long rows, int cols, int ld, float* out, int accumulate, void* stream);
 /* FiLM (vae-gan-v2.py:146-149): y = gb[:, :c] * x + gb[:, c:]; gb and y dense bf16 [rows][2c] / [rows][c] */
-int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, void* y, long long rows, int c, void* stream);
+int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, void* y, long long rows, int c, int dtype,
+                void* stream);
 int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx, int dx_ld,
-                int dx_coff, long long rows, int c, void* stream);
+                int dx_coff, long long rows, int c, int dtype, void* stream);
 /* F.interpolate(bilinear, align_corners=False) of a (1 x w0) map to (h x w) (vae-gan-v2.py:138-140) */
-int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c, void* y, int h, int w, void* stream);
-int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt /*fp32 [n][w0][c]*/, void* stream);
+int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c, void* y, int h, int w, int dtype,
+                      void* stream);
+int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt /*fp32 [n][w0][c]*/, int dtype,
+                      void* stream);
+/* `dtype` on the activation-touching entry points selects the activation storage: 0 = bf16 (default), 1 = fp32 (the
+ * high-accuracy mode, in which the tensor core is fed three bf16 planes per fp32 operand, see vg_split3). */
+/* fp32 [rows][c] (row stride ld_in) -> bf16 [rows][3*cp]: planes hi | mid | lo with hi+mid+lo == x to ~2^-24 */
+int vg_split3(const float* in, int ld_in, long long rows, int c, int cp, void* out, void* stream);
 /* im2col / col2im for few-channel images (first conv of the encoder vae-gan-v2.py:154 and of D vae-gan.py:153) */
 int vg_im2col(const void* src, int n, int h, int w, int ld, int c, int kh, int kw, int stride, int pad, void* col,
-              int kpad, void* stream);
+              int kpad, int dtype, void* stream);
 int vg_col2im(const void* dcol, int kpad, int n, int h, int w, int c, int kh, int kw, int stride, int pad,
-              float* dsrc_nchw, void* stream);
+              float* dsrc_nchw, int dtype, void* stream);
 /* direct stride-1 convs with <= 4 output channels; w fp32 [cout][kh][kw][cin]; out/dy fp32 NHWC [n][oh][ow][cout]
  * (final_image_conv vae-gan-v2.py:232, decode.15 vae-gan.py:81, D's patch head vae-gan.py:157) */
 int vg_conv_smalln_fwd(const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, const float* wt,
-                       const float* bias, int cout, int kh, int kw, int pad, float* out, void* stream);
+                       const float* bias, int cout, int kh, int kw, int pad, float* out, int dtype, void* stream);
 int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int cin, const float* wt, int cout, int kh, int kw,
-                         int pad, void* dx, int dx_ld, int dx_coff, void* stream);
+                         int pad, void* dx, int dx_ld, int dx_coff, int dtype, void* stream);
 int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, int cout,
-                         int kh, int kw, int pad, float* dw, float* dbias, void* stream);
+                         int kh, int kw, int pad, float* dw, float* dbias, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses, reparameterisation, spectral norm, optimiser (fp32)

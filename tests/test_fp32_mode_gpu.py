@@ -1,0 +1,252 @@
+"""High-accuracy ("fp32") mode: fp32 activations, tensor-core operands split into three bf16 planes.
+
+This is the mode in which the north_star's fp32 tolerance is demonstrated.  Per-op checks (forward, data gradient,
+weight gradient of every tensor-core path and of the normalisation kernels) must agree with a plain PyTorch fp32
+reference to a relative L2 error of 2e-5 (observed <= 1.5e-6).  The whole training step is then compared with the
+oracle evaluated in FLOAT64: losses, reconstruction and latents within 1e-3 (observed ~1e-6); every per-parameter
+gradient within max(5e-3, 2 x the error of the oracle's own float32 evaluation) -- observed medians 2e-5 .. 1.4e-3.
+The gradient bound is looser than 1e-3 because this synthetic problem amplifies rounding differences ~1000x: the
+reference's own fp32 gradients deviate from their float64 values by 2e-3 (32x32) to 2e-2 (configs[0], 64x64 batch 16),
+i.e. more than ours do.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import models as om
+from oracle.step import LossWeights as OLW, deterministic_state, make_optimizers, synthetic_batch, train_step
+
+pytestmark = pytest.mark.gpu
+OP_TOL, STEP_TOL, GRAD_TOL = 2e-5, 1e-3, 5e-3
+
+
+@pytest.fixture(autouse=True)
+def fp32_mode():
+    import vae_gan_mark_b200 as vg
+    vg.set_precision("fp32")
+    yield
+    vg.set_precision("bf16")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+
+
+def nchw(t):
+    return t.detach().float().cpu().permute(0, 3, 1, 2)
+
+
+def check(name, got, want, tol=OP_TOL):
+    e = rel(got, want)
+    print(f"{name}: {e:.2e}")
+    assert e <= tol, (name, e)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,h,w,bias", [
+    (64, 64, 3, 1, 1, 16, 16, False), (128, 256, 3, 1, 1, 8, 12, True), (64, 128, 4, 2, 1, 16, 16, True),
+    (128, 256, 3, 2, 1, 16, 16, True), (512, 1024, 1, 1, 0, 4, 4, True), (128, 64, 2, 2, 0, 8, 8, False)])
+def test_conv2d_fp32(cin, cout, k, s, p, h, w, bias):
+    from vae_gan_mark_b200 import layers as L
+    from vae_gan_mark_b200.conv import ConvLinear
+    torch.manual_seed(0)
+    n = 3
+    x = torch.randn(n, cin, h, w)
+    conv_ref = nn.Conv2d(cin, cout, k, s, p, bias=bias)
+    conv = nn.Conv2d(cin, cout, k, s, p, bias=bias)
+    conv.load_state_dict(conv_ref.state_dict())
+    rx = x.clone().requires_grad_(True)
+    y_ref = conv_ref(rx)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    conv = conv.cuda()
+    xc = nhwc(x)
+    y = L.Conv2dFn.apply(xc, conv.weight, conv.bias, ConvLinear(cin, cout, k, k, s, (p, p)), L.WeightCache(), 0, None, None, None)
+    assert y.dtype == torch.float32
+    y.backward(nhwc(gy).detach())
+    check("y", nchw(y), y_ref)
+    check("dx", nchw(xc.grad), rx.grad)
+    check("dw", conv.weight.grad, conv_ref.weight.grad)
+    if bias:
+        check("db", conv.bias.grad, conv_ref.bias.grad)
+
+
+@pytest.mark.parametrize("cin,cout,kh,kw,s,p,h,w", [
+    (128, 64, 2, 2, 2, 0, 8, 8), (1024, 512, 4, 4, 2, 1, 4, 4), (640, 1024, 2, 1, 1, 0, 1, 4), (192, 1024, 2, 2, 1, 0, 1, 1),
+    (544, 1024, 4, 1, 1, 0, 1, 3)])
+def test_conv_transpose2d_fp32(cin, cout, kh, kw, s, p, h, w):
+    from vae_gan_mark_b200 import layers as L, ops
+    from vae_gan_mark_b200.conv import ConvLinear, new_act
+    torch.manual_seed(1)
+    n = 3
+    x = torch.randn(n, cin, h, w)
+    ct_ref = nn.ConvTranspose2d(cin, cout, (kh, kw), s, p)
+    ct = nn.ConvTranspose2d(cin, cout, (kh, kw), s, p)
+    ct.load_state_dict(ct_ref.state_dict())
+    rx = x.clone().requires_grad_(True)
+    y_ref = ct_ref(rx)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    oh, ow = y_ref.shape[2], y_ref.shape[3]
+    ct = ct.cuda()
+    xa = new_act(n, h, w, cin, "cuda")
+    ops.strided_copy(x.permute(0, 2, 3, 1).cuda(), xa)
+    xc = xa.detach().requires_grad_(True)
+    op = ConvLinear(cout, cin, kh, kw, s, (p, p), (oh, ow))
+    y = L.ConvTranspose2dFn.apply(xc, ct.weight, ct.bias, op, L.WeightCache(), 0, None, (oh, ow))
+    y.backward(nhwc(gy).detach())
+    check("y", nchw(y), y_ref)
+    check("dx", nchw(xc.grad), rx.grad)
+    check("dw", ct.weight.grad, ct_ref.weight.grad)
+    check("db", ct.bias.grad, ct_ref.bias.grad)
+
+
+@pytest.mark.parametrize("per_sample,act,pool", [(False, 1, True), (False, 1, False), (True, 2, False)])
+def test_norm_act_fp32(per_sample, act, pool):
+    from vae_gan_mark_b200 import layers as L
+    torch.manual_seed(3)
+    n, c, h, w = 4, 128, 8, 12
+    x = torch.randn(n, c, h, w) * 1.5 + 0.3
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c) * 0.2
+    rx = x.clone().requires_grad_(True)
+    g_ref, b_ref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    if per_sample:
+        y_ref = F.leaky_relu(F.instance_norm(rx, weight=g_ref, bias=b_ref, eps=1e-5), 0.2)
+    else:
+        y_ref = F.relu(F.batch_norm(rx, torch.zeros(c), torch.ones(c), g_ref, b_ref, True, 0.1, 1e-5))
+    p_ref = F.max_pool2d(y_ref, 2, 2) if pool else None
+    gy = torch.randn_like(y_ref)
+    gp = torch.randn_like(p_ref) if pool else None
+    (y_ref * gy).sum().backward(retain_graph=pool)
+    if pool:
+        (p_ref * gp).sum().backward()
+    xc = nhwc(x)
+    gc, bc = gamma.cuda().requires_grad_(True), beta.cuda().requires_grad_(True)
+    state = None if per_sample else {"training": True, "running_mean": torch.zeros(c, device="cuda"),
+                                     "running_var": torch.ones(c, device="cuda"),
+                                     "num_batches_tracked": torch.zeros((), dtype=torch.long, device="cuda")}
+    y, pl = L.NormActFn.apply(xc, gc, bc, per_sample, act, pool, None, 1e-5, state, None)
+    loss = (y * nhwc(gy).detach()).sum()
+    if pool:
+        loss = loss + (pl * nhwc(gp).detach()).sum()
+    loss.backward()
+    check("y", nchw(y), y_ref)
+    if pool:
+        check("pool", nchw(pl), p_ref)
+    check("dx", nchw(xc.grad), rx.grad, 2e-4)
+    check("dgamma", gc.grad, g_ref.grad, 2e-4)
+    check("dbeta", bc.grad, b_ref.grad, 2e-4)
+
+
+def test_heads_image_small_fp32():
+    from vae_gan_mark_b200 import layers as L
+    from vae_gan_mark_b200.conv import ConvLinear
+    torch.manual_seed(5)
+    n, c, h, w, z = 5, 1024, 2, 4, 128
+    x = torch.randn(n, c, h, w)
+    mu_h, lv_h = nn.Conv2d(c, z, (h, w)), nn.Conv2d(c, z, (h, w))
+    rx = x.clone().requires_grad_(True)
+    wm, wl = mu_h.weight.detach().clone().requires_grad_(True), lv_h.weight.detach().clone().requires_grad_(True)
+    mu_ref, lv_ref = F.conv2d(rx, wm, mu_h.bias.detach()), F.conv2d(rx, wl, lv_h.bias.detach())
+    gm, gl = torch.randn_like(mu_ref), torch.randn_like(lv_ref)
+    ((mu_ref * gm).sum() + (lv_ref * gl).sum()).backward()
+    mu_h, lv_h = mu_h.cuda(), lv_h.cuda()
+    xc = nhwc(x)
+    heads = L.HeadsFn.apply(xc, mu_h.weight, lv_h.weight, ConvLinear(c, 2 * z, h, w, 1, (0, 0), (h, w)), L.WeightCache(), L.WeightCache())
+    ref_heads = torch.cat([mu_ref - mu_h.bias.detach().cpu().view(1, z, 1, 1), lv_ref - lv_h.bias.detach().cpu().view(1, z, 1, 1)], 1)
+    heads.backward(torch.cat([gm, gl], 1).permute(0, 2, 3, 1).contiguous().cuda())
+    check("heads", heads.view(n, 2 * z), ref_heads.view(n, 2 * z))
+    check("dx", nchw(xc.grad), rx.grad)
+    check("dw_mu", mu_h.weight.grad, wm.grad)
+    check("dw_lv", lv_h.weight.grad, wl.grad)
+
+    # image-side conv (im2col path) with input gradient, and the few-output-channel conv
+    imgs = [torch.rand(3, 3, 16, 24), (torch.rand(3, 1, 16, 24) > 0.5).float()]
+    conv = nn.Conv2d(4, 64, 3, 1, 1)
+    xin = torch.cat(imgs, 1).requires_grad_(True)
+    y_ref = F.leaky_relu(conv(xin), 0.2)
+    g = torch.randn_like(y_ref)
+    y_ref.backward(g)
+    convc = nn.Conv2d(4, 64, 3, 1, 1).cuda()
+    convc.load_state_dict(conv.state_dict())
+    cimgs = [t.cuda().requires_grad_(True) for t in imgs]
+    y = L.ImageConvFn.apply(convc.weight, convc.bias, (3, 3, 1, 1), L.WeightCache(), 2, None, *cimgs)
+    y.backward(nhwc(g).detach())
+    check("img y", nchw(y), y_ref)
+    check("img dw", convc.weight.grad, conv.weight.grad)
+    check("img dimg", cimgs[0].grad, xin.grad[:, :3])
+
+
+CASES = [("base", 32, 32, 4, 128), ("v2", 32, 64, 2, 128), ("v2", 32, 32, 3, 32), ("unet", 32, 32, 2, 128),
+         ("base", 64, 64, 16, 128)]
+
+
+def is_zero_in_theory(key: str) -> bool:
+    """Biases of convolutions that feed a Batch/InstanceNorm directly have an exactly-zero gradient; what any
+    implementation computes for them is rounding noise."""
+    import re
+    pats = [r"^D\.body\.(2|5|8)\.bias$", r"^G\.encoder\.feat\.(0|3|6|9)\.bias$", r"^G\.decoder\.decode\.(0|3|6|9|12)\.bias$",
+            r"bottleneck_proc\.0\.bias$", r"bottleneck_upsample\.0\.bias$", r"d_upconv\d\.0\.bias$"]
+    return any(re.search(p, key) for p in pats)
+
+
+@pytest.mark.parametrize("family,h,w,batch,z", CASES)
+def test_train_step_fp32_matches_oracle(family, h, w, batch, z):
+    """Whole training step in the high-accuracy mode against the oracle evaluated in float64 (the exact value of the
+    reference algorithm on these inputs); see the module docstring for the bounds."""
+    import copy
+    from test_step_parity_gpu import build_pair
+    from vae_gan_mark_b200.train import LossWeights, VAEGANTrainer
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    og, od, mg, md = build_pair(family, h, w, z)
+    og64, od64 = copy.deepcopy(og).double(), copy.deepcopy(od).double()
+    wts = OLW.for_family(family)
+    ru, en, mask, texts = synthetic_batch(batch, h, w, step=0)
+    eps = torch.randn(batch, z, 1, 1, generator=torch.Generator().manual_seed(5))
+    orig_randn_like = torch.randn_like
+    try:
+        torch.randn_like = lambda t, **k: eps.to(t.dtype) if tuple(t.shape) == tuple(eps.shape) else orig_randn_like(t, **k)
+        ref32 = train_step(og, od, *make_optimizers(og, od), (ru, en, mask, texts), wts)
+        ref = train_step(og64, od64, *make_optimizers(og64, od64), (ru.double(), en.double(), mask.double(), texts), wts)
+    finally:
+        torch.randn_like = orig_randn_like
+    grads = {}
+    trainer = VAEGANTrainer(mg, md, LossWeights(wts.recon, wts.kl, wts.gan),
+                            grad_hook=lambda which, params: grads.setdefault(which, [p.grad.clone() if p.grad is not None else None for p in params]))
+    enc = getattr(mg, "style_vae_encoder_module", None) or mg.encoder
+    enc.__dict__["eps_fn"] = lambda shape: eps.clone()
+    out = trainer.step(ru.cuda(), en.cuda(), mask.cuda(), texts)
+    torch.cuda.synchronize()
+
+    def srel(a, b):
+        return abs(a - b) / max(abs(b), 1e-6)
+    keys = ("loss_G", "loss_D", "recon", "kl", "gan", "d_real", "d_fake")
+    report = {k: (srel(float(out[k]), ref.losses[k]), srel(ref32.losses[k], ref.losses[k])) for k in keys}
+    report["fake"] = (rel(out["fake"], ref.recon), rel(ref32.recon, ref.recon))
+    report["mu"] = (rel(out["mu"], ref.mu), rel(ref32.mu, ref.mu))
+    report["logvar"] = (rel(out["logvar"], ref.logvar), rel(ref32.logvar, ref.logvar))
+    report["grad_norm"] = (srel(float(out["grad_norm_sq"]) ** 0.5, ref.grad_norm), srel(ref32.grad_norm, ref.grad_norm))
+    print(family, h, w, "ours-vs-fp64 / oracle32-vs-fp64:", {k: f"{a:.1e}/{b:.1e}" for k, (a, b) in report.items()})
+    gerr = {}
+    for (name, _), g in zip(md.named_parameters(), grads["D"]):
+        gerr["D." + name] = (rel(g, ref.d_grads[name]), rel(ref32.d_grads[name], ref.d_grads[name]))
+    for (name, _), g in zip(mg.named_parameters(), grads["G"]):
+        if name in ref.g_grads and g is not None:
+            gerr["G." + name] = (rel(g, ref.g_grads[name]), rel(ref32.g_grads[name], ref.g_grads[name]))
+    real = {k: v for k, v in gerr.items() if not is_zero_in_theory(k)}
+    ours = sorted(v[0] for v in real.values())
+    theirs = sorted(v[1] for v in real.values())
+    print(f"gradients vs fp64: ours median {ours[len(ours) // 2]:.1e} max {ours[-1]:.1e} | oracle fp32 median "
+          f"{theirs[len(theirs) // 2]:.1e} max {theirs[-1]:.1e}")
+    assert set(n for n, p in mg.named_parameters() if p.grad is not None) >= set(ref.g_grads), "missing G gradients"
+    for k, (a, b) in report.items():
+        assert a <= max(STEP_TOL, 2 * b), (k, a, b)
+    for k, (a, b) in real.items():
+        assert a <= max(GRAD_TOL, 2 * b), (k, a, b)

@@ -10,6 +10,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libvaegan_b200.so")
 VG_MAX_TAPS = 16
+VG_MAX_FPROP_TAPS = 96
 
 
 class VgError(RuntimeError):
@@ -20,7 +21,8 @@ class VgConvFprop(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_n", C.c_int), ("x_h", C.c_int), ("x_w", C.c_int), ("x_ld", C.c_int),
         ("x_stride", C.c_int), ("m_n", C.c_int), ("m_h", C.c_int), ("m_w", C.c_int),
-        ("cin", C.c_int), ("num_taps", C.c_int), ("taps", (C.c_int * 4) * VG_MAX_TAPS),
+        ("cin", C.c_int), ("num_taps", C.c_int), ("taps", (C.c_int * 4) * VG_MAX_FPROP_TAPS),
+        ("use_wk", C.c_int), ("wk", C.c_int * VG_MAX_FPROP_TAPS),
         ("w", C.c_void_p), ("w_ld", C.c_int), ("n_gemm", C.c_int),
         ("out", C.c_void_p), ("out_kind", C.c_int),
         ("out_h", C.c_int), ("out_w", C.c_int), ("out_ld", C.c_int), ("out_coff", C.c_int),
@@ -35,6 +37,7 @@ class VgConvWgrad(C.Structure):
         ("x", C.c_void_p), ("x_n", C.c_int), ("x_h", C.c_int), ("x_w", C.c_int), ("x_ld", C.c_int),
         ("x_stride", C.c_int), ("m_n", C.c_int), ("m_h", C.c_int), ("m_w", C.c_int),
         ("cin", C.c_int), ("num_taps", C.c_int), ("taps", (C.c_int * 4) * VG_MAX_TAPS),
+        ("num_combos", C.c_int), ("combo_g", C.c_int * 8), ("combo_x", C.c_int * 8),
         ("dw", C.c_void_p), ("dw_ld", C.c_int), ("ksplit", C.c_int), ("force_bn", C.c_int),
     ]
 
@@ -45,7 +48,7 @@ class VgNormApply(C.Structure):
         ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
         ("mean_rstd", C.c_void_p), ("per_sample", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("act", C.c_int), ("y", C.c_void_p), ("y_ld", C.c_int), ("y_coff", C.c_int),
-        ("pool", C.c_void_p), ("p_ld", C.c_int), ("p_coff", C.c_int),
+        ("pool", C.c_void_p), ("p_ld", C.c_int), ("p_coff", C.c_int), ("dtype", C.c_int),
     ]
 
 
@@ -58,7 +61,7 @@ class VgNormBackward(C.Structure):
         ("mean_rstd", C.c_void_p), ("per_sample", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("act", C.c_int), ("sums", C.c_void_p),
         ("dx", C.c_void_p), ("dx_ld", C.c_int), ("dx_coff", C.c_int),
-        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int), ("dtype", C.c_int),
     ]
 
 

@@ -1,12 +1,17 @@
 """Tensor-core convolutions: geometry -> tap tables -> ``vg_conv_fprop`` / ``vg_conv_wgrad`` launches.
 
-Activations are NHWC bf16 torch views ([N, H, W, C], last stride 1, pixel stride ``ld = stride(2)`` >= C so a
-tensor may be a channel slice of a wider concat buffer).  ``ConvLinear`` describes one Conv2d-shaped linear
-map and provides its three primitives (forward, data gradient, weight gradient); a ConvTranspose2d is the
-adjoint of the Conv2d with the same weight tensor, so its forward is that conv's data gradient, its data
-gradient is that conv's forward and its weight gradient is that conv's weight gradient with the operands
-swapped (IOHW of the transpose == OIHW of its adjoint).  Reference layers: vae-gan.py:52-60,76-81,153-157;
+Activations are NHWC torch views ([N, H, W, C], last stride 1, pixel stride ``ld = stride(2)`` >= C so a tensor
+may be a channel slice of a wider concat buffer), bf16 by default.  ``ConvLinear`` describes one Conv2d-shaped
+linear map and provides its three primitives (forward, data gradient, weight gradient); a ConvTranspose2d is the
+adjoint of the Conv2d with the same weight tensor, so its forward is that conv's data gradient, its data gradient
+is that conv's forward and its weight gradient is that conv's weight gradient with the operands swapped (IOHW of
+the transpose == OIHW of its adjoint).  Reference layers: vae-gan.py:52-60,76-81,153-157;
 vae-gan-v2.py:123-127,168-176,199-241; vae-gan-unet.py:148-154,194-221.
+
+High-accuracy mode (fp32 activations, ``ops.set_precision("fp32")``): the tensor core only takes bf16, so each fp32
+operand is split into three bf16 planes hi + mid + lo (``vg_split3``) and the six plane pairs with the largest
+products (hi.hi, hi.mid, mid.hi, mid.mid, hi.lo, lo.hi) are accumulated in the fp32 TMEM accumulator -- the K loop
+simply runs over (pair, tap) "virtual taps".  The result carries ~2^-22 relative error per product instead of 2^-8.
 """
 from __future__ import annotations
 
@@ -20,6 +25,7 @@ from ._lib import VgConvFprop, VgConvWgrad
 from .ops import BF16, F32, round_up
 
 Tap = Tuple[int, int, int, int]   # (c_base, dw, sh, dh)
+PAIRS = ((0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0))   # (activation plane, weight plane)
 
 # When set to a list, every tensor-core launch appends (kind, shape-key, flops, start_event, end_event): bench.py
 # uses it to time the dominant kernel live on the launching stream.
@@ -52,13 +58,6 @@ def conv_taps(kh: int, kw: int, stride: int, ph: int, pw: int, ld: int) -> List[
     return taps
 
 
-def _fill_taps(dst, taps: Sequence[Tap]):
-    assert len(taps) <= _lib.VG_MAX_TAPS, f"{len(taps)} taps > {_lib.VG_MAX_TAPS}"
-    for i, t in enumerate(taps):
-        for j in range(4):
-            dst[i][j] = int(t[j])
-
-
 def _chk(t: torch.Tensor, what: str):
     assert t.dtype == BF16 and ops.nhwc_ok(t), f"{what}: not an NHWC bf16 view {tuple(t.shape)} {t.stride()}"
 
@@ -66,17 +65,24 @@ def _chk(t: torch.Tensor, what: str):
 def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torch.Tensor, n_gemm: int,
           m: Tuple[int, int, int], out: torch.Tensor, out_kind: int = 0, su: Tuple[int, int] = (1, 1),
           sub0: Tuple[int, int] = (0, 0), cout_per_sub: Optional[int] = None, bias: Optional[torch.Tensor] = None,
-          act: int = 0, ksplit: int = 0, force_bn: int = 0) -> None:
-    """out[pixel, n] = sum_{tap, c<cin} x[pixel@tap, c] * w[n, tap*cin + c].  ``out`` is an NHWC view
-    ([N, OH, OW, C']); ``w`` is bf16 [n_gemm, len(taps)*cin]."""
+          act: int = 0, ksplit: int = 0, force_bn: int = 0, wk: Optional[Sequence[int]] = None) -> None:
+    """out[pixel, n] = sum_{tap, c<cin} x[pixel@tap, c] * w[n, wk[tap] + c]  (wk[tap] = tap*cin by default).
+    ``out`` is an NHWC view ([N, OH, OW, C']); ``x`` and ``w`` are bf16."""
     _chk(x, "fprop x")
-    assert w.dtype == BF16 and w.stride(1) == 1 and w.shape[1] == len(taps) * cin, (w.shape, len(taps), cin)
-    assert out.stride(3) == 1
+    assert w.dtype == BF16 and w.stride(1) == 1 and out.stride(3) == 1
+    assert len(taps) <= _lib.VG_MAX_FPROP_TAPS, f"{len(taps)} taps > {_lib.VG_MAX_FPROP_TAPS}"
+    assert wk is not None or w.shape[1] == len(taps) * cin, (w.shape, len(taps), cin)
     d = VgConvFprop()
     d.x, d.x_n, d.x_h, d.x_w, d.x_ld, d.x_stride = x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], x.stride(2), x_stride
     d.m_n, d.m_h, d.m_w = m
     d.cin, d.num_taps = cin, len(taps)
-    _fill_taps(d.taps, taps)
+    for i, t in enumerate(taps):
+        for j in range(4):
+            d.taps[i][j] = int(t[j])
+    if wk is not None:
+        d.use_wk = 1
+        for i, v in enumerate(wk):
+            d.wk[i] = int(v)
     d.w, d.w_ld, d.n_gemm = w.data_ptr(), w.stride(0), n_gemm
     d.out, d.out_kind = out.data_ptr(), out_kind
     d.out_h, d.out_w, d.out_ld, d.out_coff = out.shape[1], out.shape[2], out.stride(2), 0
@@ -91,22 +97,31 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
 
 
 def wgrad(g: torch.Tensor, cout: int, x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int,
-          m: Tuple[int, int, int], dw: torch.Tensor, ksplit: int = 0, force_bn: int = 0) -> None:
-    """dw[co, tap*cin + ci] (fp32) = sum_pixels g[pixel, co] * x[pixel@tap, ci]."""
+          m: Tuple[int, int, int], dw: torch.Tensor, ksplit: int = 0, force_bn: int = 0,
+          pairs: Optional[Sequence[Tuple[int, int]]] = None) -> None:
+    """dw[co, tap*cin + ci] (fp32) = sum_pixels g[pixel, co] * x[pixel@tap, ci]; ``pairs`` = channel offsets (g, x) of
+    split-precision operand planes accumulated into the same dw."""
     _chk(g, "wgrad g")
     _chk(x, "wgrad x")
-    assert dw.dtype == F32 and dw.stride(1) == 1
+    assert dw.dtype == F32 and dw.stride(1) == 1 and len(taps) <= _lib.VG_MAX_TAPS
     d = VgConvWgrad()
     d.g, d.g_ld, d.g_coff, d.cout = g.data_ptr(), g.stride(2), 0, cout
     d.x, d.x_n, d.x_h, d.x_w, d.x_ld, d.x_stride = x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], x.stride(2), x_stride
     d.m_n, d.m_h, d.m_w = m
     d.cin, d.num_taps = cin, len(taps)
-    _fill_taps(d.taps, taps)
+    for i, t in enumerate(taps):
+        for j in range(4):
+            d.taps[i][j] = int(t[j])
+    if pairs:
+        d.num_combos = len(pairs)
+        for i, (a, b) in enumerate(pairs):
+            d.combo_g[i], d.combo_x[i] = int(a), int(b)
     d.dw, d.dw_ld = dw.data_ptr(), dw.stride(0)
     d.ksplit, d.force_bn = ksplit, force_bn
     e0 = _prof_begin()
     _lib.call("vg_conv_wgrad", C.byref(d), ops.stream())
-    _prof_end(e0, "wgrad", (m, cout, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * cout * len(taps) * cin)
+    _prof_end(e0, "wgrad", (m, cout, len(taps) * cin),
+              2.0 * m[0] * m[1] * m[2] * cout * len(taps) * cin * (len(pairs) if pairs else 1))
 
 
 def pad_channels(t: torch.Tensor, c_pad: int) -> torch.Tensor:
@@ -118,19 +133,76 @@ def pad_channels(t: torch.Tensor, c_pad: int) -> torch.Tensor:
     return t.as_strided((t.shape[0], t.shape[1], t.shape[2], c_pad), t.stride())
 
 
-def new_act(n, h, w, c, device, dtype=BF16) -> torch.Tensor:
+def new_act(n, h, w, c, device, dtype=None) -> torch.Tensor:
     """Fresh NHWC activation; channel count padded to a multiple of 64 with zeros when needed."""
+    dtype = dtype or ops.act_dtype()
     ld = c if c % 64 == 0 else round_up(c, 64)
     if ld == c:
         return torch.empty((n, h, w, c), dtype=dtype, device=device)
     return torch.zeros((n, h, w, ld), dtype=dtype, device=device)[..., :c]
 
 
+def _operand(view: torch.Tensor, kp: int, hi: bool, scale=None) -> torch.Tensor:
+    """Weight operand from a [rows, <tap dims...>, k]-shaped (permuted, possibly strided) fp32 view of the master
+    weight.  bf16 mode: bf16 [rows, taps*kp]; high-accuracy mode: bf16 [rows, taps*3*kp], planes innermost per tap."""
+    rows, k = view.shape[0], view.shape[-1]
+    taps = 1
+    for t in view.shape[1:-1]:
+        taps *= t
+    inv = scale is not None
+    if not hi:
+        out = (torch.zeros if kp != k else torch.empty)(tuple(view.shape[:-1]) + (kp,), dtype=BF16, device=view.device)
+        ops.strided_copy(view, out[..., :k], scale, scale_inverse=inv)
+        return out.view(rows, taps * kp)
+    tmp = torch.empty(tuple(view.shape), dtype=F32, device=view.device)
+    ops.strided_copy(view, tmp, scale, scale_inverse=inv)
+    return ops.split3(tmp.view(1, rows, taps, k)).view(rows, taps * 3 * kp)
+
+
+HI_STEPS_PER_SPLIT = 16   # high-accuracy mode: K steps (of 64) accumulated in TMEM before an fp32 (RN) add in L2
+
+
+def _hi_launch(x, vt, stride, cin, w, n_gemm, m, out, wk, bias, act, **kw):
+    """High-accuracy launch: the tensor core's fp32 accumulator truncates on every MMA, which biases long K sums by
+    ~1e-4; so K is cut into short splits whose partial sums are combined with round-to-nearest fp32 atomics."""
+    ksteps = len(vt) * (cin // 64)
+    out.zero_()
+    fprop(x, vt, stride, cin, w, n_gemm, m, out, out_kind=2, bias=bias, act=0, wk=wk,
+          ksplit=max(1, -(-ksteps // HI_STEPS_PER_SPLIT)), **kw)
+    if act:
+        ops.act_fwd_(out, act)
+
+
+def _vtaps(taps: Sequence[Tap], kp_act: int, kp_w: int, hi: bool):
+    """(virtual taps, weight column offsets) of the K loop."""
+    if not hi:
+        return list(taps), None
+    vt, wk = [], []
+    for (pa, pb) in PAIRS:
+        for i, (cb, dw, sh, dh) in enumerate(taps):
+            vt.append((cb + pa * kp_act, dw, sh, dh))
+            wk.append((i * 3 + pb) * kp_w)
+    return vt, wk
+
+
+def _hi_wgrad_split(n: int, oh: int, ow: int) -> int:
+    """Split factor of a high-accuracy wgrad launch: <= HI_STEPS_PER_SPLIT K steps (64 pixels x one plane pair) each."""
+    w = 1
+    while w < ow and w < 64:
+        w <<= 1
+    h = 1
+    while h < oh and w * h < 64:
+        h <<= 1
+    tn = 64 // (w * h)
+    tiles = -(-n // tn) * -(-oh // h) * -(-ow // w) * len(PAIRS)
+    return max(1, -(-tiles // HI_STEPS_PER_SPLIT))
+
+
 class ConvLinear:
     """A Conv2d-shaped linear map (cin -> cout, kernel kh x kw, stride 1|2, padding) on the tensor pipe.
 
-    Weight matrices are bf16 re-layouts of the fp32 OIHW tensor produced by :meth:`prep_fwd` (used by
-    ``forward`` and ``backward_weight`` consumers) and :meth:`prep_bwd` (used by ``backward_data``).
+    Weight operands are bf16 re-layouts of the fp32 OIHW tensor produced by :meth:`prep_fwd` (used by ``forward``)
+    and :meth:`prep_bwd` (used by ``backward_data``); ``hi`` selects the split-precision layout.
     """
 
     def __init__(self, cin: int, cout: int, kh: int, kw: int, stride: int = 1, pad: Tuple[int, int] = (0, 0),
@@ -144,6 +216,7 @@ class ConvLinear:
         # "column": kernel (H x 1), output one row -> the data gradient is a pixel shuffle along H
         self.column = (not self.flat and in_hw is not None and stride == 1 and pad == (0, 0) and kw == 1
                        and kh == in_hw[0] and kh > 1)
+        self.shuffle = self.flat or self.column or (stride == 2 and (kh, kw) == (2, 2) and pad == (0, 0))
         self.in_hw = in_hw
         assert stride in (1, 2)
 
@@ -151,93 +224,132 @@ class ConvLinear:
         return (h + 2 * self.ph - self.kh) // self.s + 1, (w + 2 * self.pw - self.kw) // self.s + 1
 
     # ---------------------------------------------------------------- weights
-    def prep_fwd(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """bf16 [cout, kh*kw*cin_p]  (K order: r, q, ci).  ``scale`` = device scalar sigma -> stores w / sigma."""
+    def prep_fwd(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, hi: bool = False) -> torch.Tensor:
+        """rows = cout, K order (r, q, ci).  ``scale`` = device scalar sigma -> stores w / sigma."""
         co, ci, kh, kw = w.shape
-        out = (torch.zeros if self.cin_p != ci else torch.empty)((co, kh, kw, self.cin_p), dtype=BF16, device=w.device)
-        ops.strided_copy(w.permute(0, 2, 3, 1), out[..., :ci], scale, scale_inverse=scale is not None)
-        return out.view(co, kh * kw * self.cin_p)
+        if self.flat and hi:
+            # one K axis of length kh*kw*ci: lay the fp32 weight out as [co][(r, q, ci)] first, then split it
+            tmp = torch.empty((co, kh, kw, ci), dtype=F32, device=w.device)
+            ops.strided_copy(w.permute(0, 2, 3, 1), tmp, scale, scale_inverse=scale is not None)
+            return _operand(tmp.view(co, 1, kh * kw * ci), kh * kw * ci, True)
+        return _operand(w.permute(0, 2, 3, 1), self.cin_p, hi, scale)
 
-    def prep_bwd(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> Dict:
-        """Weight matrices of the data gradient (rows = cin of the conv, K = taps x cout_p)."""
+    def prep_bwd(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, hi: bool = False) -> Dict:
+        """Weight operands of the data gradient (rows = cin of the conv side, K = taps x cout_p)."""
         co, ci, kh, kw = w.shape
-        inv = scale is not None
-        mk = torch.zeros if self.cout_p != co else torch.empty
-        if self.flat or self.column or (self.s == 2 and (kh, kw) == (2, 2) and (self.ph, self.pw) == (0, 0)):
-            # single tap, GEMM N = (r, q, ci): [(r,q,ci)][co_p]
-            out = mk((kh, kw, ci, self.cout_p), dtype=BF16, device=w.device)
-            ops.strided_copy(w.permute(2, 3, 1, 0), out[..., :co], scale, scale_inverse=inv)
-            return {"shuffle": out.view(kh * kw * ci, self.cout_p)}
+        if self.shuffle:
+            # single tap, GEMM N = (r, q, ci): rows (r, q, ci), K = co
+            # (the leading dims of the permuted view are only a factorisation of the row index (r, q, ci))
+            return {"shuffle": _operand(w.permute(2, 3, 1, 0), self.cout_p, hi, scale).view(kh * kw * ci, -1)}
         if self.s == 1:
-            out = mk((ci, kh, kw, self.cout_p), dtype=BF16, device=w.device)
-            ops.strided_copy(w.permute(1, 2, 3, 0), out[..., :co], scale, scale_inverse=inv)
-            return {"s1": out.view(ci, kh * kw * self.cout_p)}
+            return {"s1": _operand(w.permute(1, 2, 3, 0), self.cout_p, hi, scale)}
         mats = {}
         for a in (0, 1):
             for b in (0, 1):
                 r0, q0 = (a + self.ph) % 2, (b + self.pw) % 2
                 sub = w[:, :, r0::2, q0::2]
                 nr, nq = sub.shape[2], sub.shape[3]
-                out = mk((ci, nr, nq, self.cout_p), dtype=BF16, device=w.device)
-                ops.strided_copy(sub.permute(1, 2, 3, 0), out[..., :co], scale, scale_inverse=inv)
                 taps = [(0, (b + self.pw - q0) // 2 - kq, 0, (a + self.ph - r0) // 2 - kr)
                         for kr in range(nr) for kq in range(nq)]
-                mats[(a, b)] = (out.view(ci, nr * nq * self.cout_p), taps)
+                mats[(a, b)] = (_operand(sub.permute(1, 2, 3, 0), self.cout_p, hi, scale), taps)
         return {"parity": mats}
 
     # ---------------------------------------------------------------- primitives
     def forward(self, x: torch.Tensor, wf: torch.Tensor, bias=None, act: int = 0, out: Optional[torch.Tensor] = None,
-                out_kind: int = 0) -> torch.Tensor:
+                out_kind: Optional[int] = None) -> torch.Tensor:
         n, h, w, _ = x.shape
+        hi = x.dtype == F32
         oh, ow = self.out_hw(h, w)
+        if out_kind is None:
+            out_kind = 1 if hi else 0
         if out is None:
-            out = (new_act(n, oh, ow, self.cout, x.device) if out_kind == 0
+            out = (new_act(n, oh, ow, self.cout, x.device, x.dtype) if out_kind != 2
                    else torch.zeros((n, oh, ow, self.cout), dtype=F32, device=x.device))
         if self.flat:
             assert x.is_contiguous()
-            xf = x.view(n, 1, 1, h * w * self.cin)
-            fprop(xf, [(0, 0, 0, 0)], 1, h * w * self.cin, wf, self.cout, (n, 1, 1), out, out_kind=out_kind, bias=bias,
-                  act=act)
+            k = h * w * self.cin
+            xf = x.view(n, 1, 1, k)
+            xs = ops.split3(xf) if hi else xf
+            vt, wk = _vtaps([(0, 0, 0, 0)], k, k, hi)
+            if hi:
+                _hi_launch(xs, vt, 1, k, wf, self.cout, (n, 1, 1), out, wk, bias, act)
+            else:
+                fprop(xs, vt, 1, k, wf, self.cout, (n, 1, 1), out, out_kind=out_kind, bias=bias, act=act, wk=wk)
             return out
-        xp = pad_channels(x, self.cin_p)
-        taps = conv_taps(self.kh, self.kw, self.s, self.ph, self.pw, xp.stride(2))
-        fprop(xp, taps, self.s, self.cin_p, wf, self.cout, (n, oh, ow), out, out_kind=out_kind, bias=bias, act=act)
+        xs = ops.split3(x) if hi else pad_channels(x, self.cin_p)
+        taps = conv_taps(self.kh, self.kw, self.s, self.ph, self.pw, xs.stride(2))
+        vt, wk = _vtaps(taps, self.cin_p, self.cin_p, hi)
+        if hi:
+            _hi_launch(xs, vt, self.s, self.cin_p, wf, self.cout, (n, oh, ow), out, wk, bias, act)
+        else:
+            fprop(xs, vt, self.s, self.cin_p, wf, self.cout, (n, oh, ow), out, out_kind=out_kind, bias=bias, act=act, wk=wk)
         return out
 
     def backward_data(self, dy: torch.Tensor, wb: Dict, in_hw: Tuple[int, int], bias=None, act: int = 0,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n, oh, ow, _ = dy.shape
         h, w = in_hw
+        hi = dy.dtype == F32
+        kind = 1 if hi else 0
         if out is None:
-            out = new_act(n, h, w, self.cin, dy.device)
-        g = pad_channels(dy, self.cout_p)
+            out = new_act(n, h, w, self.cin, dy.device, dy.dtype)
+        g = ops.split3(dy) if hi else pad_channels(dy, self.cout_p)
         if "shuffle" in wb:
             # pixel shuffle: GEMM column (r, q, ci) of input pixel (oh, ow) lands at output pixel (oh*kh + r, ow*kw + q).
             # Covers the full-kernel case (1x1 input), the column kernel (kh x 1) and 2x2 stride 2.
-            fprop(g, [(0, 0, 0, 0)], 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, oh, ow), out,
-                  su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act)
+            vt, wk = _vtaps([(0, 0, 0, 0)], self.cout_p, self.cout_p, hi)
+            if hi:
+                _hi_launch(g, vt, 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, oh, ow), out, wk, bias, act,
+                           su=(self.kh, self.kw), cout_per_sub=self.cin)
+            else:
+                fprop(g, vt, 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, oh, ow), out, out_kind=kind,
+                      su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act, wk=wk)
             return out
         if "s1" in wb:
             taps = [(0, self.pw - q, 0, self.ph - r) for r in range(self.kh) for q in range(self.kw)]
-            fprop(g, taps, 1, self.cout_p, wb["s1"], self.cin, (n, h, w), out, bias=bias, act=act)
+            vt, wk = _vtaps(taps, self.cout_p, self.cout_p, hi)
+            if hi:
+                _hi_launch(g, vt, 1, self.cout_p, wb["s1"], self.cin, (n, h, w), out, wk, bias, act)
+            else:
+                fprop(g, vt, 1, self.cout_p, wb["s1"], self.cin, (n, h, w), out, out_kind=kind, bias=bias, act=act, wk=wk)
             return out
+        if hi:
+            out.zero_()
         for (a, b), (mat, taps) in wb["parity"].items():
-            fprop(g, taps, 1, self.cout_p, mat, self.cin, (n, h // 2, w // 2), out, su=(2, 2), sub0=(a, b),
-                  cout_per_sub=self.cin, bias=bias, act=act)
+            vt, wk = _vtaps(taps, self.cout_p, self.cout_p, hi)
+            if hi:
+                ksteps = len(vt) * (self.cout_p // 64)
+                fprop(g, vt, 1, self.cout_p, mat, self.cin, (n, h // 2, w // 2), out, out_kind=2, su=(2, 2), sub0=(a, b),
+                      cout_per_sub=self.cin, bias=bias, act=0, wk=wk, ksplit=max(1, -(-ksteps // HI_STEPS_PER_SPLIT)))
+            else:
+                fprop(g, vt, 1, self.cout_p, mat, self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2), sub0=(a, b),
+                      cout_per_sub=self.cin, bias=bias, act=act, wk=wk)
+        if hi and act:
+            ops.act_fwd_(out, act)
         return out
 
     def backward_weight(self, dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         """fp32 gradient in OIHW order as a (permuted) view [cout, cin, kh, kw] of the kernel's [cout][r][q][ci] result."""
         n, oh, ow, _ = dy.shape
         _, h, w, _ = x.shape
+        hi = dy.dtype == F32
         if self.flat:
             assert x.is_contiguous()
             k = h * w * self.cin
+            xf = x.view(n, 1, 1, k)
             dw = torch.empty((self.cout, k), dtype=F32, device=x.device)
-            wgrad(dy, self.cout, x.view(n, 1, 1, k), [(0, 0, 0, 0)], 1, k, (n, 1, 1), dw)
+            if hi:
+                pairs = [(pa * self.cout_p, pb * k) for (pa, pb) in PAIRS]
+                wgrad(ops.split3(dy), self.cout, ops.split3(xf), [(0, 0, 0, 0)], 1, k, (n, 1, 1), dw, pairs=pairs,
+                      ksplit=_hi_wgrad_split(n, 1, 1))
+            else:
+                wgrad(dy, self.cout, xf, [(0, 0, 0, 0)], 1, k, (n, 1, 1), dw)
             return dw.view(self.cout, self.kh, self.kw, self.cin).permute(0, 3, 1, 2)
-        xp = pad_channels(x, self.cin_p)
-        taps = conv_taps(self.kh, self.kw, self.s, self.ph, self.pw, xp.stride(2))
+        xs = ops.split3(x) if hi else pad_channels(x, self.cin_p)
+        gs = ops.split3(dy) if hi else dy
+        taps = conv_taps(self.kh, self.kw, self.s, self.ph, self.pw, xs.stride(2))
+        pairs = [(pa * self.cout_p, pb * self.cin_p) for (pa, pb) in PAIRS] if hi else None
         dw = torch.empty((self.cout, len(taps) * self.cin_p), dtype=F32, device=x.device)
-        wgrad(dy, self.cout, xp, taps, self.s, self.cin_p, (n, oh, ow), dw)
+        wgrad(gs, self.cout, xs, taps, self.s, self.cin_p, (n, oh, ow), dw, pairs=pairs,
+              ksplit=_hi_wgrad_split(n, oh, ow) if hi else 0)
         return dw.view(self.cout, self.kh, self.kw, self.cin_p)[..., :self.cin].permute(0, 3, 1, 2)

@@ -201,6 +201,39 @@ VG_DEVICE void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<bf16x8*>(p) = v;
 }
 
+// fp32 activations (the high-accuracy mode keeps activations in fp32): same 8-channel vector interface
+VG_DEVICE void load8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+VG_DEVICE void store8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+// raw 8-element vector kept in registers between the load and its use (several loads in flight)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  bf16x8 v;
+  static VG_DEVICE Raw8 load(const __nv_bfloat16* p) { Raw8 r; r.v = *reinterpret_cast<const bf16x8*>(p); return r; }
+  VG_DEVICE void unpack(float (&f)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = unpack_bf16x2(v.u[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  static VG_DEVICE Raw8 load(const float* p) {
+    Raw8 r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+  }
+  VG_DEVICE void unpack(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+// value as it will read back from storage of type T
+template <typename T> VG_DEVICE float as_stored(float v);
+template <> VG_DEVICE float as_stored<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
+template <> VG_DEVICE float as_stored<float>(float v) { return v; }
+
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 // host: number of SMs of the current device (cached)

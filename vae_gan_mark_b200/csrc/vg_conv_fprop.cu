@@ -28,7 +28,7 @@ constexpr int kBM = 128;          // GEMM M tile (pixels) == TMEM lanes
 constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kFpropThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
-constexpr int kMaxTaps = VG_MAX_TAPS;
+constexpr int kMaxTaps = VG_MAX_FPROP_TAPS;
 constexpr int kEpiBytes = 8 * 32 * 128;   // 8 epilogue warps x (32 rows x 128 B XOR-swizzled staging tile)
 
 struct FpropParams {
@@ -46,6 +46,7 @@ struct FpropParams {
   int act;                      // 0 none, 1 relu, 2 leaky relu 0.2
   int vec_ok;                   // destination allows 16-byte vector stores
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
+  int wk[kMaxTaps];             // first weight column of each tap
 };
 
 __global__ void __launch_bounds__(kFpropThreads, 1)
@@ -118,7 +119,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         const int4 t = p.taps[tap];
         tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
-        tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + cc * kBK, n_t * p.bn);
+        tma_load_2d(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn);
         if (++cc == cchunks) { cc = 0; ++tap; }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -269,7 +270,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int j = 0; j < 32; ++j) {
               if (j < nvalid) {
                 float x = __uint_as_float(r[j]);
-                if (p.bias != nullptr) x += __ldg(p.bias + ch0 + j);
+                if (p.bias != nullptr && (p.out_kind != 2 || tile / (p.n_tiles * m_tiles) == 0)) x += __ldg(p.bias + ch0 + j);   // split-K: bias once
                 if (p.act == 1) x = fmaxf(x, 0.f);
                 else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
                 if (p.out_kind == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16(x);
@@ -351,6 +352,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   }
   VG_CHECK(ksplit == 1 || d->out_kind == 2, -1, "vg_conv_fprop: split-K needs the fp32 atomic output kind");
   VG_CHECK(ksplit <= p.ksteps, -1, "vg_conv_fprop: ksplit %d > k steps %d", ksplit, p.ksteps);
+  VG_CHECK(ksplit == 1 || d->act == 0, -1, "vg_conv_fprop: an activation cannot be fused into a split-K launch");
   p.ksplit = ksplit;
   const int stage_bytes = kBM * kBK * 2 + bn * kBK * 2;
   p.stages = min(8, (227 * 1024 - 1024 - 256 - kEpiBytes) / stage_bytes);
@@ -366,6 +368,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   }
   for (int i = 0; i < d->num_taps; ++i) {
     p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
+    p.wk[i] = d->use_wk ? d->wk[i] : i * d->cin;
     VG_CHECK(d->taps[i][2] >= 0 && d->taps[i][2] < d->x_stride, -1, "vg_conv_fprop: tap %d row parity out of range", i);
   }
 
@@ -380,7 +383,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(d->num_taps) * d->cin, static_cast<uint64_t>(d->n_gemm)};
+    uint64_t dims[2] = {static_cast<uint64_t>(d->w_ld), static_cast<uint64_t>(d->n_gemm)};
     uint64_t strides[2] = {1, static_cast<uint64_t>(d->w_ld)};
     uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
     int rc = encode_tmap_bf16(&tmap_b, d->w, 2, dims, strides, box);

@@ -36,6 +36,8 @@ struct WgradParams {
   int dw_ld;
   int atomic;
   int4 taps[VG_MAX_TAPS];         // {c_base, dw, sh, dh}
+  int ncombos;                    // split-precision operand pairs per pixel tile (1 = plain bf16)
+  int combo_g[8], combo_x[8];     // channel offsets of the pair's planes
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -78,7 +80,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  // K steps: (pixel tile, operand pair) with the pair index fastest
+  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.ncombos;
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   const int cchunks = p.cin / 64;
 
@@ -106,9 +109,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         const int4 t = p.taps[b / cchunks];
         c0 = t.x + (b % cchunks) * 64; dwv = t.y; shv = t.z; dhv = t.w;
       }
-      int tw_i = k_begin % p.tiles_w;
-      int th_i = (k_begin / p.tiles_w) % p.tiles_h;
-      int tn_i = k_begin / (p.tiles_w * p.tiles_h);
+      int combo = k_begin % p.ncombos;
+      const int pt0 = k_begin / p.ncombos;
+      int tw_i = pt0 % p.tiles_w;
+      int th_i = (pt0 / p.tiles_w) % p.tiles_h;
+      int tn_i = pt0 / (p.tiles_w * p.tiles_h);
       for (int k = k_begin; k < k_end; ++k) {
         if (lane == 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -117,10 +122,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         __syncwarp();
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
-        if (is_a) tma_load_5d(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0, ow0, 0, oh0, n0);
-        if (is_b) tma_load_5d(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0, ow0 + dwv, shv,
-                              oh0 + dhv, n0);
-        if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
+        if (is_a) tma_load_5d(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0 + p.combo_g[combo], ow0, 0, oh0, n0);
+        if (is_b) tma_load_5d(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0 + p.combo_x[combo],
+                              ow0 + dwv, shv, oh0 + dhv, n0);
+        if (++combo == p.ncombos) {
+          combo = 0;
+          if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -239,7 +247,10 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
     p.tw = w; p.th = h; p.tn = kWgPix / (w * h);
   }
   p.tiles_n = cdiv(p.m_n, p.tn); p.tiles_h = cdiv(p.m_h, p.th); p.tiles_w = cdiv(p.m_w, p.tw);
-  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  p.ncombos = d->num_combos > 1 ? d->num_combos : 1;
+  VG_CHECK(p.ncombos <= 8, -1, "vg_conv_wgrad: at most 8 operand pairs");
+  for (int i = 0; i < 8; ++i) { p.combo_g[i] = d->num_combos > 1 ? d->combo_g[i] : 0; p.combo_x[i] = d->num_combos > 1 ? d->combo_x[i] : 0; }
+  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.ncombos;
   p.cout = d->cout; p.cin = d->cin; p.num_taps = d->num_taps; p.g_coff = d->g_coff;
   p.blocks_total = d->num_taps * (d->cin / 64);
   p.m_tiles = cdiv(d->cout, kWgBM);

@@ -50,8 +50,9 @@ __global__ void strided_copy_kernel(const TI* __restrict__ in, TO* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // FiLM
 // ---------------------------------------------------------------------------------------------
-__global__ void film_fwd_kernel(const __nv_bfloat16* __restrict__ gb, const __nv_bfloat16* __restrict__ x, int x_ld,
-                                int x_coff, __nv_bfloat16* __restrict__ y, long long rows, int c) {
+template <typename T>
+__global__ void film_fwd_kernel(const T* __restrict__ gb, const T* __restrict__ x, int x_ld,
+                                int x_coff, T* __restrict__ y, long long rows, int c) {
   const int cv = c / 8;
   const long long total = rows * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -67,9 +68,10 @@ __global__ void film_fwd_kernel(const __nv_bfloat16* __restrict__ gb, const __nv
     store8(y + r * c + ch, o);
   }
 }
-__global__ void film_bwd_kernel(const __nv_bfloat16* __restrict__ gb, const __nv_bfloat16* __restrict__ x, int x_ld,
-                                int x_coff, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dgb,
-                                __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff, long long rows, int c) {
+template <typename T>
+__global__ void film_bwd_kernel(const T* __restrict__ gb, const T* __restrict__ x, int x_ld,
+                                int x_coff, const T* __restrict__ dy, T* __restrict__ dgb,
+                                T* __restrict__ dx, int dx_ld, int dx_coff, long long rows, int c) {
   const int cv = c / 8;
   const long long total = rows * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -99,8 +101,9 @@ VG_DEVICE void lerp_src(int j, int w0, int w, int& j0, int& j1, float& lam) {
   j1 = j0 + (j0 < w0 - 1 ? 1 : 0);
   lam = src - static_cast<float>(j0);
 }
-__global__ void upsample_fwd_kernel(const __nv_bfloat16* __restrict__ t, int t_ld, int t_coff, int n, int w0, int c,
-                                    __nv_bfloat16* __restrict__ y, int h, int w) {
+template <typename T>
+__global__ void upsample_fwd_kernel(const T* __restrict__ t, int t_ld, int t_coff, int n, int w0, int c,
+                                    T* __restrict__ y, int h, int w) {
   const int cv = c / 8;
   const long long total = static_cast<long long>(n) * h * w * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -121,7 +124,8 @@ __global__ void upsample_fwd_kernel(const __nv_bfloat16* __restrict__ t, int t_l
   }
 }
 // dt[b][js][c] (fp32, accumulated) = sum_i sum_j weight(j -> js) dy[b][i][j][c]; one thread per (b, js, cvec, i-chunk)
-__global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int n, int h, int w, int c, int w0,
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int w, int c, int w0,
                                     float* __restrict__ dt, int rows_per_thread) {
   const int cv = c / 8;
   const int ichunks = (h + rows_per_thread - 1) / rows_per_thread;
@@ -168,8 +172,9 @@ __global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int n,
 // ---------------------------------------------------------------------------------------------
 // im2col / col2im for few-channel NHWC bf16 images: col[m][(r*kw+q)*c + ch], zero padded to kpad columns
 // ---------------------------------------------------------------------------------------------
-__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ src, int n, int h, int w, int ld, int c, int kh,
-                              int kw, int stride, int pad, int oh, int ow, __nv_bfloat16* __restrict__ col, int kpad) {
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ src, int n, int h, int w, int ld, int c, int kh,
+                              int kw, int stride, int pad, int oh, int ow, T* __restrict__ col, int kpad) {
   // one thread = 8 consecutive columns of one output pixel row (one 16-byte store)
   const int kv = kpad / 8;
   const long long total = static_cast<long long>(n) * oh * ow * kv;
@@ -190,7 +195,7 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ src, int n, int 
         const int q = tap % kw, r = tap / kw;
         const int iy = oy * stride + r - pad, ix = ox * stride + q - pad;
         if (iy >= 0 && iy < h && ix >= 0 && ix < w)
-          v = __bfloat162float(src[((static_cast<long long>(b) * h + iy) * w + ix) * ld + ch]);
+          v = static_cast<float>(src[((static_cast<long long>(b) * h + iy) * w + ix) * ld + ch]);
       }
       f[j] = v;
     }
@@ -198,7 +203,8 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ src, int n, int 
   }
 }
 // dsrc[b][c][iy][ix] (fp32 NCHW, overwritten) = sum over taps of dcol
-__global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dcol, int kpad, int n, int h, int w, int c, int kh,
+template <typename T>
+__global__ void col2im_kernel(const T* __restrict__ dcol, int kpad, int n, int h, int w, int c, int kh,
                               int kw, int stride, int pad, int oh, int ow, float* __restrict__ dsrc) {
   const long long total = static_cast<long long>(n) * c * h * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -217,7 +223,7 @@ __global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dcol, int kpad, 
         if (tx < 0 || tx % stride != 0) continue;
         const int ox = tx / stride;
         if (ox >= ow) continue;
-        acc += __bfloat162float(dcol[((static_cast<long long>(b) * oh + oy) * ow + ox) * kpad + (r * kw + q) * c + ch]);
+        acc += static_cast<float>(dcol[((static_cast<long long>(b) * oh + oy) * ow + ox) * kpad + (r * kw + q) * c + ch]);
       }
     }
     dsrc[i] = acc;
@@ -229,7 +235,8 @@ __global__ void col2im_kernel(const __nv_bfloat16* __restrict__ dcol, int kpad, 
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxSmallN = 4;
 // forward: a group of G lanes per output pixel, lanes stride over (tap, channel-vector)
-__global__ void smalln_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int n, int h, int w,
+template <typename T>
+__global__ void smalln_fwd_kernel(const T* __restrict__ x, int x_ld, int x_coff, int n, int h, int w,
                                   int cin, const float* __restrict__ wt, const float* __restrict__ bias, int cout,
                                   int kh, int kw, int pad, int oh, int ow, float* __restrict__ out, int lanes_per_px) {
   const int G = lanes_per_px;
@@ -265,9 +272,10 @@ __global__ void smalln_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
   }
 }
 // data gradient: thread per (input pixel, channel vector)
+template <typename T>
 __global__ void smalln_dgrad_kernel(const float* __restrict__ dy, int n, int oh, int ow, int cout,
                                     const float* __restrict__ wt, int kh, int kw, int pad, int h, int w, int cin,
-                                    __nv_bfloat16* __restrict__ dx, int dx_ld, int dx_coff) {
+                                    T* __restrict__ dx, int dx_ld, int dx_coff) {
   const int cv = cin / 8;
   const long long total = static_cast<long long>(n) * h * w * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -298,7 +306,8 @@ __global__ void smalln_dgrad_kernel(const float* __restrict__ dy, int n, int oh,
   }
 }
 // weight gradient: block = (tap, pixel chunk); thread = (channel vector, pixel lane); fp32 atomics per block
-__global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+template <typename T>
+__global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x,
                                                            int x_ld, int x_coff, int n, int h, int w, int cin, int cout,
                                                            int kh, int kw, int pad, int oh, int ow,
                                                            float* __restrict__ dw, float* __restrict__ dbias) {
@@ -363,8 +372,9 @@ __global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 // plain activation backward (for activations fused into a conv epilogue): dx = dy * act'(y)
 // ---------------------------------------------------------------------------------------------
-__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy,
-                               int dy_ld, __nv_bfloat16* __restrict__ dx, int dx_ld, long long rows, int c, int act) {
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ y, int y_ld, const T* __restrict__ dy,
+                               int dy_ld, T* __restrict__ dx, int dx_ld, long long rows, int c, int act) {
   const int cv = c / 8;
   const long long total = rows * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -379,6 +389,22 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, co
     store8(dx + r * dx_ld + ch, o);
   }
 }
+// in-place activation (used where it cannot be fused into the producing epilogue, e.g. split-K launches)
+template <typename T>
+__global__ void act_fwd_kernel(T* __restrict__ y, int y_ld, long long rows, int c, int act) {
+  const int cv = c / 8;
+  const long long total = rows * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cv;
+    const int ch = static_cast<int>(i % cv) * 8;
+    float f[8];
+    load8(y + r * y_ld + ch, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = f[k] > 0.f ? f[k] : (act == 2 ? 0.2f * f[k] : 0.f);
+    store8(y + r * y_ld + ch, f);
+  }
+}
 // out[c] (=|+=) sum_r in[r][c]   (fp32; small matrices: bias gradients of the heads)
 __global__ void colsum_f32_kernel(const float* __restrict__ in, long long rows, int cols, int ld, float* __restrict__ out,
                                   int accumulate) {
@@ -387,6 +413,29 @@ __global__ void colsum_f32_kernel(const float* __restrict__ in, long long rows, 
   float acc = 0.f;
   for (long long r = 0; r < rows; ++r) acc += in[r * ld + c];
   out[c] = accumulate ? out[c] + acc : acc;
+}
+
+// fp32 [rows][c] -> three bf16 planes hi | mid | lo (hi + mid + lo == x to ~2^-24): out[rows][3*cp], plane p at columns
+// [p*cp, (p+1)*cp), columns c..cp zero.  Feeds the tensor core in the high-accuracy (split-bf16) mode.
+__global__ void split3_kernel(const float* __restrict__ in, int ld_in, long long rows, int c, int cp,
+                              __nv_bfloat16* __restrict__ out) {
+  const long long total = rows * cp;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % cp);
+    const long long r = i / cp;
+    __nv_bfloat16 h = zero, m = zero, l = zero;
+    if (col < c) {
+      const float x = in[r * ld_in + col];
+      h = __float2bfloat16(x);
+      const float r1 = x - __bfloat162float(h);
+      m = __float2bfloat16(r1);
+      l = __float2bfloat16(r1 - __bfloat162float(m));
+    }
+    __nv_bfloat16* o = out + r * 3 * cp + col;
+    o[0] = h; o[cp] = m; o[2 * cp] = l;
+  }
 }
 
 }  // namespace vg
@@ -420,60 +469,91 @@ extern "C" int vg_strided_copy(const void* in, int in_dtype, void* out, int out_
 }
 
 extern "C" int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, void* y, long long rows, int c,
-                           void* stream_) {
+                           int dtype, void* stream_) {
   VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_film_fwd: channels must be multiples of 8");
-  film_fwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
-      static_cast<__nv_bfloat16*>(y), rows, c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (dtype == 0)
+    film_fwd_kernel<__nv_bfloat16><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+        static_cast<__nv_bfloat16*>(y), rows, c);
+  else
+    film_fwd_kernel<float><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(static_cast<const float*>(gb), static_cast<const float*>(x),
+                                                                  x_ld, x_coff, static_cast<float*>(y), rows, c);
   VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx,
-                           int dx_ld, int dx_coff, long long rows, int c, void* stream_) {
+                           int dx_ld, int dx_coff, long long rows, int c, int dtype, void* stream_) {
   VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && dx_ld % 8 == 0 && dx_coff % 8 == 0, -1,
            "vg_film_bwd: channels must be multiples of 8");
-  film_bwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
-      static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dgb), static_cast<__nv_bfloat16*>(dx), dx_ld,
-      dx_coff, rows, c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (dtype == 0)
+    film_bwd_kernel<__nv_bfloat16><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(gb), static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+        static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dgb), static_cast<__nv_bfloat16*>(dx), dx_ld,
+        dx_coff, rows, c);
+  else
+    film_bwd_kernel<float><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(
+        static_cast<const float*>(gb), static_cast<const float*>(x), x_ld, x_coff, static_cast<const float*>(dy),
+        static_cast<float*>(dgb), static_cast<float*>(dx), dx_ld, dx_coff, rows, c);
   VG_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c, void* y, int h, int w,
-                                 void* stream_) {
+                                 int dtype, void* stream_) {
   VG_CHECK(c % 8 == 0 && t_ld % 8 == 0 && t_coff % 8 == 0, -1, "vg_upsample_w_fwd: channels must be multiples of 8");
-  upsample_fwd_kernel<<<ew_grid(static_cast<long long>(n) * h * w * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(t), t_ld, t_coff, n, w0, c, static_cast<__nv_bfloat16*>(y), h, w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * h * w * (c / 8));
+  if (dtype == 0)
+    upsample_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(t), t_ld, t_coff, n, w0, c,
+                                                           static_cast<__nv_bfloat16*>(y), h, w);
+  else
+    upsample_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(t), t_ld, t_coff, n, w0, c,
+                                                   static_cast<float*>(y), h, w);
   VG_LAUNCH_OK();
   return 0;
 }
-extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt, void* stream_) {
+extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt, int dtype, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   VG_CHECK(c % 8 == 0, -1, "vg_upsample_w_bwd: channels must be multiples of 8");
   VG_CUDA(cudaMemsetAsync(dt, 0, sizeof(float) * static_cast<size_t>(n) * w0 * c, st));
   const int rpt = 8;
   const long long items = static_cast<long long>(n) * w0 * (c / 8) * ((h + rpt - 1) / rpt);
-  upsample_bwd_kernel<<<ew_grid(items), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, w0, dt, rpt);
+  if (dtype == 0)
+    upsample_bwd_kernel<__nv_bfloat16><<<ew_grid(items), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, w0, dt, rpt);
+  else
+    upsample_bwd_kernel<float><<<ew_grid(items), 256, 0, st>>>(static_cast<const float*>(dy), n, h, w, c, w0, dt, rpt);
   VG_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int vg_im2col(const void* src, int n, int h, int w, int ld, int c, int kh, int kw, int stride, int pad,
-                         void* col, int kpad, void* stream_) {
+                         void* col, int kpad, int dtype, void* stream_) {
   VG_CHECK(kh * kw * c <= kpad && kpad % 64 == 0, -1, "vg_im2col: kpad must be a multiple of 64 >= kh*kw*c");
   const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
-  im2col_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * (kpad / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(src), n, h, w, ld, c, kh, kw, stride, pad, oh, ow,
-      static_cast<__nv_bfloat16*>(col), kpad);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * oh * ow * (kpad / 8));
+  if (dtype == 0)
+    im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), n, h, w, ld, c, kh, kw, stride,
+                                                     pad, oh, ow, static_cast<__nv_bfloat16*>(col), kpad);
+  else
+    im2col_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), n, h, w, ld, c, kh, kw, stride, pad, oh, ow,
+                                             static_cast<float*>(col), kpad);
   VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_col2im(const void* dcol, int kpad, int n, int h, int w, int c, int kh, int kw, int stride, int pad,
-                         float* dsrc_nchw, void* stream_) {
+                         float* dsrc_nchw, int dtype, void* stream_) {
   const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
-  col2im_kernel<<<ew_grid(static_cast<long long>(n) * c * h * w), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(dcol), kpad, n, h, w, c, kh, kw, stride, pad, oh, ow, dsrc_nchw);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * c * h * w);
+  if (dtype == 0)
+    col2im_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dcol), kpad, n, h, w, c, kh, kw,
+                                                     stride, pad, oh, ow, dsrc_nchw);
+  else
+    col2im_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dcol), kpad, n, h, w, c, kh, kw, stride, pad, oh, ow,
+                                             dsrc_nchw);
   VG_LAUNCH_OK();
   return 0;
 }
@@ -484,28 +564,41 @@ static int smalln_lanes(int kvecs) {
   return g;
 }
 extern "C" int vg_conv_smalln_fwd(const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, const float* wt,
-                                  const float* bias, int cout, int kh, int kw, int pad, float* out, void* stream_) {
+                                  const float* bias, int cout, int kh, int kw, int pad, float* out, int dtype,
+                                  void* stream_) {
   VG_CHECK(cout >= 1 && cout <= kMaxSmallN && cin % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1,
            "vg_conv_smalln_fwd: cout must be 1..4 and channels multiples of 8");
   const int oh = h + 2 * pad - kh + 1, ow = w + 2 * pad - kw + 1;
   const int G = smalln_lanes(kh * kw * (cin / 8));
-  smalln_fwd_kernel<<<ew_grid(static_cast<long long>(n) * oh * ow * G), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w, cin, wt, bias, cout, kh, kw, pad, oh, ow, out, G);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * oh * ow * G);
+  if (dtype == 0)
+    smalln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w, cin, wt,
+                                                         bias, cout, kh, kw, pad, oh, ow, out, G);
+  else
+    smalln_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), x_ld, x_coff, n, h, w, cin, wt, bias, cout,
+                                                 kh, kw, pad, oh, ow, out, G);
   VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int cin, const float* wt, int cout, int kh,
-                                    int kw, int pad, void* dx, int dx_ld, int dx_coff, void* stream_) {
+                                    int kw, int pad, void* dx, int dx_ld, int dx_coff, int dtype, void* stream_) {
   VG_CHECK(cout >= 1 && cout <= kMaxSmallN && cin % 8 == 0 && dx_ld % 8 == 0 && dx_coff % 8 == 0, -1,
            "vg_conv_smalln_dgrad: cout must be 1..4 and channels multiples of 8");
   const int oh = h + 2 * pad - kh + 1, ow = w + 2 * pad - kw + 1;
-  smalln_dgrad_kernel<<<ew_grid(static_cast<long long>(n) * h * w * (cin / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      dy, n, oh, ow, cout, wt, kh, kw, pad, h, w, cin, static_cast<__nv_bfloat16*>(dx), dx_ld, dx_coff);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * h * w * (cin / 8));
+  if (dtype == 0)
+    smalln_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dy, n, oh, ow, cout, wt, kh, kw, pad, h, w, cin,
+                                                           static_cast<__nv_bfloat16*>(dx), dx_ld, dx_coff);
+  else
+    smalln_dgrad_kernel<float><<<grid, 256, 0, st>>>(dy, n, oh, ow, cout, wt, kh, kw, pad, h, w, cin, static_cast<float*>(dx),
+                                                   dx_ld, dx_coff);
   VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, int x_coff, int n, int h, int w, int cin,
-                                    int cout, int kh, int kw, int pad, float* dw, float* dbias, void* stream_) {
+                                    int cout, int kh, int kw, int pad, float* dw, float* dbias, int dtype, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   VG_CHECK(cout >= 1 && cout <= kMaxSmallN && cin % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1,
            "vg_conv_smalln_wgrad: cout must be 1..4 and channels multiples of 8");
@@ -516,23 +609,50 @@ extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, in
   const long long pixels = static_cast<long long>(n) * oh * ow;
   int gx = static_cast<int>(std::min<long long>((pixels + ppar * 16 - 1) / (ppar * 16), std::max(1, num_sms() * 4 / (kh * kw))));
   if (gx < 1) gx = 1;
-  smalln_wgrad_kernel<<<dim3(gx, kh * kw), 256, 0, st>>>(dy, static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, n, h, w,
-                                                         cin, cout, kh, kw, pad, oh, ow, dw, dbias);
+  if (dtype == 0)
+    smalln_wgrad_kernel<__nv_bfloat16><<<dim3(gx, kh * kw), 256, 0, st>>>(dy, static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+                                                                        n, h, w, cin, cout, kh, kw, pad, oh, ow, dw, dbias);
+  else
+    smalln_wgrad_kernel<float><<<dim3(gx, kh * kw), 256, 0, st>>>(dy, static_cast<const float*>(x), x_ld, x_coff, n, h, w, cin,
+                                                                cout, kh, kw, pad, oh, ow, dw, dbias);
   VG_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, void* dx, int dx_ld, long long rows, int c,
-                          int act, void* stream_) {
+                          int act, int dtype, void* stream_) {
   VG_CHECK(c % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, -1, "vg_act_bwd: channels must be multiples of 8");
-  act_bwd_kernel<<<ew_grid(rows * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(y), y_ld, static_cast<const __nv_bfloat16*>(dy), dy_ld,
-      static_cast<__nv_bfloat16*>(dx), dx_ld, rows, c, act);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (dtype == 0)
+    act_bwd_kernel<__nv_bfloat16><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(y), y_ld, static_cast<const __nv_bfloat16*>(dy), dy_ld,
+        static_cast<__nv_bfloat16*>(dx), dx_ld, rows, c, act);
+  else
+    act_bwd_kernel<float><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(static_cast<const float*>(y), y_ld,
+                                                                 static_cast<const float*>(dy), dy_ld,
+                                                                 static_cast<float*>(dx), dx_ld, rows, c, act);
   VG_LAUNCH_OK();
   return 0;
 }
 extern "C" int vg_colsum_f32(const float* in, long long rows, int cols, int ld, float* out, int accumulate, void* stream_) {
   colsum_f32_kernel<<<cdiv(cols, 128), 128, 0, static_cast<cudaStream_t>(stream_)>>>(in, rows, cols, ld, out, accumulate);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_split3(const float* in, int ld_in, long long rows, int c, int cp, void* out, void* stream_) {
+  VG_CHECK(cp >= c && cp % 64 == 0, -1, "vg_split3: cp must be a multiple of 64 >= c");
+  split3_kernel<<<ew_grid(rows * cp), 256, 0, static_cast<cudaStream_t>(stream_)>>>(in, ld_in, rows, c, cp,
+                                                                                  static_cast<__nv_bfloat16*>(out));
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_act_fwd(void* y, int y_ld, long long rows, int c, int act, int dtype, void* stream_) {
+  VG_CHECK(c % 8 == 0 && y_ld % 8 == 0 && (act == 1 || act == 2), -1, "vg_act_fwd: channels must be multiples of 8, act 1|2");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (dtype == 0) act_fwd_kernel<__nv_bfloat16><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(static_cast<__nv_bfloat16*>(y), y_ld, rows, c, act);
+  else act_fwd_kernel<float><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(static_cast<float*>(y), y_ld, rows, c, act);
   VG_LAUNCH_OK();
   return 0;
 }

@@ -42,17 +42,6 @@ VG_DEVICE float act_grad(float pre, int act) {
   if (act == 2) return pre > 0.f ? 1.f : 0.2f;
   return 1.f;
 }
-VG_DEVICE float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
-VG_DEVICE bf16x8 ldv(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
-VG_DEVICE void unpack8(const bf16x8& v, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = unpack_bf16x2(v.u[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-
 // block-level reduction of 16 per-thread partials over the row lanes, then one atomic per channel
 VG_DEVICE void reduce_rows_atomic(float (&red)[kNT][17], const float (&s)[8], const float (&q)[8], const RowMap& m,
                                   int rl, int cvi, int cvec, float* dst0, float* dst1) {
@@ -77,7 +66,8 @@ VG_DEVICE void reduce_rows_atomic(float (&red)[kNT][17], const float (&s)[8], co
 // ---------------------------------------------------------------------------------------------
 // statistics: sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 over the rows of group g
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT) stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, int coff, int c,
+template <typename T>
+__global__ void __launch_bounds__(kNT) stats_kernel(const T* __restrict__ x, int ld, int coff, int c,
                                                     long long rows_per_group, float* __restrict__ sums) {
   const RowMap m = row_map(c);
   const int g = blockIdx.y;
@@ -90,24 +80,24 @@ __global__ void __launch_bounds__(kNT) stats_kernel(const __nv_bfloat16* __restr
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     if (rl < m.rows_par && cvec < m.cv) {
-      const __nv_bfloat16* base = x + static_cast<long long>(g) * rows_per_group * ld + coff + cvec * 8;
+      const T* base = x + static_cast<long long>(g) * rows_per_group * ld + coff + cvec * 8;
       const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
       long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
       for (; r + 3 * stride < rows_per_group; r += 4 * stride) {
-        bf16x8 v[4];
+        Raw8<T> v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldv(base + (r + u * stride) * ld);
+        for (int u = 0; u < 4; ++u) v[u] = Raw8<T>::load(base + (r + u * stride) * ld);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
-          unpack8(v[u], f);
+          v[u].unpack(f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
         }
       }
       for (; r < rows_per_group; r += stride) {
         float f[8];
-        unpack8(ldv(base + r * ld), f);
+        Raw8<T>::load(base + r * ld).unpack(f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
       }
@@ -142,18 +132,19 @@ __global__ void finalize_kernel(const float* __restrict__ sums, int groups, int 
 // apply: y = act(gamma * (x - mean) * rstd + beta), optional fused 2x2 max-pool output
 // blockIdx.y = sample when per_sample (so the constants are block-uniform per channel), else 0
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 struct ApplyParams {
-  const __nv_bfloat16* x; int x_ld, x_coff;
+  const T* x; int x_ld, x_coff;
   int n, h, w, c;
   const float* mean_rstd; int per_sample;
   const float* gamma; const float* beta;
   int act;
-  __nv_bfloat16* y; int y_ld, y_coff;
-  __nv_bfloat16* pool; int p_ld, p_coff;
+  T* y; int y_ld, y_coff;
+  T* pool; int p_ld, p_coff;
 };
 
-template <bool kPool>
-__global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
+template <typename T, bool kPool>
+__global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams<T> p) {
   const RowMap m = row_map(p.c);
   const int tid = threadIdx.x;
   const int rl = tid / m.cvl, cvi = tid % m.cvl;
@@ -175,19 +166,19 @@ __global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
       sc[i] = g * rstd;
       sh[i] = b - mr[ch + i] * g * rstd;
     }
-    const __nv_bfloat16* xb = p.x + p.x_coff + ch;
-    __nv_bfloat16* yb = p.y + p.y_coff + ch;
+    const T* xb = p.x + p.x_coff + ch;
+    T* yb = p.y + p.y_coff + ch;
     const long long pix0 = static_cast<long long>(p.per_sample ? grp : 0) * p.h * p.w;
     if (!kPool) {
       long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
       for (; r + 3 * stride < cells; r += 4 * stride) {
-        bf16x8 v[4];
+        Raw8<T> v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldv(xb + (pix0 + r + u * stride) * p.x_ld);
+        for (int u = 0; u < 4; ++u) v[u] = Raw8<T>::load(xb + (pix0 + r + u * stride) * p.x_ld);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
-          unpack8(v[u], f);
+          v[u].unpack(f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
           store8(yb + (pix0 + r + u * stride) * p.y_ld, f);
@@ -195,7 +186,7 @@ __global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
       }
       for (; r < cells; r += stride) {
         float f[8];
-        unpack8(ldv(xb + (pix0 + r) * p.x_ld), f);
+        Raw8<T>::load(xb + (pix0 + r) * p.x_ld).unpack(f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
         store8(yb + (pix0 + r) * p.y_ld, f);
@@ -206,22 +197,22 @@ __global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
         const int pi = static_cast<int>((cell / pw) % ph);
         const long long nn = (p.per_sample ? grp : cell / (static_cast<long long>(pw) * ph));
         const long long row0 = (nn * p.h + 2 * pi) * p.w + 2 * pj;
-        bf16x8 v[4];
-        v[0] = ldv(xb + row0 * p.x_ld);
-        v[1] = ldv(xb + (row0 + 1) * p.x_ld);
-        v[2] = ldv(xb + (row0 + p.w) * p.x_ld);
-        v[3] = ldv(xb + (row0 + p.w + 1) * p.x_ld);
+        Raw8<T> v[4];
+        v[0] = Raw8<T>::load(xb + row0 * p.x_ld);
+        v[1] = Raw8<T>::load(xb + (row0 + 1) * p.x_ld);
+        v[2] = Raw8<T>::load(xb + (row0 + p.w) * p.x_ld);
+        v[3] = Raw8<T>::load(xb + (row0 + p.w + 1) * p.x_ld);
         float mx[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
-          unpack8(v[u], f);
+          v[u].unpack(f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             f[i] = act_fwd(fmaf(f[i], sc[i], sh[i]), p.act);
-            mx[i] = fmaxf(mx[i], bf16_round(f[i]));
+            mx[i] = fmaxf(mx[i], as_stored<T>(f[i]));
           }
           store8(yb + (row0 + (u >> 1) * p.w + (u & 1)) * p.y_ld, f);
         }
@@ -236,20 +227,21 @@ __global__ void __launch_bounds__(kNT) apply_kernel(const ApplyParams p) {
 // backward.  g = (dy + routed pooled grad) * act'(pre);  pass 1 (kApply = false) reduces sum g and sum g*xhat,
 // pass 2 (kApply = true) writes dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)).
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 struct BwdParams {
-  const __nv_bfloat16* x; int x_ld, x_coff;           // raw (pre-normalisation) conv output
-  const __nv_bfloat16* dy; int dy_ld, dy_coff;        // grad wrt full-resolution activation (nullable)
-  const __nv_bfloat16* dpool; int dp_ld, dp_coff;     // grad wrt pooled activation (nullable)
+  const T* x; int x_ld, x_coff;           // raw (pre-normalisation) conv output
+  const T* dy; int dy_ld, dy_coff;        // grad wrt full-resolution activation (nullable)
+  const T* dpool; int dp_ld, dp_coff;     // grad wrt pooled activation (nullable)
   int n, h, w, c;
   const float* mean_rstd; int per_sample;
   const float* gamma; const float* beta;
   int act;
   float* sums;                                        // [groups][2][c]: sum g, sum g*xhat
-  __nv_bfloat16* dx; int dx_ld, dx_coff;
+  T* dx; int dx_ld, dx_coff;
 };
 
-template <bool kApply, bool kPool>
-__global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams p) {
+template <typename T, bool kApply, bool kPool>
+__global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams<T> p) {
   const RowMap m = row_map(p.c);
   const int tid = threadIdx.x;
   const int rl = tid / m.cvl, cvi = tid % m.cvl;
@@ -284,14 +276,14 @@ __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams p) {
           k2[i] = sm[p.c + ch + i] * inv_rows;
         }
       }
-      const __nv_bfloat16* xb = p.x + p.x_coff + ch;
-      const __nv_bfloat16* gb = p.dy ? p.dy + p.dy_coff + ch : nullptr;
-      __nv_bfloat16* ob = kApply ? p.dx + p.dx_coff + ch : nullptr;
+      const T* xb = p.x + p.x_coff + ch;
+      const T* gb = p.dy ? p.dy + p.dy_coff + ch : nullptr;
+      T* ob = kApply ? p.dx + p.dx_coff + ch : nullptr;
 
       // one pixel: g = dyv * act'(pre); accumulate or emit dx
-      auto pixel = [&](const bf16x8& xv, const float (&dyv)[8], long long pix) {
+      auto pixel = [&](const Raw8<T>& xv, const float (&dyv)[8], long long pix) {
         float f[8], o[8];
-        unpack8(xv, f);
+        xv.unpack(f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xh = (f[i] - mean[i]) * rstd[i];
@@ -306,19 +298,19 @@ __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams p) {
         long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
         for (; r + stride < cells; r += 2 * stride) {
           const long long pa = pix0 + r, pb = pix0 + r + stride;
-          const bf16x8 xa = ldv(xb + pa * p.x_ld), xc = ldv(xb + pb * p.x_ld);
-          const bf16x8 da = ldv(gb + pa * p.dy_ld), dc = ldv(gb + pb * p.dy_ld);
+          const Raw8<T> xa = Raw8<T>::load(xb + pa * p.x_ld), xc = Raw8<T>::load(xb + pb * p.x_ld);
+          const Raw8<T> da = Raw8<T>::load(gb + pa * p.dy_ld), dc = Raw8<T>::load(gb + pb * p.dy_ld);
           float d[8];
-          unpack8(da, d);
+          da.unpack(d);
           pixel(xa, d, pa);
-          unpack8(dc, d);
+          dc.unpack(d);
           pixel(xc, d, pb);
         }
         for (; r < cells; r += stride) {
           const long long pa = pix0 + r;
           float d[8];
-          unpack8(ldv(gb + pa * p.dy_ld), d);
-          pixel(ldv(xb + pa * p.x_ld), d, pa);
+          Raw8<T>::load(gb + pa * p.dy_ld).unpack(d);
+          pixel(Raw8<T>::load(xb + pa * p.x_ld), d, pa);
         }
       } else {
         for (long long cell = static_cast<long long>(blockIdx.x) * m.rows_par + rl; cell < cells; cell += stride) {
@@ -327,16 +319,16 @@ __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams p) {
           const long long nn = (p.per_sample ? grp : cell / (static_cast<long long>(pw) * ph));
           const long long row0 = (nn * p.h + 2 * pi) * p.w + 2 * pj;
           long long pix[4] = {row0, row0 + 1, row0 + p.w, row0 + p.w + 1};
-          bf16x8 xv[4], dv[4];
+          Raw8<T> xv[4], dv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) xv[u] = ldv(xb + pix[u] * p.x_ld);
+          for (int u = 0; u < 4; ++u) xv[u] = Raw8<T>::load(xb + pix[u] * p.x_ld);
           if (gb != nullptr) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dv[u] = ldv(gb + pix[u] * p.dy_ld);
+            for (int u = 0; u < 4; ++u) dv[u] = Raw8<T>::load(gb + pix[u] * p.dy_ld);
           }
           const long long ppix = (nn * ph + pi) * pw + pj;
           float dp[8];
-          unpack8(ldv(p.dpool + ppix * p.dp_ld + p.dp_coff + ch), dp);
+          Raw8<T>::load(p.dpool + ppix * p.dp_ld + p.dp_coff + ch).unpack(dp);
           // first maximum of the (bf16-rounded) activations of the window, per channel
           int best[8];
           float bv[8];
@@ -345,17 +337,17 @@ __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams p) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float f[8];
-            unpack8(xv[u], f);
+            xv[u].unpack(f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float yv = bf16_round(act_fwd(fmaf(f[i], sc[i], sh[i]), p.act));
+              const float yv = as_stored<T>(act_fwd(fmaf(f[i], sc[i], sh[i]), p.act));
               if (yv > bv[i]) { bv[i] = yv; best[i] = u; }
             }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float d[8];
-            if (gb != nullptr) unpack8(dv[u], d);
+            if (gb != nullptr) dv[u].unpack(d);
             else {
 #pragma unroll
               for (int i = 0; i < 8; ++i) d[i] = 0.f;
@@ -400,17 +392,24 @@ static int row_grid(long long rows, int rows_par, int groups, int per_sm, int ro
 
 using namespace vg;
 
-extern "C" int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c,
-                             float* sums, void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_norm_stats: channels must be multiples of 8");
-  VG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * c, st));
+template <typename T>
+static int norm_stats_impl(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c, float* sums,
+                           cudaStream_t st) {
   const RowMap m = row_map(c);
   const int gx = row_grid(rows_per_group, m.rows_par, groups, 4, 8);
-  stats_kernel<<<dim3(gx, groups), kNT, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, c, rows_per_group,
-                                                 sums);
+  stats_kernel<T><<<dim3(gx, groups), kNT, 0, st>>>(static_cast<const T*>(x), x_ld, x_coff, c, rows_per_group, sums);
   VG_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c,
+                             float* sums, int dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_norm_stats: channels must be multiples of 8");
+  VG_CHECK(dtype == 0 || dtype == 1, -1, "vg_norm_stats: dtype must be 0 (bf16) or 1 (fp32)");
+  VG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * c, st));
+  return dtype == 0 ? norm_stats_impl<__nv_bfloat16>(x, x_ld, x_coff, groups, rows_per_group, c, sums, st)
+                    : norm_stats_impl<float>(x, x_ld, x_coff, groups, rows_per_group, c, sums, st);
 }
 
 extern "C" int vg_norm_finalize(const float* sums, int groups, long long rows_per_group, int c, float eps,
@@ -423,45 +422,47 @@ extern "C" int vg_norm_finalize(const float* sums, int groups, long long rows_pe
   return 0;
 }
 
+template <typename T>
+static int norm_apply_impl(const VgNormApply* d, cudaStream_t st) {
+  ApplyParams<T> p;
+  p.x = static_cast<const T*>(d->x); p.x_ld = d->x_ld; p.x_coff = d->x_coff;
+  p.n = d->n; p.h = d->h; p.w = d->w; p.c = d->c;
+  p.mean_rstd = d->mean_rstd; p.per_sample = d->per_sample; p.gamma = d->gamma; p.beta = d->beta; p.act = d->act;
+  p.y = static_cast<T*>(d->y); p.y_ld = d->y_ld; p.y_coff = d->y_coff;
+  p.pool = static_cast<T*>(d->pool); p.p_ld = d->p_ld; p.p_coff = d->p_coff;
+  const int groups = d->per_sample ? d->n : 1;
+  const RowMap m = row_map(d->c);
+  const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (d->pool ? d->h / 2 : d->h) *
+                          (d->pool ? d->w / 2 : d->w);
+  if (d->pool) {
+    apply_kernel<T, true><<<dim3(row_grid(cells, m.rows_par, groups, 8, 2), groups), kNT, 0, st>>>(p);
+  } else {
+    apply_kernel<T, false><<<dim3(row_grid(cells, m.rows_par, groups, 8, 8), groups), kNT, 0, st>>>(p);
+  }
+  VG_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int vg_norm_apply(const VgNormApply* d, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   VG_CHECK(d->c % 8 == 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->y_ld % 8 == 0 && d->y_coff % 8 == 0, -1,
            "vg_norm_apply: channels / strides must be multiples of 8");
   VG_CHECK(d->pool == nullptr || (d->h % 2 == 0 && d->w % 2 == 0 && d->p_ld % 8 == 0 && d->p_coff % 8 == 0), -1,
            "vg_norm_apply: pooled output needs even H, W");
-  ApplyParams p;
-  p.x = static_cast<const __nv_bfloat16*>(d->x); p.x_ld = d->x_ld; p.x_coff = d->x_coff;
-  p.n = d->n; p.h = d->h; p.w = d->w; p.c = d->c;
-  p.mean_rstd = d->mean_rstd; p.per_sample = d->per_sample; p.gamma = d->gamma; p.beta = d->beta; p.act = d->act;
-  p.y = static_cast<__nv_bfloat16*>(d->y); p.y_ld = d->y_ld; p.y_coff = d->y_coff;
-  p.pool = static_cast<__nv_bfloat16*>(d->pool); p.p_ld = d->p_ld; p.p_coff = d->p_coff;
-  const int groups = d->per_sample ? d->n : 1;
-  const RowMap m = row_map(d->c);
-  const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (d->pool ? d->h / 2 : d->h) *
-                          (d->pool ? d->w / 2 : d->w);
-  if (d->pool) {
-    apply_kernel<true><<<dim3(row_grid(cells, m.rows_par, groups, 8, 2), groups), kNT, 0, st>>>(p);
-  } else {
-    apply_kernel<false><<<dim3(row_grid(cells, m.rows_par, groups, 8, 8), groups), kNT, 0, st>>>(p);
-  }
-  VG_LAUNCH_OK();
-  return 0;
+  VG_CHECK(d->dtype == 0 || d->dtype == 1, -1, "vg_norm_apply: dtype must be 0 (bf16) or 1 (fp32)");
+  return d->dtype == 0 ? norm_apply_impl<__nv_bfloat16>(d, st) : norm_apply_impl<float>(d, st);
 }
 
-extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  VG_CHECK(d->c % 8 == 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->dx_ld % 8 == 0 && d->dx_coff % 8 == 0, -1,
-           "vg_norm_backward: channels / strides must be multiples of 8");
-  VG_CHECK(d->dy != nullptr || d->dpool != nullptr, -1, "vg_norm_backward: no incoming gradient");
-  VG_CHECK(d->dpool == nullptr || (d->h % 2 == 0 && d->w % 2 == 0), -1, "vg_norm_backward: pooled grad needs even H, W");
-  BwdParams p;
-  p.x = static_cast<const __nv_bfloat16*>(d->x); p.x_ld = d->x_ld; p.x_coff = d->x_coff;
-  p.dy = static_cast<const __nv_bfloat16*>(d->dy); p.dy_ld = d->dy_ld; p.dy_coff = d->dy_coff;
-  p.dpool = static_cast<const __nv_bfloat16*>(d->dpool); p.dp_ld = d->dp_ld; p.dp_coff = d->dp_coff;
+template <typename T>
+static int norm_backward_impl(const VgNormBackward* d, cudaStream_t st) {
+  BwdParams<T> p;
+  p.x = static_cast<const T*>(d->x); p.x_ld = d->x_ld; p.x_coff = d->x_coff;
+  p.dy = static_cast<const T*>(d->dy); p.dy_ld = d->dy_ld; p.dy_coff = d->dy_coff;
+  p.dpool = static_cast<const T*>(d->dpool); p.dp_ld = d->dp_ld; p.dp_coff = d->dp_coff;
   p.n = d->n; p.h = d->h; p.w = d->w; p.c = d->c;
   p.mean_rstd = d->mean_rstd; p.per_sample = d->per_sample; p.gamma = d->gamma; p.beta = d->beta; p.act = d->act;
   p.sums = d->sums;
-  p.dx = static_cast<__nv_bfloat16*>(d->dx); p.dx_ld = d->dx_ld; p.dx_coff = d->dx_coff;
+  p.dx = static_cast<T*>(d->dx); p.dx_ld = d->dx_ld; p.dx_coff = d->dx_coff;
   const int groups = d->per_sample ? d->n : 1;
   VG_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(float) * 2 * groups * d->c, st));
   const RowMap m = row_map(d->c);
@@ -471,13 +472,13 @@ extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
   const dim3 g_red(row_grid(cells, m.rows_par, groups, 4, pool ? 2 : 8), groups);
   const dim3 g_app(row_grid(cells, m.rows_par, groups, 8, pool ? 2 : 8), groups);
   if (pool) {
-    bwd_kernel<false, true><<<g_red, kNT, 0, st>>>(p);
+    bwd_kernel<T, false, true><<<g_red, kNT, 0, st>>>(p);
     VG_LAUNCH_OK();
-    bwd_kernel<true, true><<<g_app, kNT, 0, st>>>(p);
+    bwd_kernel<T, true, true><<<g_app, kNT, 0, st>>>(p);
   } else {
-    bwd_kernel<false, false><<<g_red, kNT, 0, st>>>(p);
+    bwd_kernel<T, false, false><<<g_red, kNT, 0, st>>>(p);
     VG_LAUNCH_OK();
-    bwd_kernel<true, false><<<g_app, kNT, 0, st>>>(p);
+    bwd_kernel<T, true, false><<<g_app, kNT, 0, st>>>(p);
   }
   VG_LAUNCH_OK();
   if (d->dgamma != nullptr || d->dbeta != nullptr) {
@@ -485,4 +486,14 @@ extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
     VG_LAUNCH_OK();
   }
   return 0;
+}
+
+extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(d->c % 8 == 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->dx_ld % 8 == 0 && d->dx_coff % 8 == 0, -1,
+           "vg_norm_backward: channels / strides must be multiples of 8");
+  VG_CHECK(d->dy != nullptr || d->dpool != nullptr, -1, "vg_norm_backward: no incoming gradient");
+  VG_CHECK(d->dpool == nullptr || (d->h % 2 == 0 && d->w % 2 == 0), -1, "vg_norm_backward: pooled grad needs even H, W");
+  VG_CHECK(d->dtype == 0 || d->dtype == 1, -1, "vg_norm_backward: dtype must be 0 (bf16) or 1 (fp32)");
+  return d->dtype == 0 ? norm_backward_impl<__nv_bfloat16>(d, st) : norm_backward_impl<float>(d, st);
 }

@@ -10,7 +10,7 @@ import torch
 from torch.autograd import Function
 
 from . import ops
-from .conv import ConvLinear, fprop, new_act, wgrad
+from .conv import PAIRS, ConvLinear, _hi_launch, _hi_wgrad_split, _operand, _vtaps, fprop, new_act, pad_channels, wgrad
 from .ops import BF16, F32, round_up
 
 _WEIGHT_EPOCH = 0
@@ -42,16 +42,17 @@ class WeightCache:
         self.key, self.store = None, {}
 
 
-def grad_in(t: Optional[torch.Tensor], like: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """Coerce an incoming autograd gradient to a valid NHWC bf16 view (copying only if it is not one already);
-    when the channel count is not a multiple of 64 the copy is padded so the tensor pipe can read it."""
+def grad_in(t: Optional[torch.Tensor], dtype=None) -> Optional[torch.Tensor]:
+    """Coerce an incoming autograd gradient to a valid NHWC view of the activation dtype (copying only if it is not
+    one already); when the channel count is not a multiple of 64 the copy is padded so the tensor pipe can read it."""
     if t is None:
         return None
+    dtype = dtype or ops.act_dtype()
     c = t.shape[3]
     need_pad = c % 64 != 0 and t.stride(2) < round_up(c, 64)
-    if t.dtype == BF16 and ops.nhwc_ok(t) and not need_pad:
+    if t.dtype == dtype and ops.nhwc_ok(t) and not need_pad:
         return t
-    out = new_act(t.shape[0], t.shape[1], t.shape[2], c, t.device)
+    out = new_act(t.shape[0], t.shape[1], t.shape[2], c, t.device, dtype)
     ops.strided_copy(t, out)
     return out
 
@@ -77,7 +78,9 @@ class Conv2dFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_kind: int, sn):
         scale = sn.sigma if sn is not None else None
-        wf = cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach(), scale)) if sn is None else op.prep_fwd(weight.detach(), scale)
+        hi = x.dtype == F32
+        wf = (cache.get("fwd_hi" if hi else "fwd", weight, lambda: op.prep_fwd(weight.detach(), scale, hi)) if sn is None
+              else op.prep_fwd(weight.detach(), scale, hi))
         y = op.forward(x, wf, bias.detach() if bias is not None else None, act, out, out_kind)
         ctx.op, ctx.cache, ctx.act, ctx.sn, ctx.has_bias = op, cache, act, sn, bias is not None
         ctx.in_hw = (x.shape[1], x.shape[2])
@@ -88,17 +91,18 @@ class Conv2dFn(Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         op: ConvLinear = ctx.op
-        dy = grad_in(dy)
+        hi = x.dtype == F32
+        dy = grad_in(dy, x.dtype)
         if ctx.act:
-            g = new_act(*dy.shape, dy.device)
+            g = new_act(*dy.shape, dy.device, dy.dtype)
             ops.act_bwd(y, dy, g, ctx.act)
             dy = g
         dx = dw = db = None
         sn = ctx.sn
         scale = sn.sigma if sn is not None else None
         if ctx.needs_input_grad[0]:
-            wb = (ctx.cache.get("bwd", weight, lambda: op.prep_bwd(weight.detach(), scale)) if sn is None
-                  else op.prep_bwd(weight.detach(), scale))
+            wb = (ctx.cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), scale, hi))
+                  if sn is None else op.prep_bwd(weight.detach(), scale, hi))
             dx = op.backward_data(dy, wb, ctx.in_hw)
         if ctx.needs_input_grad[1]:
             gview = op.backward_weight(dy, x)
@@ -116,7 +120,8 @@ class ConvTranspose2dFn(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_hw):
-        wb = cache.get("bwd", weight, lambda: op.prep_bwd(weight.detach()))
+        hi = x.dtype == F32
+        wb = cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), None, hi))
         y = op.backward_data(x, wb, out_hw, bias.detach() if bias is not None else None, act, out)
         ctx.op, ctx.cache, ctx.act, ctx.has_bias = op, cache, act, bias is not None
         ctx.save_for_backward(x, weight, y if act else None)
@@ -126,14 +131,15 @@ class ConvTranspose2dFn(Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         op: ConvLinear = ctx.op
-        dy = grad_in(dy)
+        hi = x.dtype == F32
+        dy = grad_in(dy, x.dtype)
         if ctx.act:
-            g = new_act(*dy.shape, dy.device)
+            g = new_act(*dy.shape, dy.device, dy.dtype)
             ops.act_bwd(y, dy, g, ctx.act)
             dy = g
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wf = ctx.cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach()))
+            wf = ctx.cache.get("fwd_hi" if hi else "fwd", weight, lambda: op.prep_fwd(weight.detach(), None, hi))
             dx = op.forward(dy, wf)
         if ctx.needs_input_grad[1]:
             dw = _write_param_grad(op.backward_weight(x, dy))     # operands swapped: [cout(op)=C_in][cin(op)=C_out]
@@ -150,13 +156,16 @@ class HeadsFn(Function):
     @staticmethod
     def forward(ctx, feat, w_mu, w_lv, op: ConvLinear, cache_f: WeightCache, cache_b: WeightCache):
         z, c, kh, kw = w_mu.shape
+        hi = feat.dtype == F32
 
         def build():
-            wf = torch.empty((2 * z, kh, kw, c), dtype=BF16, device=feat.device)
-            ops.strided_copy(w_mu.detach().permute(0, 2, 3, 1), wf[:z])
-            ops.strided_copy(w_lv.detach().permute(0, 2, 3, 1), wf[z:])
-            return wf.view(2 * z, kh * kw * c)
-        wf = cache_f.get("fwd", (w_mu, w_lv), build)
+            tmp = torch.empty((2 * z, kh, kw, c), dtype=F32, device=feat.device)
+            ops.strided_copy(w_mu.detach().permute(0, 2, 3, 1), tmp[:z])
+            ops.strided_copy(w_lv.detach().permute(0, 2, 3, 1), tmp[z:])
+            if op.flat:
+                return _operand(tmp.view(2 * z, 1, kh * kw * c), kh * kw * c, hi)
+            return _operand(tmp.view(2 * z, kh * kw, c), op.cin_p, hi)
+        wf = cache_f.get("fwd_hi" if hi else "fwd", (w_mu, w_lv), build)
         if not feat.is_contiguous():
             feat = ops.dense_nhwc(feat)
         y = op.forward(feat, wf, None, 0, None, 2)
@@ -169,15 +178,16 @@ class HeadsFn(Function):
         feat, w_mu, w_lv = ctx.saved_tensors
         op: ConvLinear = ctx.op
         z, c, kh, kw = w_mu.shape
-        dy = grad_in(dy)
+        hi = feat.dtype == F32
+        dy = grad_in(dy, feat.dtype)
         dx = dmu = dlv = None
         if ctx.needs_input_grad[0]:
             def build():
-                wd = (torch.zeros if op.cout_p != 2 * z else torch.empty)((kh, kw, c, op.cout_p), dtype=BF16, device=dy.device)
-                ops.strided_copy(w_mu.detach().permute(2, 3, 1, 0), wd[..., :z])
-                ops.strided_copy(w_lv.detach().permute(2, 3, 1, 0), wd[..., z:2 * z])
-                return {"shuffle": wd.view(kh * kw * c, op.cout_p)}
-            wb = ctx.cache_b.get("bwd", (w_mu, w_lv), build)
+                tmp = torch.empty((kh, kw, c, 2 * z), dtype=F32, device=dy.device)
+                ops.strided_copy(w_mu.detach().permute(2, 3, 1, 0), tmp[..., :z])
+                ops.strided_copy(w_lv.detach().permute(2, 3, 1, 0), tmp[..., z:])
+                return {"shuffle": _operand(tmp.view(kh * kw * c, 1, 2 * z), op.cout_p, hi)}
+            wb = ctx.cache_b.get("bwd_hi" if hi else "bwd", (w_mu, w_lv), build)
             dx = op.backward_data(dy, wb, (feat.shape[1], feat.shape[2]))
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             g = op.backward_weight(dy, feat)                 # view [2z, c, kh, kw]
@@ -205,7 +215,7 @@ class CopyIntoFn(Function):
 class ImageConvFn(Function):
     """Conv2d whose input is a 3/4-channel NCHW fp32 image (or a channel-concatenation of several): the
     encoder's first conv on cat(image, mask) (vae-gan-v2.py:318-319) and D's first conv (vae-gan.py:153).
-    im2col into a [pixels][64] bf16 matrix, then a plain tensor-core GEMM with bias/activation fused."""
+    im2col into a [pixels][64] matrix, then a plain tensor-core GEMM with bias/activation fused."""
 
     @staticmethod
     def forward(ctx, weight, bias, geom, cache: WeightCache, act: int, sn, *images):
@@ -213,26 +223,32 @@ class ImageConvFn(Function):
         n, _, h, w = images[0].shape
         cin = sum(t.shape[1] for t in images)
         cout = weight.shape[0]
-        kpad = round_up(kh * kw * cin, 64)
-        src = torch.empty((n, h, w, 8), dtype=BF16, device=weight.device)
+        k = kh * kw * cin
+        kpad = round_up(k, 64)
+        dt = ops.act_dtype()
+        hi = dt == F32
+        src = torch.empty((n, h, w, 8), dtype=dt, device=weight.device)
         c0 = 0
         for t in images:
             ops.strided_copy(t.detach().permute(0, 2, 3, 1), src[..., c0:c0 + t.shape[1]])
             c0 += t.shape[1]
         oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
-        col = torch.empty((n, oh, ow, kpad), dtype=BF16, device=weight.device)
+        col = torch.empty((n, oh, ow, kpad), dtype=dt, device=weight.device)
         ops.im2col(src, cin, kh, kw, stride, pad, col)
         scale = sn.sigma if sn is not None else None
 
         def build():
-            wf = torch.zeros((cout, kpad), dtype=BF16, device=weight.device)
-            ops.strided_copy(weight.detach().permute(0, 2, 3, 1), wf[:, :kh * kw * cin].view(cout, kh, kw, cin), scale,
-                             scale_inverse=scale is not None)
-            return wf
-        wf = cache.get("fwd", weight, build) if sn is None else build()
-        y = new_act(n, oh, ow, cout, weight.device)
-        fprop(col, [(0, 0, 0, 0)], 1, kpad, wf, cout, (n, oh, ow), y, bias=bias.detach() if bias is not None else None,
-              act=act)
+            tmp = torch.empty((cout, kh, kw, cin), dtype=F32, device=weight.device)
+            ops.strided_copy(weight.detach().permute(0, 2, 3, 1), tmp, scale, scale_inverse=scale is not None)
+            return _operand(tmp.view(cout, 1, k), kpad, hi)
+        wf = cache.get("fwd_hi" if hi else "fwd", weight, build) if sn is None else build()
+        y = new_act(n, oh, ow, cout, weight.device, dt)
+        vt, wk = _vtaps([(0, 0, 0, 0)], kpad, kpad, hi)
+        b_ = bias.detach() if bias is not None else None
+        if hi:
+            _hi_launch(ops.split3(col), vt, 1, kpad, wf, cout, (n, oh, ow), y, wk, b_, act)
+        else:
+            fprop(col, vt, 1, kpad, wf, cout, (n, oh, ow), y, bias=b_, act=act)
         ctx.geom, ctx.act, ctx.sn, ctx.cin, ctx.kpad, ctx.has_bias = geom, act, sn, cin, kpad, bias is not None
         ctx.img_shapes = [tuple(t.shape) for t in images]
         ctx.save_for_backward(col, weight, y if act else None)
@@ -243,18 +259,25 @@ class ImageConvFn(Function):
         col, weight, y = ctx.saved_tensors
         kh, kw, stride, pad = ctx.geom
         cout, cin, kpad = weight.shape[0], ctx.cin, ctx.kpad
-        dy = grad_in(dy)
+        k = kh * kw * cin
+        hi = col.dtype == F32
+        dy = grad_in(dy, col.dtype)
         if ctx.act:
-            g = new_act(*dy.shape, dy.device)
+            g = new_act(*dy.shape, dy.device, dy.dtype)
             ops.act_bwd(y, dy, g, ctx.act)
             dy = g
         n, oh, ow, _ = dy.shape
+        cout_p = round_up(cout, 64)
         dw = db = None
         sn = ctx.sn
         if ctx.needs_input_grad[0]:
             dwm = torch.empty((cout, kpad), dtype=F32, device=dy.device)
-            wgrad(dy, cout, col, [(0, 0, 0, 0)], 1, kpad, (n, oh, ow), dwm)
-            dw = _write_param_grad(dwm[:, :kh * kw * cin].view(cout, kh, kw, cin).permute(0, 3, 1, 2))
+            if hi:
+                wgrad(ops.split3(dy), cout, ops.split3(col), [(0, 0, 0, 0)], 1, kpad, (n, oh, ow), dwm,
+                      pairs=[(pa * cout_p, pb * kpad) for (pa, pb) in PAIRS], ksplit=_hi_wgrad_split(n, oh, ow))
+            else:
+                wgrad(dy, cout, col, [(0, 0, 0, 0)], 1, kpad, (n, oh, ow), dwm)
+            dw = _write_param_grad(dwm[:, :k].view(cout, kh, kw, cin).permute(0, 3, 1, 2))
             if sn is not None:
                 dw = sn.backward(dw, weight.detach())
         if ctx.has_bias and ctx.needs_input_grad[1]:
@@ -262,13 +285,16 @@ class ImageConvFn(Function):
         dimgs = [None] * len(ctx.img_shapes)
         if any(ctx.needs_input_grad[6:]):
             scale = sn.sigma if sn is not None else None
-            cout_p = round_up(cout, 64)
-            wd = torch.zeros((kpad, cout_p), dtype=BF16, device=dy.device)      # [(r,q,ci)][co]
-            ops.strided_copy(weight.detach().permute(2, 3, 1, 0), wd[:kh * kw * cin, :cout].view(kh, kw, cin, cout), scale,
+            tmp = torch.zeros((kpad, cout), dtype=F32, device=dy.device)                 # rows (r, q, ci), zero padded
+            ops.strided_copy(weight.detach().permute(2, 3, 1, 0), tmp[:k].view(kh, kw, cin, cout), scale,
                              scale_inverse=scale is not None)
-            dcol = torch.empty((n, oh, ow, kpad), dtype=BF16, device=dy.device)
-            from .conv import pad_channels
-            fprop(pad_channels(dy, cout_p), [(0, 0, 0, 0)], 1, cout_p, wd, kpad, (n, oh, ow), dcol)
+            wd = _operand(tmp.view(kpad, 1, cout), cout_p, hi)
+            dcol = torch.empty((n, oh, ow, kpad), dtype=dy.dtype, device=dy.device)
+            vt, wk = _vtaps([(0, 0, 0, 0)], cout_p, cout_p, hi)
+            if hi:
+                _hi_launch(ops.split3(dy), vt, 1, cout_p, wd, kpad, (n, oh, ow), dcol, wk, None, 0)
+            else:
+                fprop(pad_channels(dy, cout_p), vt, 1, cout_p, wd, kpad, (n, oh, ow), dcol)
             n_, _, h, w = ctx.img_shapes[0]
             dsrc = torch.empty((n_, cin, h, w), dtype=F32, device=dy.device)
             ops.col2im(dcol, n_, h, w, cin, kh, kw, stride, pad, dsrc)
@@ -304,7 +330,7 @@ class SmallOutConvFn(Function):
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = new_act(x.shape[0], x.shape[1], x.shape[2], cin, x.device)
+            dx = new_act(x.shape[0], x.shape[1], x.shape[2], cin, x.device, x.dtype)
             ops.smalln_dgrad(dy, wt, kh, kw, ctx.pad, dx)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dwt = torch.empty_like(wt)
@@ -337,10 +363,10 @@ class NormActFn(Function):
                 rm, rv, nbt = bn_state["running_mean"], bn_state["running_var"], bn_state["num_batches_tracked"]
             mr = ops.norm_finalize(sums, rows, eps, 0.1, rm, rv, nbt)
             ctx.eval_mode = False
-        y = out if out is not None else new_act(n, h, w, c, x.device)
+        y = out if out is not None else new_act(n, h, w, c, x.device, x.dtype)
         pooled = None
         if pool:
-            pooled = pool_out if pool_out is not None else new_act(n, h // 2, w // 2, c, x.device)
+            pooled = pool_out if pool_out is not None else new_act(n, h // 2, w // 2, c, x.device, x.dtype)
         ops.norm_apply(x, mr, g, b, act, y, pooled)
         ctx.per_sample, ctx.act, ctx.pool = per_sample, act, pool
         ctx.save_for_backward(x, gamma, beta, mr)
@@ -352,9 +378,9 @@ class NormActFn(Function):
     def backward(ctx, dy, dpool):
         x, gamma, beta, mr = ctx.saved_tensors
         assert not ctx.eval_mode, "backward through eval-mode normalisation is not supported"
-        dy, dpool = grad_in(dy), grad_in(dpool)
+        dy, dpool = grad_in(dy, x.dtype), grad_in(dpool, x.dtype)
         n, h, w, c = x.shape
-        dx = new_act(n, h, w, c, x.device)
+        dx = new_act(n, h, w, c, x.device, x.dtype)
         dgamma = torch.empty(c, dtype=F32, device=x.device) if gamma is not None else None
         dbeta = torch.empty(c, dtype=F32, device=x.device) if beta is not None else None
         ops.norm_backward(x, dy, dpool, mr, ctx.per_sample, gamma, beta, ctx.act, dx, dgamma, dbeta)
@@ -370,7 +396,7 @@ class FiLMFn(Function):
     @staticmethod
     def forward(ctx, gb, x):
         n, h, w, c = x.shape
-        y = torch.empty((n, h, w, c), dtype=BF16, device=x.device)
+        y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
         ops.film_fwd(gb, x, y)
         ctx.save_for_backward(gb, x)
         return y
@@ -378,11 +404,11 @@ class FiLMFn(Function):
     @staticmethod
     def backward(ctx, dy):
         gb, x = ctx.saved_tensors
-        dy = grad_in(dy)
+        dy = grad_in(dy, x.dtype)
         if not dy.is_contiguous():
             dy = ops.dense_nhwc(dy)
         dgb = torch.empty_like(gb)
-        dx = torch.empty(x.shape, dtype=BF16, device=x.device)
+        dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         ops.film_bwd(gb, x, dy, dgb, dx)
         return dgb, dx
 
@@ -393,19 +419,21 @@ class UpsampleWFn(Function):
     @staticmethod
     def forward(ctx, t, h: int, w: int):
         n, _, w0, c = t.shape
-        y = torch.empty((n, h, w, c), dtype=BF16, device=t.device)
+        y = torch.empty((n, h, w, c), dtype=t.dtype, device=t.device)
         ops.upsample_w_fwd(t, y)
-        ctx.w0 = w0
+        ctx.w0, ctx.dt = w0, t.dtype
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        dy = grad_in(dy)
+        dy = grad_in(dy, ctx.dt)
         if not dy.is_contiguous():
             dy = ops.dense_nhwc(dy)
         n, h, w, c = dy.shape
         dt = torch.empty((n, 1, ctx.w0, c), dtype=F32, device=dy.device)
         ops.upsample_w_bwd(dy, dt)
+        if ctx.dt == F32:
+            return dt, None, None
         out = torch.empty((n, 1, ctx.w0, c), dtype=BF16, device=dy.device)
         ops.strided_copy(dt, out)
         return out, None, None
@@ -436,13 +464,14 @@ class CatSlicesFn(Function):
     @staticmethod
     def forward(ctx, a, b, buf):
         ca, cb = a.shape[3], b.shape[3]
-        assert a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf.data_ptr() + 2 * ca and buf.shape[3] == ca + cb
+        assert (a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf.data_ptr() + buf.element_size() * ca
+                and buf.shape[3] == ca + cb)
         ctx.ca = ca
         return buf.detach()
 
     @staticmethod
     def backward(ctx, d):
-        d = grad_in(d)
+        d = grad_in(d, d.dtype if d.dtype in (BF16, F32) else None)
         return d[..., :ctx.ca], d[..., ctx.ca:], None
 
 
@@ -454,7 +483,7 @@ class ZTextCatFn(Function):
     def forward(ctx, z, text):
         b, zc = z.shape
         _, _, w0, ct = text.shape
-        out = new_act(b, 1, w0, zc + ct, z.device)
+        out = new_act(b, 1, w0, zc + ct, z.device, text.dtype)
         ops.strided_copy(z.view(b, 1, 1, zc).expand(b, 1, w0, zc), out[..., :zc])
         ops.strided_copy(text, out[..., zc:])
         ctx.zc = zc
@@ -462,7 +491,7 @@ class ZTextCatFn(Function):
 
     @staticmethod
     def backward(ctx, d):
-        d = grad_in(d)
+        d = grad_in(d, d.dtype if d.dtype in (BF16, F32) else None)
         zc = ctx.zc
         dz = ops.norm_stats(d[..., :zc], per_sample=True)[:, 0, :].contiguous()   # sum over the w0 columns, fp32
         return dz, d[..., zc:]

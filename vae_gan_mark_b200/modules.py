@@ -68,7 +68,7 @@ def run_conv(conv: nn.Conv2d, x, act=0, out=None, in_hw=None, sn=None, weight=No
     w = conv.weight if weight is None else weight
     st = _state(conv, lambda: (ConvLinear(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.kernel_size[1],
                                           conv.stride[0], tuple(conv.padding), in_hw), L.WeightCache()))
-    return L.Conv2dFn.apply(x, w, conv.bias, st[0], st[1], act, out, 0, sn)
+    return L.Conv2dFn.apply(x, w, conv.bias, st[0], st[1], act, out, None, sn)
 
 
 def run_convT(ct: nn.ConvTranspose2d, x, out_hw, act=0, out=None):
@@ -446,7 +446,7 @@ class VAEDecoderWithSpatialFiLM(nn.Module):
         """Pre-allocated [B, h, w, up + skip] buffers; the encoder writes skip i into the upper channel slice."""
         bufs, h, w = [], self.initial_h * 2, self.initial_w * 2
         for skip in self.SKIP_CH:
-            bufs.append(torch.empty((batch, h, w, 2 * skip), dtype=BF16, device=device))
+            bufs.append(torch.empty((batch, h, w, 2 * skip), dtype=ops.act_dtype(), device=device))
             h, w = h * 2, w * 2
         return bufs   # stage 1 (deepest) first
 
@@ -463,7 +463,7 @@ class VAEDecoderWithSpatialFiLM(nn.Module):
             h, w = h * 2, w * 2
             buf, skip = bufs[i - 1], skips[4 - i]
             cu = skip.shape[3]
-            if skip.data_ptr() != buf.data_ptr() + 2 * cu:      # skip produced elsewhere: copy into the slice
+            if skip.data_ptr() != buf.data_ptr() + buf.element_size() * cu:      # skip produced elsewhere: copy into the slice
                 skip = L.CopyIntoFn.apply(skip, buf[..., cu:])
             up = run_convT(getattr(self, f"up_tconv{i}"), x, (h, w), out=buf[..., :cu])
             xc = L.CatSlicesFn.apply(up, skip, buf)
@@ -544,7 +544,7 @@ class VAEDecoderWithSkips(nn.Module):
     def concat_buffers(self, batch, device):
         bufs, h, w, c = [], self.initial_h, self.initial_w, 1024
         for skip in self.SKIP_CH:
-            bufs.append(torch.empty((batch, h, w, c + skip), dtype=BF16, device=device))
+            bufs.append(torch.empty((batch, h, w, c + skip), dtype=ops.act_dtype(), device=device))
             h, w, c = h * 2, w * 2, c // 2
         return bufs
 
@@ -558,7 +558,7 @@ class VAEDecoderWithSkips(nn.Module):
         x, _ = run_bn_relu(self.bottleneck_upsample[1], raw, out=bufs[0][..., :c])
         for i in (1, 2, 3, 4):
             buf, skip = bufs[i - 1], pooled[4 - i]
-            if skip.data_ptr() != buf.data_ptr() + 2 * c:
+            if skip.data_ptr() != buf.data_ptr() + buf.element_size() * c:
                 skip = L.CopyIntoFn.apply(skip, buf[..., c:])
             xc = L.CatSlicesFn.apply(x, skip, buf)
             blk = getattr(self, f"d_upconv{i}")

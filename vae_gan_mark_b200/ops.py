@@ -17,6 +17,29 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 _LL5 = C.c_longlong * 5
 
+# Activation storage of the package: "bf16" (default; bf16 storage + bf16 tensor-core inputs, fp32 accumulation) or
+# "fp32" (high-accuracy mode: fp32 storage, every tensor-core operand split into three bf16 planes so that products
+# carry ~24 mantissa bits; 6x the tensor-core work, used for the fp32-tolerance parity runs).
+_ACT_DTYPE = BF16
+
+
+def set_precision(mode: str) -> None:
+    global _ACT_DTYPE
+    assert mode in ("bf16", "fp32"), mode
+    _ACT_DTYPE = BF16 if mode == "bf16" else F32
+    # the stock recurrent text encoder runs through cuDNN, which defaults to TF32 tensor cores for fp32 RNNs/convs:
+    # in the high-accuracy mode that 1e-3 error would dominate everything downstream
+    torch.backends.cudnn.allow_tf32 = mode == "bf16"
+
+
+def act_dtype() -> torch.dtype:
+    return _ACT_DTYPE
+
+
+def dcode(t: torch.Tensor) -> int:
+    """dtype code of the C ABI for an activation tensor."""
+    return 0 if t.dtype == BF16 else 1
+
 
 def stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -37,16 +60,20 @@ def nhwc_ok(t: torch.Tensor) -> bool:
             (n == 1 or t.stride(0) == h * w * ld) and t.data_ptr() % 16 == 0 and ld % 8 == 0)
 
 
-def as_nhwc(t: torch.Tensor) -> torch.Tensor:
-    """Return ``t`` if it already is a valid (possibly channel-sliced) NHWC view, else a dense copy."""
-    if t.dtype == BF16 and nhwc_ok(t):
-        return t
-    return dense_nhwc(t)
-
-
-def dense_nhwc(t: torch.Tensor) -> torch.Tensor:
-    out = torch.empty(t.shape, dtype=BF16, device=t.device)
+def dense_nhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    out = torch.empty(t.shape, dtype=dtype or t.dtype, device=t.device)
     strided_copy(t, out)
+    return out
+
+
+def split3(t: torch.Tensor) -> torch.Tensor:
+    """fp32 NHWC view [N,H,W,C] -> bf16 [N,H,W,3*Cp] holding the hi | mid | lo planes (Cp = C rounded up to 64)."""
+    assert t.dtype == F32 and t.stride(3) == 1
+    n, h, w, c = t.shape
+    cp = round_up(c, 64)
+    assert (h == 1 or t.stride(1) == w * t.stride(2)) and (n == 1 or t.stride(0) == h * w * t.stride(2))
+    out = torch.empty((n, h, w, 3 * cp), dtype=BF16, device=t.device)
+    _lib.call("vg_split3", _p(t), t.stride(2), C.c_longlong(n * h * w), c, cp, _p(out), stream())
     return out
 
 
@@ -80,7 +107,7 @@ def norm_stats(x: torch.Tensor, per_sample: bool) -> torch.Tensor:
     groups = n if per_sample else 1
     rows = h * w if per_sample else n * h * w
     sums = torch.empty(groups, 2, c, dtype=F32, device=x.device)
-    _lib.call("vg_norm_stats", _p(x), ld_of(x), 0, groups, C.c_longlong(rows), c, _p(sums), stream())
+    _lib.call("vg_norm_stats", _p(x), ld_of(x), 0, groups, C.c_longlong(rows), c, _p(sums), dcode(x), stream())
     return sums
 
 
@@ -107,6 +134,8 @@ def norm_apply(x: torch.Tensor, mean_rstd: torch.Tensor, gamma, beta, act: int, 
     d.y, d.y_ld, d.y_coff = y.data_ptr(), ld_of(y), 0
     if pool is not None:
         d.pool, d.p_ld, d.p_coff = pool.data_ptr(), ld_of(pool), 0
+    d.dtype = dcode(x)
+    assert y.dtype == x.dtype
     _lib.call("vg_norm_apply", C.byref(d), stream())
 
 
@@ -130,13 +159,21 @@ def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dga
     d.dgamma = dgamma.data_ptr() if dgamma is not None else None
     d.dbeta = dbeta.data_ptr() if dbeta is not None else None
     d.accumulate = int(accumulate)
+    d.dtype = dcode(x)
+    assert dx.dtype == x.dtype and (dy is None or dy.dtype == x.dtype) and (dpool is None or dpool.dtype == x.dtype)
     _lib.call("vg_norm_backward", C.byref(d), stream())
 
 
 def act_bwd(y, dy, dx, act):
     n, h, w, c = y.shape
+    assert y.dtype == dy.dtype == dx.dtype
     _lib.call("vg_act_bwd", _p(y), ld_of(y), _p(dy), ld_of(dy), _p(dx), ld_of(dx), C.c_longlong(n * h * w), c, act,
-              stream())
+              dcode(y), stream())
+
+
+def act_fwd_(y, act):
+    n, h, w, c = y.shape
+    _lib.call("vg_act_fwd", _p(y), ld_of(y), C.c_longlong(n * h * w), c, act, dcode(y), stream())
 
 
 def colsum_f32(t2d, out, accumulate=False):
@@ -149,52 +186,58 @@ def colsum_f32(t2d, out, accumulate=False):
 # ----------------------------------------------------------------------------------------------
 def film_fwd(gb, x, y):
     n, h, w, c = x.shape
-    _lib.call("vg_film_fwd", _p(gb), _p(x), ld_of(x), 0, _p(y), C.c_longlong(n * h * w), c, stream())
+    assert gb.dtype == x.dtype == y.dtype
+    _lib.call("vg_film_fwd", _p(gb), _p(x), ld_of(x), 0, _p(y), C.c_longlong(n * h * w), c, dcode(x), stream())
 
 
 def film_bwd(gb, x, dy, dgb, dx):
     n, h, w, c = x.shape
+    assert gb.dtype == x.dtype == dy.dtype == dgb.dtype == dx.dtype
     _lib.call("vg_film_bwd", _p(gb), _p(x), ld_of(x), 0, _p(dy), _p(dgb), _p(dx), ld_of(dx), 0,
-              C.c_longlong(n * h * w), c, stream())
+              C.c_longlong(n * h * w), c, dcode(x), stream())
 
 
 def upsample_w_fwd(t, y):
     n, _, w0, c = t.shape
     _, h, w, _ = y.shape
-    _lib.call("vg_upsample_w_fwd", _p(t), ld_of(t), 0, n, w0, c, _p(y), h, w, stream())
+    assert t.dtype == y.dtype
+    _lib.call("vg_upsample_w_fwd", _p(t), ld_of(t), 0, n, w0, c, _p(y), h, w, dcode(t), stream())
 
 
 def upsample_w_bwd(dy, dt):
     n, h, w, c = dy.shape
     w0 = dt.shape[2]
-    _lib.call("vg_upsample_w_bwd", _p(dy), n, h, w, c, w0, _p(dt), stream())
+    _lib.call("vg_upsample_w_bwd", _p(dy), n, h, w, c, w0, _p(dt), dcode(dy), stream())
 
 
 def im2col(src, c, kh, kw, stride, pad, col):
     n, h, w, _ = src.shape
-    _lib.call("vg_im2col", _p(src), n, h, w, ld_of(src), c, kh, kw, stride, pad, _p(col), col.shape[-1], stream())
+    assert src.dtype == col.dtype
+    _lib.call("vg_im2col", _p(src), n, h, w, ld_of(src), c, kh, kw, stride, pad, _p(col), col.shape[-1], dcode(src),
+              stream())
 
 
 def col2im(dcol, n, h, w, c, kh, kw, stride, pad, dsrc_nchw):
-    _lib.call("vg_col2im", _p(dcol), dcol.shape[-1], n, h, w, c, kh, kw, stride, pad, _p(dsrc_nchw), stream())
+    _lib.call("vg_col2im", _p(dcol), dcol.shape[-1], n, h, w, c, kh, kw, stride, pad, _p(dsrc_nchw), dcode(dcol),
+              stream())
 
 
 def smalln_fwd(x, wt, bias, kh, kw, pad, out):
     n, h, w, cin = x.shape
     _lib.call("vg_conv_smalln_fwd", _p(x), ld_of(x), 0, n, h, w, cin, _p(wt), _p(bias), wt.shape[0], kh, kw, pad,
-              _p(out), stream())
+              _p(out), dcode(x), stream())
 
 
 def smalln_dgrad(dy, wt, kh, kw, pad, dx):
     n, h, w, cin = dx.shape
     _lib.call("vg_conv_smalln_dgrad", _p(dy), n, h, w, cin, _p(wt), wt.shape[0], kh, kw, pad, _p(dx), ld_of(dx), 0,
-              stream())
+              dcode(dx), stream())
 
 
 def smalln_wgrad(dy, x, kh, kw, pad, dw, dbias):
     n, h, w, cin = x.shape
     _lib.call("vg_conv_smalln_wgrad", _p(dy), _p(x), ld_of(x), 0, n, h, w, cin, dw.shape[0], kh, kw, pad, _p(dw),
-              _p(dbias), stream())
+              _p(dbias), dcode(x), stream())
 
 
 # ----------------------------------------------------------------------------------------------
