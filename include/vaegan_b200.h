@@ -32,7 +32,10 @@ extern "C" {
 const char* vg_last_error(void);
 int vg_version(void);
 int vg_device_info(int* sm_count, int* cc_major, int* cc_minor);   /* host pointers */
-unsigned long long vg_launch_count(void);   /* kernels this library has launched so far in this process */
+unsigned long long vg_launch_count(void);
+/* Cap the grid of the persistent tensor-core kernels at n SMs (0 = all) so that a concurrent stream of small,
+ * latency-bound kernels (the recurrent text encoder) finds free SMs; host-side setting, read at launch time. */
+int vg_set_conv_sm_limit(int n);   /* kernels this library has launched so far in this process */
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core implicit GEMMs (tcgen05 / TMEM / TMA)

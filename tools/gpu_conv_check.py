@@ -150,6 +150,8 @@ CASES = {
     "perf_fprop_film4": (case_perf, dict(kind="fprop")),
     "perf_wgrad_film4": (case_perf, dict(kind="wgrad")),
     "perf_fprop_c64": (case_perf, dict(kind="fprop", cin=64, cout=64, n=16)),
+    "perf_fprop_film4_b64": (case_perf, dict(kind="fprop", n=64, iters=3)),
+    "perf_wgrad_film4_b64": (case_perf, dict(kind="wgrad", n=64, iters=3)),
     "perf_fprop_1x1_k256": (case_perf, dict(kind="fprop", cin=256, cout=512, n=16, k=1)),
     "perf_fprop_1x1_k512": (case_perf, dict(kind="fprop", cin=512, cout=256, n=16, k=1)),
     "perf_wgrad_c64": (case_perf, dict(kind="wgrad", cin=64, cout=64, n=16)),

@@ -238,6 +238,8 @@ static inline int cdiv(long long a, long long b) { return static_cast<int>((a + 
 
 // host: number of SMs of the current device (cached)
 int num_sms();
+// SMs the persistent tensor-core kernels may occupy (vg_set_conv_sm_limit leaves the rest to concurrent small kernels)
+int conv_sms();
 
 // host: encode a tiled TMA descriptor for a bf16 tensor with 128-byte swizzle (rank 2..5).
 // dims/strides are in elements, innermost first; strides[0] is implicitly 1.

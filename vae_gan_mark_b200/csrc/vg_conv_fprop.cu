@@ -333,7 +333,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   p.tiles_n = cdiv(p.m_n, p.tn); p.tiles_h = cdiv(p.m_h, p.th); p.tiles_w = cdiv(p.m_w, p.tw);
   p.cin = d->cin; p.num_taps = d->num_taps; p.n_gemm = d->n_gemm;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
-  const int sms = num_sms();
+  const int sms = conv_sms();
   // N tile: the widest that still leaves enough tiles to fill the machine
   int bn = 256;
   if (d->n_gemm <= 64) bn = 64;

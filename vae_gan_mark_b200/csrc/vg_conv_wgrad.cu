@@ -254,7 +254,7 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   p.cout = d->cout; p.cin = d->cin; p.num_taps = d->num_taps; p.g_coff = d->g_coff;
   p.blocks_total = d->num_taps * (d->cin / 64);
   p.m_tiles = cdiv(d->cout, kWgBM);
-  const int sms = num_sms();
+  const int sms = conv_sms();
   int nb = min(4, p.blocks_total);
   if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
   p.nb = nb; p.bn = nb * 64;

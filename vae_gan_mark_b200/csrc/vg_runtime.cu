@@ -18,6 +18,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_sm_limit = 0;
+
+int conv_sms() {
+  const int n = num_sms();
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -78,6 +85,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 extern "C" const char* vg_last_error(void) { return vg::g_err; }
 
 extern "C" int vg_version(void) { return VG_API_VERSION; }
+
+extern "C" int vg_set_conv_sm_limit(int n) {
+  vg::g_sm_limit = n;
+  return 0;
+}
 
 extern "C" unsigned long long vg_launch_count(void) { return vg::g_launches; }
 

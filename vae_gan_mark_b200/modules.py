@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 from torch.nn.utils import spectral_norm
 
+from . import _lib
 from . import layers as L
 from . import ops
 from .conv import ConvLinear, new_act
@@ -179,6 +180,7 @@ class TransformerTextEncoder(nn.Module):
 
 
 _SIDE_STREAMS = {}
+CONV_SMS_WHILE_TEXT = 136   # of 148
 
 
 def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
@@ -197,8 +199,13 @@ def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
         if reduce_width:
             text = text.mean(dim=3, keepdim=True)
         t = L.ToNHWCFn.apply(text)
+    # while the side stream is busy, keep a few SMs out of the persistent conv grids so its small kernels can run
+    _lib.call("vg_set_conv_sm_limit", CONV_SMS_WHILE_TEXT)
+    if t.requires_grad:      # same for the backward: the text encoder's backward overlaps the style encoder's
+        t.register_hook(lambda g: (_lib.call("vg_set_conv_sm_limit", CONV_SMS_WHILE_TEXT), g)[1])
 
     def join():
+        _lib.call("vg_set_conv_sm_limit", 0)
         cur.wait_stream(side)
         t.record_stream(cur)
         return t

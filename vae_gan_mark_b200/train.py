@@ -184,6 +184,7 @@ class VAEGANTrainer:
             gan = L.hinge_loss(fake_preds, None)
             loss_g = w.recon * recon + klw * kl + w.gan * gan
             loss_g.backward()
+        _lib.call("vg_set_conv_sm_limit", 0)      # (raised again by the text-feature gradient hook during the backward)
         if self.grad_hook is not None:
             self.grad_hook("G", self.opt_G.params)
         self.opt_G.step(max_norm=self.clip_norm)
