@@ -255,6 +255,12 @@ def run_ours(args, wl):
     conv_ms = sum(v[0] for v in by.values()) / prof_steps
     conv_flops = sum(v[1] for v in by.values()) / prof_steps
     pk = peaks()
+    traffic = None       # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(f"conv_{tkind}_kernel{tkey}", {}).get("traffic_bytes_per_launch")
+    except Exception:
+        pass
     achieved = tflops / (tms / 1e3) / 1e12
     step_ms = ms / args.steps
     alg_tflop_step = STEP_GFLOP_PER_IMG[args.workload] * B / 1e3
@@ -298,7 +304,7 @@ def run_ours(args, wl):
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16 GEMM)",
+                         "frac": achieved / pk["tf"], "traffic": traffic, "peak_source": pk["src"] + " (sustained bf16 GEMM)",
                          "kernel": f"conv_{tkind}_kernel", "shape": str(tkey), "launches_per_step": tcnt / prof_steps,
                          "kernel_ms_per_step": tms / prof_steps,
                          "all_conv_ms_per_step": conv_ms, "all_conv_tflops": conv_flops / (conv_ms / 1e3) / 1e12,
