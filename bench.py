@@ -162,6 +162,13 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     B, h, w = wl["batch"], wl["h"], wl["w"]
     G, D = build_models(wl, dev)
+    if args.diag_freeze_text:
+        # DIAGNOSTIC ONLY (never a bench value): replace the recurrent text encoder by its cached, detached output to
+        # see how much of the step it costs on the critical path.  The JSON line is tagged "diagnostic".
+        enc = G.char_text_encoder_module
+        with torch.no_grad():
+            frozen = enc([TEXTS[i % len(TEXTS)] for i in range(wl["batch"])]).detach().clone()
+        enc.forward = lambda texts: frozen
     reducer = DataParallelReducer(world) if world > 1 else None
     if reducer is not None:
         reducer.broadcast_parameters(list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()))
@@ -315,6 +322,8 @@ def run_ours(args, wl):
         }
         if in_sync is not None:
             line["dp_params_in_sync"] = in_sync
+        if args.diag_freeze_text:
+            line["diagnostic"] = "text encoder output cached -- NOT a bench value"
         print(json.dumps(line), flush=True)
     if world > 1:
         # A process group whose collectives were captured in a CUDA graph can hang in destroy_process_group();
@@ -335,6 +344,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-convs", default="", help="write the per-shape tensor-core kernel timing table to this file")
+    ap.add_argument("--diag-freeze-text", action="store_true",
+                    help="diagnostic: cache the text encoder output (result is tagged, not a bench value)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

@@ -150,6 +150,11 @@ int vg_norm_backward(const VgNormBackward* desc /*host*/, void* stream);
 int vg_strided_copy(const void* in, int in_dtype, void* out, int out_dtype, const long long* dims,
                     const long long* in_strides, const long long* out_strides, const float* scale, int scale_inverse,
                     int accumulate, void* stream);
+
+/* Test hook: walks the tiled-copy plan of vg_strided_copy on fp32 HOST buffers (no GPU needed) so the tiling logic
+ * can be checked on CPU.  Returns the tile count; 0 means the plan falls back to the generic kernel. */
+long long vg_debug_copy_plan_host(const float* in, float* out, const long long* dims, const long long* in_strides,
+                                  const long long* out_strides);
 /* dx = dy * act'(y) for an activation that was fused into a conv epilogue (act 1 ReLU, 2 LeakyReLU(0.2)); bf16 rows */
 int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, void* dx, int dx_ld, long long rows, int c, int act,
                int dtype, void* stream);
@@ -184,6 +189,24 @@ int vg_conv_smalln_dgrad(const float* dy, int n, int h, int w, int cin, const fl
                          int pad, void* dx, int dx_ld, int dx_coff, int dtype, void* stream);
 int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, int x_coff, int n, int h, int w, int cin, int cout,
                          int kh, int kw, int pad, float* dw, float* dbias, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Recurrent text encoder: the time recurrence of one bidirectional GRU layer (torch.nn.GRU semantics, gate order
+ * r, z, n; replaces the cuDNN RNN the reference reaches through nn.GRU, vae-gan-v2.py:84-89,105).  One launch
+ * walks all `steps` time steps of both directions; hidden must be 256.  All tensors fp32, device, contiguous:
+ *   xproj [batch][steps][2][3*hidden]  x W_ih^T + b_ih of direction 0 | direction 1 (a time-parallel GEMM, caller's)
+ *   w_hh  [2][3*hidden][hidden], b_hh [2][3*hidden]
+ *   out   [batch][steps][2*hidden]     h_t of direction d in columns [d*hidden, (d+1)*hidden)  (h_0 = 0)
+ *   gates [2][batch][steps][4][hidden] r, z, n and (W_hn h + b_hn), saved for the backward (may be NULL)
+ * backward: dout = gradient of `out`; writes dgx [batch][steps][2][3*hidden] (gradient w.r.t. xproj) and
+ *   dgh [2][batch][steps][3*hidden] (gradient w.r.t. h W_hh^T + b_hh); weight gradients are GEMMs of these. */
+int vg_gru_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh, float* out, float* gates, int batch,
+                   int steps, int hidden, void* stream);
+int vg_gru_seq_bwd(const float* dout, const float* out, const float* gates, const float* w_hh, float* dgx, float* dgh,
+                   int batch, int steps, int hidden, void* stream);
+/* How many 8-CTA clusters of the forward (backward != 0: backward) kernel the device keeps resident at once, for
+ * batch_group = 8 or 16 rows per cluster; the launchers use the smallest group that runs in a single wave. */
+int vg_gru_max_active_clusters(int backward, int batch_group);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses, reparameterisation, spectral norm, optimiser (fp32)

@@ -106,3 +106,64 @@ def test_conv_tap_geometry():
             assert 2 * dh + sh == r - p and 2 * dw + cb // ld == q - p and cb % ld == 0
     op = ConvLinear(64, 128, 4, 4, 2, (1, 1))
     assert op.out_hw(64, 448) == (32, 224)
+
+
+def _plan_copy(src: "np.ndarray", dst_shape, perm):
+    """dst = src.transpose(perm) materialised through the tiled-copy plan on host buffers."""
+    import ctypes
+    import numpy as np
+    from vae_gan_mark_b200 import _lib
+    lib = _lib.lib()
+    fn = lib.vg_debug_copy_plan_host
+    fn.restype = ctypes.c_longlong
+    view = src.transpose(perm)
+    dst = np.full(dst_shape, np.nan, dtype=np.float32)
+    nd = view.ndim
+    dims = [1] * (5 - nd) + list(view.shape)
+    iss = [0] * (5 - nd) + [s // 4 for s in view.strides]
+    oss = [0] * (5 - nd) + [s // 4 for s in dst.strides]
+    LL5 = ctypes.c_longlong * 5
+    tiles = fn(src.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), dst.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+               LL5(*dims), LL5(*iss), LL5(*oss))
+    return tiles, dst, view
+
+
+def test_tiled_copy_plan_matches_numpy():
+    """The tiling logic of vg_strided_copy (weight / gradient re-layouts, NCHW<->NHWC) walked on the host."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    cases = [((70, 33, 3, 3), (0, 2, 3, 1)),      # OIHW -> [Cout][r][s][Cin]
+             ((70, 33, 3, 3), (2, 3, 1, 0)),      # OIHW -> [r][s][Cin][Cout]
+             ((40, 3, 3, 24), (0, 3, 1, 2)),      # [Cout][r][s][Cin] -> OIHW
+             ((3, 5, 17, 19), (0, 2, 3, 1)),      # NCHW -> NHWC
+             ((3, 17, 19, 8), (0, 3, 1, 2)),      # NHWC -> NCHW
+             ((5000,), (0,)), ((1,), (0,)), ((7, 1, 9), (2, 1, 0)),
+             ((2, 3, 4, 5, 6), (4, 2, 0, 3, 1)), ((129, 65), (1, 0)), ((64, 64, 4, 4), (1, 2, 3, 0))]
+    for shape, perm in cases:
+        src = rng.standard_normal(shape).astype(np.float32)
+        tiles, dst, view = _plan_copy(src, tuple(shape[p] for p in perm), perm)
+        assert tiles > 0, (shape, perm)
+        np.testing.assert_array_equal(dst, view, err_msg=f"{shape} {perm}")
+    for _ in range(40):
+        nd = int(rng.integers(1, 6))
+        shape = tuple(int(x) for x in rng.integers(1, 40, size=nd))
+        perm = tuple(int(x) for x in rng.permutation(nd))
+        src = rng.standard_normal(shape).astype(np.float32)
+        tiles, dst, view = _plan_copy(src, tuple(shape[p] for p in perm), perm)
+        assert tiles > 0
+        np.testing.assert_array_equal(dst, view, err_msg=f"{shape} {perm}")
+    # channel-slice destination (write into part of a wider NHWC buffer) and a broadcast source
+    import ctypes
+    from vae_gan_mark_b200 import _lib
+    fn = _lib.lib().vg_debug_copy_plan_host
+    fn.restype = ctypes.c_longlong
+    LL5 = ctypes.c_longlong * 5
+    src = rng.standard_normal((4, 24)).astype(np.float32)
+    dst = np.zeros((4, 6, 40), dtype=np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    sub = dst[:, :, 8:32]
+    tiles = fn(src.ctypes.data_as(fp), ctypes.cast(sub.ctypes.data, fp), LL5(1, 1, 4, 6, 24), LL5(0, 0, 24, 0, 1),
+               LL5(0, 0, 240, 40, 1))
+    assert tiles > 0
+    np.testing.assert_array_equal(dst[:, :, 8:32], np.broadcast_to(src[:, None, :], (4, 6, 24)))
+    assert not dst[:, :, :8].any() and not dst[:, :, 32:].any()

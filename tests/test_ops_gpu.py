@@ -370,3 +370,74 @@ def test_fused_adam_and_clip_match_torch():
     ref_sd = opt_ref.state_dict()
     assert set(sd["state"].keys()) == set(ref_sd["state"].keys())
     check("exp_avg", sd["state"][0]["exp_avg"], ref_sd["state"][0]["exp_avg"], 1e-5)
+
+
+def test_strided_copy_layouts_exact():
+    """vg_strided_copy (tiled through shared memory) against torch for the re-layouts the step uses: weight OIHW ->
+    GEMM layouts, gradients back, NCHW <-> NHWC, channel-slice destinations, broadcast sources, scale, accumulate.
+    fp32 -> fp32 must be bit-exact; bf16 destinations must equal torch's round-to-nearest conversion."""
+    from vae_gan_mark_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    cases = [((512, 256, 3, 3), (0, 2, 3, 1)), ((512, 256, 3, 3), (2, 3, 1, 0)), ((128, 3, 3, 200), (0, 3, 1, 2)),
+             ((64, 128, 4, 4), (1, 2, 3, 0)), ((3, 5, 37, 41), (0, 2, 3, 1)), ((3, 37, 41, 8), (0, 3, 1, 2)),
+             ((100003,), (0,)), ((2, 3, 4, 5, 6), (4, 2, 0, 3, 1)), ((1024, 1024, 2, 2), (0, 2, 3, 1))]
+    for shape, perm in cases:
+        src = torch.randn(shape, generator=g).cuda()
+        view = src.permute(perm)
+        for dt in (torch.float32, torch.bfloat16):
+            out = torch.full(view.shape, float("nan"), dtype=dt, device="cuda")
+            ops.strided_copy(view, out)
+            assert torch.equal(out, view.to(dt)), (shape, perm, dt)
+        srcb = src.to(torch.bfloat16).permute(perm)
+        out = torch.empty(view.shape, dtype=torch.float32, device="cuda")
+        ops.strided_copy(srcb, out)
+        assert torch.equal(out, srcb.float()), (shape, perm, "bf16->fp32")
+    # channel-slice destination + broadcast source
+    z = torch.randn(4, 24, generator=g).cuda()
+    buf = torch.zeros(4, 1, 6, 40, device="cuda", dtype=torch.bfloat16)
+    ops.strided_copy(z.view(4, 1, 1, 24).expand(4, 1, 6, 24), buf[..., 8:32])
+    assert torch.equal(buf[..., 8:32], z.to(torch.bfloat16).view(4, 1, 1, 24).expand(4, 1, 6, 24))
+    assert not buf[..., :8].any() and not buf[..., 32:].any()
+    # device scalar (inverse) scale as used for W / sigma
+    w = torch.randn(96, 40, 4, 4, generator=g).cuda()
+    sigma = torch.tensor([1.7], device="cuda")
+    out = torch.empty(96, 4, 4, 40, device="cuda")
+    ops.strided_copy(w.permute(0, 2, 3, 1), out, sigma, scale_inverse=True)
+    torch.testing.assert_close(out, w.permute(0, 2, 3, 1) / 1.7, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("batch,steps,precision", [(5, 7, "fp32"), (16, 60, "fp32"), (64, 3, "fp32"), (16, 60, "bf16")])
+def test_gru_text_encoder_matches_torch_gru(batch, steps, precision):
+    """CharacterTokenEncoder's cluster-kernel biGRU (vg_gru.cu: one launch per layer walks all time steps) against
+    torch.nn.GRU in float64 on the CPU: outputs, input gradient and every parameter gradient.  The recurrence is
+    all-fp32 FMA; the time-parallel GEMMs around it are fp32 in the high-accuracy mode (tolerance 1e-4 relative L2)
+    and TF32 in bf16 mode, like the reference's cuDNN GRU (tolerance 5e-3)."""
+    import vae_gan_mark_b200
+    from vae_gan_mark_b200 import modules as M
+    vae_gan_mark_b200.set_precision(precision)
+    try:
+        _gru_case(M, batch, steps, 1e-4 if precision == "fp32" else 5e-3)
+    finally:
+        vae_gan_mark_b200.set_precision("bf16")
+
+
+def _gru_case(M, batch, steps, tol):
+    torch.manual_seed(batch * 100 + steps)
+    enc = M.CharacterTokenEncoder(M.ALPHABET_STR, 128, 256, 2, 8).cuda().train()
+    enc.rnn.dropout = 0.0
+    ref = nn.GRU(128, 256, num_layers=2, batch_first=True, bidirectional=True).double()
+    ref.load_state_dict({k: v.detach().cpu().double() for k, v in enc.rnn.state_dict().items()})
+    idx = torch.randint(0, enc.vocab_size, (batch, steps))
+    emb_w = enc.embedding.weight.detach().cpu().double().requires_grad_(True)
+    out_ref, _ = ref(F.embedding(idx, emb_w, padding_idx=0))
+    y_ref = F.adaptive_avg_pool1d(out_ref.permute(0, 2, 1), 8).unsqueeze(2)
+    gy = torch.randn(y_ref.shape, dtype=torch.float64)
+    y_ref.backward(gy)
+    before = M._lib.lib().vg_launch_count()
+    y = enc(idx.cuda())
+    y.backward(gy.float().cuda())
+    assert M._lib.lib().vg_launch_count() - before == 4          # 2 layers x (forward + backward) launches
+    check("gru out", y, y_ref, tol)
+    check("gru d embedding", enc.embedding.weight.grad, emb_w.grad, tol)
+    for (name, p), (_, pr) in zip(enc.rnn.named_parameters(), ref.named_parameters()):
+        check(f"gru d {name}", p.grad, pr.grad, tol)

@@ -75,6 +75,21 @@ def main():
     wt = torch.randn(512, 512, 3, 3, device=dev)
     out = torch.empty(512, 3, 3, 512, device=dev, dtype=BF16)
     report("strided_copy OIHW->OHWI bf16", wt.shape, wt.numel() * 6, timeit(lambda: ops.strided_copy(wt.permute(0, 2, 3, 1), out)))
+    out2 = torch.empty(3, 3, 512, 512, device=dev, dtype=BF16)
+    report("strided_copy OIHW->HWIO bf16", wt.shape, wt.numel() * 6, timeit(lambda: ops.strided_copy(wt.permute(2, 3, 1, 0), out2)))
+    gw = torch.randn(512, 3, 3, 512, device=dev)
+    out3 = torch.empty(512, 512, 3, 3, device=dev)
+    report("strided_copy OHWI->OIHW fp32", gw.shape, gw.numel() * 8, timeit(lambda: ops.strided_copy(gw.permute(0, 3, 1, 2), out3)))
+    # text-map upsample (write-only) and its backward (read-only), image-side im2col
+    for (n, h, w, c) in [(64, 128, 128, 512), (64, 64, 64, 512)]:
+        tm = torch.randn(n, 1, w // 16, c, device=dev).to(BF16)
+        up = torch.empty(n, h, w, c, device=dev, dtype=BF16)
+        dtm = torch.empty(n, 1, w // 16, c, device=dev)
+        report("upsample_w_fwd", up.shape, up.numel() * 2, timeit(lambda: ops.upsample_w_fwd(tm, up)))
+        report("upsample_w_bwd", up.shape, up.numel() * 2, timeit(lambda: ops.upsample_w_bwd(up, dtm)))
+    img = torch.randn(64, 128, 128, 8, device=dev).to(BF16)
+    col = torch.empty(64, 128, 128, 64, device=dev, dtype=BF16)
+    report("im2col 3x3 c4 -> 64", col.shape, col.numel() * 2 + img.numel() * 2, timeit(lambda: ops.im2col(img, 4, 3, 3, 1, 1, col)))
     t = torch.randn(1024, 1024, 64, device=dev)
     report("torch copy (reference point)", t.shape, t.numel() * 8, timeit(lambda: t.clone()))
 

@@ -47,6 +47,160 @@ __global__ void strided_copy_kernel(const TI* __restrict__ in, TO* __restrict__ 
   }
 }
 
+// Tiled variant: every block moves one <=4096-element tile through shared memory, reading it in the order of
+// the input strides and writing it in the order of the output strides, so both sides of a permutation
+// (OIHW -> [Cout][r][s][Cin], OIHW -> [r][s][Cin][Cout], [Cout][r][s][Cin] -> OIHW, NCHW <-> NHWC) move in
+// >=128-byte runs.  Slots 0..4 are the (merged) dims sorted by input stride ("ld") and by output stride ("st").
+constexpr int kCopyTileMax = 4096;
+constexpr int kCopySmem = 6144;
+struct CopySide {
+  int tile[5], dim[5], ntile[5], div[5], ss[5];
+  unsigned magic[5];          // ceil(2^32 / tile) for tile >= 2 (exact quotient for numerators < 2^16)
+  long long gs[5];
+};
+struct TiledCopyParams {
+  CopySide ld, st;
+  int tile_elems;
+};
+__host__ __device__ __forceinline__ unsigned copy_mulhi(unsigned x, unsigned y) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(x, y);
+#else
+  return static_cast<unsigned>((static_cast<unsigned long long>(x) * y) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ bool copy_decode(const CopySide& s, const int (&ext)[5], int l, long long& goff, int& soff) {
+  unsigned r = static_cast<unsigned>(l);
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const unsigned t = static_cast<unsigned>(s.tile[k]);
+    const unsigned q = t == 1u ? r : copy_mulhi(r, s.magic[k]);
+    const int c = static_cast<int>(r - q * t);
+    r = q;
+    ok = ok && c < ext[k];
+    goff += static_cast<long long>(c) * s.gs[k];
+    soff += c * s.ss[k];
+  }
+  return ok;
+}
+__host__ __device__ __forceinline__ long long copy_origin(const CopySide& s, unsigned bid, int (&ext)[5]) {
+  long long g = 0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int t = static_cast<int>((bid / static_cast<unsigned>(s.div[k])) % static_cast<unsigned>(s.ntile[k]));
+    const int o = t * s.tile[k];
+    ext[k] = s.tile[k] < s.dim[k] - o ? s.tile[k] : s.dim[k] - o;
+    g += static_cast<long long>(o) * s.gs[k];
+  }
+  return g;
+}
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) tiled_copy_kernel(const TI* __restrict__ in, TO* __restrict__ out,
+                                                         const __grid_constant__ TiledCopyParams p,
+                                                         const float* __restrict__ scale, int scale_inverse,
+                                                         int accumulate) {
+  __shared__ float sm[kCopySmem];
+  float sc = 1.f;
+  if (scale != nullptr) sc = scale_inverse ? 1.f / *scale : *scale;
+  int ext[5];
+  const long long ibase = copy_origin(p.ld, blockIdx.x, ext);
+  for (int l = threadIdx.x; l < p.tile_elems; l += 256) {
+    long long goff = ibase;
+    int soff = 0;
+    if (copy_decode(p.ld, ext, l, goff, soff)) sm[soff] = static_cast<float>(in[goff]);
+  }
+  __syncthreads();
+  const long long obase = copy_origin(p.st, blockIdx.x, ext);
+  for (int l = threadIdx.x; l < p.tile_elems; l += 256) {
+    long long goff = obase;
+    int soff = 0;
+    if (copy_decode(p.st, ext, l, goff, soff)) {
+      float v = sm[soff] * sc;
+      if (accumulate) v += static_cast<float>(out[goff]);
+      out[goff] = static_cast<TO>(v);
+    }
+  }
+}
+
+// Plans the tiling; returns the number of tiles, or 0 when the generic kernel should be used.
+static long long plan_tiled_copy(const long long* dims, const long long* is, const long long* os, TiledCopyParams& p) {
+  long long d[5], a[5], b[5];
+  int n = 0;
+  for (int i = 0; i < 5; ++i)
+    if (dims[i] > 1) { d[n] = dims[i]; a[n] = is[i]; b[n] = os[i]; ++n; }
+  for (int i = 0; i + 1 < n;) {   // merge dims that are contiguous on both sides
+    if (a[i] == a[i + 1] * d[i + 1] && b[i] == b[i + 1] * d[i + 1]) {
+      d[i] *= d[i + 1]; a[i] = a[i + 1]; b[i] = b[i + 1];
+      for (int j = i + 1; j + 1 < n; ++j) { d[j] = d[j + 1]; a[j] = a[j + 1]; b[j] = b[j + 1]; }
+      --n;
+    } else {
+      ++i;
+    }
+  }
+  if (n == 0) { n = 1; d[0] = 1; a[0] = 1; b[0] = 1; }
+  for (int i = 0; i < n; ++i)
+    if (d[i] >= (1LL << 31) || a[i] < 0 || b[i] <= 0) return 0;
+  for (int i = n; i < 5; ++i) { d[i] = 1; a[i] = 0; b[i] = 0; }
+  int lo[5] = {0, 1, 2, 3, 4}, so[5] = {0, 1, 2, 3, 4};
+  auto key = [](long long stride, long long dim) { return (dim == 1 || stride == 0) ? (1LL << 62) : stride; };
+  std::stable_sort(lo, lo + 5, [&](int x, int y) { return key(a[x], d[x]) < key(a[y], d[y]); });
+  std::stable_sort(so, so + 5, [&](int x, int y) { return key(b[x], d[x]) < key(b[y], d[y]); });
+  long long t[5] = {1, 1, 1, 1, 1};
+  auto cdiv = [](long long x, long long y) { return (x + y - 1) / y; };
+  long long prod = 1;
+  for (int second = 1; second >= 0; --second) {   // second = also extend each side into its next contiguous dim
+    for (int i = 0; i < 5; ++i) t[i] = 1;
+    const int s0 = so[0];
+    t[s0] = std::min<long long>(d[s0], 64);
+    if (second && t[s0] < 64 && n > 1) {
+      const int s1 = so[1];
+      if (b[s1] == b[s0] * d[s0]) t[s1] = std::min<long long>(d[s1], cdiv(64, t[s0]));
+    }
+    const int l0 = lo[0];
+    t[l0] = std::max<long long>(t[l0], std::min<long long>(d[l0], 32));
+    if (second && t[l0] == d[l0] && t[l0] < 32 && n > 1) {
+      const int l1 = lo[1];
+      if (a[l1] == a[l0] * d[l0]) t[l1] = std::max<long long>(t[l1], std::min<long long>(d[l1], cdiv(32, t[l0])));
+    }
+    prod = 1;
+    for (int i = 0; i < 5; ++i) prod *= t[i];
+    if (prod <= kCopyTileMax) break;
+  }
+  for (int k = 0; k < 5 && prod < 1024; ++k) {   // small tiles: grow along the output-fast dims
+    const int i = so[k];
+    const long long nt = std::min<long long>(d[i], t[i] * cdiv(1024, prod));
+    prod = prod / t[i] * nt;
+    t[i] = nt;
+  }
+  if (prod > kCopyTileMax) return 0;
+  // shared-memory strides follow the output order; odd strides keep the transposing phase off a single bank
+  int ss[5];
+  long long run = 1;
+  for (int k = 0; k < 5; ++k) {
+    const int i = so[k];
+    ss[i] = static_cast<int>(run);
+    run *= t[i];
+    if (k < 4 && run > 1 && run % 2 == 0 && t[so[k + 1]] > 1) run += 1;
+  }
+  if (run > kCopySmem) return 0;
+  long long ntile[5], div[5], tiles = 1;
+  for (int i = 0; i < 5; ++i) { ntile[i] = cdiv(d[i], t[i]); div[i] = tiles; tiles *= ntile[i]; }
+  if (tiles >= (1LL << 31)) return 0;
+  auto fill = [&](CopySide& s, const int* order, const long long* gstride) {
+    for (int k = 0; k < 5; ++k) {
+      const int i = order[k];
+      s.tile[k] = static_cast<int>(t[i]); s.dim[k] = static_cast<int>(d[i]); s.ntile[k] = static_cast<int>(ntile[i]);
+      s.div[k] = static_cast<int>(div[i]); s.ss[k] = ss[i]; s.gs[k] = gstride[i];
+      s.magic[k] = t[i] >= 2 ? static_cast<unsigned>(((1ULL << 32) + t[i] - 1) / t[i]) : 0u;
+    }
+  };
+  fill(p.ld, lo, a);
+  fill(p.st, so, b);
+  p.tile_elems = static_cast<int>(prod);
+  return tiles;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FiLM
 // ---------------------------------------------------------------------------------------------
@@ -101,17 +255,23 @@ VG_DEVICE void lerp_src(int j, int w0, int w, int& j0, int& j1, float& lam) {
   j1 = j0 + (j0 < w0 - 1 ? 1 : 0);
   lam = src - static_cast<float>(j0);
 }
+// every output row is the same interpolated line: one thread interpolates 8 channels of one column once and
+// stores them to rows_per_thread rows (write-only traffic, 16-byte stores, 8 lanes = 128 contiguous bytes)
 template <typename T>
 __global__ void upsample_fwd_kernel(const T* __restrict__ t, int t_ld, int t_coff, int n, int w0, int c,
-                                    T* __restrict__ y, int h, int w) {
-  const int cv = c / 8;
-  const long long total = static_cast<long long>(n) * h * w * cv;
+                                    T* __restrict__ y, int h, int w, int rows_per_thread) {
+  const unsigned cv = static_cast<unsigned>(c / 8);
+  const unsigned line = static_cast<unsigned>(w) * cv;                 // vectors per output row
+  const unsigned ichunks = static_cast<unsigned>((h + rows_per_thread - 1) / rows_per_thread);
+  const long long total = static_cast<long long>(n) * ichunks * line;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(i % cv) * 8;
-    const long long pix = i / cv;
-    const int j = static_cast<int>(pix % w);
-    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const unsigned bi = static_cast<unsigned>(i / line);              // b * ichunks + chunk
+    const unsigned v = static_cast<unsigned>(i - static_cast<long long>(bi) * line);
+    const int j = static_cast<int>(v / cv);
+    const int ch = static_cast<int>(v - static_cast<unsigned>(j) * cv) * 8;
+    const int b = static_cast<int>(bi / ichunks);
+    const int r0 = static_cast<int>(bi - static_cast<unsigned>(b) * ichunks) * rows_per_thread;
     int j0, j1;
     float lam;
     lerp_src(j, w0, w, j0, j1, lam);
@@ -120,7 +280,9 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ t, int t_ld, int t_cof
     load8(t + (static_cast<long long>(b) * w0 + j1) * t_ld + t_coff + ch, bb);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = (1.f - lam) * a[k] + lam * bb[k];
-    store8(y + pix * c + ch, o);
+    T* dst = y + ((static_cast<long long>(b) * h + r0) * w + j) * c + ch;
+    const int r1 = min(h, r0 + rows_per_thread);
+    for (int r = r0; r < r1; ++r, dst += static_cast<long long>(w) * c) store8(dst, o);
   }
 }
 // dt[b][js][c] (fp32, accumulated) = sum_i sum_j weight(j -> js) dy[b][i][j][c]; one thread per (b, js, cvec, i-chunk)
@@ -172,34 +334,47 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int 
 // ---------------------------------------------------------------------------------------------
 // im2col / col2im for few-channel NHWC bf16 images: col[m][(r*kw+q)*c + ch], zero padded to kpad columns
 // ---------------------------------------------------------------------------------------------
+constexpr int kIm2colMaxK = 1024;
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ src, int n, int h, int w, int ld, int c, int kh,
                               int kw, int stride, int pad, int oh, int ow, T* __restrict__ col, int kpad) {
-  // one thread = 8 consecutive columns of one output pixel row (one 16-byte store)
-  const int kv = kpad / 8;
-  const long long total = static_cast<long long>(n) * oh * ow * kv;
+  // one thread = 8 consecutive columns of one output pixel row (one 16-byte store); the column -> (r, q, ch)
+  // decode is tabulated once per block so the inner loop carries no integer division
+  __shared__ int tab[kIm2colMaxK];
   const int kvalid = kh * kw * c;
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+    int e = -1;
+    if (k < kvalid) {
+      const int ch = k % c, tap = k / c;
+      e = ((tap / kw) << 16) | ((tap % kw) << 8) | ch;
+    }
+    tab[k] = e;
+  }
+  __syncthreads();
+  const unsigned kv = static_cast<unsigned>(kpad / 8);
+  const long long total = static_cast<long long>(n) * oh * ow * kv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k0 = static_cast<int>(i % kv) * 8;
-    const long long m = i / kv;
-    const int ox = static_cast<int>(m % ow), oy = static_cast<int>((m / ow) % oh);
-    const int b = static_cast<int>(m / (static_cast<long long>(ow) * oh));
+    const unsigned m = static_cast<unsigned>(i / kv);
+    const int k0 = static_cast<int>(i - static_cast<long long>(m) * kv) * 8;
+    const unsigned row = m / static_cast<unsigned>(ow);
+    const int ox = static_cast<int>(m - row * ow);
+    const int b = static_cast<int>(row / static_cast<unsigned>(oh));
+    const int oy = static_cast<int>(row - static_cast<unsigned>(b) * oh);
+    const T* img = src + static_cast<long long>(b) * h * w * ld;
+    const int y0 = oy * stride - pad, x0 = ox * stride - pad;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
+      const int e = tab[k0 + j];
       float v = 0.f;
-      if (k < kvalid) {
-        const int ch = k % c, tap = k / c;
-        const int q = tap % kw, r = tap / kw;
-        const int iy = oy * stride + r - pad, ix = ox * stride + q - pad;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w)
-          v = static_cast<float>(src[((static_cast<long long>(b) * h + iy) * w + ix) * ld + ch]);
+      if (e >= 0) {
+        const int iy = y0 + (e >> 16), ix = x0 + ((e >> 8) & 255);
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = static_cast<float>(img[(iy * w + ix) * ld + (e & 255)]);
       }
       f[j] = v;
     }
-    store8(col + m * kpad + k0, f);
+    store8(col + static_cast<long long>(m) * kpad + k0, f);
   }
 }
 // dsrc[b][c][iy][ix] (fp32 NCHW, overwritten) = sum over taps of dcol
@@ -442,6 +617,31 @@ __global__ void split3_kernel(const float* __restrict__ in, int ld_in, long long
 
 using namespace vg;
 
+// Host walk of the tiled plan on fp32 host buffers (same decode code as the kernel): lets the CPU test suite check
+// the tiling logic without a GPU.  Returns the number of tiles (0 = the plan falls back to the generic kernel).
+extern "C" long long vg_debug_copy_plan_host(const float* in, float* out, const long long* dims,
+                                             const long long* in_strides, const long long* out_strides) {
+  TiledCopyParams p;
+  const long long tiles = plan_tiled_copy(dims, in_strides, out_strides, p);
+  static float sm[kCopySmem];
+  for (long long bid = 0; bid < tiles; ++bid) {
+    int ext[5];
+    const long long ibase = copy_origin(p.ld, static_cast<unsigned>(bid), ext);
+    for (int l = 0; l < p.tile_elems; ++l) {
+      long long goff = ibase;
+      int soff = 0;
+      if (copy_decode(p.ld, ext, l, goff, soff)) sm[soff] = in[goff];
+    }
+    const long long obase = copy_origin(p.st, static_cast<unsigned>(bid), ext);
+    for (int l = 0; l < p.tile_elems; ++l) {
+      long long goff = obase;
+      int soff = 0;
+      if (copy_decode(p.st, ext, l, goff, soff)) out[goff] = sm[soff];
+    }
+  }
+  return tiles;
+}
+
 extern "C" int vg_strided_copy(const void* in, int in_dtype, void* out, int out_dtype, const long long* dims,
                                const long long* in_strides, const long long* out_strides, const float* scale,
                                int scale_inverse, int accumulate, void* stream_) {
@@ -453,17 +653,25 @@ extern "C" int vg_strided_copy(const void* in, int in_dtype, void* out, int out_
     VG_CHECK(dims[i] >= 1, -1, "vg_strided_copy: dims must be >= 1");
     total *= dims[i];
   }
-  const int g = ew_grid(total);
-  if (in_dtype == 0 && out_dtype == 0)
-    strided_copy_kernel<float, float><<<g, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), p, scale, scale_inverse, accumulate);
-  else if (in_dtype == 0 && out_dtype == 1)
-    strided_copy_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out), p, scale, scale_inverse, accumulate);
-  else if (in_dtype == 1 && out_dtype == 0)
-    strided_copy_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<float*>(out), p, scale, scale_inverse, accumulate);
-  else if (in_dtype == 1 && out_dtype == 1)
-    strided_copy_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), p, scale, scale_inverse, accumulate);
-  else
-    VG_CHECK(false, -1, "vg_strided_copy: dtype codes are 0 (fp32) and 1 (bf16)");
+  VG_CHECK(in_dtype >= 0 && in_dtype <= 1 && out_dtype >= 0 && out_dtype <= 1, -1,
+           "vg_strided_copy: dtype codes are 0 (fp32) and 1 (bf16)");
+  TiledCopyParams tp;
+  const long long tiles = plan_tiled_copy(dims, in_strides, out_strides, tp);
+  const int g = tiles > 0 ? static_cast<int>(tiles) : ew_grid(total);
+#define VG_COPY_DISPATCH(TI, TO)                                                                                      \
+  do {                                                                                                                \
+    if (tiles > 0)                                                                                                    \
+      tiled_copy_kernel<TI, TO><<<g, 256, 0, st>>>(static_cast<const TI*>(in), static_cast<TO*>(out), tp, scale,      \
+                                                   scale_inverse, accumulate);                                        \
+    else                                                                                                              \
+      strided_copy_kernel<TI, TO><<<g, 256, 0, st>>>(static_cast<const TI*>(in), static_cast<TO*>(out), p, scale,     \
+                                                     scale_inverse, accumulate);                                      \
+  } while (0)
+  if (in_dtype == 0 && out_dtype == 0) VG_COPY_DISPATCH(float, float);
+  else if (in_dtype == 0 && out_dtype == 1) VG_COPY_DISPATCH(float, __nv_bfloat16);
+  else if (in_dtype == 1 && out_dtype == 0) VG_COPY_DISPATCH(__nv_bfloat16, float);
+  else VG_COPY_DISPATCH(__nv_bfloat16, __nv_bfloat16);
+#undef VG_COPY_DISPATCH
   VG_LAUNCH_OK();
   return 0;
 }
@@ -504,13 +712,14 @@ extern "C" int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int
                                  int dtype, void* stream_) {
   VG_CHECK(c % 8 == 0 && t_ld % 8 == 0 && t_coff % 8 == 0, -1, "vg_upsample_w_fwd: channels must be multiples of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  const int grid = ew_grid(static_cast<long long>(n) * h * w * (c / 8));
+  const int rpt = h >= 64 ? 8 : (h >= 16 ? 4 : 1);
+  const int grid = ew_grid(static_cast<long long>(n) * ((h + rpt - 1) / rpt) * w * (c / 8));
   if (dtype == 0)
     upsample_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(t), t_ld, t_coff, n, w0, c,
-                                                           static_cast<__nv_bfloat16*>(y), h, w);
+                                                           static_cast<__nv_bfloat16*>(y), h, w, rpt);
   else
     upsample_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(t), t_ld, t_coff, n, w0, c,
-                                                   static_cast<float*>(y), h, w);
+                                                   static_cast<float*>(y), h, w, rpt);
   VG_LAUNCH_OK();
   return 0;
 }
@@ -531,6 +740,8 @@ extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int
 extern "C" int vg_im2col(const void* src, int n, int h, int w, int ld, int c, int kh, int kw, int stride, int pad,
                          void* col, int kpad, int dtype, void* stream_) {
   VG_CHECK(kh * kw * c <= kpad && kpad % 64 == 0, -1, "vg_im2col: kpad must be a multiple of 64 >= kh*kw*c");
+  VG_CHECK(kpad <= kIm2colMaxK && kh < 256 && kw < 256 && c < 256, -1, "vg_im2col: kpad <= 1024, kernel extents and c < 256");
+  VG_CHECK(static_cast<long long>(n) * h * w * ld < (1LL << 31), -1, "vg_im2col: image tensor too large");
   const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const int grid = ew_grid(static_cast<long long>(n) * oh * ow * (kpad / 8));

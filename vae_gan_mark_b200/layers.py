@@ -439,6 +439,67 @@ class UpsampleWFn(Function):
         return out, None, None
 
 
+class _gru_gemm_precision:
+    """The time-parallel GEMMs of the GRU layer run through cuBLAS.  In bf16 mode they may use TF32 tensor cores, which
+    is what the reference's cuDNN GRU does by default (torch.backends.cudnn.allow_tf32 = True); the high-accuracy
+    mode keeps them in full fp32."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = ops.act_dtype() == BF16
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+class GRULayerFn(Function):
+    """One bidirectional, batch_first GRU layer with hidden size 256 (torch.nn.GRU semantics; the text encoder of
+    vae-gan-v2.py:84-89,105).  The input projections of all time steps and the weight / input gradients are
+    time-parallel library GEMMs; the recurrence itself -- the part that costs the stock path ~1000 launches per
+    training step -- is one cluster kernel per direction pair (vg_gru.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        b, t, i = x.shape
+        h = w_hh_f.shape[1]
+        w_ih = torch.cat([w_ih_f.detach(), w_ih_r.detach()], 0)          # [6H, I]
+        b_ih = torch.cat([b_ih_f.detach(), b_ih_r.detach()], 0)
+        w_hh = torch.stack([w_hh_f.detach(), w_hh_r.detach()], 0)        # [2, 3H, H]
+        b_hh = torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0)
+        xm = x.detach().reshape(b * t, i).float()
+        with _gru_gemm_precision():
+            xproj = torch.addmm(b_ih, xm, w_ih.t())                      # [B*T, 6H] == [B, T, 2, 3H]
+        out = torch.empty((b, t, 2 * h), dtype=F32, device=x.device)
+        gates = torch.empty((2, b, t, 4, h), dtype=F32, device=x.device)
+        ops.gru_seq_fwd(xproj, w_hh, b_hh, out, gates)
+        ctx.save_for_backward(xm, w_ih, w_hh, out, gates)
+        ctx.dims = (b, t, i, h)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xm, w_ih, w_hh, out, gates = ctx.saved_tensors
+        b, t, i, h = ctx.dims
+        dout = dout.contiguous().float()
+        dgx = torch.empty((b, t, 2, 3 * h), dtype=F32, device=dout.device)
+        dgh = torch.empty((2, b, t, 3 * h), dtype=F32, device=dout.device)
+        ops.gru_seq_bwd(dout, out, gates, w_hh, dgx, dgh)
+        dgx_m = dgx.view(b * t, 6 * h)
+        hprev = torch.zeros((2, b, t, h), dtype=F32, device=dout.device)  # h_{t-1} of each direction's recurrence
+        hprev[0, :, 1:] = out[:, :-1, :h]
+        hprev[1, :, :-1] = out[:, 1:, h:]
+        dgh_m = dgh.view(2, b * t, 3 * h)
+        with _gru_gemm_precision():
+            dx = (dgx_m @ w_ih).view(b, t, i) if ctx.needs_input_grad[0] else None
+            dw_ih = dgx_m.t() @ xm                                            # [6H, I]
+            dw_hh = torch.bmm(dgh_m.transpose(1, 2), hprev.view(2, b * t, h))  # [2, 3H, H]
+        db_ih = dgx_m.sum(0)
+        db_hh = dgh_m.sum(1)
+        return (dx, dw_ih[:3 * h], dw_hh[0], db_ih[:3 * h], db_hh[0], dw_ih[3 * h:], dw_hh[1], db_ih[3 * h:], db_hh[1])
+
+
 class ToNHWCFn(Function):
     """NCHW fp32 -> NHWC bf16 (module boundary / stock-torch text encoder output)."""
 

@@ -148,7 +148,19 @@ class CharacterTokenEncoder(nn.Module):
             idx = texts_batch
         else:
             idx = self.tokens_to_indices(texts_batch, max_len_chars_for_tokenization).to(self.embedding.weight.device)
-        out, _ = self.rnn(self.embedding(idx))
+        emb = self.embedding(idx)
+        rnn = self.rnn
+        if emb.is_cuda and rnn.hidden_size == 256 and rnn.bidirectional and rnn.batch_first and rnn.bias:
+            # cluster-kernel recurrence (vg_gru.cu); self.rnn is only the parameter container
+            out = emb
+            for layer in range(rnn.num_layers):
+                params = [getattr(rnn, f"{name}_l{layer}{suffix}") for suffix in ("", "_reverse")
+                          for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                out = L.GRULayerFn.apply(out, *params)
+                if layer < rnn.num_layers - 1 and rnn.dropout > 0 and self.training:
+                    out = torch.nn.functional.dropout(out, rnn.dropout, True)
+        else:                                   # other hidden sizes: stock cuDNN recurrence
+            out, _ = rnn(emb)
         return self.adaptive_pool(out.permute(0, 2, 1)).unsqueeze(2)
 
 
@@ -181,6 +193,10 @@ class TransformerTextEncoder(nn.Module):
 
 _SIDE_STREAMS = {}
 CONV_SMS_WHILE_TEXT = 136   # of 148
+# The side-stream overlap was built for the stock cuDNN recurrence (~1000 launch-bound kernels).  With the cluster-kernel
+# recurrence the text encoder is < 1 ms of a ~33 ms step and its 128-CTA cluster launches cannot share the machine with
+# the persistent conv grids anyway, so it runs inline by default.
+TEXT_SIDE_STREAM = False
 
 
 def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
@@ -188,6 +204,12 @@ def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
     with the style encoder's convolutions instead of serialising with them; autograd replays the backward on the same
     stream, where it overlaps with the style encoder's backward.  Returns (NHWC bf16 text map, join) -- call join()
     before consuming the map on the current stream."""
+    if not TEXT_SIDE_STREAM:
+        text = module(texts)
+        if reduce_width:
+            text = text.mean(dim=3, keepdim=True)
+        t = L.ToNHWCFn.apply(text)
+        return t, (lambda: t)
     cur = torch.cuda.current_stream()
     dev = cur.device
     side = _SIDE_STREAMS.get(dev)

@@ -307,6 +307,23 @@ def spectral_bwd(g2d, w2d, u, v, sigma, dw, accumulate=False):
               _p(scratch), stream())
 
 
+def gru_seq_fwd(xproj, w_hh, b_hh, out, gates):
+    """Time recurrence of one bidirectional GRU layer; xproj [B,T,2,3H], out [B,T,2H], gates [2,B,T,4,H] (fp32)."""
+    b, t = out.shape[0], out.shape[1]
+    h = w_hh.shape[2]
+    for x in (xproj, w_hh, b_hh, out, gates):
+        assert x.dtype == F32 and x.is_contiguous()
+    _lib.call("vg_gru_seq_fwd", _p(xproj), _p(w_hh), _p(b_hh), _p(out), _p(gates), b, t, h, stream())
+
+
+def gru_seq_bwd(dout, out, gates, w_hh, dgx, dgh):
+    b, t = out.shape[0], out.shape[1]
+    h = w_hh.shape[2]
+    for x in (dout, out, gates, w_hh, dgx, dgh):
+        assert x.dtype == F32 and x.is_contiguous()
+    _lib.call("vg_gru_seq_bwd", _p(dout), _p(out), _p(gates), _p(w_hh), _p(dgx), _p(dgh), b, t, h, stream())
+
+
 def sumsq(g, out, zero_first=True):
     _lib.call("vg_sumsq", _p(g), C.c_longlong(g.numel()), _p(out), int(zero_first), stream())
 
