@@ -75,6 +75,10 @@ typedef struct VgConvFprop {
   int act;                  /* 0 none, 1 ReLU, 2 LeakyReLU(0.2) */
   int ksplit;               /* 0 = auto; >1 requires out_kind 2 (caller zeroes out) */
   int force_bn;             /* 0 = auto; 64/128/256 forces the N tile (testing) */
+  int b_mn_major;           /* 0: w is [n_gemm][K] (K contiguous).  1: w is [w_rows = K per tap][w_ld] with the N index
+                               contiguous: GEMM column n of tap t sits at w[k][wk[t] + n] (use_wk required).  This is a
+                               conv's FORWARD operand [Cout][taps*Cin] read as B of its own data gradient */
+  int w_rows;               /* b_mn_major: rows of w (K extent of one tap; rows beyond read as zero) */
 } VgConvFprop;
 int vg_conv_fprop(const VgConvFprop* desc /*host*/, void* stream);
 
@@ -108,6 +112,11 @@ int vg_conv_wgrad(const VgConvWgrad* desc /*host*/, void* stream);
 /* sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 (fp32, zeroed internally) */
 int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c, float* sums,
                   int dtype /*0 bf16, 1 fp32 activations*/, void* stream);
+/* Batch statistics of a [n][h][w][c] tensor whose h (>= 3) rows stand for virt_h rows: row 0 and row h-1 count once,
+ * interior rows (virt_h-2)/(h-2) times.  Used for the FiLM parameter maps (vae-gan-v2.py:138-145), whose rows are all
+ * equal except the first and the last, so that 3 rows carry the whole map; finalize with rows = n*virt_h*w. */
+int vg_norm_stats_rows(const void* x, int x_ld, int x_coff, int n, int h, int w, int c, int virt_h, float* sums,
+                       int dtype, void* stream);
 /* mean_rstd[g][0][c] = mean, [g][1][c] = 1/sqrt(var+eps); when groups == 1 and running_mean != NULL also updates the
  * running statistics (momentum, unbiased variance) and increments *num_batches_tracked (int64, nullable). */
 int vg_norm_finalize(const float* sums, int groups, long long rows_per_group, int c, float eps, float* mean_rstd,
@@ -137,6 +146,8 @@ typedef struct VgNormBackward {
   float* dgamma; float* dbeta;          /* fp32 [c], nullable */
   int accumulate;                       /* add into dgamma/dbeta instead of overwriting */
   int dtype;                            /* activation storage: 0 bf16, 1 fp32 */
+  int virt_h;                           /* 0, or: the h (>= 3) rows stand for virt_h rows whose interior rows are all
+                                           equal (see vg_norm_stats_rows); dy then holds per-class SUMS of gradients */
 } VgNormBackward;
 int vg_norm_backward(const VgNormBackward* desc /*host*/, void* stream);
 
@@ -167,6 +178,13 @@ int vg_film_fwd(const void* gb, const void* x, int x_ld, int x_coff, void* y, lo
                 void* stream);
 int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx, int dx_ld,
                 int dx_coff, long long rows, int c, int dtype, void* stream);
+/* FiLM whose parameter map gb has gh = 3 rows per image (first row | any interior row | last row): the maps of
+ * vae-gan-v2.py:138-145 are row-constant away from the zero-padded border.  y = gamma(class of row) * x + beta(...).
+ * The backward writes dx and, into dgb [n][3][w][2c], the gradient SUMMED over the rows of each class. */
+int vg_film_rows_fwd(const void* gb, int gh, const void* x, int x_ld, int x_coff, void* y, int n, int h, int w, int c,
+                     int dtype, void* stream);
+int vg_film_rows_bwd(const void* gb, int gh, const void* x, int x_ld, int x_coff, const void* dy, void* dgb, void* dx,
+                     int dx_ld, int dx_coff, int n, int h, int w, int c, int dtype, void* stream);
 /* F.interpolate(bilinear, align_corners=False) of a (1 x w0) map to (h x w) (vae-gan-v2.py:138-140) */
 int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c, void* y, int h, int w, int dtype,
                       void* stream);

@@ -1,0 +1,124 @@
+"""FiLM row de-duplication (modules.FILM_ROW_DEDUP): the (gamma, beta) maps of SpatialFiLMLayer (vae-gan-v2.py:117-149)
+are computed on 3 representative rows (first | interior | last) instead of all h, because the upsampled text map they
+are computed from has h identical rows.  This is an exact restatement, so the de-duplicated path must reproduce the
+literal path -- output, gradient of the main feature map, gradient of the text map, every parameter gradient and the
+BatchNorm running statistics -- to fp32 rounding in the high-accuracy mode (2e-5 relative L2; the weight gradient
+2e-4, its split-K fp32 atomics sum in a different order) and to bf16 rounding in bf16 mode (2e-2).  It is also
+checked against the CPU oracle's SpatialFiLMLayer, and on one whole training step."""
+import copy
+
+import pytest
+import torch
+
+from oracle import models as om
+from oracle.step import LossWeights as OLW, deterministic_state, make_optimizers, synthetic_batch, train_step
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def run_layer(layer, x_main, text, gy, dedup):
+    from vae_gan_mark_b200 import modules as M
+    M.FILM_ROW_DEDUP = dedup
+    try:
+        for p in layer.parameters():
+            p.grad = None
+        xm = x_main.detach().clone().requires_grad_(True)
+        tx = text.detach().clone().requires_grad_(True)
+        y = layer(xm, tx)
+        y.backward(gy)
+        out = {"y": y.detach().float(), "dx": xm.grad.float(), "dtext": tx.grad.float()}
+        for k, p in layer.named_parameters():
+            out["d" + k] = p.grad.detach().clone()
+        for k, b in layer.named_buffers():
+            out["buf " + k] = b.detach().clone().float()
+        return out
+    finally:
+        M.FILM_ROW_DEDUP = False
+
+
+@pytest.mark.parametrize("precision,tol,h,w,w0", [("fp32", 2e-5, 8, 16, 4), ("fp32", 2e-5, 3, 8, 2), ("fp32", 2e-5, 32, 32, 2),
+                                                   ("bf16", 2e-2, 16, 32, 4)])
+def test_film_layer_dedup_equals_literal(precision, tol, h, w, w0):
+    import vae_gan_mark_b200 as vg
+    from vae_gan_mark_b200 import modules as M
+    vg.set_precision(precision)
+    try:
+        torch.manual_seed(7)
+        dt = torch.float32 if precision == "fp32" else torch.bfloat16
+        b, t_ch, c = 3, 64, 128
+        layer = M.SpatialFiLMLayer(t_ch, c).cuda().train()
+        state0 = copy.deepcopy(layer.state_dict())
+        x_main = torch.randn(b, h, w, c, device="cuda").to(dt)
+        text = torch.randn(b, 1, w0, t_ch, device="cuda").to(dt)
+        gy = torch.randn(b, h, w, c, device="cuda").to(dt)
+        lit = run_layer(layer, x_main, text, gy, dedup=False)
+        layer.load_state_dict(state0)
+        ded = run_layer(layer, x_main, text, gy, dedup=True)
+        for k in lit:
+            e = rel(ded[k], lit[k])
+            bound = tol * (10 if (k.startswith("dparam_predictor") and precision == "fp32") else 1)
+            print(f"{precision} h={h} {k}: {e:.2e}")
+            assert e <= bound, (k, e)
+        if precision == "fp32":
+            # and against the CPU restatement of the reference layer
+            ref = om.SpatialFiLMLayer(t_ch, c).train()
+            ref.load_state_dict({k: v.cpu() for k, v in state0.items()})
+            xm = x_main.cpu().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            tx = text.cpu().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            y = ref(xm, tx)
+            y.backward(gy.cpu().permute(0, 3, 1, 2))
+            assert rel(ded["y"].cpu().permute(0, 3, 1, 2), y) <= 1e-4
+            assert rel(ded["dx"].cpu().permute(0, 3, 1, 2), xm.grad) <= 1e-4
+            assert rel(ded["dtext"].cpu().permute(0, 3, 1, 2), tx.grad) <= 1e-3
+            for k, p in ref.named_parameters():
+                assert rel(ded["d" + k], p.grad) <= 1e-3, k
+    finally:
+        vg.set_precision("bf16")
+
+
+def test_whole_step_dedup_equals_literal_fp32():
+    """One full v2 training step (32x64 patches) with and without the de-duplication, high-accuracy mode: losses
+    within 1e-5 (squared gradient norm 1e-3), updated parameters coincide except for sign flips of ~zero gradients."""
+    import vae_gan_mark_b200 as vg
+    from vae_gan_mark_b200 import modules as M
+    from vae_gan_mark_b200.train import LossWeights, VAEGANTrainer
+    vg.set_precision("fp32")
+    try:
+        results = []
+        for dedup in (False, True):
+            torch.manual_seed(11)
+            G = M.VAEGAN_UNet_SpatialFiLM(4, 32, patch_shape=(64, 32)).cuda().train()
+            D = M.Discriminator(3).cuda().train()
+            G.load_state_dict(deterministic_state(G, 5))
+            D.load_state_dict(deterministic_state(D, 6))
+            G.char_text_encoder_module.rnn.dropout = 0.0
+            ru, en, mask, texts = synthetic_batch(2, 32, 64, step=0)
+            eps = torch.randn(2, 32, 1, 1, generator=torch.Generator().manual_seed(3))
+            G.style_vae_encoder_module.eps_fn = lambda shape: eps
+            tr = VAEGANTrainer(G, D, LossWeights.for_family("v2"))
+            M.FILM_ROW_DEDUP = dedup
+            out = tr.step(ru.cuda(), en.cuda(), mask.cuda(), texts)
+            M.FILM_ROW_DEDUP = False
+            losses = {k: float(v) for k, v in out.items() if v.numel() == 1}
+            results.append((losses, {k: v.detach().clone() for k, v in G.state_dict().items()}))
+        (l0, s0), (l1, s1) = results
+        for k in l0:
+            # the gradient norm is a sum of heavily cancelling terms (see test_fp32_mode_gpu): 1e-3, losses 1e-5
+            tol = 1e-3 if k == "grad_norm_sq" else 1e-5
+            assert abs(l0[k] - l1[k]) <= tol * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
+        # Post-step parameters: the first Adam step moves every element by lr * sign(g) (m / sqrt(v) = +-1), so an
+        # element whose gradient is ~0 may land 2 * lr away; everything else must coincide.
+        lr = 1e-4
+        for k in s0:
+            if s0[k].dtype.is_floating_point:
+                diff = (s1[k].double() - s0[k].double()).abs()
+                assert float(diff.max()) <= 2.1 * lr, (k, float(diff.max()))
+                assert float((diff > 1e-5).double().mean()) <= 0.01, (k, float((diff > 1e-5).double().mean()))
+    finally:
+        M.FILM_ROW_DEDUP = False
+        vg.set_precision("bf16")

@@ -24,13 +24,23 @@ except Exception:
 
 
 def timeit(fn, iters=10, warm=3):
-    for _ in range(warm):
-        fn()
+    """Average device time of one call: `iters` calls are captured into one CUDA graph so that the host-side cost of
+    issuing a call (ctypes + Python, ~20 us) does not hide the duration of short kernels."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
@@ -90,6 +100,9 @@ def main():
     img = torch.randn(64, 128, 128, 8, device=dev).to(BF16)
     col = torch.empty(64, 128, 128, 64, device=dev, dtype=BF16)
     report("im2col 3x3 c4 -> 64", col.shape, col.numel() * 2 + img.numel() * 2, timeit(lambda: ops.im2col(img, 4, 3, 3, 1, 1, col)))
+    hw = torch.randn(256, 65536, device=dev)
+    hb = torch.empty(256, 65536, device=dev, dtype=BF16)
+    report("strided_copy contiguous fp32->bf16 16.7M", hw.shape, hw.numel() * 6, timeit(lambda: ops.strided_copy(hw, hb)))
     t = torch.randn(1024, 1024, 64, device=dev)
     report("torch copy (reference point)", t.shape, t.numel() * 8, timeit(lambda: t.clone()))
 

@@ -28,6 +28,7 @@ class VgConvFprop(C.Structure):
         ("out_h", C.c_int), ("out_w", C.c_int), ("out_ld", C.c_int), ("out_coff", C.c_int),
         ("su_h", C.c_int), ("su_w", C.c_int), ("sub_h0", C.c_int), ("sub_w0", C.c_int), ("cout_per_sub", C.c_int),
         ("bias", C.c_void_p), ("act", C.c_int), ("ksplit", C.c_int), ("force_bn", C.c_int),
+        ("b_mn_major", C.c_int), ("w_rows", C.c_int),
     ]
 
 
@@ -62,6 +63,7 @@ class VgNormBackward(C.Structure):
         ("act", C.c_int), ("sums", C.c_void_p),
         ("dx", C.c_void_p), ("dx_ld", C.c_int), ("dx_coff", C.c_int),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int), ("dtype", C.c_int),
+        ("virt_h", C.c_int),
     ]
 
 

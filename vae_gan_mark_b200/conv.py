@@ -65,13 +65,16 @@ def _chk(t: torch.Tensor, what: str):
 def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torch.Tensor, n_gemm: int,
           m: Tuple[int, int, int], out: torch.Tensor, out_kind: int = 0, su: Tuple[int, int] = (1, 1),
           sub0: Tuple[int, int] = (0, 0), cout_per_sub: Optional[int] = None, bias: Optional[torch.Tensor] = None,
-          act: int = 0, ksplit: int = 0, force_bn: int = 0, wk: Optional[Sequence[int]] = None) -> None:
+          act: int = 0, ksplit: int = 0, force_bn: int = 0, wk: Optional[Sequence[int]] = None,
+          b_mn_major: bool = False) -> None:
     """out[pixel, n] = sum_{tap, c<cin} x[pixel@tap, c] * w[n, wk[tap] + c]  (wk[tap] = tap*cin by default).
-    ``out`` is an NHWC view ([N, OH, OW, C']); ``x`` and ``w`` are bf16."""
+    ``out`` is an NHWC view ([N, OH, OW, C']); ``x`` and ``w`` are bf16.
+    ``b_mn_major``: w is [K rows (c), columns] and out[pixel, n] = sum x[pixel@tap, c] * w[c, wk[tap] + n]."""
     _chk(x, "fprop x")
     assert w.dtype == BF16 and w.stride(1) == 1 and out.stride(3) == 1
     assert len(taps) <= _lib.VG_MAX_FPROP_TAPS, f"{len(taps)} taps > {_lib.VG_MAX_FPROP_TAPS}"
     assert wk is not None or w.shape[1] == len(taps) * cin, (w.shape, len(taps), cin)
+    assert not b_mn_major or wk is not None
     d = VgConvFprop()
     d.x, d.x_n, d.x_h, d.x_w, d.x_ld, d.x_stride = x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], x.stride(2), x_stride
     d.m_n, d.m_h, d.m_w = m
@@ -91,6 +94,7 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
     d.cout_per_sub = cout_per_sub or n_gemm
     d.bias = bias.data_ptr() if bias is not None else None
     d.act, d.ksplit, d.force_bn = act, ksplit, force_bn
+    d.b_mn_major, d.w_rows = int(b_mn_major), w.shape[0]
     e0 = _prof_begin()
     _lib.call("vg_conv_fprop", C.byref(d), ops.stream())
     _prof_end(e0, "fprop", (m, n_gemm, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * n_gemm * len(taps) * cin)
@@ -220,6 +224,16 @@ class ConvLinear:
         self.in_hw = in_hw
         assert stride in (1, 2)
 
+    def prefer_mn(self, gemm_pixels: int) -> bool:
+        """Data gradient in bf16 mode: read the forward operand as an MN-major B operand (no transposed weight copy,
+        but the tensor pipe runs ~20 % slower on MN-major B -- measured 1478 -> 1170 TFLOP/s on the 128x128x512 3x3
+        layer) or make the transposed K-major copy first?  Estimated cost of each in microseconds."""
+        nk = self.cin * self.cout * self.kh * self.kw
+        slowdown_us = 0.4 * gemm_pixels * nk / 1.4e9
+        copies = 4 if (self.s == 2 and not self.shuffle) else 1
+        copy_us = 5.0 * copies + nk * 6 / 1e6
+        return slowdown_us < copy_us
+
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         return (h + 2 * self.ph - self.kh) // self.s + 1, (w + 2 * self.pw - self.kw) // self.s + 1
 
@@ -294,6 +308,29 @@ class ConvLinear:
         if out is None:
             out = new_act(n, h, w, self.cin, dy.device, dy.dtype)
         g = ops.split3(dy) if hi else pad_channels(dy, self.cout_p)
+        if "mn" in wb:
+            # bf16 mode: the forward operand [cout][(r, q, ci_p)] is read as the MN-major B operand (K = cout rows,
+            # N = ci columns of one tap); no transposed copy of the weights exists
+            assert not hi
+            wf = wb["mn"]
+            if self.shuffle:
+                fprop(g, [(0, 0, 0, 0)], 1, self.cout_p, wf, self.kh * self.kw * self.cin, (n, oh, ow), out, out_kind=kind,
+                      su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act, wk=[0], b_mn_major=True)
+            elif self.s == 1:
+                taps = [(0, self.pw - q, 0, self.ph - r) for r in range(self.kh) for q in range(self.kw)]
+                wk = [(r * self.kw + q) * self.cin_p for r in range(self.kh) for q in range(self.kw)]
+                fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h, w), out, out_kind=kind, bias=bias, act=act, wk=wk,
+                      b_mn_major=True)
+            else:
+                for a in (0, 1):
+                    for b in (0, 1):
+                        r0, q0 = (a + self.ph) % 2, (b + self.pw) % 2
+                        rs, qs = range(r0, self.kh, 2), range(q0, self.kw, 2)
+                        taps = [(0, (b + self.pw - q) // 2, 0, (a + self.ph - r) // 2) for r in rs for q in qs]
+                        wk = [(r * self.kw + q) * self.cin_p for r in rs for q in qs]
+                        fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2),
+                              sub0=(a, b), cout_per_sub=self.cin, bias=bias, act=act, wk=wk, b_mn_major=True)
+            return out
         if "shuffle" in wb:
             # pixel shuffle: GEMM column (r, q, ci) of input pixel (oh, ow) lands at output pixel (oh*kh + r, ow*kw + q).
             # Covers the full-kernel case (1x1 input), the column kernel (kh x 1) and 2x2 stride 2.

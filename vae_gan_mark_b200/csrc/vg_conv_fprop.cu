@@ -9,6 +9,10 @@
 //   stride-2 conv (and the adjoint of a stride-2 ConvTranspose) is the same kernel.
 // * W (bf16, [n_gemm][taps*Cin], K contiguous) is a 2-D TMA box {64, BN}.
 // * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
+// * b_mn_major: W is instead given as [K rows][N columns] (N contiguous) -- the forward operand [Cout][taps*Cin] of a
+//   conv read as the B operand of its own DATA GRADIENT (K = Cout, N = Cin of one tap).  It is loaded as BN/64 boxes of
+//   {64 N, 64 K} = the canonical MN-major SWIZZLE_128B layout, and the tensor core transposes it for free, so the data
+//   gradient needs no second, transposed copy of the weights.
 // * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered fp32 TMEM
 //   accumulator; 4 epilogue warps drain TMEM with tcgen05.ld, add bias / activation, and store bf16 or
 //   fp32 NHWC rows (optionally scattered as a pixel shuffle for ConvTranspose, optionally into a channel
@@ -45,6 +49,7 @@ struct FpropParams {
   const float* bias;
   int act;                      // 0 none, 1 relu, 2 leaky relu 0.2
   int vec_ok;                   // destination allows 16-byte vector stores
+  int b_mn;                     // B operand is MN-major (see header comment)
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
   int wk[kMaxTaps];             // first weight column of each tap
 };
@@ -94,8 +99,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
   const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (one lane per box) =====================
+    const int b_boxes = p.b_mn ? p.bn / 64 : 1;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -113,20 +119,30 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int tap = k_begin / cchunks;
       int cc = k_begin % cchunks;
       for (int k = k_begin; k < k_end; ++k) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        }
+        __syncwarp();
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-        const int4 t = p.taps[tap];
-        tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
-        tma_load_2d(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn);
+        if (lane == 0) {
+          const int4 t = p.taps[tap];
+          tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
+        } else if (lane <= b_boxes) {
+          if (p.b_mn)   // box (lane-1): N columns [n_t*bn + 64*(lane-1), +64) of this tap, K rows [cc*64, +64)
+            tma_load_2d(sb + (lane - 1) * (64 * 128), &tmap_b, &full_bar[stage], p.wk[tap] + n_t * p.bn + (lane - 1) * 64,
+                        cc * kBK);
+          else
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn);
+        }
         if (++cc == cchunks) { cc = 0; ++tap; }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, p.b_mn);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -146,7 +162,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < kBK / kUmmaK; ++j) {
           const uint64_t da = umma_smem_desc_sw128(sa + j * kUmmaK * 2, 16, 1024);
-          const uint64_t db = umma_smem_desc_sw128(sb + j * kUmmaK * 2, 16, 1024);
+          // MN-major B: 16 K rows = 2 groups of 8 rows (SBO = 1024 B apart); 64-column N groups one box (8 KB) apart
+          const uint64_t db = p.b_mn ? umma_smem_desc_sw128(sb + j * kUmmaK * 128, 64 * 128, 1024)
+                                     : umma_smem_desc_sw128(sb + j * kUmmaK * 2, 16, 1024);
           umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
@@ -360,6 +378,8 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   p.out_h = d->out_h; p.out_w = d->out_w; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.su_h = d->su_h; p.su_w = d->su_w; p.sub_h0 = d->sub_h0; p.sub_w0 = d->sub_w0; p.cout_per_sub = d->cout_per_sub;
   p.bias = d->bias; p.act = d->act;
+  p.b_mn = d->b_mn_major ? 1 : 0;
+  VG_CHECK(!p.b_mn || d->w_rows >= 1, -1, "vg_conv_fprop: b_mn_major needs w_rows (number of K rows of the weight matrix)");
   {
     const int esz = d->out_kind == 0 ? 2 : 4;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((static_cast<long long>(d->out_ld) * esz) % 16 == 0) &&
@@ -383,9 +403,9 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(d->w_ld), static_cast<uint64_t>(d->n_gemm)};
+    uint64_t dims[2] = {static_cast<uint64_t>(d->w_ld), static_cast<uint64_t>(p.b_mn ? d->w_rows : d->n_gemm)};
     uint64_t strides[2] = {1, static_cast<uint64_t>(d->w_ld)};
-    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(p.b_mn ? 64 : bn)};
     int rc = encode_tmap_bf16(&tmap_b, d->w, 2, dims, strides, box);
     if (rc) return rc;
   }

@@ -105,11 +105,23 @@ __global__ void __launch_bounds__(256) tiled_copy_kernel(const TI* __restrict__ 
   if (scale != nullptr) sc = scale_inverse ? 1.f / *scale : *scale;
   int ext[5];
   const long long ibase = copy_origin(p.ld, blockIdx.x, ext);
-  for (int l = threadIdx.x; l < p.tile_elems; l += 256) {
+  // all (up to 16) loads of a thread are issued before the first use: with one 4-byte load in flight per thread the
+  // kernel is bound by latency x bytes-in-flight (~0.6 TB/s), not by HBM
+  constexpr int kPerThread = kCopyTileMax / 256;
+  float v[kPerThread];
+  int so[kPerThread];
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u) {
+    const int l = threadIdx.x + u * 256;
     long long goff = ibase;
     int soff = 0;
-    if (copy_decode(p.ld, ext, l, goff, soff)) sm[soff] = static_cast<float>(in[goff]);
+    const bool ok = l < p.tile_elems && copy_decode(p.ld, ext, l, goff, soff);
+    so[u] = ok ? soff : -1;
+    v[u] = ok ? static_cast<float>(in[goff]) : 0.f;
   }
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u)
+    if (so[u] >= 0) sm[so[u]] = v[u];
   __syncthreads();
   const long long obase = copy_origin(p.st, blockIdx.x, ext);
   for (int l = threadIdx.x; l < p.tile_elems; l += 256) {
@@ -167,9 +179,9 @@ static long long plan_tiled_copy(const long long* dims, const long long* is, con
     for (int i = 0; i < 5; ++i) prod *= t[i];
     if (prod <= kCopyTileMax) break;
   }
-  for (int k = 0; k < 5 && prod < 1024; ++k) {   // small tiles: grow along the output-fast dims
+  for (int k = 0; k < 5 && prod < 2048; ++k) {   // small tiles: grow along the output-fast dims
     const int i = so[k];
-    const long long nt = std::min<long long>(d[i], t[i] * cdiv(1024, prod));
+    const long long nt = std::min<long long>(d[i], t[i] * (2048 / prod));
     prod = prod / t[i] * nt;
     t[i] = nt;
   }
@@ -241,6 +253,81 @@ __global__ void film_bwd_kernel(const T* __restrict__ gb, const T* __restrict__ 
     store8(dgb + r * 2 * c + ch, o1);      // d gamma
     store8(dgb + r * 2 * c + c + ch, d);   // d beta
     store8(dx + r * dx_ld + dx_coff + ch, o2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FiLM with row-class parameter maps: gb has only gh (= 3) rows per image -- first row, any interior row, last row --
+// because the maps the reference builds (vae-gan-v2.py:138-145) are row-constant except at the zero-padded border.
+// ---------------------------------------------------------------------------------------------
+VG_DEVICE int film_row_class(int yy, int h, int gh) { return yy == 0 ? 0 : (yy == h - 1 ? gh - 1 : 1); }
+
+template <typename T>
+__global__ void film_rows_fwd_kernel(const T* __restrict__ gb, int gh, const T* __restrict__ x, int x_ld, int x_coff,
+                                     T* __restrict__ y, int n, int h, int w, int c) {
+  const int cv = c / 8;
+  const long long total = static_cast<long long>(n) * h * w * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cv;                       // pixel (b, yy, xx)
+    const int ch = static_cast<int>(i - r * cv) * 8;
+    const int xx = static_cast<int>(r % w);
+    const long long by = r / w;
+    const int yy = static_cast<int>(by % h);
+    const long long b = by / h;
+    const T* g = gb + ((b * gh + film_row_class(yy, h, gh)) * w + xx) * 2 * c + ch;
+    float ga[8], be[8], xv[8], o[8];
+    load8(g, ga);
+    load8(g + c, be);
+    load8(x + r * x_ld + x_coff + ch, xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(ga[k], xv[k], be[k]);
+    store8(y + r * c + ch, o);
+  }
+}
+// one thread = 8 channels of one image column: walks the h rows, writes dx and the per-class SUMS of d gamma / d beta
+template <typename T>
+__global__ void film_rows_bwd_kernel(const T* __restrict__ gb, int gh, const T* __restrict__ x, int x_ld, int x_coff,
+                                     const T* __restrict__ dy, T* __restrict__ dgb, T* __restrict__ dx, int dx_ld,
+                                     int dx_coff, int n, int h, int w, int c) {
+  const int cv = c / 8;
+  const long long total = static_cast<long long>(n) * w * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long bx = i / cv;
+    const int ch = static_cast<int>(i - bx * cv) * 8;
+    const int xx = static_cast<int>(bx % w);
+    const long long b = bx / w;
+    float gam[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) load8(gb + ((b * gh + (k == 2 ? gh - 1 : k)) * w + xx) * 2 * c + ch, gam[k]);
+    float ag[8], ab[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ag[k] = ab[k] = 0.f;
+#pragma unroll 4
+    for (int yy = 0; yy < h; ++yy) {
+      const long long r = (b * h + yy) * w + xx;
+      float xv[8], d[8], o[8];
+      load8(x + r * x_ld + x_coff + ch, xv);
+      load8(dy + r * c + ch, d);
+      const int k = yy == 0 ? 0 : (yy == h - 1 ? 2 : 1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = d[e] * gam[k][e];
+      store8(dx + r * dx_ld + dx_coff + ch, o);
+      if (k == 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ag[e] = fmaf(d[e], xv[e], ag[e]); ab[e] += d[e]; }
+      } else {
+        T* o2 = dgb + ((b * gh + (k == 2 ? gh - 1 : 0)) * w + xx) * 2 * c + ch;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = d[e] * xv[e];
+        store8(o2, o);
+        store8(o2 + c, d);
+      }
+    }
+    T* o1 = dgb + ((b * gh + 1) * w + xx) * 2 * c + ch;
+    store8(o1, ag);
+    store8(o1 + c, ab);
   }
 }
 
@@ -704,6 +791,43 @@ extern "C" int vg_film_bwd(const void* gb, const void* x, int x_ld, int x_coff, 
     film_bwd_kernel<float><<<ew_grid(rows * (c / 8)), 256, 0, st>>>(
         static_cast<const float*>(gb), static_cast<const float*>(x), x_ld, x_coff, static_cast<const float*>(dy),
         static_cast<float*>(dgb), static_cast<float*>(dx), dx_ld, dx_coff, rows, c);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_film_rows_fwd(const void* gb, int gh, const void* x, int x_ld, int x_coff, void* y, int n, int h, int w,
+                                int c, int dtype, void* stream_) {
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_film_rows_fwd: channels must be multiples of 8");
+  VG_CHECK(gh == 3 && h >= 3, -1, "vg_film_rows_fwd: the parameter map must have 3 rows and the image at least 3");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * h * w * (c / 8));
+  if (dtype == 0)
+    film_rows_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(gb), gh,
+                                                            static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+                                                            static_cast<__nv_bfloat16*>(y), n, h, w, c);
+  else
+    film_rows_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(gb), gh, static_cast<const float*>(x), x_ld,
+                                                    x_coff, static_cast<float*>(y), n, h, w, c);
+  VG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int vg_film_rows_bwd(const void* gb, int gh, const void* x, int x_ld, int x_coff, const void* dy, void* dgb,
+                                void* dx, int dx_ld, int dx_coff, int n, int h, int w, int c, int dtype, void* stream_) {
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && dx_ld % 8 == 0 && dx_coff % 8 == 0, -1,
+           "vg_film_rows_bwd: channels must be multiples of 8");
+  VG_CHECK(gh == 3 && h >= 3, -1, "vg_film_rows_bwd: the parameter map must have 3 rows and the image at least 3");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const long long items = static_cast<long long>(n) * w * (c / 8);
+  const int grid = static_cast<int>((items + 127) / 128);
+  if (dtype == 0)
+    film_rows_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(gb), gh, static_cast<const __nv_bfloat16*>(x), x_ld, x_coff,
+        static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dgb), static_cast<__nv_bfloat16*>(dx), dx_ld,
+        dx_coff, n, h, w, c);
+  else
+    film_rows_bwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(gb), gh, static_cast<const float*>(x), x_ld,
+                                                    x_coff, static_cast<const float*>(dy), static_cast<float*>(dgb),
+                                                    static_cast<float*>(dx), dx_ld, dx_coff, n, h, w, c);
   VG_LAUNCH_OK();
   return 0;
 }

@@ -66,9 +66,18 @@ VG_DEVICE void reduce_rows_atomic(float (&red)[kNT][17], const float (&s)[8], co
 // ---------------------------------------------------------------------------------------------
 // statistics: sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 over the rows of group g
 // ---------------------------------------------------------------------------------------------
+// Row classes ("virtual height"): a tensor of cls_h rows per image may stand for a taller one whose interior rows are
+// all equal (the FiLM parameter maps, vae-gan-v2.py:138-145: a 3x3 conv of a row-constant input differs only in its
+// first and last row).  Row 0 and row cls_h-1 then count once, every other row `wmid` times.
+VG_DEVICE float row_class_weight(long long pixel, int cls_w, int cls_h, float wmid) {
+  const int yy = static_cast<int>((pixel / cls_w) % cls_h);
+  return (yy == 0 || yy == cls_h - 1) ? 1.f : wmid;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kNT) stats_kernel(const T* __restrict__ x, int ld, int coff, int c,
-                                                    long long rows_per_group, float* __restrict__ sums) {
+                                                    long long rows_per_group, float* __restrict__ sums, int cls_w,
+                                                    int cls_h, float wmid) {
   const RowMap m = row_map(c);
   const int g = blockIdx.y;
   const int tid = threadIdx.x;
@@ -83,6 +92,15 @@ __global__ void __launch_bounds__(kNT) stats_kernel(const T* __restrict__ x, int
       const T* base = x + static_cast<long long>(g) * rows_per_group * ld + coff + cvec * 8;
       const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
       long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
+      if (cls_h > 0) {      // weighted rows (small tensors only): plain loop
+        for (; r < rows_per_group; r += stride) {
+          float f[8];
+          Raw8<T>::load(base + r * ld).unpack(f);
+          const float wt = row_class_weight(r, cls_w, cls_h, wmid);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] = fmaf(wt, f[i], s[i]); q[i] = fmaf(wt * f[i], f[i], q[i]); }
+        }
+      }
       for (; r + 3 * stride < rows_per_group; r += 4 * stride) {
         Raw8<T> v[4];
 #pragma unroll
@@ -238,6 +256,7 @@ struct BwdParams {
   int act;
   float* sums;                                        // [groups][2][c]: sum g, sum g*xhat
   T* dx; int dx_ld, dx_coff;
+  int virt_h;                                         // > 0: the h rows stand for virt_h rows (row classes, see above)
 };
 
 template <typename T, bool kApply, bool kPool>
@@ -250,7 +269,8 @@ __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams<T> p) {
   const int ph = kPool ? p.h / 2 : p.h, pw = kPool ? p.w / 2 : p.w;
   const long long cells = static_cast<long long>(n_count) * ph * pw;
   const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
-  const float inv_rows = 1.f / (static_cast<float>(n_count) * p.h * p.w);
+  const float inv_rows = 1.f / (static_cast<float>(n_count) * (p.virt_h > 0 ? p.virt_h : p.h) * p.w);
+  const float wmid = p.virt_h > 0 ? static_cast<float>(p.virt_h - 2) / static_cast<float>(p.h - 2) : 1.f;
   const long long pix0 = static_cast<long long>(p.per_sample ? grp : 0) * p.h * p.w;
   __shared__ float red[kApply ? 1 : kNT][17];
   for (int cv0 = 0; cv0 < m.cv; cv0 += m.cvl) {
@@ -291,7 +311,19 @@ __global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams<T> p) {
           if (kApply) o[i] = sc[i] * (g - k1[i] - xh * k2[i]);
           else { s[i] += g; q[i] = fmaf(g, xh, q[i]); }
         }
-        if (kApply) store8(ob + pix * p.dx_ld, o);
+        if (kApply) {
+          if (p.virt_h > 0) {
+            // g is already the sum over the rows of this class; the mean terms enter once per represented row
+            const float wt = row_class_weight(pix, p.w, p.h, wmid);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xh = (f[i] - mean[i]) * rstd[i];
+              const float g = dyv[i] * act_grad(fmaf(f[i], sc[i], sh[i]), p.act);
+              o[i] = sc[i] * (g - wt * (k1[i] + xh * k2[i]));
+            }
+          }
+          store8(ob + pix * p.dx_ld, o);
+        }
       };
 
       if (!kPool) {
@@ -394,12 +426,26 @@ using namespace vg;
 
 template <typename T>
 static int norm_stats_impl(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c, float* sums,
-                           cudaStream_t st) {
+                           cudaStream_t st, int cls_w = 0, int cls_h = 0, float wmid = 1.f) {
   const RowMap m = row_map(c);
   const int gx = row_grid(rows_per_group, m.rows_par, groups, 4, 8);
-  stats_kernel<T><<<dim3(gx, groups), kNT, 0, st>>>(static_cast<const T*>(x), x_ld, x_coff, c, rows_per_group, sums);
+  stats_kernel<T><<<dim3(gx, groups), kNT, 0, st>>>(static_cast<const T*>(x), x_ld, x_coff, c, rows_per_group, sums, cls_w,
+                                                    cls_h, wmid);
   VG_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int vg_norm_stats_rows(const void* x, int x_ld, int x_coff, int n, int h, int w, int c, int virt_h,
+                                  float* sums, int dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0, -1, "vg_norm_stats_rows: channels must be multiples of 8");
+  VG_CHECK(dtype == 0 || dtype == 1, -1, "vg_norm_stats_rows: dtype must be 0 (bf16) or 1 (fp32)");
+  VG_CHECK(h >= 3 && virt_h >= h, -1, "vg_norm_stats_rows: need h >= 3 rows standing for virt_h >= h rows");
+  VG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
+  const float wmid = static_cast<float>(virt_h - 2) / static_cast<float>(h - 2);
+  const long long rows = static_cast<long long>(n) * h * w;
+  return dtype == 0 ? norm_stats_impl<__nv_bfloat16>(x, x_ld, x_coff, 1, rows, c, sums, st, w, h, wmid)
+                    : norm_stats_impl<float>(x, x_ld, x_coff, 1, rows, c, sums, st, w, h, wmid);
 }
 
 extern "C" int vg_norm_stats(const void* x, int x_ld, int x_coff, int groups, long long rows_per_group, int c,
@@ -463,6 +509,7 @@ static int norm_backward_impl(const VgNormBackward* d, cudaStream_t st) {
   p.mean_rstd = d->mean_rstd; p.per_sample = d->per_sample; p.gamma = d->gamma; p.beta = d->beta; p.act = d->act;
   p.sums = d->sums;
   p.dx = static_cast<T*>(d->dx); p.dx_ld = d->dx_ld; p.dx_coff = d->dx_coff;
+  p.virt_h = d->virt_h;
   const int groups = d->per_sample ? d->n : 1;
   VG_CUDA(cudaMemsetAsync(d->sums, 0, sizeof(float) * 2 * groups * d->c, st));
   const RowMap m = row_map(d->c);
@@ -495,5 +542,7 @@ extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
   VG_CHECK(d->dy != nullptr || d->dpool != nullptr, -1, "vg_norm_backward: no incoming gradient");
   VG_CHECK(d->dpool == nullptr || (d->h % 2 == 0 && d->w % 2 == 0), -1, "vg_norm_backward: pooled grad needs even H, W");
   VG_CHECK(d->dtype == 0 || d->dtype == 1, -1, "vg_norm_backward: dtype must be 0 (bf16) or 1 (fp32)");
+  VG_CHECK(d->virt_h == 0 || (d->virt_h >= d->h && d->h >= 3 && !d->per_sample && d->dpool == nullptr), -1,
+           "vg_norm_backward: virt_h needs h >= 3 rows, batch statistics and no pooling");
   return d->dtype == 0 ? norm_backward_impl<__nv_bfloat16>(d, st) : norm_backward_impl<float>(d, st);
 }

@@ -58,6 +58,14 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   VG_CHECK(enc != nullptr, -3, "cuTensorMapEncodeTiled is not available from the driver");
+  // cuTensorMapEncodeTiled is a driver entry point and needs a current context on the CALLING thread.  PyTorch's
+  // autograd worker threads may not have bound one yet when the first thing a backward pass does is encode a map
+  // (CUDA_ERROR_INVALID_CONTEXT); cudaFree(0) binds the device's primary context to this thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    VG_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   cuuint64_t gdim[5], gstride[4];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) {

@@ -83,6 +83,7 @@ class Conv2dFn(Function):
               else op.prep_fwd(weight.detach(), scale, hi))
         y = op.forward(x, wf, bias.detach() if bias is not None else None, act, out, out_kind)
         ctx.op, ctx.cache, ctx.act, ctx.sn, ctx.has_bias = op, cache, act, sn, bias is not None
+        ctx.wf = wf if (sn is not None and not hi) else None     # W / sigma of THIS call, reused by its data gradient
         ctx.in_hw = (x.shape[1], x.shape[2])
         ctx.save_for_backward(x, weight, y if act else None)
         return y
@@ -101,8 +102,13 @@ class Conv2dFn(Function):
         sn = ctx.sn
         scale = sn.sigma if sn is not None else None
         if ctx.needs_input_grad[0]:
-            wb = (ctx.cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), scale, hi))
-                  if sn is None else op.prep_bwd(weight.detach(), scale, hi))
+            if not hi and op.prefer_mn(x.shape[0] * x.shape[1] * x.shape[2]):
+                # small GEMM, big weight: the forward operand doubles as the (MN-major) operand of the data gradient
+                wb = {"mn": ctx.wf if sn is not None else
+                      ctx.cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach(), None, False))}
+            else:
+                wb = (ctx.cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), scale, hi))
+                      if sn is None else op.prep_bwd(weight.detach(), scale, hi))
             dx = op.backward_data(dy, wb, ctx.in_hw)
         if ctx.needs_input_grad[1]:
             gview = op.backward_weight(dy, x)
@@ -121,7 +127,10 @@ class ConvTranspose2dFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_hw):
         hi = x.dtype == F32
-        wb = cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), None, hi))
+        if not hi and op.prefer_mn(x.shape[0] * x.shape[1] * x.shape[2]):
+            wb = {"mn": cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach(), None, False))}
+        else:
+            wb = cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), None, hi))
         y = op.backward_data(x, wb, out_hw, bias.detach() if bias is not None else None, act, out)
         ctx.op, ctx.cache, ctx.act, ctx.has_bias = op, cache, act, bias is not None
         ctx.save_for_backward(x, weight, y if act else None)
@@ -349,15 +358,19 @@ class NormActFn(Function):
     Returns (y, pooled-or-None).  ``out`` lets the full-resolution result land in a slice of a concat buffer."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, per_sample: bool, act: int, pool: bool, out, eps: float, bn_state, pool_out=None):
+    def forward(ctx, x, gamma, beta, per_sample: bool, act: int, pool: bool, out, eps: float, bn_state, pool_out=None,
+                virt_h: int = 0):
+        """``virt_h`` > 0: the h (= 3) rows of x stand for virt_h rows whose interior rows are all equal (row-class
+        FiLM maps); the statistics weight them accordingly and the backward expects per-class gradient sums."""
         n, h, w, c = x.shape
+        ctx.virt_h = virt_h
         g, b = (gamma.detach() if gamma is not None else None), (beta.detach() if beta is not None else None)
         if bn_state is not None and not bn_state["training"]:
             mr = torch.stack([bn_state["running_mean"], torch.rsqrt(bn_state["running_var"] + eps)]).unsqueeze(0).contiguous()
             ctx.eval_mode = True
         else:
-            sums = ops.norm_stats(x, per_sample)
-            rows = h * w if per_sample else n * h * w
+            sums = ops.norm_stats_rows(x, virt_h) if virt_h else ops.norm_stats(x, per_sample)
+            rows = h * w if per_sample else n * (virt_h or h) * w
             rm = rv = nbt = None
             if bn_state is not None:
                 rm, rv, nbt = bn_state["running_mean"], bn_state["running_var"], bn_state["num_batches_tracked"]
@@ -383,8 +396,10 @@ class NormActFn(Function):
         dx = new_act(n, h, w, c, x.device, x.dtype)
         dgamma = torch.empty(c, dtype=F32, device=x.device) if gamma is not None else None
         dbeta = torch.empty(c, dtype=F32, device=x.device) if beta is not None else None
-        ops.norm_backward(x, dy, dpool, mr, ctx.per_sample, gamma, beta, ctx.act, dx, dgamma, dbeta)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        if ctx.virt_h and not dy.is_contiguous():
+            dy = ops.dense_nhwc(dy)
+        ops.norm_backward(x, dy, dpool, mr, ctx.per_sample, gamma, beta, ctx.act, dx, dgamma, dbeta, virt_h=ctx.virt_h)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -411,6 +426,32 @@ class FiLMFn(Function):
         dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         ops.film_bwd(gb, x, dy, dgb, dx)
         return dgb, dx
+
+
+class FiLMRowsFn(Function):
+    """FiLM with a 3-row parameter map gb3 [B,3,w,2C] (first | interior | last row class); exact restatement of
+    FiLMFn for maps that are row-constant away from the border.  d gb3 is the gradient summed over each class."""
+
+    @staticmethod
+    def forward(ctx, gb3, x):
+        n, h, w, c = x.shape
+        if not gb3.is_contiguous():
+            gb3 = ops.dense_nhwc(gb3)
+        y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+        ops.film_rows_fwd(gb3, x, y)
+        ctx.save_for_backward(gb3, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        gb3, x = ctx.saved_tensors
+        dy = grad_in(dy, x.dtype)
+        if not dy.is_contiguous():
+            dy = ops.dense_nhwc(dy)
+        dgb3 = torch.empty_like(gb3)
+        dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        ops.film_rows_bwd(gb3, x, dy, dgb3, dx)
+        return dgb3, dx
 
 
 class UpsampleWFn(Function):

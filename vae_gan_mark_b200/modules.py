@@ -79,8 +79,8 @@ def run_convT(ct: nn.ConvTranspose2d, x, out_hw, act=0, out=None):
     return L.ConvTranspose2dFn.apply(x, ct.weight, ct.bias, st[0], st[1], act, out, tuple(out_hw))
 
 
-def run_bn_relu(bn: nn.BatchNorm2d, x, pool=False, out=None, pool_out=None):
-    return L.NormActFn.apply(x, bn.weight, bn.bias, False, RELU, pool, out, bn.eps, _bn_state(bn), pool_out)
+def run_bn_relu(bn: nn.BatchNorm2d, x, pool=False, out=None, pool_out=None, virt_h=0):
+    return L.NormActFn.apply(x, bn.weight, bn.bias, False, RELU, pool, out, bn.eps, _bn_state(bn), pool_out, virt_h)
 
 
 def run_image_conv(conv: nn.Conv2d, images: Sequence[torch.Tensor], act=0, sn=None, weight=None):
@@ -197,6 +197,9 @@ CONV_SMS_WHILE_TEXT = 136   # of 148
 # recurrence the text encoder is < 1 ms of a ~33 ms step and its 128-CTA cluster launches cannot share the machine with
 # the persistent conv grids anyway, so it runs inline by default.
 TEXT_SIDE_STREAM = False
+# SpatialFiLMLayer: compute the FiLM parameter maps on 3 representative rows instead of all h (exact; see the layer).
+# Off by default so that the default path performs the reference's computation op for op.
+FILM_ROW_DEDUP = False
 
 
 def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
@@ -444,6 +447,16 @@ class SpatialFiLMLayer(nn.Module):
         """x_main: NHWC bf16 [B,h,w,C]; text_base_nhwc: NHWC bf16 [B,1,w0,T]."""
         _, h, w, _ = x_main.shape
         pp = self.param_predictor
+        if FILM_ROW_DEDUP and h >= 3:
+            # The upsampled text map has h IDENTICAL rows (its source is one row high), so the 3x3 conv output -- and
+            # everything pointwise after it -- is the same for every interior row; only the first and last row differ
+            # (zero padding).  Three rows (first | interior | last) therefore carry the whole (gamma, beta) map
+            # exactly; BatchNorm weights the interior row h-2 times.  Results are identical to the literal path.
+            t3 = L.UpsampleWFn.apply(text_base_nhwc, 3, w)
+            raw3 = run_conv(pp[0], t3)
+            y3, _ = run_bn_relu(pp[1], raw3, virt_h=h)
+            gb3 = run_conv(pp[3], y3)
+            return L.FiLMRowsFn.apply(gb3, x_main)
         t = L.UpsampleWFn.apply(text_base_nhwc, h, w)
         raw = run_conv(pp[0], t)
         y, _ = run_bn_relu(pp[1], raw)

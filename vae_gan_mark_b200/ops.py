@@ -111,6 +111,15 @@ def norm_stats(x: torch.Tensor, per_sample: bool) -> torch.Tensor:
     return sums
 
 
+def norm_stats_rows(x: torch.Tensor, virt_h: int) -> torch.Tensor:
+    """Batch statistics of a tensor whose h rows stand for ``virt_h`` rows (interior rows all equal)."""
+    n, h, w, c = x.shape
+    sums = torch.empty(1, 2, c, dtype=F32, device=x.device)
+    assert x.is_contiguous()
+    _lib.call("vg_norm_stats_rows", _p(x), ld_of(x), 0, n, h, w, c, virt_h, _p(sums), dcode(x), stream())
+    return sums
+
+
 def norm_finalize(sums: torch.Tensor, rows: int, eps: float, momentum: float = 0.1,
                   running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None,
                   num_batches_tracked: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -139,7 +148,8 @@ def norm_apply(x: torch.Tensor, mean_rstd: torch.Tensor, gamma, beta, act: int, 
     _lib.call("vg_norm_apply", C.byref(d), stream())
 
 
-def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dgamma, dbeta, accumulate=False):
+def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dgamma, dbeta, accumulate=False,
+                  virt_h: int = 0):
     n, h, w, c = x.shape
     groups = n if per_sample else 1
     sums = torch.empty(groups, 2, c, dtype=F32, device=x.device)
@@ -160,6 +170,8 @@ def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dga
     d.dbeta = dbeta.data_ptr() if dbeta is not None else None
     d.accumulate = int(accumulate)
     d.dtype = dcode(x)
+    d.virt_h = virt_h
+    assert virt_h == 0 or (x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous())
     assert dx.dtype == x.dtype and (dy is None or dy.dtype == x.dtype) and (dpool is None or dpool.dtype == x.dtype)
     _lib.call("vg_norm_backward", C.byref(d), stream())
 
@@ -195,6 +207,21 @@ def film_bwd(gb, x, dy, dgb, dx):
     assert gb.dtype == x.dtype == dy.dtype == dgb.dtype == dx.dtype
     _lib.call("vg_film_bwd", _p(gb), _p(x), ld_of(x), 0, _p(dy), _p(dgb), _p(dx), ld_of(dx), 0,
               C.c_longlong(n * h * w), c, dcode(x), stream())
+
+
+def film_rows_fwd(gb3, x, y):
+    n, h, w, c = x.shape
+    assert gb3.dtype == x.dtype == y.dtype and gb3.is_contiguous() and y.is_contiguous()
+    assert tuple(gb3.shape) == (n, 3, w, 2 * c), (gb3.shape, x.shape)
+    _lib.call("vg_film_rows_fwd", _p(gb3), 3, _p(x), ld_of(x), 0, _p(y), n, h, w, c, dcode(x), stream())
+
+
+def film_rows_bwd(gb3, x, dy, dgb3, dx):
+    n, h, w, c = x.shape
+    assert gb3.dtype == x.dtype == dy.dtype == dgb3.dtype == dx.dtype
+    assert gb3.is_contiguous() and dy.is_contiguous() and dgb3.is_contiguous()
+    _lib.call("vg_film_rows_bwd", _p(gb3), 3, _p(x), ld_of(x), 0, _p(dy), _p(dgb3), _p(dx), ld_of(dx), 0, n, h, w, c,
+              dcode(x), stream())
 
 
 def upsample_w_fwd(t, y):
