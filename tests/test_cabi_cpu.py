@@ -167,3 +167,29 @@ def test_tiled_copy_plan_matches_numpy():
     assert tiles > 0
     np.testing.assert_array_equal(dst[:, :, 8:32], np.broadcast_to(src[:, None, :], (4, 6, 24)))
     assert not dst[:, :, :8].any() and not dst[:, :, 32:].any()
+
+
+def test_channels_last_weights_keep_the_state_dict_contract():
+    """VAEGANTrainer stores conv weights channels_last (train.weights_channels_last); keys, shapes, dtypes and values
+    of the state_dict must not change, loading a checkpoint must keep the memory order, and spectral-norm weights
+    must keep OIHW."""
+    import torch
+    from vae_gan_mark_b200 import modules as M
+    from vae_gan_mark_b200.train import weights_channels_last
+    torch.manual_seed(0)
+    G = M.VAEGAN_UNet_SpatialFiLM(4, 32, patch_shape=(64, 32))
+    D = M.Discriminator(3)
+    before = {k: v.clone() for k, v in list(G.state_dict().items()) + list(D.state_dict().items())}
+    n = weights_channels_last(G) + weights_channels_last(D)
+    assert n > 20
+    after = dict(list(G.state_dict().items()) + list(D.state_dict().items()))
+    assert list(before) == list(after)
+    for k in before:
+        assert before[k].shape == after[k].shape and before[k].dtype == after[k].dtype and torch.equal(before[k], after[k]), k
+    w = G.style_vae_encoder_module.e_conv2[0].weight
+    assert w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()
+    for name, p in D.named_parameters():
+        if name.endswith("weight_orig"):
+            assert p.is_contiguous(), name
+    G.load_state_dict({k: v for k, v in before.items() if k in G.state_dict()})
+    assert G.style_vae_encoder_module.e_conv2[0].weight.is_contiguous(memory_format=torch.channels_last)

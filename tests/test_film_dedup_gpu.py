@@ -118,7 +118,8 @@ def test_whole_step_dedup_equals_literal_fp32():
             if s0[k].dtype.is_floating_point:
                 diff = (s1[k].double() - s0[k].double()).abs()
                 assert float(diff.max()) <= 2.1 * lr, (k, float(diff.max()))
-                assert float((diff > 1e-5).double().mean()) <= 0.01, (k, float((diff > 1e-5).double().mean()))
+                flipped = int((diff > 1e-5).sum())
+                assert flipped <= max(2, 0.01 * diff.numel()), (k, flipped, diff.numel())
     finally:
         M.FILM_ROW_DEDUP = False
         vg.set_precision("bf16")

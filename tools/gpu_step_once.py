@@ -13,6 +13,9 @@ from vae_gan_mark_b200.train import LossWeights, VAEGANTrainer  # noqa: E402
 
 def main():
     wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "v2_128"]
+    if len(sys.argv) > 2 and sys.argv[2] == "dedup":
+        from vae_gan_mark_b200 import modules as M
+        M.FILM_ROW_DEDUP = True
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     G, D = bench.build_models(wl, dev)

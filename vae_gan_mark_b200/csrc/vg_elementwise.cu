@@ -57,6 +57,8 @@ struct CopySide {
   int tile[5], dim[5], ntile[5], div[5], ss[5];
   unsigned magic[5];          // ceil(2^32 / tile) for tile >= 2 (exact quotient for numerators < 2^16)
   long long gs[5];
+  int gsi[5];                 // gs as int: offsets INSIDE a tile stay below 2^31 (checked by the planner)
+  int nt;                     // slots [0, nt) have tile > 1 (the only ones the per-element decode walks)
 };
 struct TiledCopyParams {
   CopySide ld, st;
@@ -69,18 +71,20 @@ __host__ __device__ __forceinline__ unsigned copy_mulhi(unsigned x, unsigned y) 
   return static_cast<unsigned>((static_cast<unsigned long long>(x) * y) >> 32);
 #endif
 }
-__host__ __device__ __forceinline__ bool copy_decode(const CopySide& s, const int (&ext)[5], int l, long long& goff, int& soff) {
+__host__ __device__ __forceinline__ bool copy_decode(const CopySide& s, const int (&ext)[5], int l, int& goff, int& soff) {
   unsigned r = static_cast<unsigned>(l);
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const unsigned t = static_cast<unsigned>(s.tile[k]);
-    const unsigned q = t == 1u ? r : copy_mulhi(r, s.magic[k]);
-    const int c = static_cast<int>(r - q * t);
-    r = q;
-    ok = ok && c < ext[k];
-    goff += static_cast<long long>(c) * s.gs[k];
-    soff += c * s.ss[k];
+    if (k < s.nt) {
+      const unsigned t = static_cast<unsigned>(s.tile[k]);
+      const unsigned q = copy_mulhi(r, s.magic[k]);
+      const int c = static_cast<int>(r - q * t);
+      r = q;
+      ok = ok && c < ext[k];
+      goff += c * s.gsi[k];
+      soff += c * s.ss[k];
+    }
   }
   return ok;
 }
@@ -113,26 +117,58 @@ __global__ void __launch_bounds__(256) tiled_copy_kernel(const TI* __restrict__ 
 #pragma unroll
   for (int u = 0; u < kPerThread; ++u) {
     const int l = threadIdx.x + u * 256;
-    long long goff = ibase;
-    int soff = 0;
+    int goff = 0, soff = 0;
     const bool ok = l < p.tile_elems && copy_decode(p.ld, ext, l, goff, soff);
     so[u] = ok ? soff : -1;
-    v[u] = ok ? static_cast<float>(in[goff]) : 0.f;
+    v[u] = ok ? static_cast<float>(in[ibase + goff]) : 0.f;
   }
 #pragma unroll
   for (int u = 0; u < kPerThread; ++u)
     if (so[u] >= 0) sm[so[u]] = v[u];
   __syncthreads();
   const long long obase = copy_origin(p.st, blockIdx.x, ext);
+#pragma unroll 4
   for (int l = threadIdx.x; l < p.tile_elems; l += 256) {
-    long long goff = obase;
-    int soff = 0;
+    int goff = 0, soff = 0;
     if (copy_decode(p.st, ext, l, goff, soff)) {
       float v = sm[soff] * sc;
-      if (accumulate) v += static_cast<float>(out[goff]);
-      out[goff] = static_cast<TO>(v);
+      if (accumulate) v += static_cast<float>(out[obase + goff]);
+      out[obase + goff] = static_cast<TO>(v);
     }
   }
+}
+
+// Same-order copy (both sides dense): 8 elements per thread per trip, 16/32-byte accesses
+template <typename TI, typename TO>
+__global__ void contig_copy_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n8,
+                                   const float* __restrict__ scale, int scale_inverse, int accumulate) {
+  float sc = 1.f;
+  if (scale != nullptr) sc = scale_inverse ? 1.f / *scale : *scale;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8(in + i * 8, f);
+    if (accumulate) {
+      float o[8];
+      load8(out + i * 8, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc, o[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] *= sc;
+    }
+    store8(out + i * 8, f);
+  }
+}
+static bool same_order_dense(const long long* dims, const long long* is, const long long* os, long long* total) {
+  long long run = 1;
+  for (int i = 4; i >= 0; --i) {
+    if (dims[i] == 1) continue;
+    if (is[i] != run || os[i] != run) return false;
+    run *= dims[i];
+  }
+  *total = run;
+  return true;
 }
 
 // Plans the tiling; returns the number of tiles, or 0 when the generic kernel should be used.
@@ -199,16 +235,28 @@ static long long plan_tiled_copy(const long long* dims, const long long* is, con
   long long ntile[5], div[5], tiles = 1;
   for (int i = 0; i < 5; ++i) { ntile[i] = cdiv(d[i], t[i]); div[i] = tiles; tiles *= ntile[i]; }
   if (tiles >= (1LL << 31)) return 0;
-  auto fill = [&](CopySide& s, const int* order, const long long* gstride) {
+  bool fits = true;
+  auto fill = [&](CopySide& s, const int* order_in, const long long* gstride) {
+    int order[5], m = 0;
+    for (int k = 0; k < 5; ++k)
+      if (t[order_in[k]] > 1) order[m++] = order_in[k];      // tiled dims first (stride order kept) ...
+    s.nt = m;
+    for (int k = 0; k < 5; ++k)
+      if (t[order_in[k]] <= 1) order[m++] = order_in[k];     // ... then the ones the per-element decode skips
+    long long span = 0;
     for (int k = 0; k < 5; ++k) {
       const int i = order[k];
+      span += (t[i] - 1) * gstride[i];
+      s.gsi[k] = static_cast<int>(gstride[i]);
       s.tile[k] = static_cast<int>(t[i]); s.dim[k] = static_cast<int>(d[i]); s.ntile[k] = static_cast<int>(ntile[i]);
       s.div[k] = static_cast<int>(div[i]); s.ss[k] = ss[i]; s.gs[k] = gstride[i];
       s.magic[k] = t[i] >= 2 ? static_cast<unsigned>(((1ULL << 32) + t[i] - 1) / t[i]) : 0u;
     }
+    if (span >= (1LL << 31)) fits = false;
   };
   fill(p.ld, lo, a);
   fill(p.st, so, b);
+  if (!fits) return 0;
   p.tile_elems = static_cast<int>(prod);
   return tiles;
 }
@@ -715,15 +763,13 @@ extern "C" long long vg_debug_copy_plan_host(const float* in, float* out, const 
     int ext[5];
     const long long ibase = copy_origin(p.ld, static_cast<unsigned>(bid), ext);
     for (int l = 0; l < p.tile_elems; ++l) {
-      long long goff = ibase;
-      int soff = 0;
-      if (copy_decode(p.ld, ext, l, goff, soff)) sm[soff] = in[goff];
+      int goff = 0, soff = 0;
+      if (copy_decode(p.ld, ext, l, goff, soff)) sm[soff] = in[ibase + goff];
     }
     const long long obase = copy_origin(p.st, static_cast<unsigned>(bid), ext);
     for (int l = 0; l < p.tile_elems; ++l) {
-      long long goff = obase;
-      int soff = 0;
-      if (copy_decode(p.st, ext, l, goff, soff)) out[goff] = sm[soff];
+      int goff = 0, soff = 0;
+      if (copy_decode(p.st, ext, l, goff, soff)) out[obase + goff] = sm[soff];
     }
   }
   return tiles;
@@ -742,6 +788,22 @@ extern "C" int vg_strided_copy(const void* in, int in_dtype, void* out, int out_
   }
   VG_CHECK(in_dtype >= 0 && in_dtype <= 1 && out_dtype >= 0 && out_dtype <= 1, -1,
            "vg_strided_copy: dtype codes are 0 (fp32) and 1 (bf16)");
+  long long dense_total = 0;
+  if (same_order_dense(dims, in_strides, out_strides, &dense_total) && dense_total % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(in) & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+    const long long n8 = dense_total / 8;
+    const int gd = ew_grid(n8);
+#define VG_CONTIG_DISPATCH(TI, TO)                                                                                      \
+  contig_copy_kernel<TI, TO><<<gd, 256, 0, st>>>(static_cast<const TI*>(in), static_cast<TO*>(out), n8, scale,        \
+                                                 scale_inverse, accumulate)
+    if (in_dtype == 0 && out_dtype == 0) VG_CONTIG_DISPATCH(float, float);
+    else if (in_dtype == 0 && out_dtype == 1) VG_CONTIG_DISPATCH(float, __nv_bfloat16);
+    else if (in_dtype == 1 && out_dtype == 0) VG_CONTIG_DISPATCH(__nv_bfloat16, float);
+    else VG_CONTIG_DISPATCH(__nv_bfloat16, __nv_bfloat16);
+#undef VG_CONTIG_DISPATCH
+    VG_LAUNCH_OK();
+    return 0;
+  }
   TiledCopyParams tp;
   const long long tiles = plan_tiled_copy(dims, in_strides, out_strides, tp);
   const int g = tiles > 0 ? static_cast<int>(tiles) : ew_grid(total);

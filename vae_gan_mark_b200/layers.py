@@ -57,9 +57,13 @@ def grad_in(t: Optional[torch.Tensor], dtype=None) -> Optional[torch.Tensor]:
     return out
 
 
-def _write_param_grad(view_oihw: torch.Tensor) -> torch.Tensor:
-    """Materialise an fp32 gradient given as a permuted view into a fresh contiguous tensor in parameter layout."""
-    out = torch.empty(view_oihw.shape, dtype=F32, device=view_oihw.device)
+def _write_param_grad(view_oihw: torch.Tensor, like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 gradient, given as an OIHW-shaped (permuted) view of the kernel's [O][kh][kw][I] result, in the memory
+    order of the parameter ``like``.  For channels_last parameters the view already IS that order: no copy."""
+    if like is not None and view_oihw.stride() == like.stride():
+        return view_oihw
+    out = torch.empty_like(like, dtype=F32) if like is not None else torch.empty(view_oihw.shape, dtype=F32,
+                                                                                 device=view_oihw.device)
     ops.strided_copy(view_oihw, out)
     return out
 
@@ -112,7 +116,7 @@ class Conv2dFn(Function):
             dx = op.backward_data(dy, wb, ctx.in_hw)
         if ctx.needs_input_grad[1]:
             gview = op.backward_weight(dy, x)
-            dw = _write_param_grad(gview)
+            dw = _write_param_grad(gview, weight)
             if sn is not None:
                 dw = sn.backward(dw, weight.detach())
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -151,7 +155,7 @@ class ConvTranspose2dFn(Function):
             wf = ctx.cache.get("fwd_hi" if hi else "fwd", weight, lambda: op.prep_fwd(weight.detach(), None, hi))
             dx = op.forward(dy, wf)
         if ctx.needs_input_grad[1]:
-            dw = _write_param_grad(op.backward_weight(x, dy))     # operands swapped: [cout(op)=C_in][cin(op)=C_out]
+            dw = _write_param_grad(op.backward_weight(x, dy), weight)     # operands swapped: [cout(op)=C_in][cin(op)=C_out]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy)
         return dx, dw, db, None, None, None, None, None
@@ -200,7 +204,7 @@ class HeadsFn(Function):
             dx = op.backward_data(dy, wb, (feat.shape[1], feat.shape[2]))
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             g = op.backward_weight(dy, feat)                 # view [2z, c, kh, kw]
-            dmu, dlv = _write_param_grad(g[:z]), _write_param_grad(g[z:])
+            dmu, dlv = _write_param_grad(g[:z], w_mu), _write_param_grad(g[z:], w_lv)
         return dx, dmu, dlv, None, None, None
 
 
@@ -286,7 +290,7 @@ class ImageConvFn(Function):
                       pairs=[(pa * cout_p, pb * kpad) for (pa, pb) in PAIRS], ksplit=_hi_wgrad_split(n, oh, ow))
             else:
                 wgrad(dy, cout, col, [(0, 0, 0, 0)], 1, kpad, (n, oh, ow), dwm)
-            dw = _write_param_grad(dwm[:, :k].view(cout, kh, kw, cin).permute(0, 3, 1, 2))
+            dw = _write_param_grad(dwm[:, :k].view(cout, kh, kw, cin).permute(0, 3, 1, 2), weight)
             if sn is not None:
                 dw = sn.backward(dw, weight.detach())
         if ctx.has_bias and ctx.needs_input_grad[1]:
@@ -328,7 +332,7 @@ class SmallOutConvFn(Function):
         oh, ow = h + 2 * pad - kh + 1, w + 2 * pad - kw + 1
         out = torch.empty((n, oh, ow, cout), dtype=F32, device=x.device)
         ops.smalln_fwd(x, wt, bias.detach() if bias is not None else None, kh, kw, pad, out)
-        ctx.pad, ctx.has_bias = pad, bias is not None
+        ctx.pad, ctx.has_bias, ctx.w_param = pad, bias is not None, weight
         ctx.save_for_backward(x, wt)
         return out
 
@@ -345,7 +349,7 @@ class SmallOutConvFn(Function):
             dwt = torch.empty_like(wt)
             db_ = torch.empty(cout, dtype=F32, device=x.device) if ctx.has_bias else None
             ops.smalln_wgrad(dy, x, kh, kw, ctx.pad, dwt, db_)
-            dw = _write_param_grad(dwt.permute(0, 3, 1, 2))
+            dw = _write_param_grad(dwt.permute(0, 3, 1, 2), ctx.w_param)
             db = db_
         return dx, dw, db, None
 

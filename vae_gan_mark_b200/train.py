@@ -83,8 +83,10 @@ class FusedAdam:
             t = self._table_host_graph
         for i, (p, m, v) in enumerate(zip(self.params, self.exp_avg, self.exp_avg_sq)):
             g = p.grad
-            if g is not None and not g.is_contiguous():
-                g = g.contiguous()
+            if g is not None and g.stride() != p.stride():
+                # the kernels walk p, g, m, v as flat arrays: the gradient must share the parameter's memory order
+                # (OIHW, or channels_last for conv weights -- see weights_channels_last)
+                g = torch.empty_like(p).copy_(g)
                 p.grad = g
             t[i, 0], t[i, 1] = p.data_ptr(), (g.data_ptr() if g is not None else 0)
             t[i, 2], t[i, 3], t[i, 4] = m.data_ptr(), v.data_ptr(), p.numel()
@@ -151,10 +153,32 @@ def frozen(module: torch.nn.Module):
             p.requires_grad_(f)
 
 
+def weights_channels_last(module: torch.nn.Module) -> int:
+    """Store the 4-D conv / conv-transpose weights of ``module`` in channels_last memory order ([O][kh][kw][I]).
+
+    Shapes, dtypes and state_dict keys do not change (``load_state_dict`` / ``state_dict`` are oblivious to strides),
+    but this is the order the tensor core consumes and produces: the forward operand becomes a plain fp32 -> bf16
+    conversion, and the weight-gradient kernel's [O][kh][kw][I] result IS the gradient -- autograd adopts it without
+    a re-layout copy.  Spectral-norm weights keep the OIHW order their u / v vectors are defined in.  Returns the
+    number of tensors converted."""
+    count = 0
+    for name, p in module.named_parameters():
+        if p.dim() == 4 and not name.endswith("weight_orig") and p.shape[2] * p.shape[3] > 1 and p.shape[1] > 1:
+            if not p.data.is_contiguous(memory_format=torch.channels_last):
+                p.data = p.data.contiguous(memory_format=torch.channels_last)
+                if p.grad is not None:
+                    p.grad = None
+                count += 1
+    return count
+
+
 class VAEGANTrainer:
     def __init__(self, G: torch.nn.Module, D: torch.nn.Module, weights: LossWeights, lr_g=1e-4, lr_d=1e-4,
-                 clip_norm: float = 1.0, grad_hook=None):
+                 clip_norm: float = 1.0, grad_hook=None, channels_last_weights: bool = True):
         self.G, self.D, self.w, self.clip_norm = G, D, weights, clip_norm
+        if channels_last_weights:
+            weights_channels_last(G)
+            weights_channels_last(D)
         self.opt_G = FusedAdam(G.parameters(), lr=lr_g)
         self.opt_D = FusedAdam(D.parameters(), lr=lr_d)
         self.grad_hook = grad_hook        # called as grad_hook("D"|"G", params) after each backward (DP allreduce)
