@@ -155,6 +155,11 @@ def run_ours(args, wl):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner at communicator
+    # creation, for one) is sent to stderr instead; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -356,7 +361,7 @@ def run_ours(args, wl):
             line["config"]["film_row_dedup"] = True
         if args.diag_freeze_text:
             line["diagnostic"] = "text encoder output cached -- NOT a bench value"
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # A process group whose collectives were captured in a CUDA graph can hang in destroy_process_group();
         # everything is printed and synchronised by now, so leave without the teardown.
