@@ -4,9 +4,9 @@ whose forward/backward run on the hand-written sm_100a kernels (layers.py).
 The parameter containers are stock ``nn.Conv2d`` / ``nn.ConvTranspose2d`` / ``nn.BatchNorm2d`` /
 ``nn.InstanceNorm2d`` / ``spectral_norm`` objects arranged exactly as in the reference, so ``state_dict()``,
 ``parameters()`` order, ``.to()``, ``.train()/.eval()`` and checkpoint loading behave identically; they are
-never *called* -- the executors below read their tensors and launch our kernels.  Only the recurrent text
-encoder (``CharacterTokenEncoder``; <2% of the FLOPs) and the 384->64 text projection run as
-stock torch modules.
+never *called* -- the executors below read their tensors and launch our kernels.  Stock torch is left only for
+the embedding lookup, the time-parallel GEMMs and the pooling of the text encoder (``CharacterTokenEncoder``; its GRU
+recurrence runs on vg_gru.cu) and for the 384->64 text projection of the base model.
 
 Like the reference, constructors read the module-level ``PATCH_SHAPE`` = (W, H) unless ``patch_shape`` is given.
 
@@ -117,10 +117,11 @@ class _SNCall:
 
 
 # ------------------------------------------------------------------------------------------------
-# text encoders (stock torch)
+# text encoders
 # ------------------------------------------------------------------------------------------------
 class CharacterTokenEncoder(nn.Module):
-    """vae-gan-v2.py:65-114.  Stock Embedding + biGRU + adaptive pool; output (B, 2*hid, 1, W/16) fp32."""
+    """vae-gan-v2.py:65-114.  Embedding + biGRU (cluster-kernel recurrence, layers.GRULayerFn) + adaptive pool;
+    output (B, 2*hid, 1, W/16) fp32.  ``self.rnn`` is a stock nn.GRU used as the parameter container."""
 
     def __init__(self, alphabet_str, emb_dim, rnn_hidden_dim, rnn_layers, target_feature_width):
         super().__init__()
