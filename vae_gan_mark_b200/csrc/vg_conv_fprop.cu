@@ -33,7 +33,8 @@ constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle
 constexpr int kUmmaK = 16;
 constexpr int kFpropThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int kMaxTaps = VG_MAX_FPROP_TAPS;
-constexpr int kEpiBytes = 8 * 32 * 128;   // 8 epilogue warps x (32 rows x 128 B XOR-swizzled staging tile)
+constexpr int kEpiStageBytes = 8 * 32 * 128;          // 8 epilogue warps x (32 rows x 128 B XOR-swizzled staging tile)
+constexpr int kEpiBytes = kEpiStageBytes + 8 * 32 * 4;  // + per-warp 32-float bias window (read back as broadcast float4)
 
 struct FpropParams {
   int m_n, m_h, m_w;            // output pixel grid
@@ -186,6 +187,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int r_h = (row / p.tw) % p.th;
     const int r_n = row / (p.tw * p.th);
     uint8_t* stg = epi_smem + (warp - 4) * (32 * 128);
+    float* bias_win = reinterpret_cast<float*>(epi_smem + kEpiStageBytes) + (warp - 4) * 32;
     const int esz = p.out_kind == 0 ? 2 : 4;
     const int chunk_cols = p.out_kind == 0 ? 64 : 32;
     const bool plain = (p.bias == nullptr) && (p.act == 0);
@@ -220,13 +222,25 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const int ngh = ng0 + hh * 32;
               const int ch0 = ngh % p.cout_per_sub;
               const int nvalid = min(32, p.n_gemm - ngh);
+              // the 32 bias values of this column window: one coalesced load per warp, then broadcast float4 reads
+              // (a per-element __ldg made bias-carrying layers LSU-bound: 64 loads per thread per 64 columns)
+              if (p.bias != nullptr) {
+                __syncwarp();
+                bias_win[lane] = lane < nvalid ? __ldg(p.bias + ch0 + lane) : 0.f;
+                __syncwarp();
+              }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(r[hh * 32 + j]);
-                if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + ch0 + j);
-                if (p.act == 1) x = fmaxf(x, 0.f);
-                else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
-                r[hh * 32 + j] = __float_as_uint(x);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr) b4 = *reinterpret_cast<const float4*>(bias_win + 4 * j4);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float x = __uint_as_float(r[hh * 32 + 4 * j4 + e]) + bb[e];
+                  if (p.act == 1) x = fmaxf(x, 0.f);
+                  else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+                  r[hh * 32 + 4 * j4 + e] = __float_as_uint(x);
+                }
               }
             }
           }
