@@ -79,6 +79,12 @@ typedef struct VgConvFprop {
                                contiguous: GEMM column n of tap t sits at w[k][wk[t] + n] (use_wk required).  This is a
                                conv's FORWARD operand [Cout][taps*Cin] read as B of its own data gradient */
   int w_rows;               /* b_mn_major: rows of w (K extent of one tap; rows beyond read as zero) */
+  int num_groups;           /* 0/1: one problem.  2..4: independent problems sharing x, w, M, N and the destination,
+                               differing in their taps (listed group after group in taps[] / wk[]) and in the sub-pixel
+                               offset they write -- the output-parity classes of a stride-2 data gradient in ONE launch.
+                               sub_h0 / sub_w0 are ignored; no split-K */
+  int group_ntaps[4];       /* taps of each group; must add up to num_taps */
+  int group_sub[4][2];      /* (sub_h0, sub_w0) of each group */
 } VgConvFprop;
 int vg_conv_fprop(const VgConvFprop* desc /*host*/, void* stream);
 

@@ -66,10 +66,11 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
           m: Tuple[int, int, int], out: torch.Tensor, out_kind: int = 0, su: Tuple[int, int] = (1, 1),
           sub0: Tuple[int, int] = (0, 0), cout_per_sub: Optional[int] = None, bias: Optional[torch.Tensor] = None,
           act: int = 0, ksplit: int = 0, force_bn: int = 0, wk: Optional[Sequence[int]] = None,
-          b_mn_major: bool = False) -> None:
+          b_mn_major: bool = False, groups: Optional[Sequence[Tuple[int, Tuple[int, int]]]] = None) -> None:
     """out[pixel, n] = sum_{tap, c<cin} x[pixel@tap, c] * w[n, wk[tap] + c]  (wk[tap] = tap*cin by default).
     ``out`` is an NHWC view ([N, OH, OW, C']); ``x`` and ``w`` are bf16.
-    ``b_mn_major``: w is [K rows (c), columns] and out[pixel, n] = sum x[pixel@tap, c] * w[c, wk[tap] + n]."""
+    ``b_mn_major``: w is [K rows (c), columns] and out[pixel, n] = sum x[pixel@tap, c] * w[c, wk[tap] + n].
+    ``groups``: [(number of taps, (sub_h0, sub_w0)), ...] -- up to 4 problems in one launch, taps listed group by group."""
     _chk(x, "fprop x")
     assert w.dtype == BF16 and w.stride(1) == 1 and out.stride(3) == 1
     assert len(taps) <= _lib.VG_MAX_FPROP_TAPS, f"{len(taps)} taps > {_lib.VG_MAX_FPROP_TAPS}"
@@ -95,6 +96,12 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
     d.bias = bias.data_ptr() if bias is not None else None
     d.act, d.ksplit, d.force_bn = act, ksplit, force_bn
     d.b_mn_major, d.w_rows = int(b_mn_major), w.shape[0]
+    if groups is not None:
+        assert 2 <= len(groups) <= 4 and sum(g[0] for g in groups) == len(taps) and ksplit in (0, 1)
+        d.num_groups = len(groups)
+        for i, (nt, (sh, sw)) in enumerate(groups):
+            d.group_ntaps[i] = nt
+            d.group_sub[i][0], d.group_sub[i][1] = sh, sw
     e0 = _prof_begin()
     _lib.call("vg_conv_fprop", C.byref(d), ops.stream())
     _prof_end(e0, "fprop", (m, n_gemm, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * n_gemm * len(taps) * cin)
@@ -234,6 +241,20 @@ class ConvLinear:
         copy_us = 5.0 * copies + nk * 6 / 1e6
         return slowdown_us < copy_us
 
+    def _parity_taps(self, col_step: int):
+        """Taps, weight-column offsets and groups of the stride-2 data gradient: output pixel (2i + a, 2j + b) collects
+        the kernel taps (r, q) with r = a + ph, q = b + pw (mod 2), reading dy at (i + (a + ph - r) / 2, ...)."""
+        taps, wk, groups = [], [], []
+        for a in (0, 1):
+            for b in (0, 1):
+                r0, q0 = (a + self.ph) % 2, (b + self.pw) % 2
+                rs, qs = range(r0, self.kh, 2), range(q0, self.kw, 2)
+                taps += [(0, (b + self.pw - q) // 2, 0, (a + self.ph - r) // 2) for r in rs for q in qs]
+                wk += [(r * self.kw + q) * col_step for r in rs for q in qs]
+                groups.append((len(rs) * len(qs), (a, b)))
+        assert all(nt > 0 for nt, _ in groups), "stride-2 data gradient needs a kernel of at least 2x2"
+        return taps, wk, groups
+
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         return (h + 2 * self.ph - self.kh) // self.s + 1, (w + 2 * self.pw - self.kw) // self.s + 1
 
@@ -257,6 +278,8 @@ class ConvLinear:
             return {"shuffle": _operand(w.permute(2, 3, 1, 0), self.cout_p, hi, scale).view(kh * kw * ci, -1)}
         if self.s == 1:
             return {"s1": _operand(w.permute(1, 2, 3, 0), self.cout_p, hi, scale)}
+        if not hi and all(len(range(r0, self.kh, 2)) > 0 for r0 in (0, 1)) and all(len(range(q0, self.kw, 2)) > 0 for q0 in (0, 1)):
+            return {"parity_k": _operand(w.permute(1, 2, 3, 0), self.cout_p, False, scale)}
         mats = {}
         for a in (0, 1):
             for b in (0, 1):
@@ -322,14 +345,16 @@ class ConvLinear:
                 fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h, w), out, out_kind=kind, bias=bias, act=act, wk=wk,
                       b_mn_major=True)
             else:
-                for a in (0, 1):
-                    for b in (0, 1):
-                        r0, q0 = (a + self.ph) % 2, (b + self.pw) % 2
-                        rs, qs = range(r0, self.kh, 2), range(q0, self.kw, 2)
-                        taps = [(0, (b + self.pw - q) // 2, 0, (a + self.ph - r) // 2) for r in rs for q in qs]
-                        wk = [(r * self.kw + q) * self.cin_p for r in rs for q in qs]
-                        fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2),
-                              sub0=(a, b), cout_per_sub=self.cin, bias=bias, act=act, wk=wk, b_mn_major=True)
+                taps, wk, groups = self._parity_taps(self.cin_p)
+                fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2),
+                      cout_per_sub=self.cin, bias=bias, act=act, wk=wk, b_mn_major=True, groups=groups)
+            return out
+        if "parity_k" in wb:
+            # K-major operand [cin][(r, q)][cout_p] holding every tap; the four output-parity classes are the four
+            # groups of ONE launch, each reading its own taps through the column offsets
+            taps, wk, groups = self._parity_taps(self.cout_p)
+            fprop(g, taps, 1, self.cout_p, wb["parity_k"], self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2),
+                  cout_per_sub=self.cin, bias=bias, act=act, wk=wk, groups=groups)
             return out
         if "shuffle" in wb:
             # pixel shuffle: GEMM column (r, q, ci) of input pixel (oh, ow) lands at output pixel (oh*kh + r, ow*kw + q).

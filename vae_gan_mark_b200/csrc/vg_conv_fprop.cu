@@ -51,6 +51,9 @@ struct FpropParams {
   int act;                      // 0 none, 1 relu, 2 leaky relu 0.2
   int vec_ok;                   // destination allows 16-byte vector stores
   int b_mn;                     // B operand is MN-major (see header comment)
+  // groups: independent problems sharing A, W, M, N and the destination, differing in their taps and in the
+  // sub-pixel they write (the 4 output-parity classes of a stride-2 data gradient): one launch instead of four
+  int ngroups, g_tap0[4], g_ntaps[4], g_sub_h0[4], g_sub_w0[4];
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
   int wk[kMaxTaps];             // first weight column of each tap
 };
@@ -98,7 +101,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_base_slot;
 
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
-  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
+  const int tiles_per_group = m_tiles * p.n_tiles * p.ksplit;
+  const int total_tiles = tiles_per_group * p.ngroups;
+  const int cchunks_all = p.cin / kBK;
 
   if (warp == 0) {
     // ===================== TMA producer (one lane per box) =====================
@@ -106,18 +111,21 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_t = tile % p.n_tiles;
-      int rest = tile / p.n_tiles;
+      const int grp = tile / tiles_per_group;
+      const int tl = tile - grp * tiles_per_group;
+      const int n_t = tl % p.n_tiles;
+      int rest = tl / p.n_tiles;
       const int m_t = rest % m_tiles;
       const int split = rest / m_tiles;
       const int tw_i = m_t % p.tiles_w;
       const int th_i = (m_t / p.tiles_w) % p.tiles_h;
       const int tn_i = m_t / (p.tiles_w * p.tiles_h);
       const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
-      const int k_begin = static_cast<int>((static_cast<long long>(p.ksteps) * split) / p.ksplit);
-      const int k_end = static_cast<int>((static_cast<long long>(p.ksteps) * (split + 1)) / p.ksplit);
-      const int cchunks = p.cin / kBK;
-      int tap = k_begin / cchunks;
+      const int cchunks = cchunks_all;
+      const int ksteps = p.g_ntaps[grp] * cchunks;
+      const int k_begin = static_cast<int>((static_cast<long long>(ksteps) * split) / p.ksplit);
+      const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
+      int tap = p.g_tap0[grp] + k_begin / cchunks;
       int cc = k_begin % cchunks;
       for (int k = k_begin; k < k_end; ++k) {
         if (lane == 0) {
@@ -149,9 +157,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = (tile / p.n_tiles) / m_tiles;
-      const int k_begin = static_cast<int>((static_cast<long long>(p.ksteps) * split) / p.ksplit);
-      const int k_end = static_cast<int>((static_cast<long long>(p.ksteps) * (split + 1)) / p.ksplit);
+      const int grp = tile / tiles_per_group;
+      const int split = ((tile - grp * tiles_per_group) / p.n_tiles) / m_tiles;
+      const int ksteps = p.g_ntaps[grp] * cchunks_all;
+      const int k_begin = static_cast<int>((static_cast<long long>(ksteps) * split) / p.ksplit);
+      const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -194,8 +204,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_t = tile % p.n_tiles;
-      const int m_t = (tile / p.n_tiles) % m_tiles;
+      const int grp = tile / tiles_per_group;
+      const int tl = tile - grp * tiles_per_group;
+      const int sub_h0 = p.g_sub_h0[grp], sub_w0 = p.g_sub_w0[grp];
+      const int n_t = tl % p.n_tiles;
+      const int m_t = (tl / p.n_tiles) % m_tiles;
       const int tw_i = m_t % p.tiles_w;
       const int th_i = (m_t / p.tiles_w) % p.tiles_h;
       const int tn_i = m_t / (p.tiles_w * p.tiles_h);
@@ -270,7 +283,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int sub = ngh / p.cout_per_sub;
           const int ch0 = ngh - sub * p.cout_per_sub;
           const long long delta =
-              (static_cast<long long>(p.sub_h0 + sub / p.su_w) * p.out_w + (p.sub_w0 + sub % p.su_w)) * p.out_ld +
+              (static_cast<long long>(sub_h0 + sub / p.su_w) * p.out_w + (sub_w0 + sub % p.su_w)) * p.out_ld +
               p.out_coff + ch0 + (esz == 2 ? (seg & 3) * 8 : seg * 4);
           uint8_t* gout = reinterpret_cast<uint8_t*>(p.out) + delta * esz;
           const bool seg_ok = seg * 16 < valid_bytes;
@@ -295,14 +308,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (row_ok && ng0 < p.n_gemm) {
             const int sub = ng0 / p.cout_per_sub;   // uniform over the chunk when cout_per_sub % 32 == 0
             const int ch0 = ng0 - sub * p.cout_per_sub;
-            const int dh = p.sub_h0 + sub / p.su_w, dw = p.sub_w0 + sub % p.su_w;
+            const int dh = sub_h0 + sub / p.su_w, dw = sub_w0 + sub % p.su_w;
             const long long off = my_base + (static_cast<long long>(dh) * p.out_w + dw) * p.out_ld + p.out_coff + ch0;
             const int nvalid = min(32, p.n_gemm - ng0);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nvalid) {
                 float x = __uint_as_float(r[j]);
-                if (p.bias != nullptr && (p.out_kind != 2 || tile / (p.n_tiles * m_tiles) == 0)) x += __ldg(p.bias + ch0 + j);   // split-K: bias once
+                if (p.bias != nullptr && (p.out_kind != 2 || tl / (p.n_tiles * m_tiles) == 0)) x += __ldg(p.bias + ch0 + j);   // split-K: bias once
                 if (p.act == 1) x = fmaxf(x, 0.f);
                 else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
                 if (p.out_kind == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16(x);
@@ -393,6 +406,21 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   p.su_h = d->su_h; p.su_w = d->su_w; p.sub_h0 = d->sub_h0; p.sub_w0 = d->sub_w0; p.cout_per_sub = d->cout_per_sub;
   p.bias = d->bias; p.act = d->act;
   p.b_mn = d->b_mn_major ? 1 : 0;
+  p.ngroups = d->num_groups > 1 ? d->num_groups : 1;
+  VG_CHECK(p.ngroups <= 4, -1, "vg_conv_fprop: at most 4 groups");
+  if (p.ngroups == 1) {
+    p.g_tap0[0] = 0; p.g_ntaps[0] = d->num_taps; p.g_sub_h0[0] = d->sub_h0; p.g_sub_w0[0] = d->sub_w0;
+  } else {
+    int t0 = 0;
+    for (int g = 0; g < p.ngroups; ++g) {
+      VG_CHECK(d->group_ntaps[g] >= 1, -1, "vg_conv_fprop: group %d has no taps", g);
+      p.g_tap0[g] = t0; p.g_ntaps[g] = d->group_ntaps[g];
+      p.g_sub_h0[g] = d->group_sub[g][0]; p.g_sub_w0[g] = d->group_sub[g][1];
+      t0 += d->group_ntaps[g];
+    }
+    VG_CHECK(t0 == d->num_taps, -1, "vg_conv_fprop: group tap counts (%d) do not add up to num_taps (%d)", t0, d->num_taps);
+    VG_CHECK(ksplit == 1, -1, "vg_conv_fprop: groups cannot be combined with split-K");
+  }
   VG_CHECK(!p.b_mn || d->w_rows >= 1, -1, "vg_conv_fprop: b_mn_major needs w_rows (number of K rows of the weight matrix)");
   {
     const int esz = d->out_kind == 0 ? 2 : 4;
@@ -429,7 +457,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
+  const int total_tiles = m_tiles * p.n_tiles * p.ksplit * p.ngroups;
   const int grid = min(total_tiles, sms);
   conv_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tmap_a, tmap_b, p);
   VG_LAUNCH_OK();
