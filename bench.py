@@ -123,6 +123,77 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def run_stock_gpu(args, wl):
+    """Extra baseline ("the real bar to beat"): the reference's modules (oracle restatement) and step
+    body on the SAME GPU under stock PyTorch / cuDNN -- once as the reference runs them (fp32, cuDNN's default TF32
+    convolutions, torch.optim.Adam) and once under bf16 autocast with channels_last tensors.  None of this repo's
+    kernels are involved.  Rank 0 only; prints one JSON line with "impl": "stock-gpu"."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    import torch.nn.functional as F
+    from torch.nn.utils import clip_grad_norm_
+    from oracle import models as om
+    from oracle.step import LossWeights, deterministic_state, hinge_loss, kl_term, make_optimizers, synthetic_batch
+    dev = torch.device("cuda", 0)
+    fam, h, w, z, B = wl["family"], wl["h"], wl["w"], wl["z"], wl["batch"]
+    wts = LossWeights.for_family(fam)
+    results = {}
+    for mode in ("fp32_tf32conv", "bf16_autocast_channels_last"):
+        if fam == "base":
+            G = om.VAEGAN(4, z, 64, 3, patch_hw=(h, w))
+        elif fam == "v2":
+            G = om.VAEGAN_UNet_SpatialFiLM(4, z, patch_hw=(h, w))
+        else:
+            G = om.VAEGAN_UNet_CharEmb(4, z, patch_hw=(h, w), repaired=True)
+        D = om.Discriminator(3)
+        G.load_state_dict(deterministic_state(G, 1234)); D.load_state_dict(deterministic_state(D, 4321))
+        G, D = G.to(dev).train(), D.to(dev).train()
+        cl = mode.startswith("bf16")
+        if cl:
+            G, D = G.to(memory_format=torch.channels_last), D.to(memory_format=torch.channels_last)
+        og, od = make_optimizers(G, D)
+        ru, en, mask, texts = synthetic_batch(B, h, w, step=0)
+        ru, en, mask = ru.to(dev), en.to(dev), mask.to(dev)
+        if cl:
+            ru, en, mask = (t.contiguous(memory_format=torch.channels_last) for t in (ru, en, mask))
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cl):
+                fake, mu, logvar = G(ru, mask, texts)
+                od.zero_grad()
+                loss_d = (hinge_loss(D(en), 1) + hinge_loss(D(fake.detach()), 0)) * 0.5
+            loss_d.backward()
+            od.step()
+            og.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cl):
+                loss_g = (wts.recon * F.l1_loss(fake.float(), en) + wts.kl * kl_term(mu.float(), logvar.float())
+                          + wts.gan * hinge_loss(D(fake), None))
+            loss_g.backward()
+            clip_grad_norm_(G.parameters(), max_norm=1.0)
+            og.step()
+        for _ in range(max(3, args.warmup)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        results[mode] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms}
+        del G, D, og, od
+        torch.cuda.empty_cache()
+    best = max(results.values(), key=lambda r: r["images_per_s"])
+    print(json.dumps({"impl": "stock-gpu", "metric": "train_images_per_sec", "value": best["images_per_s"], "unit": "images/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": best["ms_per_step"],
+                      "higher_is_better": True, "data": "synthetic",
+                      "config": {"workload": wl["name"], "per_gpu_batch": B,
+                                 "what": "reference modules (oracle restatement) + step body under stock PyTorch/cuDNN on this GPU"},
+                      "modes": results}), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
@@ -376,7 +447,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "stock-gpu"])
     ap.add_argument("--workload", default="v2_128", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -394,6 +465,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.impl == "stock-gpu":
+        run_stock_gpu(args, wl)
     else:
         run_ours(args, wl)
 
