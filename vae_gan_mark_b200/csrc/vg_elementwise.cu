@@ -554,6 +554,36 @@ __global__ void smalln_fwd_kernel(const T* __restrict__ x, int x_ld, int x_coff,
   const int cv = cin / 8;
   const int kvecs = kh * kw * cv;
   const int lane_in_g = threadIdx.x % G;
+  if (kh == 1 && kw == 1 && pad == 0 && kvecs == G) {
+    // pointwise conv with one channel vector per lane (final_image_conv, vae-gan-v2.py:232): the lane's weights stay
+    // in registers, the pixel index needs no decoding, each warp reads 32/G whole pixel rows (contiguous bytes)
+    float wreg[kMaxSmallN][8];
+    for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wreg[o][k] = o < cout ? __ldg(wt + static_cast<long long>(o) * cin + lane_in_g * 8 + k) : 0.f;
+    float bv[kMaxSmallN];
+    for (int o = 0; o < kMaxSmallN; ++o) bv[o] = (bias != nullptr && o < cout) ? bias[o] : 0.f;
+    const long long padded = ((pixels + (32 / G) - 1) / (32 / G)) * (32 / G);
+    for (long long px = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G; px < padded;
+         px += static_cast<long long>(gridDim.x) * blockDim.x / G) {
+      float acc[kMaxSmallN] = {0.f, 0.f, 0.f, 0.f};
+      if (px < pixels) {
+        float f[8];
+        load8(x + px * x_ld + x_coff + lane_in_g * 8, f);
+#pragma unroll
+        for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o] = fmaf(f[k], wreg[o][k], acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < kMaxSmallN; ++o) {
+        float v = acc[o];
+        for (int s = G / 2; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane_in_g == 0 && px < pixels && o < cout) out[px * cout + o] = v + bv[o];
+      }
+    }
+    return;
+  }
   for (long long px = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
        px < ((pixels + (32 / G) - 1) / (32 / G)) * (32 / G);      // keep whole warps in the loop for the shuffles
        px += static_cast<long long>(gridDim.x) * blockDim.x / G) {
@@ -588,6 +618,30 @@ __global__ void smalln_dgrad_kernel(const float* __restrict__ dy, int n, int oh,
                                     T* __restrict__ dx, int dx_ld, int dx_coff) {
   const int cv = cin / 8;
   const long long total = static_cast<long long>(n) * h * w * cv;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (kh == 1 && kw == 1 && pad == 0 && nthreads % cv == 0) {
+    // pointwise: the thread's channel vector never changes -> weights in registers, no index decoding
+    const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int ch = static_cast<int>(i0 % cv) * 8;
+    float wreg[kMaxSmallN][8];
+    for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wreg[o][k] = o < cout ? __ldg(wt + static_cast<long long>(o) * cin + ch + k) : 0.f;
+    for (long long i = i0; i < total; i += nthreads) {
+      const long long pix = i / cv;
+      const float* g = dy + pix * cout;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int o = 0; o < cout; ++o) {
+        const float gv = g[o];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(gv, wreg[o][k], acc[k]);
+      }
+      store8(dx + pix * dx_ld + dx_coff + ch, acc);
+    }
+    return;
+  }
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(i % cv) * 8;
@@ -643,15 +697,19 @@ __global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restri
     if (pl < ppar && cvec < cv) {
       for (long long px = static_cast<long long>(blockIdx.x) * ppar + pl; px < pixels;
            px += static_cast<long long>(gridDim.x) * ppar) {
-        const int ox = static_cast<int>(px % ow), oy = static_cast<int>((px / ow) % oh);
-        const int b = static_cast<int>(px / (static_cast<long long>(ow) * oh));
         const float* g = dy + px * cout;
         if (tap == 0 && cvec == 0)
           for (int o = 0; o < cout; ++o) bacc[o] += g[o];
-        const int iy = oy + r - pad, ix = ox + q - pad;
-        if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+        long long xpix = px;                        // pointwise conv: input pixel == output pixel
+        if (kh * kw > 1 || pad != 0) {
+          const int ox = static_cast<int>(px % ow), oy = static_cast<int>((px / ow) % oh);
+          const int b = static_cast<int>(px / (static_cast<long long>(ow) * oh));
+          const int iy = oy + r - pad, ix = ox + q - pad;
+          if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+          xpix = (static_cast<long long>(b) * h + iy) * w + ix;
+        }
         float f[8];
-        load8(x + ((static_cast<long long>(b) * h + iy) * w + ix) * x_ld + x_coff + ch, f);
+        load8(x + xpix * x_ld + x_coff + ch, f);
         for (int o = 0; o < cout; ++o) {
           const float gv = g[o];
 #pragma unroll
