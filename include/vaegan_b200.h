@@ -85,6 +85,9 @@ typedef struct VgConvFprop {
                                sub_h0 / sub_w0 are ignored; no split-K */
   int group_ntaps[4];       /* taps of each group; must add up to num_taps */
   int group_sub[4][2];      /* (sub_h0, sub_w0) of each group */
+  int halo_mode;            /* 0 = auto (3x3 stride-1 tap sets with n_gemm <= 64 and >= 64K pixels load each 18 x 10
+                               activation halo once and address the nine taps as shifted UMMA descriptors; the weights
+                               stay resident in shared memory when they fit); -1 = never; 1 = force (testing) */
 } VgConvFprop;
 int vg_conv_fprop(const VgConvFprop* desc /*host*/, void* stream);
 

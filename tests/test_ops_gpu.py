@@ -441,3 +441,29 @@ def _gru_case(M, batch, steps, tol):
     check("gru d embedding", enc.embedding.weight.grad, emb_w.grad, tol)
     for (name, p), (_, pr) in zip(enc.rnn.named_parameters(), ref.named_parameters()):
         check(f"gru d {name}", p.grad, pr.grad, tol)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 24, 64, 64), (3, 40, 20, 128, 64), (2, 16, 8, 64, 128), (1, 50, 30, 64, 32),
+                                            (2, 17, 9, 192, 64)])
+def test_halo_mode_conv_equals_per_tap_path(n, h, w, cin, cout):
+    """fprop halo mode (the 18 x 10 activation halo of a 16 x 8 pixel tile is loaded once per 64-channel chunk and the
+    nine taps are nine shifted UMMA descriptors into it; weights resident in shared memory when they fit) must
+    reproduce the per-tap path: same products, same fp32 accumulator -- only the order of the K loop differs."""
+    from vae_gan_mark_b200 import conv
+    from vae_gan_mark_b200.conv import ConvLinear
+    torch.manual_seed(3)
+    op = ConvLinear(cin, cout, 3, 3, 1, (1, 1))
+    x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
+    bias = torch.randn(cout, device="cuda")
+    wf = op.prep_fwd(wt)
+    outs = {}
+    for mode in (-1, 1):
+        conv.HALO_MODE = mode
+        try:
+            outs[mode] = op.forward(x, wf, bias, 1).float()
+        finally:
+            conv.HALO_MODE = 0
+    check("halo vs per-tap", outs[1], outs[-1], 1e-4)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), bf(wt.cpu()).cuda(), bias, padding=1)).permute(0, 2, 3, 1)
+    check("halo vs torch", outs[1], ref, TOL)

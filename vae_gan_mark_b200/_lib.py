@@ -30,6 +30,7 @@ class VgConvFprop(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("ksplit", C.c_int), ("force_bn", C.c_int),
         ("b_mn_major", C.c_int), ("w_rows", C.c_int),
         ("num_groups", C.c_int), ("group_ntaps", C.c_int * 4), ("group_sub", (C.c_int * 2) * 4),
+        ("halo_mode", C.c_int),
     ]
 
 

@@ -62,11 +62,15 @@ def _chk(t: torch.Tensor, what: str):
     assert t.dtype == BF16 and ops.nhwc_ok(t), f"{what}: not an NHWC bf16 view {tuple(t.shape)} {t.stride()}"
 
 
+HALO_MODE = 0      # VgConvFprop.halo_mode: 0 auto, -1 never, 1 force (tests)
+
+
 def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torch.Tensor, n_gemm: int,
           m: Tuple[int, int, int], out: torch.Tensor, out_kind: int = 0, su: Tuple[int, int] = (1, 1),
           sub0: Tuple[int, int] = (0, 0), cout_per_sub: Optional[int] = None, bias: Optional[torch.Tensor] = None,
           act: int = 0, ksplit: int = 0, force_bn: int = 0, wk: Optional[Sequence[int]] = None,
-          b_mn_major: bool = False, groups: Optional[Sequence[Tuple[int, Tuple[int, int]]]] = None) -> None:
+          b_mn_major: bool = False, groups: Optional[Sequence[Tuple[int, Tuple[int, int]]]] = None,
+          halo_mode: Optional[int] = None) -> None:
     """out[pixel, n] = sum_{tap, c<cin} x[pixel@tap, c] * w[n, wk[tap] + c]  (wk[tap] = tap*cin by default).
     ``out`` is an NHWC view ([N, OH, OW, C']); ``x`` and ``w`` are bf16.
     ``b_mn_major``: w is [K rows (c), columns] and out[pixel, n] = sum x[pixel@tap, c] * w[c, wk[tap] + n].
@@ -96,6 +100,7 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
     d.bias = bias.data_ptr() if bias is not None else None
     d.act, d.ksplit, d.force_bn = act, ksplit, force_bn
     d.b_mn_major, d.w_rows = int(b_mn_major), w.shape[0]
+    d.halo_mode = HALO_MODE if halo_mode is None else halo_mode
     if groups is not None:
         assert 2 <= len(groups) <= 4 and sum(g[0] for g in groups) == len(taps) and ksplit in (0, 1)
         d.num_groups = len(groups)

@@ -33,6 +33,8 @@ constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle
 constexpr int kUmmaK = 16;
 constexpr int kFpropThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int kMaxTaps = VG_MAX_FPROP_TAPS;
+constexpr int kHaloW = 10, kHaloH = 18, kHaloRows = kHaloW * kHaloH;   // halo of the 16 x 8 pixel tile
+constexpr int kHaloBytes = 23 * 1024;                                    // 180 rows x 128 B, padded to a 1024 multiple
 constexpr int kEpiStageBytes = 8 * 32 * 128;          // 8 epilogue warps x (32 rows x 128 B XOR-swizzled staging tile)
 constexpr int kEpiBytes = kEpiStageBytes + 8 * 32 * 4;  // + per-warp 32-float bias window (read back as broadcast float4)
 
@@ -54,6 +56,19 @@ struct FpropParams {
   // groups: independent problems sharing A, W, M, N and the destination, differing in their taps and in the
   // sub-pixel they write (the 4 output-parity classes of a stride-2 data gradient): one launch instead of four
   int ngroups, g_tap0[4], g_ntaps[4], g_sub_h0[4], g_sub_w0[4];
+  // halo mode (3x3 stride-1 convs with few output channels, which are bound by the L2 -> smem traffic of re-reading
+  // the activations once per tap): the pixel tile is 16 rows x 8 columns, its 18 x 10 halo is loaded ONCE per
+  // 64-channel chunk, and the nine taps are nine UMMA descriptors into that one buffer (start shifted by
+  // (dh+1)*10 + (dw+1) rows, 8-row groups 10 rows = 1280 bytes apart).  One pipeline stage = halo + the 9 weight tiles.
+  int halo;                     // 0 off; 1: on.  (2: base_offset = swizzle phase of the start address -- WRONG on
+                                // sm_100a, kept for the record: the hardware derives the phase from the absolute
+                                // shared-memory address, so shifted starts need base_offset 0; checked in
+                                // tools/gpu_halo_check.py)
+  int a_bytes, b_bytes;         // bytes of A and of B in one stage
+  int nacc, acc_cols;           // TMEM accumulators in flight: 2 x 256 columns, or 4 x 128 when bn <= 128 (narrow tiles are
+                                // bound by the MMA -> epilogue -> MMA round trip per accumulator, not by the tensor pipe)
+  int w_bytes;                  // halo mode with resident weights: all 9 x (cin/64) weight tiles live in shared memory for
+                                // the whole kernel (loaded once per CTA), the stages hold only the activation halos
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
   int wk[kMaxTaps];             // first weight column of each tap
 };
@@ -64,15 +79,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B bn*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = kBM * kBK * 2;
-  const uint32_t b_bytes = p.bn * kBK * 2;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.a_bytes);
+  const uint32_t b_bytes = static_cast<uint32_t>(p.b_bytes);
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint8_t* wres = smem + static_cast<size_t>(p.stages) * stage_bytes;            // resident weights (w_bytes, may be 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + p.w_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tmem_full = bars + 2 * p.stages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint64_t* w_bar = tmem_empty + 4;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 256;
 
   const int warp = threadIdx.x >> 5;
@@ -85,10 +102,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 256);
+      mbar_init(&tmem_empty[i], p.nacc == 4 ? 128 : 256);
     }
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -110,6 +128,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int b_boxes = p.b_mn ? p.bn / 64 : 1;
     int stage = 0;
     uint32_t phase = 0;
+    if (p.w_bytes > 0 && blockIdx.x < total_tiles) {
+      // resident weights: tile (cc, tap) at wres + (cc*9 + tap) * bn*128; one barrier for all of them
+      if (lane == 0) mbar_arrive_expect_tx(w_bar, p.w_bytes);
+      __syncwarp();
+      for (int i = lane; i < 9 * cchunks_all; i += 32)
+        tma_load_2d(wres + static_cast<size_t>(i) * (p.bn * 128), &tmap_b, w_bar, p.wk[i % 9] + (i / 9) * kBK, 0);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int grp = tile / tiles_per_group;
       const int tl = tile - grp * tiles_per_group;
@@ -125,6 +150,24 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int ksteps = p.g_ntaps[grp] * cchunks;
       const int k_begin = static_cast<int>((static_cast<long long>(ksteps) * split) / p.ksplit);
       const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
+      if (p.halo) {
+        // one stage per 64-channel chunk: the halo (lane 0) and the nine weight tiles (lanes 1..9)
+        for (int cc = 0; cc < cchunks; ++cc) {
+          if (lane == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kHaloRows * 128 + (p.w_bytes > 0 ? 0 : 9 * p.bn * 128));
+          }
+          __syncwarp();
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          if (lane == 0)
+            tma_load_5d(sa, &tmap_a, &full_bar[stage], p.taps[0].x + cc * kBK, ow0 - 1, 0, oh0 - 1, n0);
+          else if (lane <= 9 && p.w_bytes == 0)
+            tma_load_2d(sa + a_bytes + (lane - 1) * (p.bn * 128), &tmap_b, &full_bar[stage], p.wk[lane - 1] + cc * kBK,
+                        n_t * p.bn);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       int tap = p.g_tap0[grp] + k_begin / cchunks;
       int cc = k_begin % cchunks;
       for (int k = k_begin; k < k_end; ++k) {
@@ -156,6 +199,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.w_bytes > 0 && blockIdx.x < total_tiles) {
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+    }
+    uint32_t halo_a16[9];      // start of each tap's view inside the halo buffer, in 16-byte units
+#pragma unroll
+    for (int t = 0; t < 9; ++t) halo_a16[t] = static_cast<uint32_t>(((p.taps[t].w + 1) * kHaloW + (p.taps[t].y + 1)) * 128) >> 4;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int grp = tile / tiles_per_group;
       const int split = ((tile - grp * tiles_per_group) / p.n_tiles) / m_tiles;
@@ -164,25 +214,49 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
+      if (p.halo) {
+        // Issue cost matters here: an N = 64 MMA occupies the tensor pipe for ~20 cycles, so the issuing thread must
+        // not spend more than that per MMA.  The descriptors of one stage differ only in their start-address field:
+        // build one per operand and ADD the (precomputed, 16-byte unit) tap and K offsets.
+        const uint32_t b_tap16 = static_cast<uint32_t>(p.bn * 128) >> 4;
+        for (int cc = 0; cc < cchunks_all; ++cc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = p.w_bytes > 0 ? smem_u32(wres) + static_cast<uint32_t>(cc * 9 * p.bn * 128) : sa + a_bytes;
+          const uint64_t da0 = umma_smem_desc_sw128(sa, 16, kHaloW * 128);
+          const uint64_t db0 = umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+#pragma unroll
+            for (int j = 0; j < kBK / kUmmaK; ++j)
+              umma_bf16(d_tmem, da0 + halo_a16[t] + 2 * j, db0 + t * b_tap16 + 2 * j, idesc, (cc > 0 || t > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int k = k_begin; k < k_end; ++k) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
         const uint32_t sb = sa + a_bytes;
+        const uint64_t da0 = umma_smem_desc_sw128(sa, 16, 1024);
+        // MN-major B: 16 K rows = 2 groups of 8 rows (SBO = 1024 B apart); 64-column N groups one box (8 KB) apart
+        const uint64_t db0 = p.b_mn ? umma_smem_desc_sw128(sb, 64 * 128, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
+        const uint32_t b_step16 = p.b_mn ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
 #pragma unroll
-        for (int j = 0; j < kBK / kUmmaK; ++j) {
-          const uint64_t da = umma_smem_desc_sw128(sa + j * kUmmaK * 2, 16, 1024);
-          // MN-major B: 16 K rows = 2 groups of 8 rows (SBO = 1024 B apart); 64-column N groups one box (8 KB) apart
-          const uint64_t db = p.b_mn ? umma_smem_desc_sw128(sb + j * kUmmaK * 128, 64 * 128, 1024)
-                                     : umma_smem_desc_sw128(sb + j * kUmmaK * 2, 16, 1024);
-          umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
-        }
+        for (int j = 0; j < kBK / kUmmaK; ++j)
+          umma_bf16(d_tmem, da0 + 2 * j, db0 + j * b_step16, idesc, (k > k_begin || j > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
@@ -201,9 +275,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int esz = p.out_kind == 0 ? 2 : 4;
     const int chunk_cols = p.out_kind == 0 ? 64 : 32;
     const bool plain = (p.bias == nullptr) && (p.act == 0);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // Narrow tiles (bn <= 128, four accumulators): the two warp groups (warps 4-7 / 8-11) drain ALTERNATE tiles, each
+    // the whole tile width, so two epilogues are in flight -- their per-tile latency chain (TMEM load -> staging ->
+    // stores), not their instruction count, is what bounds the 64-channel layers.  Wide tiles: both groups work on
+    // the same tile and split its column chunks.
+    const bool split = p.nacc == 4;
+    const int c_first = split ? 0 : colhalf * chunk_cols, c_step = split ? chunk_cols : 2 * chunk_cols;
+    int seq = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++seq) {
+      if (split && (seq & 1) != colhalf) continue;
+      const int acc = seq % p.nacc;
+      const uint32_t acc_phase = static_cast<uint32_t>(seq / p.nacc) & 1u;
       const int grp = tile / tiles_per_group;
       const int tl = tile - grp * tiles_per_group;
       const int sub_h0 = p.g_sub_h0[grp], sub_w0 = p.g_sub_w0[grp];
@@ -219,9 +301,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * p.acc_cols);
       if (p.vec_ok && p.out_kind != 2) {
-        for (int c = colhalf * chunk_cols; c < p.bn; c += 2 * chunk_cols) {
+        for (int c = c_first; c < p.bn; c += c_step) {
           const int ng0 = n_t * p.bn + c;        // first GEMM column of this chunk
           if (ng0 >= p.n_gemm) break;
           uint32_t r[64];
@@ -298,7 +380,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           __syncwarp();
         }
-      } else if (colhalf == 0) {
+      } else if (split || colhalf == 0) {
         // generic path (odd alignments, split-K atomics): each thread stores its own row
         for (int c = 0; c < p.bn; c += 32) {
           uint32_t r[32];
@@ -328,7 +410,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -374,7 +455,24 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   FpropParams p;
   memset(&p, 0, sizeof(p));
   p.m_n = d->m_n; p.m_h = d->m_h; p.m_w = d->m_w;
-  pick_pixel_tile(p.m_n, p.m_h, p.m_w, kBM, &p.tn, &p.th, &p.tw);
+  // halo mode: a 3x3 stride-1 tap set (every offset of [-1,1]^2 once, one channel base), K-major weights, no groups,
+  // no split-K; chosen for narrow N and many pixels, where the 9-fold re-read of A through L2 is the bound
+  int halo = 0;
+  if (d->halo_mode >= 0 && d->num_taps == 9 && d->x_stride == 1 && !d->b_mn_major && d->num_groups <= 1 && d->ksplit <= 1 &&
+      d->out_kind != 2 && d->m_h >= 16 && d->m_w >= 8) {
+    unsigned seen = 0;
+    bool ok = true;
+    for (int i = 0; i < 9; ++i) {
+      const int dw = d->taps[i][1], dh = d->taps[i][3];
+      if (dw < -1 || dw > 1 || dh < -1 || dh > 1 || d->taps[i][2] != 0 || d->taps[i][0] != d->taps[0][0]) { ok = false; break; }
+      seen |= 1u << ((dh + 1) * 3 + (dw + 1));
+    }
+    const long long pixels = static_cast<long long>(d->m_n) * d->m_h * d->m_w;
+    if (ok && seen == 0x1FFu && (d->halo_mode > 0 || (d->n_gemm <= 64 && pixels >= 65536))) halo = d->halo_mode > 0 ? d->halo_mode : 1;
+  }
+  p.halo = halo;
+  if (halo) { p.tn = 1; p.th = 16; p.tw = 8; }
+  else pick_pixel_tile(p.m_n, p.m_h, p.m_w, kBM, &p.tn, &p.th, &p.tw);
   p.tiles_n = cdiv(p.m_n, p.tn); p.tiles_h = cdiv(p.m_h, p.th); p.tiles_w = cdiv(p.m_w, p.tw);
   p.cin = d->cin; p.num_taps = d->num_taps; p.n_gemm = d->n_gemm;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
@@ -386,6 +484,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   else if (m_tiles * cdiv(d->n_gemm, 256) < sms && d->n_gemm % 256 != 0) bn = 128;
   else if (m_tiles * cdiv(d->n_gemm, 256) < sms / 2) bn = 128;
   if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 256) bn = d->force_bn;
+  if (halo) bn = 64;      // one stage holds the halo and all nine 64-wide weight tiles
   p.bn = bn;
   p.n_tiles = cdiv(d->n_gemm, bn);
   p.ksteps = d->num_taps * (d->cin / kBK);
@@ -399,8 +498,18 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   VG_CHECK(ksplit <= p.ksteps, -1, "vg_conv_fprop: ksplit %d > k steps %d", ksplit, p.ksteps);
   VG_CHECK(ksplit == 1 || d->act == 0, -1, "vg_conv_fprop: an activation cannot be fused into a split-K launch");
   p.ksplit = ksplit;
-  const int stage_bytes = kBM * kBK * 2 + bn * kBK * 2;
-  p.stages = min(8, (227 * 1024 - 1024 - 256 - kEpiBytes) / stage_bytes);
+  p.nacc = bn <= 128 ? 4 : 2;
+  p.acc_cols = 512 / p.nacc;
+  p.a_bytes = halo ? kHaloBytes : kBM * kBK * 2;
+  p.b_bytes = halo ? 9 * bn * kBK * 2 : bn * kBK * 2;
+  const int smem_budget = 227 * 1024 - 1024 - 256 - kEpiBytes;
+  if (halo && p.n_tiles == 1) {
+    // weights resident when they leave room for at least two halo stages
+    const int wb = 9 * (d->cin / kBK) * bn * kBK * 2;
+    if (smem_budget - wb >= 2 * p.a_bytes) { p.w_bytes = wb; p.b_bytes = 0; }
+  }
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  p.stages = min(8, (smem_budget - p.w_bytes) / stage_bytes);
   p.out = d->out; p.out_kind = d->out_kind;
   p.out_h = d->out_h; p.out_w = d->out_w; p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.su_h = d->su_h; p.su_w = d->su_w; p.sub_h0 = d->sub_h0; p.sub_w0 = d->sub_w0; p.cout_per_sub = d->cout_per_sub;
@@ -441,6 +550,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     uint64_t dims[5] = {ld * s, W / s, static_cast<uint64_t>(s), H / s, static_cast<uint64_t>(d->x_n)};
     uint64_t strides[5] = {1, ld * s, W * ld, W * ld * s, H * W * ld};
     uint32_t box[5] = {kBK, static_cast<uint32_t>(p.tw), 1, static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.tn)};
+    if (halo) { box[1] = kHaloW; box[3] = kHaloH; }
     int rc = encode_tmap_bf16(&tmap_a, d->x, 5, dims, strides, box);
     if (rc) return rc;
   }
@@ -451,7 +561,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     int rc = encode_tmap_bf16(&tmap_b, d->w, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiBytes;
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + p.w_bytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiBytes;
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
