@@ -193,3 +193,23 @@ def test_channels_last_weights_keep_the_state_dict_contract():
             assert p.is_contiguous(), name
     G.load_state_dict({k: v for k, v in before.items() if k in G.state_dict()})
     assert G.style_vae_encoder_module.e_conv2[0].weight.is_contiguous(memory_format=torch.channels_last)
+
+
+def test_torch_library_ops_registered_with_fake_impls():
+    """torch.ops.vaegan.* exist after importing torch_ops, and their fake implementations infer shapes / dtypes on
+    meta tensors (no GPU, no kernel call)."""
+    import torch
+    import vae_gan_mark_b200.torch_ops  # noqa: F401
+    x = torch.empty(2, 16, 12, 64, dtype=torch.bfloat16, device="meta")
+    w = torch.empty(128, 64, 3, 3, device="meta")
+    y = torch.ops.vaegan.conv2d(x, w, None, 1, 1, 1, 1)
+    assert y.shape == (2, 16, 12, 128) and y.dtype == torch.bfloat16
+    y2 = torch.ops.vaegan.conv2d(x, torch.empty(128, 64, 4, 4, device="meta"), None, 2, 1, 1, 0)
+    assert y2.shape == (2, 8, 6, 128)
+    wt = torch.empty(64, 32, 2, 2, device="meta")
+    assert torch.ops.vaegan.conv_transpose2d(x, wt, None, 2, 0, 32, 24, 0).shape == (2, 32, 24, 32)
+    yb, mr = torch.ops.vaegan.batch_norm_act(x, torch.empty(64, device="meta"), torch.empty(64, device="meta"), 1e-5, 1)
+    assert yb.shape == x.shape and mr.shape == (1, 2, 64) and mr.dtype == torch.float32
+    for name in ("conv2d", "conv2d_dgrad", "conv2d_wgrad", "conv_transpose2d", "batch_norm_act", "batch_norm_act_backward",
+                 "film", "film_backward"):
+        assert hasattr(torch.ops.vaegan, name), name
