@@ -249,7 +249,20 @@ def run_ours(args, wl):
     if reducer is not None:
         reducer.broadcast_parameters(list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()))
     wts = LossWeights.for_family(wl["family"])
-    trainer = VAEGANTrainer(G, D, wts, grad_hook=reducer.hook if reducer else None)
+    perceptual = None
+    if args.perceptual:
+        # the reference's VGG16 features[:16] perceptual term (vae-gan.py:300-311,422).  Pretrained
+        # weights cannot be obtained offline: seeded He-initialised weights of the same architecture (same FLOPs).
+        from vae_gan_mark_b200.modules import VGGPerceptual
+        perceptual = VGGPerceptual().to(dev)
+        gen_w = torch.Generator().manual_seed(77)
+        for p_ in perceptual.features.parameters():
+            if p_.dim() == 4:
+                p_.data.copy_(torch.randn(p_.shape, generator=gen_w) * (2.0 / (p_.shape[1] * 9)) ** 0.5)
+            else:
+                p_.data.zero_()
+        wts.perc = {"base": 0.05}.get(wl["family"], 0.1)      # vae-gan.py:38, vae-gan-v2.py:45, vae-gan-unet.py:46
+    trainer = VAEGANTrainer(G, D, wts, grad_hook=reducer.hook if reducer else None, perceptual=perceptual)
 
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     pool = 2
@@ -410,7 +423,9 @@ def run_ours(args, wl):
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "image": [h, w],
                        "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "precision": "bf16 storage + tcgen05 bf16 MMA, fp32 accumulate, fp32 master weights",
                        "l2": "per-step working set (activations >> 1 GB) far exceeds the 126 MB L2; 2 input batches cycled",
-                       "perceptual_term": "excluded (weights unavailable offline)"},
+                       "perceptual_term": ("included: VGG16 features[:16] with seeded random weights (pretrained weights "
+                                           "unavailable offline), weight %.2f" % wts.perc) if args.perceptual
+                       else "excluded (weights unavailable offline; --perceptual adds it with random weights)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
@@ -452,6 +467,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-convs", default="", help="write the per-shape tensor-core kernel timing table to this file")
+    ap.add_argument("--perceptual", action="store_true",
+                    help="include the VGG16 features[:16] perceptual term (random-init weights) in loss_G")
     ap.add_argument("--film-row-dedup", action="store_true",
                     help="run the whole bench with the exact FiLM row de-duplication on (config.film_row_dedup = true)")
     ap.add_argument("--no-dedup-extra", action="store_true", help="skip the extra de-duplicated timing pass")

@@ -175,6 +175,12 @@ int vg_strided_copy(const void* in, int in_dtype, void* out, int out_dtype, cons
  * can be checked on CPU.  Returns the tile count; 0 means the plan falls back to the generic kernel. */
 long long vg_debug_copy_plan_host(const float* in, float* out, const long long* dims, const long long* in_strides,
                                   const long long* out_strides);
+/* MaxPool2d(2, 2) on NHWC activations [n][h][w][c] (pixel stride x_ld), y / dy dense [n][h/2][w/2][c], dx dense
+ * [n][h][w][c] (fully written; the gradient goes to the first maximum of each window).  The VGG16 feature extractor of
+ * the perceptual loss (vae-gan.py:300-311) is the user; the U-Net's pools are fused into the normalisation kernels. */
+int vg_maxpool2x2_fwd(const void* x, int x_ld, void* y, int n, int h, int w, int c, int dtype, void* stream);
+int vg_maxpool2x2_bwd(const void* x, int x_ld, const void* dy, void* dx, int n, int h, int w, int c, int dtype, void* stream);
+
 /* dx = dy * act'(y) for an activation that was fused into a conv epilogue (act 1 ReLU, 2 LeakyReLU(0.2)); bf16 rows */
 int vg_act_bwd(const void* y, int y_ld, const void* dy, int dy_ld, void* dx, int dx_ld, long long rows, int c, int act,
                int dtype, void* stream);

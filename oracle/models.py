@@ -353,3 +353,28 @@ class VAEGAN_UNet_CharEmb(nn.Module):
         dec = self.image_vae_decoder_module
         img = dec.forward_repaired(z, t, pooled) if self.repaired else dec(z, t, skips)
         return img, mu, logvar
+
+
+
+class VGGPerceptual(nn.Module):
+    """vae-gan.py:300-311 -- get_vgg_feat + perceptual_loss: L1 between VGG16 features[:16] of the ImageNet-normalised
+    images.  ``features`` restates torchvision's ``vgg16().features[:16]`` (cfg 64,64,M,128,128,M,256,256,256; same
+    Sequential indices, so a torchvision state_dict loads), checked against torchvision itself in
+    tests/test_oracle_golden.py.  PARITY UNPINNED for the pretrained IMAGENET1K_V1 weights the reference downloads
+    (not available offline): tests use seeded random weights."""
+
+    def __init__(self):
+        super().__init__()
+        layers, cin = [], 3
+        for v in (64, 64, "M", 128, 128, "M", 256, 256, 256):
+            if v == "M":
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(inplace=True)]
+                cin = v
+        self.features = nn.Sequential(*layers).eval()
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1), persistent=False)
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1), persistent=False)
+
+    def forward(self, fake, real):
+        return F.l1_loss(self.features((fake - self.mean) / self.std), self.features((real - self.mean) / self.std))

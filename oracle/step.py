@@ -28,6 +28,7 @@ class LossWeights:
     recon: float
     kl: float
     gan: float
+    perc: float = 0.0      # PERC_WEIGHT (vae-gan.py:38); only used when train_step is given a perceptual module
 
     @staticmethod
     def for_family(family: str) -> "LossWeights":
@@ -107,7 +108,7 @@ class StepResult:
 
 
 def train_step(G, D, opt_G, opt_D, batch, weights: LossWeights, seed: Optional[int] = None,
-               clip_norm: float = 1.0, keep_grads: bool = True) -> StepResult:
+               clip_norm: float = 1.0, keep_grads: bool = True, perceptual=None) -> StepResult:
     """One iteration of the reference's hot loop (vae-gan.py:399-428) with perceptual weight 0.
 
     The D gradients are snapshotted right after ``loss_D.backward()`` because the reference's
@@ -132,6 +133,10 @@ def train_step(G, D, opt_G, opt_D, batch, weights: LossWeights, seed: Optional[i
     kl = kl_term(mu, logvar)
     gan = hinge_loss(fake_preds, None)
     loss_g = weights.recon * recon + weights.kl * kl + weights.gan * gan
+    perc = None
+    if perceptual is not None and weights.perc != 0.0:          # vae-gan.py:422-423
+        perc = perceptual(fake, en)
+        loss_g = loss_g + weights.perc * perc
     loss_g.backward()
     g_grads = ({k: p.grad.detach().clone() for k, p in G.named_parameters() if p.grad is not None}
                if keep_grads else {})
@@ -140,7 +145,8 @@ def train_step(G, D, opt_G, opt_D, batch, weights: LossWeights, seed: Optional[i
 
     return StepResult(
         losses={"loss_G": float(loss_g), "loss_D": float(loss_d), "recon": float(recon), "kl": float(kl),
-                "gan": float(gan), "d_real": float(loss_d_real), "d_fake": float(loss_d_fake)},
+                "gan": float(gan), "d_real": float(loss_d_real), "d_fake": float(loss_d_fake),
+                **({"perc": float(perc)} if perc is not None else {})},
         recon=fake.detach(), mu=mu.detach(), logvar=logvar.detach(), d_grads=d_grads, g_grads=g_grads,
         grad_norm=float(gn))
 

@@ -86,3 +86,22 @@ def test_unet_shipped_forward_is_unrunnable():
     ru, en, mask, texts = synthetic_batch(2, 32, 32)
     with pytest.raises(RuntimeError):
         G(ru, mask, texts)
+
+
+def test_oracle_vgg_features_match_torchvision():
+    """oracle.models.VGGPerceptual.features restates torchvision's vgg16().features[:16] (what vae-gan.py:303-304
+    builds): same state_dict keys, and identical outputs for the same (random) weights."""
+    import torch
+    torchvision = pytest.importorskip("torchvision")
+    from oracle import models as om
+    torch.manual_seed(0)
+    tv = torchvision.models.vgg16(weights=None).features[:16].eval()
+    ours = om.VGGPerceptual()
+    assert list(tv.state_dict().keys()) == list(ours.features.state_dict().keys())
+    ours.features.load_state_dict(tv.state_dict())
+    x = torch.rand(2, 3, 32, 48)
+    assert torch.equal(ours.features(x), tv(x))
+    fake, real = torch.rand(2, 3, 32, 32), torch.rand(2, 3, 32, 32)
+    norm = lambda t: (t - ours.mean) / ours.std   # noqa: E731
+    want = torch.nn.functional.l1_loss(tv(norm(fake)), tv(norm(real)))
+    assert torch.allclose(ours(fake, real), want, rtol=0, atol=0)

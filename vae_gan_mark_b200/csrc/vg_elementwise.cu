@@ -738,6 +738,73 @@ __global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restri
 
 
 // ---------------------------------------------------------------------------------------------
+// MaxPool2d(2, 2) on NHWC activations (VGG16 features of the perceptual loss, vae-gan.py:300-311); the backward
+// routes each pooled gradient to the FIRST maximum of its window (PyTorch's tie rule), recomputed from the input
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int n, int h, int w, int c) {
+  const int cv = c / 8, ph = h / 2, pw = w / 2;
+  const long long total = static_cast<long long>(n) * ph * pw * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long cell = i / cv;
+    const int ch = static_cast<int>(i - cell * cv) * 8;
+    const int pj = static_cast<int>(cell % pw);
+    const long long r = cell / pw;
+    const int pi = static_cast<int>(r % ph);
+    const long long b = r / ph;
+    const long long row0 = (b * h + 2 * pi) * w + 2 * pj;
+    float m[8], f[8];
+    load8(x + row0 * x_ld + ch, m);
+    const long long offs[3] = {row0 + 1, row0 + w, row0 + w + 1};
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      load8(x + offs[u] * x_ld + ch, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+    }
+    store8(y + cell * c + ch, m);
+  }
+}
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, T* __restrict__ dx, int n,
+                                   int h, int w, int c) {
+  const int cv = c / 8, ph = h / 2, pw = w / 2;
+  const long long total = static_cast<long long>(n) * ph * pw * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long cell = i / cv;
+    const int ch = static_cast<int>(i - cell * cv) * 8;
+    const int pj = static_cast<int>(cell % pw);
+    const long long r = cell / pw;
+    const int pi = static_cast<int>(r % ph);
+    const long long b = r / ph;
+    const long long row0 = (b * h + 2 * pi) * w + 2 * pj;
+    const long long offs[4] = {row0, row0 + 1, row0 + w, row0 + w + 1};
+    float f[4][8], g[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(x + offs[u] * x_ld + ch, f[u]);
+    load8(dy + cell * c + ch, g);
+    int best[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      best[k] = 0;
+      float bv = f[0][k];
+#pragma unroll
+      for (int u = 1; u < 4; ++u)
+        if (f[u][k] > bv) { bv = f[u][k]; best[k] = u; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = best[k] == u ? g[k] : 0.f;
+      store8(dx + offs[u] * c + ch, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // plain activation backward (for activations fused into a conv epilogue): dx = dy * act'(y)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -1070,6 +1137,34 @@ extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, in
   else
     smalln_wgrad_kernel<float><<<dim3(gx, kh * kw), 256, 0, st>>>(dy, static_cast<const float*>(x), x_ld, x_coff, n, h, w, cin,
                                                                 cout, kh, kw, pad, oh, ow, dw, dbias);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_maxpool2x2_fwd(const void* x, int x_ld, void* y, int n, int h, int w, int c, int dtype, void* stream_) {
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && h % 2 == 0 && w % 2 == 0, -1, "vg_maxpool2x2_fwd: c % 8, even H and W");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * (h / 2) * (w / 2) * (c / 8));
+  if (dtype == 0)
+    maxpool_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                          static_cast<__nv_bfloat16*>(y), n, h, w, c);
+  else
+    maxpool_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), x_ld, static_cast<float*>(y), n, h, w, c);
+  VG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int vg_maxpool2x2_bwd(const void* x, int x_ld, const void* dy, void* dx, int n, int h, int w, int c, int dtype,
+                                 void* stream_) {
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && h % 2 == 0 && w % 2 == 0, -1, "vg_maxpool2x2_bwd: c % 8, even H and W");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * (h / 2) * (w / 2) * (c / 8));
+  if (dtype == 0)
+    maxpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                          static_cast<const __nv_bfloat16*>(dy),
+                                                          static_cast<__nv_bfloat16*>(dx), n, h, w, c);
+  else
+    maxpool_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), x_ld, static_cast<const float*>(dy),
+                                                  static_cast<float*>(dx), n, h, w, c);
   VG_LAUNCH_OK();
   return 0;
 }

@@ -432,6 +432,28 @@ class FiLMFn(Function):
         return dgb, dx
 
 
+class MaxPool2x2Fn(Function):
+    """nn.MaxPool2d(2, 2) on an NHWC activation (VGG16 features of the perceptual loss, vae-gan.py:300-311)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, h, w, c = x.shape
+        y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+        ops.maxpool_fwd(x, y)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = grad_in(dy, x.dtype)
+        if not dy.is_contiguous():
+            dy = ops.dense_nhwc(dy)
+        dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        ops.maxpool_bwd(x, dy, dx)
+        return dx
+
+
 class FiLMRowsFn(Function):
     """FiLM with a 3-row parameter map gb3 [B,3,w,2C] (first | interior | last row class); exact restatement of
     FiLMFn for maps that are row-constant away from the border.  d gb3 is the gradient summed over each class."""

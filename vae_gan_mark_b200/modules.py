@@ -192,6 +192,74 @@ class TransformerTextEncoder(nn.Module):
         return self.fc(e)
 
 
+class VGGPerceptual(nn.Module):
+    """Perceptual loss of the reference (vae-gan.py:300-311,422; vae-gan-v2.py:501-511): L1 between the VGG16
+    ``features[:16]`` maps of the ImageNet-normalised fake and real images.
+
+    ``self.features`` has the layout of ``torchvision.models.vgg16().features[:16]`` (convs at indices 0, 2, 5, 7, 10,
+    12, 14), so ``self.features.load_state_dict(vgg16(weights=...).features[:16].state_dict())`` loads the pretrained
+    weights the reference downloads; none are available offline, so parity is tested with seeded random weights.  The
+    weights are frozen (the reference leaves ``requires_grad`` on and wastes their weight gradients); the seven 3x3
+    convs run on the tensor-core kernel with the ReLU fused into the epilogue, the two pools on ``vg_maxpool2x2``.
+    """
+
+    CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256)
+
+    def __init__(self):
+        super().__init__()
+        layers, cin = [], 3
+        for v in self.CFG:
+            if v == "M":
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                layers += [nn.Conv2d(cin, v, 3, padding=1), nn.ReLU(inplace=True)]
+                cin = v
+        self.features = nn.Sequential(*layers)
+        for p in self.features.parameters():
+            p.requires_grad_(False)
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1), persistent=False)
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1), persistent=False)
+
+    def extract(self, img: torch.Tensor) -> torch.Tensor:
+        """(B,3,H,W) fp32 image in [0,1] -> NHWC feature map (B,H/4,W/4,256)."""
+        x = None
+        first = True
+        for m in self.features:
+            if isinstance(m, nn.Conv2d):
+                if first:
+                    x = run_image_conv(m, [(img - self.mean) / self.std], act=RELU)
+                    first = False
+                else:
+                    x = run_conv(m, x, act=RELU)
+            elif isinstance(m, nn.MaxPool2d):
+                x = L.MaxPool2x2Fn.apply(x)
+        return x
+
+    def forward(self, fake: torch.Tensor, real: torch.Tensor) -> torch.Tensor:
+        _require_cuda(fake)
+        with torch.no_grad():
+            fr = self.extract(real)
+        ff = self.extract(fake)
+        return L.l1_loss(_to_f32(ff), _to_f32(fr))
+
+
+class _ToF32Fn(torch.autograd.Function):
+    """Dense fp32 copy of an activation (the loss kernels read fp32); the gradient comes back in the activation dtype."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dt = x.dtype
+        return ops.dense_nhwc(x, F32) if x.dtype != F32 or not x.is_contiguous() else x
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.dense_nhwc(g.contiguous(), ctx.dt) if ctx.dt != F32 else g
+
+
+def _to_f32(x):
+    return _ToF32Fn.apply(x)
+
+
 _SIDE_STREAMS = {}
 CONV_SMS_WHILE_TEXT = 136   # of 148
 # The side-stream overlap was built for the stock cuDNN recurrence (~1000 launch-bound kernels).  With the cluster-kernel

@@ -176,6 +176,18 @@ def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dga
     _lib.call("vg_norm_backward", C.byref(d), stream())
 
 
+def maxpool_fwd(x, y):
+    n, h, w, c = x.shape
+    assert x.dtype == y.dtype and y.is_contiguous() and nhwc_ok(x)
+    _lib.call("vg_maxpool2x2_fwd", _p(x), ld_of(x), _p(y), n, h, w, c, dcode(x), stream())
+
+
+def maxpool_bwd(x, dy, dx):
+    n, h, w, c = x.shape
+    assert x.dtype == dy.dtype == dx.dtype and dy.is_contiguous() and dx.is_contiguous() and nhwc_ok(x)
+    _lib.call("vg_maxpool2x2_bwd", _p(x), ld_of(x), _p(dy), _p(dx), n, h, w, c, dcode(x), stream())
+
+
 def act_bwd(y, dy, dx, act):
     n, h, w, c = y.shape
     assert y.dtype == dy.dtype == dx.dtype

@@ -33,6 +33,7 @@ class LossWeights:
     recon: float = 1.0
     kl: float = 0.001
     gan: float = 0.15
+    perc: float = 0.0       # PERC_WEIGHT (0.05 base, 0.1 v2 / unet in the reference); used when a VGGPerceptual is given
 
     @staticmethod
     def for_family(family: str) -> "LossWeights":
@@ -174,8 +175,11 @@ def weights_channels_last(module: torch.nn.Module) -> int:
 
 class VAEGANTrainer:
     def __init__(self, G: torch.nn.Module, D: torch.nn.Module, weights: LossWeights, lr_g=1e-4, lr_d=1e-4,
-                 clip_norm: float = 1.0, grad_hook=None, channels_last_weights: bool = True):
+                 clip_norm: float = 1.0, grad_hook=None, channels_last_weights: bool = True, perceptual=None):
+        """``perceptual``: an optional ``modules.VGGPerceptual`` (frozen); its loss enters loss_G with weight
+        ``weights.perc`` (vae-gan.py:422-423)."""
         self.G, self.D, self.w, self.clip_norm = G, D, weights, clip_norm
+        self.perceptual = perceptual
         if channels_last_weights:
             weights_channels_last(G)
             weights_channels_last(D)
@@ -207,14 +211,21 @@ class VAEGANTrainer:
             recon = L.l1_loss(fake, en)
             gan = L.hinge_loss(fake_preds, None)
             loss_g = w.recon * recon + klw * kl + w.gan * gan
+            perc = None
+            if self.perceptual is not None and w.perc != 0.0:
+                perc = self.perceptual(fake, en)
+                loss_g = loss_g + w.perc * perc
             loss_g.backward()
         _lib.call("vg_set_conv_sm_limit", 0)      # (raised again by the text-feature gradient hook during the backward)
         if self.grad_hook is not None:
             self.grad_hook("G", self.opt_G.params)
         self.opt_G.step(max_norm=self.clip_norm)
-        return {"loss_G": loss_g.detach(), "loss_D": loss_d.detach(), "recon": recon.detach(), "kl": kl.detach(),
-                "gan": gan.detach(), "d_real": loss_d_real.detach(), "d_fake": loss_d_fake.detach(),
-                "grad_norm_sq": self.opt_G.norm_sq, "fake": fake.detach(), "mu": mu.detach(), "logvar": logvar.detach()}
+        out = {"loss_G": loss_g.detach(), "loss_D": loss_d.detach(), "recon": recon.detach(), "kl": kl.detach(),
+               "gan": gan.detach(), "d_real": loss_d_real.detach(), "d_fake": loss_d_fake.detach(),
+               "grad_norm_sq": self.opt_G.norm_sq, "fake": fake.detach(), "mu": mu.detach(), "logvar": logvar.detach()}
+        if perc is not None:
+            out["perc"] = perc.detach()
+        return out
 
     # ------------------------------------------------------------------ CUDA graph
     def capture(self, ru, en, mask, texts, warmup: int = 3, kl_weight: Optional[float] = None):
