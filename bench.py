@@ -263,6 +263,8 @@ def run_ours(args, wl):
                 p_.data.zero_()
         wts.perc = {"base": 0.05}.get(wl["family"], 0.1)      # vae-gan.py:38, vae-gan-v2.py:45, vae-gan-unet.py:46
     trainer = VAEGANTrainer(G, D, wts, grad_hook=reducer.hook if reducer else None, perceptual=perceptual)
+    if reducer is not None and not args.no_overlap:
+        reducer.install_hooks(trainer.opt_G.params, trainer.opt_D.params)   # all-reduces issued during the backward
 
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     pool = 2
@@ -467,6 +469,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-convs", default="", help="write the per-shape tensor-core kernel timing table to this file")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="DP: all-reduce after the backward pass instead of from autograd hooks during it")
     ap.add_argument("--perceptual", action="store_true",
                     help="include the VGG16 features[:16] perceptual term (random-init weights) in loss_G")
     ap.add_argument("--film-row-dedup", action="store_true",

@@ -15,6 +15,50 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _worker_overlap(rank, world, port, ret):
+    """Same check with the all-reduces issued from autograd hooks during the backward, over two consecutive steps,
+    with one parameter that receives no gradient (its bucket must still be reduced by hook())."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vae_gan_mark_b200.parallel import DataParallelReducer
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    unused = torch.nn.Parameter(torch.zeros(3))
+    params = list(net.parameters()) + [unused]
+    red = DataParallelReducer(world, bucket_bytes=300)
+    red.install_hooks(params)
+    out = []
+    for step in range(2):
+        for p in params:
+            p.grad = None
+        g = torch.Generator().manual_seed(70 + step)
+        x_all, y_all = torch.randn(6, 8, generator=g), torch.randn(6, 4, generator=g)
+        xs, ys = x_all[rank * 3:(rank + 1) * 3], y_all[rank * 3:(rank + 1) * 3]
+        torch.nn.functional.mse_loss(net(xs), ys).backward()
+        launched_during_backward = sum(st["launched"] for st in red._states)
+        red.hook("G", params)
+        ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+        ref.load_state_dict(net.state_dict())
+        torch.nn.functional.mse_loss(ref(x_all), y_all).backward()
+        ok = all(torch.allclose(p.grad, q.grad, atol=1e-6) for p, q in zip(net.parameters(), ref.parameters()))
+        out.append((ok, launched_during_backward, unused.grad is None))
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_allreduce_from_autograd_hooks():
+    world, port = 2, 31000 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_overlap, args=(world, port, ret), nprocs=world, join=True)
+    for rank in range(world):
+        for ok, launched, unused_none in ret[rank]:
+            assert ok, "averaged gradients differ from the global-batch gradient"
+            assert launched >= 1, "no bucket was launched from the autograd hooks"
+            assert unused_none
+
+
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

@@ -21,7 +21,9 @@ class DataParallelReducer:
     def __init__(self, world_size: int, bucket_bytes: int = 32 << 20, group=None):
         self.world, self.bucket_bytes, self.group = world_size, bucket_bytes, group
         self._pending: List = []
-        self._hooked: Dict[int, List] = {}
+        self._states: List[Dict] = []
+        self._state_of: Dict[int, Dict] = {}
+        self.overlap = False
 
     # ------------------------------------------------------------------ setup
     def broadcast_parameters(self, tensors: Sequence[torch.Tensor], src: int = 0) -> None:
@@ -73,10 +75,46 @@ class DataParallelReducer:
             torch._foreach_copy_(views, list(flat.split([v.numel() for v in views])))
         self._pending = []
 
+    # ------------------------------------------------------------------ overlap with the backward pass
+    def install_hooks(self, *param_lists: Sequence[torch.nn.Parameter]) -> None:
+        """Launch every bucket's all-reduce from autograd as soon as its last gradient has been accumulated
+        (``register_post_accumulate_grad_hook``), so the exchange overlaps with the rest of the backward pass; ``hook``
+        then only launches what is left (buckets with a parameter that got no gradient) and waits.  Buckets follow
+        the reverse parameter order, which is the order the backward produces gradients in.  Works inside CUDA-graph
+        capture: the collectives are recorded at the point of the backward where they were issued."""
+        if self.world <= 1:
+            return
+        for params in param_lists:
+            for bucket in self.make_buckets(list(params)):
+                state = {"params": bucket, "ready": 0, "launched": False}
+                self._states.append(state)
+                for p in bucket:
+                    self._state_of[id(p)] = state
+                    p.register_post_accumulate_grad_hook(self._on_grad)
+        self.overlap = True
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        st = self._state_of.get(id(p))
+        if st is None or not self.overlap:
+            return
+        st["ready"] += 1
+        if st["ready"] == len(st["params"]) and not st["launched"]:
+            st["launched"] = True
+            self._launch(st["params"])
+
     def hook(self, which: str, params: Sequence[torch.nn.Parameter]) -> None:
         """``grad_hook`` of VAEGANTrainer: called after each backward; returns with averaged gradients in place."""
         if self.world <= 1:
             return
-        for bucket in self.make_buckets(params):
-            self._launch(bucket)
+        if self.overlap:
+            mine = {id(p) for p in params}
+            for st in self._states:
+                if id(st["params"][0]) not in mine:
+                    continue
+                if not st["launched"] and st["ready"] > 0:      # a bucket some of whose parameters got no gradient
+                    self._launch(st["params"])
+                st["ready"], st["launched"] = 0, False
+        else:
+            for bucket in self.make_buckets(params):
+                self._launch(bucket)
         self.wait()
