@@ -23,11 +23,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic conv GFLOP per image of one train step (SURVEY.md section 8a / BASELINE.md section 2)
-STEP_GFLOP_PER_IMG = {"v2_128": 411.4, "base_64": 6.34, "unet_256": 265.3}
+STEP_GFLOP_PER_IMG = {"v2_128": 411.4, "base_64": 6.34, "unet_256": 265.3, "unet_256_z512": 267.1}
 WORKLOADS = {
     "v2_128": dict(family="v2", h=128, w=128, batch=64, z=128, name="vae-gan-v2 128x128 b64/GPU"),
     "base_64": dict(family="base", h=64, w=64, batch=16, z=128, name="vae-gan base 64x64 b16"),
     "unet_256": dict(family="unet", h=256, w=256, batch=32, z=128, name="vae-gan-unet (repaired) 256x256 b32/GPU"),
+    # BASELINE configs[4]: latent dim 512 (568 M generator parameters); sweep the batch with --batch
+    "unet_256_z512": dict(family="unet", h=256, w=256, batch=32, z=512, name="vae-gan-unet (repaired) 256x256 z512"),
 }
 
 
