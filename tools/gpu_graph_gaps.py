@@ -13,13 +13,13 @@ from vae_gan_mark_b200.train import LossWeights, VAEGANTrainer  # noqa: E402
 
 
 def main():
-    wl = bench.WORKLOADS["v2_128"]
+    wl = bench.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "v2_128"]
     if len(sys.argv) > 1 and sys.argv[1] == "dedup":
         from vae_gan_mark_b200 import modules as M
         M.FILM_ROW_DEDUP = True
     dev = torch.device("cuda", 0)
     G, D = bench.build_models(wl, dev)
-    tr = VAEGANTrainer(G, D, LossWeights.for_family("v2"))
+    tr = VAEGANTrainer(G, D, LossWeights.for_family(wl["family"]))
     B, h, w = wl["batch"], wl["h"], wl["w"]
     gen = torch.Generator(device=dev).manual_seed(1)
     batch = (torch.rand(B, 3, h, w, device=dev, generator=gen), torch.rand(B, 3, h, w, device=dev, generator=gen),

@@ -563,23 +563,48 @@ __global__ void smalln_fwd_kernel(const T* __restrict__ x, int x_ld, int x_coff,
       for (int k = 0; k < 8; ++k) wreg[o][k] = o < cout ? __ldg(wt + static_cast<long long>(o) * cin + lane_in_g * 8 + k) : 0.f;
     float bv[kMaxSmallN];
     for (int o = 0; o < kMaxSmallN; ++o) bv[o] = (bias != nullptr && o < cout) ? bias[o] : 0.f;
-    const long long padded = ((pixels + (32 / G) - 1) / (32 / G)) * (32 / G);
-    for (long long px = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G; px < padded;
-         px += static_cast<long long>(gridDim.x) * blockDim.x / G) {
-      float acc[kMaxSmallN] = {0.f, 0.f, 0.f, 0.f};
-      if (px < pixels) {
-        float f[8];
-        load8(x + px * x_ld + x_coff + lane_in_g * 8, f);
+    // four pixels per trip: all four 16-byte loads are in flight before the first use
+    const long long gstride = static_cast<long long>(gridDim.x) * blockDim.x / G;
+    const long long px0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    const long long trips = (pixels + 4 * gstride - 1) / (4 * gstride);       // identical for every thread (shuffles)
+    for (long long trip = 0; trip < trips; ++trip) {
+      Raw8<T> raw[4];
+      long long pxs[4];
 #pragma unroll
-        for (int o = 0; o < kMaxSmallN; ++o)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[o] = fmaf(f[k], wreg[o][k], acc[o]);
+      for (int u = 0; u < 4; ++u) {
+        pxs[u] = px0 + (trip * 4 + u) * gstride;
+        if (pxs[u] < pixels) raw[u] = Raw8<T>::load(x + pxs[u] * x_ld + x_coff + lane_in_g * 8);
       }
 #pragma unroll
-      for (int o = 0; o < kMaxSmallN; ++o) {
-        float v = acc[o];
-        for (int s = G / 2; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        if (lane_in_g == 0 && px < pixels && o < cout) out[px * cout + o] = v + bv[o];
+      for (int u = 0; u < 4; ++u) {
+        float acc[kMaxSmallN] = {0.f, 0.f, 0.f, 0.f};
+        if (pxs[u] < pixels) {
+          float f[8];
+          raw[u].unpack(f);
+#pragma unroll
+          for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[o] = fmaf(f[k], wreg[o][k], acc[o]);
+        }
+        if (G == 8) {
+          // transposing reduction of the 4 partial outputs over the 8 lanes of the pixel: 4 shuffles instead of 12;
+          // lane l ends up with the full sum of output (l >> 1) & 3
+          const bool hi4 = lane_in_g & 4, hi2 = lane_in_g & 2;
+          const float r0 = __shfl_xor_sync(0xffffffffu, hi4 ? acc[0] : acc[2], 4);
+          const float r1 = __shfl_xor_sync(0xffffffffu, hi4 ? acc[1] : acc[3], 4);
+          const float a0 = (hi4 ? acc[2] : acc[0]) + r0, a1 = (hi4 ? acc[3] : acc[1]) + r1;
+          float b = (hi2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi2 ? a0 : a1, 2);
+          b += __shfl_xor_sync(0xffffffffu, b, 1);
+          const int o = (lane_in_g >> 1) & 3;
+          if ((lane_in_g & 1) == 0 && pxs[u] < pixels && o < cout) out[pxs[u] * cout + o] = b + bv[o];
+        } else {
+#pragma unroll
+          for (int o = 0; o < kMaxSmallN; ++o) {
+            float v = acc[o];
+            for (int sft = G / 2; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+            if (lane_in_g == 0 && pxs[u] < pixels && o < cout) out[pxs[u] * cout + o] = v + bv[o];
+          }
+        }
       }
     }
     return;
@@ -627,18 +652,28 @@ __global__ void smalln_dgrad_kernel(const float* __restrict__ dy, int n, int oh,
     for (int o = 0; o < kMaxSmallN; ++o)
 #pragma unroll
       for (int k = 0; k < 8; ++k) wreg[o][k] = o < cout ? __ldg(wt + static_cast<long long>(o) * cin + ch + k) : 0.f;
-    for (long long i = i0; i < total; i += nthreads) {
-      const long long pix = i / cv;
-      const float* g = dy + pix * cout;
-      float acc[8];
+    for (long long i = i0; i < total; i += 4 * nthreads) {
+      float gv[4][kMaxSmallN];
+      long long pix[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-      for (int o = 0; o < cout; ++o) {
-        const float gv = g[o];
+      for (int u = 0; u < 4; ++u) {
+        const long long iu = i + u * nthreads;
+        pix[u] = iu < total ? iu / cv : -1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(gv, wreg[o][k], acc[k]);
+        for (int o = 0; o < kMaxSmallN; ++o) gv[u][o] = (pix[u] >= 0 && o < cout) ? __ldg(dy + pix[u] * cout + o) : 0.f;
       }
-      store8(dx + pix * dx_ld + dx_coff + ch, acc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (pix[u] < 0) continue;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(gv[u][o], wreg[o][k], acc[k]);
+        store8(dx + pix[u] * dx_ld + dx_coff + ch, acc);
+      }
     }
     return;
   }
@@ -669,6 +704,80 @@ __global__ void smalln_dgrad_kernel(const float* __restrict__ dy, int n, int oh,
     store8(dx + pix * dx_ld + dx_coff + ch, acc);
   }
 }
+// pointwise (1x1, pad 0) weight gradient: thread = (pixel lane, channel vector); four pixels per trip with all loads in
+// flight first; registers -> shared memory across the pixel lanes of the block -> one fp32 atomic per (block, element)
+template <typename T>
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x, int x_ld,
+                                                       int x_coff, long long pixels, int cin, int cout,
+                                                       float* __restrict__ dw, float* __restrict__ dbias) {
+  const int cv = cin / 8;                 // <= 32 (checked by the host)
+  const int ppar = 256 / cv;
+  const int tid = threadIdx.x;
+  const int pl = tid / cv, cvi = tid % cv;
+  const int ch = cvi * 8;
+  float acc[kMaxSmallN][8], bacc[kMaxSmallN];
+#pragma unroll
+  for (int o = 0; o < kMaxSmallN; ++o) {
+    bacc[o] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[o][k] = 0.f;
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * ppar;
+  if (pl < ppar) {
+    for (long long px = static_cast<long long>(blockIdx.x) * ppar + pl; px < pixels; px += 4 * stride) {
+      Raw8<T> raw[4];
+      float g[4][kMaxSmallN];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pu = px + u * stride;
+        const bool ok = pu < pixels;
+        if (ok) raw[u] = Raw8<T>::load(x + pu * x_ld + x_coff + ch);
+#pragma unroll
+        for (int o = 0; o < kMaxSmallN; ++o) g[u][o] = (ok && o < cout) ? __ldg(dy + pu * cout + o) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (px + u * stride >= pixels) continue;
+        float f[8];
+        raw[u].unpack(f);
+#pragma unroll
+        for (int o = 0; o < kMaxSmallN; ++o) {
+          bacc[o] += g[u][o];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[o][k] = fmaf(g[u][o], f[k], acc[o][k]);
+        }
+      }
+    }
+  }
+  __shared__ float red[256][8 * kMaxSmallN + 1];
+#pragma unroll
+  for (int o = 0; o < kMaxSmallN; ++o)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[tid][o * 8 + k] = acc[o][k];
+  __syncthreads();
+  // thread t reduces element (t % 32) of channel vector (t / 32) over the pixel lanes
+  for (int item = tid; item < cv * 32; item += 256) {
+    const int v = item >> 5, e = item & 31, o = e >> 3, k = e & 7;
+    if (o < cout) {
+      float a = 0.f;
+      for (int p2 = 0; p2 < ppar; ++p2) a += red[p2 * cv + v][e];
+      atomicAdd(dw + static_cast<long long>(o) * cin + v * 8 + k, a);
+    }
+  }
+  if (dbias != nullptr) {
+    __syncthreads();
+    if (cvi == 0 && pl < ppar)
+#pragma unroll
+      for (int o = 0; o < kMaxSmallN; ++o) red[pl][o] = bacc[o];
+    __syncthreads();
+    if (tid < cout) {
+      float a = 0.f;
+      for (int p2 = 0; p2 < ppar; ++p2) a += red[p2][tid];
+      atomicAdd(dbias + tid, a);
+    }
+  }
+}
+
 // weight gradient: block = (tap, pixel chunk); thread = (channel vector, pixel lane); fp32 atomics per block
 template <typename T>
 __global__ void __launch_bounds__(256) smalln_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x,
@@ -1129,6 +1238,17 @@ extern "C" int vg_conv_smalln_wgrad(const float* dy, const void* x, int x_ld, in
   if (dbias) VG_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * cout, st));
   const int cv = cin / 8, cvl = cv < 256 ? cv : 256, ppar = 256 / cvl;
   const long long pixels = static_cast<long long>(n) * oh * ow;
+  if (kh == 1 && kw == 1 && pad == 0 && cv <= 32 && 256 % cv == 0) {
+    const int gp = static_cast<int>(std::min<long long>((pixels + ppar * 8 - 1) / (ppar * 8), static_cast<long long>(num_sms()) * 8));
+    if (dtype == 0)
+      pw_wgrad_kernel<__nv_bfloat16><<<std::max(gp, 1), 256, 0, st>>>(dy, static_cast<const __nv_bfloat16*>(x), x_ld, x_coff, pixels,
+                                                                    cin, cout, dw, dbias);
+    else
+      pw_wgrad_kernel<float><<<std::max(gp, 1), 256, 0, st>>>(dy, static_cast<const float*>(x), x_ld, x_coff, pixels, cin, cout,
+                                                            dw, dbias);
+    VG_LAUNCH_OK();
+    return 0;
+  }
   int gx = static_cast<int>(std::min<long long>((pixels + ppar * 16 - 1) / (ppar * 16), std::max(1, num_sms() * 4 / (kh * kw))));
   if (gx < 1) gx = 1;
   if (dtype == 0)
