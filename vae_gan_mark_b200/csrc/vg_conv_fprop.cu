@@ -13,12 +13,15 @@
 //   conv read as the B operand of its own DATA GRADIENT (K = Cout, N = Cin of one tap).  It is loaded as BN/64 boxes of
 //   {64 N, 64 K} = the canonical MN-major SWIZZLE_128B layout, and the tensor core transposes it for free, so the data
 //   gradient needs no second, transposed copy of the weights.
-// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered fp32 TMEM
-//   accumulator; 4 epilogue warps drain TMEM with tcgen05.ld, add bias / activation, and store bf16 or
-//   fp32 NHWC rows (optionally scattered as a pixel shuffle for ConvTranspose, optionally into a channel
-//   slice of a wider buffer = fused concat, optionally fp32 atomics for split-K).
-// * Persistent: grid = min(tiles, #SMs); warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM
-//   allocator, 4..7 = epilogue.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into fp32 TMEM accumulators (2 x 256 columns, or
+//   4 x 128 for BN <= 128); 8 epilogue warps drain TMEM with tcgen05.ld, add bias / activation, stage the tile in
+//   XOR-swizzled shared memory and store bf16 or fp32 NHWC rows with 16-byte coalesced stores (optionally scattered
+//   as a pixel shuffle for ConvTranspose, optionally into a channel slice of a wider buffer = fused concat,
+//   optionally fp32 atomics for split-K).
+// * Persistent: grid = min(tiles, #SMs); warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
+//   4..11 = epilogue.
+// * Per-launch variants: tile groups (the four parity classes of a stride-2 data gradient in one launch) and the
+//   halo mode for narrow 3x3 layers (FpropParams).
 //
 // This one kernel serves Conv2d fprop, Conv2d dgrad (flipped weights), ConvTranspose2d fprop/dgrad and the
 // GEMM-shaped layers (1x1 convs, full-kernel heads, bottleneck ConvT) of the reference models

@@ -216,7 +216,7 @@ class VAEGANTrainer:
                 perc = self.perceptual(fake, en)
                 loss_g = loss_g + w.perc * perc
             loss_g.backward()
-        _lib.call("vg_set_conv_sm_limit", 0)      # (raised again by the text-feature gradient hook during the backward)
+        _lib.call("vg_set_conv_sm_limit", 0)      # (only ever raised by the optional side-stream text path)
         if self.grad_hook is not None:
             self.grad_hook("G", self.opt_G.params)
         self.opt_G.step(max_norm=self.clip_norm)
