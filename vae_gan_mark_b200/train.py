@@ -227,6 +227,31 @@ class VAEGANTrainer:
             out["perc"] = perc.detach()
         return out
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def checkpoint(self, **extra) -> Dict:
+        """The reference's checkpoint dictionary (vae-gan-v2.py:802-808; vae-gan.py:449-456): module state_dicts plus
+        torch.optim.Adam-compatible optimiser state_dicts.  ``extra`` entries (epoch, scheduler states, ...) are passed
+        through.  Save with ``torch.save``; a checkpoint written by the reference loads with ``load_checkpoint``."""
+        ck = {"model_state_dict": self.G.state_dict(), "disc_state_dict": self.D.state_dict(),
+              "opt_G_state_dict": self.opt_G.state_dict(), "opt_D_state_dict": self.opt_D.state_dict()}
+        ck.update(extra)
+        return ck
+
+    def load_checkpoint(self, ck: Dict, strict: bool = False) -> None:
+        """Inverse of ``checkpoint`` (the reference resumes with strict=False, vae-gan-v2.py:968-972).  Keeps the memory
+        order of the parameters, invalidates the cached operand layouts, and drops a captured graph's claim to be
+        current -- call ``capture`` again before ``replay``."""
+        self.G.load_state_dict(ck["model_state_dict"], strict=strict)
+        self.D.load_state_dict(ck["disc_state_dict"], strict=strict)
+        opt_g = ck.get("opt_G_state_dict", ck.get("optG_state_dict"))
+        opt_d = ck.get("opt_D_state_dict", ck.get("optD_state_dict"))
+        if opt_g is not None:
+            self.opt_G.load_state_dict(opt_g)
+        if opt_d is not None:
+            self.opt_D.load_state_dict(opt_d)
+        L.bump_weight_epoch()
+        self._graph = None
+
     # ------------------------------------------------------------------ CUDA graph
     def capture(self, ru, en, mask, texts, warmup: int = 3, kl_weight: Optional[float] = None):
         """Record one full step into a CUDA graph.  ``texts`` is tokenised / embedded once here (the graph takes the
