@@ -420,49 +420,68 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ t, int t_ld, int t_cof
     for (int r = r0; r < r1; ++r, dst += static_cast<long long>(w) * c) store8(dst, o);
   }
 }
-// dt[b][js][c] (fp32, accumulated) = sum_i sum_j weight(j -> js) dy[b][i][j][c]; one thread per (b, js, cvec, i-chunk)
+// dt[b][js][c] (fp32, accumulated) = sum_i sum_j weight(j -> js) dy[b][i][j][c].
+// One thread = 8 channels x a run of `jlen` destination columns x `rows_per_thread` rows: every dy element is read
+// exactly once (each column feeds the two sources it was interpolated from); a run is short enough (<= half the
+// upsampling ratio) to touch at most three consecutive sources, whose partial sums live in registers.
 template <typename T>
 __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int w, int c, int w0,
-                                    float* __restrict__ dt, int rows_per_thread) {
+                                    float* __restrict__ dt, int rows_per_thread, int jlen) {
   const int cv = c / 8;
   const int ichunks = (h + rows_per_thread - 1) / rows_per_thread;
-  const long long total = static_cast<long long>(n) * w0 * cv * ichunks;
+  const int jruns = (w + jlen - 1) / jlen;
+  const long long total = static_cast<long long>(n) * jruns * cv * ichunks;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(idx % cv) * 8;
     long long r = idx / cv;
-    const int js = static_cast<int>(r % w0);
-    r /= w0;
+    const int jr = static_cast<int>(r % jruns);
+    r /= jruns;
     const int ic = static_cast<int>(r % ichunks);
     const int b = static_cast<int>(r / ichunks);
-    float acc[8];
+    const int j_begin = jr * jlen, j_end = min(w, j_begin + jlen);
+    const int i_begin = ic * rows_per_thread, i_end = min(h, i_begin + rows_per_thread);
+    int base, tmp;
+    float lam0;
+    lerp_src(j_begin, w0, w, base, tmp, lam0);
+    float acc[3][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    // destination columns whose source interval touches js: a conservative window, filtered exactly below
-    const float ratio = static_cast<float>(w) / static_cast<float>(w0);
-    int jlo = static_cast<int>((static_cast<float>(js) - 1.f) * ratio) - 2;
-    int jhi = static_cast<int>((static_cast<float>(js) + 2.f) * ratio) + 2;
-    if (jlo < 0) jlo = 0;
-    if (jhi > w - 1) jhi = w - 1;
-    for (int j = jlo; j <= jhi; ++j) {
+    for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[s3][k] = 0.f;
+    for (int j = j_begin; j < j_end; ++j) {
       int j0, j1;
       float lam;
       lerp_src(j, w0, w, j0, j1, lam);
-      float wgt = 0.f;
-      if (j0 == js) wgt += 1.f - lam;
-      if (j1 == js) wgt += lam;
-      if (wgt == 0.f) continue;
-      const int i_end = min(h, (ic + 1) * rows_per_thread);
-      for (int i = ic * rows_per_thread; i < i_end; ++i) {
+      float colsum[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) colsum[k] = 0.f;
+      for (int i = i_begin; i < i_end; ++i) {
         float d[8];
         load8(dy + ((static_cast<long long>(b) * h + i) * w + j) * c + ch, d);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, d[k], acc[k]);
+        for (int k = 0; k < 8; ++k) colsum[k] += d[k];
+      }
+      const int s0 = j0 - base, s1 = j1 - base;          // 0..2 by construction of jlen
+#pragma unroll
+      for (int s3 = 0; s3 < 3; ++s3) {
+        const float wgt = (s3 == s0 ? 1.f - lam : 0.f) + (s3 == s1 ? lam : 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[s3][k] = fmaf(wgt, colsum[k], acc[s3][k]);
       }
     }
-    float* o = dt + (static_cast<long long>(b) * w0 + js) * c + ch;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(o + k, acc[k]);
+    for (int s3 = 0; s3 < 3; ++s3) {
+      if (base + s3 >= w0) break;
+      float* o = dt + (static_cast<long long>(b) * w0 + base + s3) * c + ch;
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) any = any || acc[s3][k] != 0.f;
+      if (any) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(o + k, acc[s3][k]);
+      }
+    }
   }
 }
 
@@ -1148,11 +1167,14 @@ extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int
   VG_CHECK(c % 8 == 0, -1, "vg_upsample_w_bwd: channels must be multiples of 8");
   VG_CUDA(cudaMemsetAsync(dt, 0, sizeof(float) * static_cast<size_t>(n) * w0 * c, st));
   const int rpt = 8;
-  const long long items = static_cast<long long>(n) * w0 * (c / 8) * ((h + rpt - 1) / rpt);
+  // a run of jlen columns spans at most jlen * w0 / w < 1 source steps plus the two-tap footprint: <= 3 sources
+  const int jlen = std::max(1, w / (2 * w0));
+  const long long items = static_cast<long long>(n) * ((w + jlen - 1) / jlen) * (c / 8) * ((h + rpt - 1) / rpt);
   if (dtype == 0)
-    upsample_bwd_kernel<__nv_bfloat16><<<ew_grid(items), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, w0, dt, rpt);
+    upsample_bwd_kernel<__nv_bfloat16><<<ew_grid(items), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, w0, dt,
+                                                                     rpt, jlen);
   else
-    upsample_bwd_kernel<float><<<ew_grid(items), 256, 0, st>>>(static_cast<const float*>(dy), n, h, w, c, w0, dt, rpt);
+    upsample_bwd_kernel<float><<<ew_grid(items), 256, 0, st>>>(static_cast<const float*>(dy), n, h, w, c, w0, dt, rpt, jlen);
   VG_LAUNCH_OK();
   return 0;
 }
