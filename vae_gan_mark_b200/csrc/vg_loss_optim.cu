@@ -150,24 +150,42 @@ __global__ void hinge_bwd_kernel(const float* __restrict__ p, long long n, int m
 // ---------------------------------------------------------------------------------------------
 // spectral norm.  W: fp32 [rows][cols] (OIHW flattened), u [rows], v [cols]
 // ---------------------------------------------------------------------------------------------
-// t[j] = sum_i W[i][j] u[i]; nrm[0] += sum t^2
+// t[j] += sum_{i in this block's row chunk} W[i][j] u[i]   (t zeroed by the caller; blockIdx.y = row chunk).
+// One thread per column over ALL rows was a chain of `rows` dependent loads on 16 blocks (27 us for 512 x 4096);
+// splitting the rows over blockIdx.y fills the machine.  |t|^2 is taken by the next kernel.
 __global__ void sn_wtu_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows, int cols,
-                              float* __restrict__ t, float* __restrict__ nrm) {
+                              float* __restrict__ t, int rows_per_block) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  float acc = 0.f;
-  if (j < cols)
-    for (int i = 0; i < rows; ++i) acc = fmaf(w[static_cast<long long>(i) * cols + j], u[i], acc);
-  if (j < cols) t[j] = acc;
-  const float s = block_sum(j < cols ? acc * acc : 0.f);
-  if (threadIdx.x == 0) atomicAdd(nrm, s);
+  if (j >= cols) return;
+  const int i0 = blockIdx.y * rows_per_block, i1 = min(rows, i0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = i0;
+  for (; i + 3 < i1; i += 4) {
+    a0 = fmaf(w[static_cast<long long>(i) * cols + j], u[i], a0);
+    a1 = fmaf(w[static_cast<long long>(i + 1) * cols + j], u[i + 1], a1);
+    a2 = fmaf(w[static_cast<long long>(i + 2) * cols + j], u[i + 2], a2);
+    a3 = fmaf(w[static_cast<long long>(i + 3) * cols + j], u[i + 3], a3);
+  }
+  for (; i < i1; ++i) a0 = fmaf(w[static_cast<long long>(i) * cols + j], u[i], a0);
+  atomicAdd(t + j, (a0 + a1) + (a2 + a3));
 }
-// s[i] = sum_j W[i][j] * t[j] * tscale, tscale = 1/max(sqrt(nrm_t), eps) (or 1 when nrm_t == nullptr); nrm_s += sum s^2
-__global__ void sn_wv_kernel(const float* __restrict__ w, const float* __restrict__ t, const float* __restrict__ nrm_t,
+// s[i] = sum_j W[i][j] * t[j] * tscale, tscale = 1/max(|t|, eps) (or 1 when nrm_t == nullptr: t is already a unit vector);
+// every block takes |t|^2 itself from the t it reads anyway (block 0 publishes it in *nrm_t); nrm_s += sum s^2
+__global__ void sn_wv_kernel(const float* __restrict__ w, const float* __restrict__ t, float* __restrict__ nrm_t,
                              float eps, int rows, int cols, float* __restrict__ s, float* __restrict__ nrm_s) {
   const int i = blockIdx.x;
-  const float tscale = nrm_t ? 1.f / fmaxf(sqrtf(*nrm_t), eps) : 1.f;
-  float acc = 0.f;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) acc = fmaf(w[static_cast<long long>(i) * cols + j], t[j], acc);
+  float acc = 0.f, tt = 0.f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float tv = t[j];
+    acc = fmaf(w[static_cast<long long>(i) * cols + j], tv, acc);
+    tt = fmaf(tv, tv, tt);
+  }
+  float tscale = 1.f;
+  if (nrm_t != nullptr) {
+    const float t2 = block_sum(tt);          // identical in every block (same data, same order)
+    tscale = 1.f / fmaxf(sqrtf(t2), eps);
+    if (i == 0 && threadIdx.x == 0) *nrm_t = t2;
+  }
   const float r = block_sum(acc) * tscale;
   if (threadIdx.x == 0) {
     s[i] = r;
@@ -412,7 +430,9 @@ extern "C" int vg_spectral_sigma(const float* w, int rows, int cols, float* u, f
   float* nrm = s + rows;       // [2]
   VG_CUDA(cudaMemsetAsync(nrm, 0, 2 * sizeof(float), ST));
   if (training) {
-    sn_wtu_kernel<<<cdiv(cols, 256), 256, 0, ST>>>(w, u, rows, cols, t, nrm);
+    VG_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, ST));
+    const int rpb = std::max(8, cdiv(rows, 32));
+    sn_wtu_kernel<<<dim3(cdiv(cols, 256), cdiv(rows, rpb)), 256, 0, ST>>>(w, u, rows, cols, t, rpb);
     VG_LAUNCH_OK();
     sn_wv_kernel<<<rows, 256, 0, ST>>>(w, t, nrm, eps, rows, cols, s, nrm + 1);
   } else {
