@@ -378,3 +378,125 @@ class VGGPerceptual(nn.Module):
 
     def forward(self, fake, real):
         return F.l1_loss(self.features((fake - self.mean) / self.std), self.features((real - self.mean) / self.std))
+
+
+# ------------------------------------------------------------------------------------------------
+# vae-gan-oldv.py family: 3-level U-Net, gated skips, 4-row text map
+# ------------------------------------------------------------------------------------------------
+class CharacterTokenEncoderOldV(nn.Module):
+    """vae-gan-oldv.py:74-148 -- Embedding -> biGRU -> Conv1d(k=3) -> adaptive avg pool to W/16 -> the row repeated
+    ``target_feature_height`` (4) times -> + learned positional encoding (1, C, 4, W/16)."""
+
+    def __init__(self, alphabet_str, emb_dim, rnn_hidden_dim, rnn_layers, target_feature_width, target_feature_height=4):
+        super().__init__()
+        self.lut = {ch: i + 1 for i, ch in enumerate(alphabet_str)}
+        self.embedding = nn.Embedding(len(alphabet_str) + 1, emb_dim, padding_idx=0)
+        self.rnn = nn.GRU(emb_dim, rnn_hidden_dim, num_layers=rnn_layers, batch_first=True, bidirectional=True,
+                          dropout=0.1 if rnn_layers > 1 else 0)
+        self.rnn_output_dim = 2 * rnn_hidden_dim
+        self.target_feature_width, self.target_feature_height = target_feature_width, target_feature_height
+        self.conv1d = nn.Conv1d(self.rnn_output_dim, self.rnn_output_dim, kernel_size=3, padding=1)
+        self.register_parameter("pos_enc", nn.Parameter(
+            torch.randn(1, self.rnn_output_dim, target_feature_height, target_feature_width) * 0.02))
+
+    def tokenize(self, texts, max_len=60):
+        idx = torch.zeros(len(texts), max_len, dtype=torch.long)
+        for r, t in enumerate(texts):
+            ids = [self.lut.get(ch, 0) for ch in t][:max_len]
+            if ids:
+                idx[r, :len(ids)] = torch.tensor(ids, dtype=torch.long)
+        return idx
+
+    def forward(self, texts, max_len=60):
+        idx = self.tokenize(texts, max_len).to(self.embedding.weight.device)
+        out, _ = self.rnn(self.embedding(idx))
+        x = F.adaptive_avg_pool1d(self.conv1d(out.permute(0, 2, 1)), self.target_feature_width)
+        x = x.unsqueeze(2).expand(-1, -1, self.target_feature_height, -1)
+        return x + self.pos_enc                                            # (B, 2*hid, 4, W/16)
+
+
+class VAEEncoderWithSkips3(nn.Module):
+    """vae-gan-oldv.py:187-224 -- three double-conv levels (32/64/128) + bottleneck 256, heads with kernel (H/8, W/8)."""
+
+    def __init__(self, in_ch, z_ch, patch_hw, skip_chans=(32, 64, 128), bottleneck_ch=256):
+        super().__init__()
+        self.e_conv1 = double_conv(in_ch, skip_chans[0])
+        self.pool1 = nn.MaxPool2d(2, 2)
+        self.e_conv2 = double_conv(skip_chans[0], skip_chans[1])
+        self.pool2 = nn.MaxPool2d(2, 2)
+        self.e_conv3 = double_conv(skip_chans[1], skip_chans[2])
+        self.pool3 = nn.MaxPool2d(2, 2)
+        self.bottleneck_conv = double_conv(skip_chans[2], bottleneck_ch)
+        k = (patch_hw[0] // 8, patch_hw[1] // 8)
+        self.mu_head = nn.Conv2d(bottleneck_ch, z_ch, kernel_size=k)
+        self.logvar_head = nn.Conv2d(bottleneck_ch, z_ch, kernel_size=k)
+
+    def forward(self, x):
+        s1 = self.e_conv1(x)
+        s2 = self.e_conv2(self.pool1(s1))
+        s3 = self.e_conv3(self.pool2(s2))
+        b = self.bottleneck_conv(self.pool3(s3))
+        return self.mu_head(b), self.logvar_head(b), [s1, s2, s3]
+
+
+class GatedSkipConnection(nn.Module):
+    """vae-gan-oldv.py:226-231 -- skip * sigmoid(alpha), alpha (1, C, 1, 1) initialised to 0.3."""
+
+    def __init__(self, channels, alpha_init=0.3):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1, channels, 1, 1) * alpha_init)
+
+    def forward(self, skip_feat):
+        return skip_feat * torch.sigmoid(self.alpha)
+
+
+class VAEDecoderWithSpatialFiLM3(nn.Module):
+    """vae-gan-oldv.py:235-320 -- ConvT(k=(H/8,1)) -> BN -> ReLU; 3 x [ConvT2x2 s2 -> cat(gated skip) -> FiLM ->
+    double conv]; Conv1x1; Sigmoid.  The text map has 4 rows, so every FiLM interpolation is a true 2-D bilinear
+    resize, and the bottleneck input is the map resized to (1, W/8)."""
+
+    def __init__(self, z_ch, text_channels_in, out_ch_image, patch_h, patch_w, skip_chans=(32, 64, 128), bottleneck_ch=256):
+        super().__init__()
+        self.initial_h, self.initial_w = patch_h // 8, patch_w // 8
+        self.skip_gates = nn.ModuleList([GatedSkipConnection(skip_chans[2]), GatedSkipConnection(skip_chans[1]),
+                                         GatedSkipConnection(skip_chans[0])])
+        self.bottleneck_proc = nn.Sequential(
+            nn.ConvTranspose2d(z_ch + text_channels_in, bottleneck_ch, kernel_size=(self.initial_h, 1), stride=1, padding=0),
+            *_bn_relu(bottleneck_ch))
+        c = bottleneck_ch
+        for i, s in enumerate((skip_chans[2], skip_chans[1], skip_chans[0]), start=1):
+            setattr(self, f"up_tconv{i}", nn.ConvTranspose2d(c, s, kernel_size=2, stride=2))
+            setattr(self, f"spatial_film{i}", SpatialFiLMLayer(text_channels_in, 2 * s))
+            setattr(self, f"conv_block{i}", double_conv(2 * s, s))
+            c = s
+        self.final_image_conv = nn.Conv2d(skip_chans[0], out_ch_image, kernel_size=1)
+        self.output_activation_fn = nn.Sigmoid()
+
+    def forward(self, z, text_base, skips):
+        t0 = F.interpolate(text_base, size=(1, self.initial_w), mode="bilinear", align_corners=False)
+        x = self.bottleneck_proc(torch.cat([z.expand(-1, -1, 1, self.initial_w), t0], 1))
+        for i in (1, 2, 3):
+            x = getattr(self, f"up_tconv{i}")(x)
+            x = torch.cat([x, self.skip_gates[i - 1](skips[3 - i])], 1)
+            x = getattr(self, f"spatial_film{i}")(x, text_base)
+            x = getattr(self, f"conv_block{i}")(x)
+        return self.output_activation_fn(self.final_image_conv(x))
+
+
+class VAEGAN_UNet_SpatialFiLM_OldV(nn.Module):
+    """vae-gan-oldv.py:323-368 (the script calls it VAEGAN_UNet_SpatialFiLM too)."""
+
+    def __init__(self, in_ch_style=4, z_ch_style=128, out_ch_img=3, alphabet_str_text=ALPHABET_STR,
+                 char_emb_dim_text=128, char_rnn_hidden_dim_text=256, char_rnn_layers_text=2, patch_hw=(64, 448)):
+        super().__init__()
+        self.char_text_encoder_module = CharacterTokenEncoderOldV(
+            alphabet_str_text, char_emb_dim_text, char_rnn_hidden_dim_text, char_rnn_layers_text, patch_hw[1] // 16, 4)
+        self.style_vae_encoder_module = VAEEncoderWithSkips3(in_ch_style, z_ch_style, patch_hw)
+        self.image_vae_decoder_module = VAEDecoderWithSpatialFiLM3(
+            z_ch_style, self.char_text_encoder_module.rnn_output_dim, out_ch_img, patch_hw[0], patch_hw[1])
+
+    def forward(self, image, mask, texts):
+        mu, logvar, skips = self.style_vae_encoder_module(torch.cat([image, mask], 1))
+        z = reparameterize(mu, logvar)
+        text_base = self.char_text_encoder_module(texts)
+        return self.image_vae_decoder_module(z, text_base, skips), mu, logvar

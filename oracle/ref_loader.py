@@ -94,6 +94,8 @@ def build(family: str, h: int, w: int, z_ch: int = 128):
             G = mod.VAEGAN_UNet_SpatialFiLM(in_ch_style=4, z_ch_style=z_ch)
         elif family == "unet":
             G = mod.VAEGAN_UNet_CharEmb(in_ch_for_style_encoder=4, z_ch_for_style=z_ch)
+        elif family == "oldv":
+            G = mod.VAEGAN_UNet_SpatialFiLM(in_ch_style=4, z_ch_style=z_ch)
         else:
             raise ValueError(family)
         D = mod.Discriminator(3)

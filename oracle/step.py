@@ -33,8 +33,9 @@ class LossWeights:
     @staticmethod
     def for_family(family: str) -> "LossWeights":
         # vae-gan.py:35-38 ; vae-gan-v2.py:42-45 ; vae-gan-unet.py:43-46   (perceptual weight forced to 0)
+        # vae-gan-oldv.py:40-44: KL 0.001, GAN 0.07
         return {"base": LossWeights(1.0, 0.005, 0.1), "v2": LossWeights(1.0, 0.001, 0.15),
-                "unet": LossWeights(1.0, 0.001, 0.15)}[family]
+                "unet": LossWeights(1.0, 0.001, 0.15), "oldv": LossWeights(1.0, 0.001, 0.07)}[family]
 
 
 def hinge_loss(preds, target):

@@ -30,6 +30,7 @@ CASES = {
     "v2_32x64_b2": ("v2", 32, 64, 2, 128),
     "v2_32x32_b3_z32": ("v2", 32, 32, 3, 32),
     "unet_32x32_b2": ("unet", 32, 32, 2, 128),
+    "oldv_32x64_b2": ("oldv", 32, 64, 2, 128),         # vae-gan-oldv.py: 3-level U-Net, gated skips, 4-row text map
 }
 
 

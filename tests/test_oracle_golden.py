@@ -12,7 +12,7 @@ from oracle import models as om
 from oracle.step import LossWeights, deterministic_state, make_optimizers, synthetic_batch, train_step
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["base_32x32_b4", "base_64x64_b16", "v2_32x64_b2", "v2_32x32_b3_z32", "unet_32x32_b2"]
+CASES = ["base_32x32_b4", "base_64x64_b16", "v2_32x64_b2", "v2_32x32_b3_z32", "unet_32x32_b2", "oldv_32x64_b2"]
 
 
 def summarize(t, n=6):
@@ -27,6 +27,8 @@ def build_oracle(family, h, w, z):
         G = om.VAEGAN(4, z, 64, 3, patch_hw=(h, w))
     elif family == "v2":
         G = om.VAEGAN_UNet_SpatialFiLM(4, z, patch_hw=(h, w))
+    elif family == "oldv":
+        G = om.VAEGAN_UNet_SpatialFiLM_OldV(4, z, patch_hw=(h, w))
     else:
         G = om.VAEGAN_UNet_CharEmb(4, z, patch_hw=(h, w), repaired=True)
     return G, om.Discriminator(3)
