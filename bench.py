@@ -23,13 +23,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic conv GFLOP per image of one train step (SURVEY.md section 8a / BASELINE.md section 2)
-STEP_GFLOP_PER_IMG = {"v2_128": 411.4, "base_64": 6.34, "unet_256": 265.3, "unet_256_z512": 267.1}
+STEP_GFLOP_PER_IMG = {"v2_128": 411.4, "base_64": 6.34, "unet_256": 265.3, "unet_256_z512": 267.1,
+                      "oldv_64x448": 589.0}     # oldv: same 3 F_G + 8 F_D - first-layer dgrads rule, F_G = 192.5, F_D = 1.455
 WORKLOADS = {
     "v2_128": dict(family="v2", h=128, w=128, batch=64, z=128, name="vae-gan-v2 128x128 b64/GPU"),
     "base_64": dict(family="base", h=64, w=64, batch=16, z=128, name="vae-gan base 64x64 b16"),
     "unet_256": dict(family="unet", h=256, w=256, batch=32, z=128, name="vae-gan-unet (repaired) 256x256 b32/GPU"),
     # BASELINE configs[4]: latent dim 512 (568 M generator parameters); sweep the batch with --batch
     "unet_256_z512": dict(family="unet", h=256, w=256, batch=32, z=512, name="vae-gan-unet (repaired) 256x256 z512"),
+    # vae-gan-oldv.py at its own PATCH_SHAPE (448, 64) and BATCH_SIZE 16 (vae-gan-oldv.py:27,31); SURVEY 8f row f3
+    "oldv_64x448": dict(family="oldv", h=64, w=448, batch=16, z=128, name="vae-gan-oldv 64x448 b16/GPU"),
 }
 
 
@@ -90,6 +93,8 @@ def cpu_reference_rate(wl, sample_batch: int, steps: int, warmup: int):
         G = om.VAEGAN(4, z, 64, 3, patch_hw=(h, w))
     elif fam == "v2":
         G = om.VAEGAN_UNet_SpatialFiLM(4, z, patch_hw=(h, w))
+    elif fam == "oldv":
+        G = om.VAEGAN_UNet_SpatialFiLM_OldV(4, z, patch_hw=(h, w))
     else:
         G = om.VAEGAN_UNet_CharEmb(4, z, patch_hw=(h, w), repaired=True)
     D = om.Discriminator(3)
@@ -146,6 +151,8 @@ def run_stock_gpu(args, wl):
             G = om.VAEGAN(4, z, 64, 3, patch_hw=(h, w))
         elif fam == "v2":
             G = om.VAEGAN_UNet_SpatialFiLM(4, z, patch_hw=(h, w))
+        elif fam == "oldv":
+            G = om.VAEGAN_UNet_SpatialFiLM_OldV(4, z, patch_hw=(h, w))
         else:
             G = om.VAEGAN_UNet_CharEmb(4, z, patch_hw=(h, w), repaired=True)
         D = om.Discriminator(3)
@@ -208,6 +215,8 @@ def build_models(wl, device):
         G = M.VAEGAN(4, z, 64, 3, patch_shape=(w, h), text_embedder=lambda t: torch.randn(len(t), 384))
     elif fam == "v2":
         G = M.VAEGAN_UNet_SpatialFiLM(4, z, patch_shape=(w, h))
+    elif fam == "oldv":
+        G = M.VAEGAN_UNet_SpatialFiLM_OldV(4, z, patch_shape=(w, h))
     else:
         G = M.VAEGAN_UNet_CharEmb(4, z, patch_shape=(w, h))
     D = M.Discriminator(3)

@@ -205,6 +205,18 @@ int vg_upsample_w_fwd(const void* t, int t_ld, int t_coff, int n, int w0, int c,
                       void* stream);
 int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int w0, float* dt /*fp32 [n][w0][c]*/, int dtype,
                       void* stream);
+/* Bilinear resize along H only (align_corners=False); with the W-only pair above it composes F.interpolate(bilinear)
+ * of a multi-row map (the 4-row text map of vae-gan-oldv.py:165-176,286-291).  t / dt: [n][h0][w][c], y / dy:
+ * [n][h][w][c], all dense; dt is fp32 and fully written. */
+int vg_upsample_h_fwd(const void* t, int n, int h0, int w, int c, void* y, int h, int dtype, void* stream);
+int vg_upsample_h_bwd(const void* dy, int n, int h, int w, int c, int h0, float* dt, int dtype, void* stream);
+/* Per-channel gate y = x * scale[c] (GatedSkipConnection, vae-gan-oldv.py:226-231; scale = sigmoid(alpha), fp32 [c]),
+ * written into a channel slice (y_ld, y_coff).  Backward in one pass: dx = dy * scale, dscale[0..c) = sum dy * x
+ * (dscale is fp32 [2*c]; the second half is scratch). */
+int vg_channel_scale_fwd(const void* x, int x_ld, const float* scale, void* y, int y_ld, int y_coff, long long rows, int c,
+                         int dtype, void* stream);
+int vg_channel_scale_bwd(const void* x, int x_ld, const void* dy, int dy_ld, int dy_coff, const float* scale, void* dx,
+                         int dx_ld, long long rows, int c, float* dscale, int dtype, void* stream);
 /* `dtype` on the activation-touching entry points selects the activation storage: 0 = bf16 (default), 1 = fp32 (the
  * high-accuracy mode, in which the tensor core is fed three bf16 planes per fp32 operand, see vg_split3). */
 /* fp32 [rows][c] (row stride ld_in) -> bf16 [rows][3*cp]: planes hi | mid | lo with hi+mid+lo == x to ~2^-24 */

@@ -88,6 +88,7 @@ def test_state_dict_contract_matches_oracle():
         (M.Discriminator(), om.Discriminator()),
         (M.VAEGAN_UNet_SpatialFiLM(patch_shape=(64, 32)), om.VAEGAN_UNet_SpatialFiLM(patch_hw=(32, 64))),
         (M.VAEGAN_UNet_CharEmb(patch_shape=(32, 32)), om.VAEGAN_UNet_CharEmb(patch_hw=(32, 32))),
+        (M.VAEGAN_UNet_SpatialFiLM_OldV(patch_shape=(64, 32)), om.VAEGAN_UNet_SpatialFiLM_OldV(patch_hw=(32, 64))),
     ]
     for mine, ora in pairs:
         a, b = mine.state_dict(), ora.state_dict()

@@ -187,7 +187,7 @@ def test_heads_image_small_fp32():
 
 
 CASES = [("base", 32, 32, 4, 128), ("v2", 32, 64, 2, 128), ("v2", 32, 32, 3, 32), ("unet", 32, 32, 2, 128),
-         ("base", 64, 64, 16, 128)]
+         ("base", 64, 64, 16, 128), ("oldv", 32, 64, 2, 128)]
 
 
 def is_zero_in_theory(key: str) -> bool:

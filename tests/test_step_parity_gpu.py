@@ -37,6 +37,9 @@ def build_pair(family, h, w, z):
     elif family == "v2":
         og = om.VAEGAN_UNet_SpatialFiLM(4, z, patch_hw=(h, w))
         mg = M.VAEGAN_UNet_SpatialFiLM(4, z, patch_shape=(w, h))
+    elif family == "oldv":
+        og = om.VAEGAN_UNet_SpatialFiLM_OldV(4, z, patch_hw=(h, w))
+        mg = M.VAEGAN_UNet_SpatialFiLM_OldV(4, z, patch_shape=(w, h))
     else:
         og = om.VAEGAN_UNet_CharEmb(4, z, patch_hw=(h, w), repaired=True)
         mg = M.VAEGAN_UNet_CharEmb(4, z, patch_shape=(w, h))
@@ -53,7 +56,7 @@ def build_pair(family, h, w, z):
 
 
 CASES = [("base", 32, 32, 4, 128), ("v2", 32, 64, 2, 128), ("v2", 32, 32, 3, 32), ("unet", 32, 32, 2, 128),
-         ("base", 64, 64, 16, 128)]
+         ("base", 64, 64, 16, 128), ("oldv", 32, 64, 2, 128), ("oldv", 64, 64, 5, 64)]
 
 
 @pytest.mark.parametrize("family,h,w,batch,z", CASES)

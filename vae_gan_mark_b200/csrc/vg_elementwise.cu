@@ -486,6 +486,74 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bilinear resize along H only (align_corners=False): y[b][i][x][:] = (1-mu) t[b][i0][x][:] + mu t[b][i1][x][:].
+// With the W-only kernels above this composes F.interpolate(..., mode='bilinear') of a multi-row map (the 4-row text
+// map of vae-gan-oldv.py:165-176, 286-291) -- bilinear interpolation is separable.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample_h_fwd_kernel(const T* __restrict__ t, int n, int h0, int w, int c, T* __restrict__ y, int h) {
+  const int cv = c / 8;
+  const long long total = static_cast<long long>(n) * h * w * cv;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(idx % cv) * 8;
+    long long r = idx / cv;
+    const int x = static_cast<int>(r % w);
+    r /= w;
+    const int i = static_cast<int>(r % h);
+    const long long b = r / h;
+    int i0, i1;
+    float mu;
+    lerp_src(i, h0, h, i0, i1, mu);
+    float a[8], bb[8], o[8];
+    load8(t + ((b * h0 + i0) * w + x) * c + ch, a);
+    load8(t + ((b * h0 + i1) * w + x) * c + ch, bb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (1.f - mu) * a[k] + mu * bb[k];
+    store8(y + ((b * h + i) * w + x) * c + ch, o);
+  }
+}
+// dt[b][r][x][:] = sum_i weight(i -> r) dy[b][i][x][:]   (one thread per source element; fp32 output)
+template <typename T>
+__global__ void upsample_h_bwd_kernel(const T* __restrict__ dy, int n, int h, int w, int c, int h0, float* __restrict__ dt) {
+  const int cv = c / 8;
+  const long long total = static_cast<long long>(n) * h0 * w * cv;
+  const float ratio = static_cast<float>(h) / static_cast<float>(h0);
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(idx % cv) * 8;
+    long long r = idx / cv;
+    const int x = static_cast<int>(r % w);
+    r /= w;
+    const int rs = static_cast<int>(r % h0);
+    const long long b = r / h0;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    int ilo = static_cast<int>((static_cast<float>(rs) - 1.f) * ratio) - 2;
+    int ihi = static_cast<int>((static_cast<float>(rs) + 2.f) * ratio) + 2;
+    if (ilo < 0) ilo = 0;
+    if (ihi > h - 1) ihi = h - 1;
+    for (int i = ilo; i <= ihi; ++i) {
+      int i0, i1;
+      float mu;
+      lerp_src(i, h0, h, i0, i1, mu);
+      float wgt = 0.f;
+      if (i0 == rs) wgt += 1.f - mu;
+      if (i1 == rs) wgt += mu;
+      if (wgt == 0.f) continue;
+      float d[8];
+      load8(dy + ((b * h + i) * w + x) * c + ch, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, d[k], acc[k]);
+    }
+    float* o = dt + ((b * h0 + rs) * w + x) * c + ch;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // im2col / col2im for few-channel NHWC bf16 images: col[m][(r*kw+q)*c + ch], zero padded to kpad columns
 // ---------------------------------------------------------------------------------------------
 constexpr int kIm2colMaxK = 1024;
@@ -1175,6 +1243,30 @@ extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int
                                                                      rpt, jlen);
   else
     upsample_bwd_kernel<float><<<ew_grid(items), 256, 0, st>>>(static_cast<const float*>(dy), n, h, w, c, w0, dt, rpt, jlen);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_upsample_h_fwd(const void* t, int n, int h0, int w, int c, void* y, int h, int dtype, void* stream_) {
+  VG_CHECK(c % 8 == 0 && h0 >= 1 && h >= 1, -1, "vg_upsample_h_fwd: channels must be a multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * h * w * (c / 8));
+  if (dtype == 0)
+    upsample_h_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(t), n, h0, w, c,
+                                                             static_cast<__nv_bfloat16*>(y), h);
+  else
+    upsample_h_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(t), n, h0, w, c, static_cast<float*>(y), h);
+  VG_LAUNCH_OK();
+  return 0;
+}
+extern "C" int vg_upsample_h_bwd(const void* dy, int n, int h, int w, int c, int h0, float* dt, int dtype, void* stream_) {
+  VG_CHECK(c % 8 == 0 && h0 >= 1 && h >= 1, -1, "vg_upsample_h_bwd: channels must be a multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int grid = ew_grid(static_cast<long long>(n) * h0 * w * (c / 8));
+  if (dtype == 0)
+    upsample_h_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), n, h, w, c, h0, dt);
+  else
+    upsample_h_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dy), n, h, w, c, h0, dt);
   VG_LAUNCH_OK();
   return 0;
 }

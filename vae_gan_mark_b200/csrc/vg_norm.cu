@@ -409,6 +409,58 @@ __global__ void affine_grad_kernel(const float* __restrict__ sums, int groups, i
   if (dbeta) dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-channel gate (GatedSkipConnection, vae-gan-oldv.py:226-231): y = x * s[c] written into a (slice of a) buffer;
+// backward in ONE pass: dx = dy * s[c] and ds[c] += sum_rows dy * x.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNT) scale_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ s,
+                                                        T* __restrict__ y, int y_ld, int y_coff, long long rows, int c) {
+  const int cv = c / 8;
+  const long long total = rows * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cv;
+    const int ch = static_cast<int>(i - r * cv) * 8;
+    float f[8];
+    Raw8<T>::load(x + r * x_ld + ch).unpack(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= s[ch + k];
+    store8(y + r * y_ld + y_coff + ch, f);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kNT) scale_bwd_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, int dy_ld,
+                                                        int dy_coff, const float* __restrict__ sc, T* __restrict__ dx, int dx_ld,
+                                                        long long rows, int c, float* __restrict__ ds) {
+  const RowMap m = row_map(c);
+  const int tid = threadIdx.x;
+  const int rl = tid / m.cvl, cvi = tid % m.cvl;
+  __shared__ float red[kNT][17];
+  for (int cv0 = 0; cv0 < m.cv; cv0 += m.cvl) {
+    const int cvec = cv0 + cvi;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    if (rl < m.rows_par && cvec < m.cv) {
+      const int ch = cvec * 8;
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = sc[ch + i];
+      const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
+      for (long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl; r < rows; r += stride) {
+        float f[8], d[8], o[8];
+        Raw8<T>::load(x + r * x_ld + ch).unpack(f);
+        Raw8<T>::load(dy + r * dy_ld + dy_coff + ch).unpack(d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i] = d[i] * g[i]; s[i] = fmaf(d[i], f[i], s[i]); }
+        store8(dx + r * dx_ld + ch, o);
+      }
+    }
+    reduce_rows_atomic(red, s, q, m, rl, cvi, cvec, ds, ds + c);     // ds[c..2c) receives the (unused) zeros of q
+  }
+}
+
 // grid.x for a row-walking kernel: enough blocks to cover the rows, at most `per_sm` blocks per SM (per group)
 static int row_grid(long long rows, int rows_par, int groups, int per_sm, int rows_per_thread) {
   long long blocks = (rows + static_cast<long long>(rows_par) * rows_per_thread - 1) /
@@ -545,4 +597,40 @@ extern "C" int vg_norm_backward(const VgNormBackward* d, void* stream_) {
   VG_CHECK(d->virt_h == 0 || (d->virt_h >= d->h && d->h >= 3 && !d->per_sample && d->dpool == nullptr), -1,
            "vg_norm_backward: virt_h needs h >= 3 rows, batch statistics and no pooling");
   return d->dtype == 0 ? norm_backward_impl<__nv_bfloat16>(d, st) : norm_backward_impl<float>(d, st);
+}
+
+extern "C" int vg_channel_scale_fwd(const void* x, int x_ld, const float* scale, void* y, int y_ld, int y_coff, long long rows,
+                                    int c, int dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && y_coff % 8 == 0, -1, "vg_channel_scale_fwd: multiples of 8");
+  const long long items = rows * (c / 8);
+  const int grid = static_cast<int>(std::min<long long>((items + kNT - 1) / kNT, static_cast<long long>(num_sms()) * 16));
+  if (dtype == 0)
+    scale_fwd_kernel<__nv_bfloat16><<<std::max(grid, 1), kNT, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld, scale,
+                                                                      static_cast<__nv_bfloat16*>(y), y_ld, y_coff, rows, c);
+  else
+    scale_fwd_kernel<float><<<std::max(grid, 1), kNT, 0, st>>>(static_cast<const float*>(x), x_ld, scale, static_cast<float*>(y),
+                                                              y_ld, y_coff, rows, c);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+/* dscale: fp32 [2*c] scratch-and-result: the first c entries receive sum dy*x (zeroed here) */
+extern "C" int vg_channel_scale_bwd(const void* x, int x_ld, const void* dy, int dy_ld, int dy_coff, const float* scale,
+                                    void* dx, int dx_ld, long long rows, int c, float* dscale, int dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  VG_CHECK(c % 8 == 0 && x_ld % 8 == 0 && dy_ld % 8 == 0 && dy_coff % 8 == 0 && dx_ld % 8 == 0, -1,
+           "vg_channel_scale_bwd: multiples of 8");
+  VG_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * 2 * c, st));
+  const RowMap m = row_map(c);
+  const int gx = row_grid(rows, m.rows_par, 1, 4, 8);
+  if (dtype == 0)
+    scale_bwd_kernel<__nv_bfloat16><<<gx, kNT, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_ld,
+                                                       static_cast<const __nv_bfloat16*>(dy), dy_ld, dy_coff, scale,
+                                                       static_cast<__nv_bfloat16*>(dx), dx_ld, rows, c, dscale);
+  else
+    scale_bwd_kernel<float><<<gx, kNT, 0, st>>>(static_cast<const float*>(x), x_ld, static_cast<const float*>(dy), dy_ld, dy_coff,
+                                               scale, static_cast<float*>(dx), dx_ld, rows, c, dscale);
+  VG_LAUNCH_OK();
+  return 0;
 }

@@ -506,6 +506,70 @@ class UpsampleWFn(Function):
         return out, None, None
 
 
+class Upsample2DFn(Function):
+    """F.interpolate(t, size=(h, w), mode='bilinear', align_corners=False) of a multi-row NHWC map [n,h0,w0,c]
+    (the 4-row text map of vae-gan-oldv.py:165-176 and its (1, W/8) resize at :286-291).  Bilinear interpolation is
+    separable: the H pass runs on the narrow map, the W pass then writes the full-size tensor once."""
+
+    @staticmethod
+    def forward(ctx, t, h: int, w: int):
+        n, h0, w0, c = t.shape
+        if not t.is_contiguous():
+            t = ops.dense_nhwc(t)
+        th = t
+        if h != h0:
+            th = torch.empty((n, h, w0, c), dtype=t.dtype, device=t.device)
+            ops.upsample_h_fwd(t, th)
+        y = torch.empty((n, h, w, c), dtype=t.dtype, device=t.device)
+        ops.upsample_w_fwd(th.view(n * h, 1, w0, c), y.view(n * h, 1, w, c))
+        ctx.h0, ctx.w0, ctx.dt = h0, w0, t.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = grad_in(dy, ctx.dt)
+        if not dy.is_contiguous():
+            dy = ops.dense_nhwc(dy)
+        n, h, w, c = dy.shape
+        h0, w0 = ctx.h0, ctx.w0
+        dth = torch.empty((n * h, 1, w0, c), dtype=F32, device=dy.device)
+        ops.upsample_w_bwd(dy.view(n * h, 1, w, c), dth)
+        dt = dth.view(n, h, w0, c)
+        if h != h0:
+            dt = torch.empty((n, h0, w0, c), dtype=F32, device=dy.device)
+            ops.upsample_h_bwd(dth.view(n, h, w0, c), dt)
+        if ctx.dt == F32:
+            return dt, None, None
+        out = torch.empty((n, h0, w0, c), dtype=BF16, device=dy.device)
+        ops.strided_copy(dt, out)
+        return out, None, None
+
+
+class ChannelGateFn(Function):
+    """skip * sigmoid(alpha) (GatedSkipConnection, vae-gan-oldv.py:226-231) written straight into the skip half of a
+    concat buffer; ``scale`` = sigmoid(alpha) as fp32 [C] (the sigmoid of C numbers and its gradient stay in autograd).
+    The backward is one pass over (x, dy): dx = dy * scale and dscale = sum over pixels of dy * x."""
+
+    @staticmethod
+    def forward(ctx, x, scale, out):
+        n, h, w, c = x.shape
+        scale = scale.detach().contiguous()
+        y = out if out is not None else new_act(n, h, w, c, x.device, x.dtype)
+        ops.channel_scale_fwd(x, scale, y)
+        ctx.save_for_backward(x, scale)
+        return y.detach() if out is not None else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        n, h, w, c = x.shape
+        dy = grad_in(dy, x.dtype)
+        dx = new_act(n, h, w, c, x.device, x.dtype)
+        ds = torch.empty(2 * c, dtype=F32, device=x.device)
+        ops.channel_scale_bwd(x, dy, scale, dx, ds)
+        return dx, ds[:c], None
+
+
 class _gru_gemm_precision:
     """The time-parallel GEMMs of the GRU layer run through cuBLAS.  In bf16 mode they may use TF32 tensor cores, which
     is what the reference's cuDNN GRU does by default (torch.backends.cudnn.allow_tf32 = True); the high-accuracy

@@ -144,7 +144,8 @@ class CharacterTokenEncoder(nn.Module):
                 idx[r, :len(ids)] = torch.tensor(ids, dtype=torch.long)
         return idx
 
-    def forward(self, texts_batch, max_len_chars_for_tokenization=60):
+    def rnn_outputs(self, texts_batch, max_len_chars_for_tokenization=60):
+        """Embedding + biGRU: (B, L, 2*hid) fp32."""
         if torch.is_tensor(texts_batch):      # already tokenised (B, max_len) indices, e.g. a CUDA-graph static input
             idx = texts_batch
         else:
@@ -162,7 +163,54 @@ class CharacterTokenEncoder(nn.Module):
                     out = torch.nn.functional.dropout(out, rnn.dropout, True)
         else:                                   # other hidden sizes: stock cuDNN recurrence
             out, _ = rnn(emb)
+        return out
+
+    def forward(self, texts_batch, max_len_chars_for_tokenization=60):
+        out = self.rnn_outputs(texts_batch, max_len_chars_for_tokenization)
         return self.adaptive_pool(out.permute(0, 2, 1)).unsqueeze(2)
+
+
+class _SeqToNHWCFn(torch.autograd.Function):
+    """(B, L, C) fp32 sequence -> NHWC activation [B,1,L,C] (the GRU output as the input of the Conv1d, run as a 1x3
+    convolution on the tensor pipe); the gradient comes back as fp32 (B, L, C)."""
+
+    @staticmethod
+    def forward(ctx, seq):
+        b, l, c = seq.shape
+        out = new_act(b, 1, l, c, seq.device)
+        ops.strided_copy(seq.detach().reshape(b, 1, l, c), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        b, _, l, c = g.shape
+        out = torch.empty((b, l, c), dtype=F32, device=g.device)
+        ops.strided_copy(g, out.view(b, 1, l, c))
+        return out
+
+
+class CharacterTokenEncoderOldV(CharacterTokenEncoder):
+    """vae-gan-oldv.py:74-148 (the script's ``CharacterTokenEncoder``): Embedding -> biGRU -> Conv1d(k=3, p=1) ->
+    adaptive average pool to W/16 -> the row repeated ``target_feature_height`` (4) times -> + learned positional
+    encoding (1, C, 4, W/16).  Output (B, 2*hid, 4, W/16) fp32.  The Conv1d runs as a 1x3 convolution over the NHWC view
+    [B,1,L,C] of the GRU output on the tensor-core kernel; ``self.conv1d`` is only the parameter container."""
+
+    def __init__(self, alphabet_str, emb_dim, rnn_hidden_dim, rnn_layers, target_feature_width, target_feature_height=4):
+        super().__init__(alphabet_str, emb_dim, rnn_hidden_dim, rnn_layers, target_feature_width)
+        del self.adaptive_pool                 # the reference pools with F.adaptive_avg_pool1d (no submodule)
+        self.target_feature_height = target_feature_height
+        self.conv1d = nn.Conv1d(self.rnn_output_dim, self.rnn_output_dim, kernel_size=3, padding=1)
+        self.register_parameter("pos_enc", nn.Parameter(
+            torch.randn(1, self.rnn_output_dim, target_feature_height, target_feature_width) * 0.02))
+
+    def forward(self, texts_batch, max_len_chars_for_tokenization=60):
+        out = self.rnn_outputs(texts_batch, max_len_chars_for_tokenization)          # (B, L, C) fp32
+        b, l, c = out.shape
+        c1 = self.conv1d
+        st = _state(c1, lambda: (ConvLinear(c, c, 1, 3, 1, (0, 1), (1, l)), L.WeightCache()))
+        y = L.Conv2dFn.apply(_SeqToNHWCFn.apply(out), c1.weight.unsqueeze(2), c1.bias, st[0], st[1], 0, None, None, None)
+        x = torch.nn.functional.adaptive_avg_pool1d(y.view(b, l, c).float().permute(0, 2, 1), self.target_feature_width)
+        return x.unsqueeze(2).expand(-1, -1, self.target_feature_height, -1) + self.pos_enc
 
 
 class TransformerTextEncoder(nn.Module):
@@ -513,9 +561,16 @@ class SpatialFiLMLayer(nn.Module):
         self.num_features_main = num_features_main
 
     def forward(self, x_main, text_base_nhwc):
-        """x_main: NHWC bf16 [B,h,w,C]; text_base_nhwc: NHWC bf16 [B,1,w0,T]."""
+        """x_main: NHWC bf16 [B,h,w,C]; text_base_nhwc: NHWC bf16 [B,1,w0,T] (vae-gan-v2.py) or [B,4,w0,T]
+        (vae-gan-oldv.py: a true 2-D bilinear resize, no identical rows to exploit)."""
         _, h, w, _ = x_main.shape
         pp = self.param_predictor
+        if text_base_nhwc.shape[1] != 1:
+            t = L.Upsample2DFn.apply(text_base_nhwc, h, w)
+            raw = run_conv(pp[0], t)
+            y, _ = run_bn_relu(pp[1], raw)
+            gb = run_conv(pp[3], y)
+            return L.FiLMFn.apply(gb, x_main)
         if FILM_ROW_DEDUP and h >= 3:
             # The upsampled text map has h IDENTICAL rows (its source is one row high), so the 3x3 conv output -- and
             # everything pointwise after it -- is the same for every interior row; only the first and last row differ
@@ -726,3 +781,135 @@ class VAEGAN_UNet_CharEmb(nn.Module):
         self.__dict__["_last_kl"] = kl
         t = join()
         return dec.decode_repaired(z, t, pooled, bufs), mu, logvar
+
+
+# ------------------------------------------------------------------------------------------------
+# vae-gan-oldv.py family: 3-level U-Net, gated skips, 4-row text map
+# ------------------------------------------------------------------------------------------------
+class VAEEncoderWithSkips3(nn.Module):
+    """vae-gan-oldv.py:187-224 (the script's ``VAEEncoderWithSkips``): three double-conv levels (32/64/128 channels) with
+    MaxPool2x2 between, a 256-channel bottleneck and full-kernel heads over the (H/8, W/8) map."""
+
+    def __init__(self, in_ch=4, z_ch=Z_CH, skip_chans=(32, 64, 128), bottleneck_ch=256, patch_shape=None):
+        super().__init__()
+        self.e_conv1 = _double_conv(in_ch, skip_chans[0])
+        self.pool1 = nn.MaxPool2d(2, 2)
+        self.e_conv2 = _double_conv(skip_chans[0], skip_chans[1])
+        self.pool2 = nn.MaxPool2d(2, 2)
+        self.e_conv3 = _double_conv(skip_chans[1], skip_chans[2])
+        self.pool3 = nn.MaxPool2d(2, 2)
+        self.bottleneck_conv = _double_conv(skip_chans[2], bottleneck_ch)
+        h, w = _hw(patch_shape)
+        self.feature_map_h, self.feature_map_w = h // 8, w // 8
+        self.mu_head = nn.Conv2d(bottleneck_ch, z_ch, kernel_size=(self.feature_map_h, self.feature_map_w))
+        self.logvar_head = nn.Conv2d(bottleneck_ch, z_ch, kernel_size=(self.feature_map_h, self.feature_map_w))
+
+    def encode(self, images, eps=None):
+        """Returns (mu, logvar, z, kl, [s1, s2, s3]); the skips are NHWC activations (the gates of the decoder write
+        their scaled copies into the concat buffers)."""
+        skips, x = [], None
+        for i in range(3):
+            s, x = run_double_conv(getattr(self, f"e_conv{i + 1}"), x, images=images if i == 0 else None, pool=True)
+            skips.append(s)
+        feat, _ = run_double_conv(self.bottleneck_conv, x)
+        mu, lv, z, kl = run_heads(self.mu_head, self.logvar_head, feat, self, eps)
+        return mu, lv, z, kl, skips
+
+    def forward(self, x):
+        _require_cuda(x)
+        mu, lv, _, _, skips = self.encode([x])
+        return mu, lv, skips        # skips are NHWC here (internal layout of this package)
+
+
+class GatedSkipConnection(nn.Module):
+    """vae-gan-oldv.py:226-231: skip * sigmoid(alpha), alpha (1, C, 1, 1) initialised to 0.3."""
+
+    def __init__(self, channels, alpha_init=0.3):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1, channels, 1, 1) * alpha_init)
+
+    def forward(self, skip_feat, out=None):
+        """skip_feat: NHWC activation; ``out``: optional channel slice of a concat buffer that receives the result."""
+        return L.ChannelGateFn.apply(skip_feat, torch.sigmoid(self.alpha).reshape(-1), out)
+
+
+class VAEDecoderWithSpatialFiLM3(nn.Module):
+    """vae-gan-oldv.py:235-320 (the script's ``VAEDecoderWithSpatialFiLM``): ConvT(k=(H/8,1)) -> BN -> ReLU on
+    cat(z, text map resized to (1, W/8)); 3 x [ConvT2x2 s2 -> cat(gated skip) -> FiLM -> double conv]; Conv1x1; Sigmoid."""
+
+    def __init__(self, z_ch, text_channels_in, out_ch_image, patch_h, patch_w, skip_chans=(32, 64, 128), bottleneck_ch=256):
+        super().__init__()
+        self.initial_h, self.initial_w = patch_h // 8, patch_w // 8
+        self.skip_chans = tuple(skip_chans)
+        self.skip_gates = nn.ModuleList([GatedSkipConnection(skip_chans[2]), GatedSkipConnection(skip_chans[1]),
+                                         GatedSkipConnection(skip_chans[0])])
+        self.bottleneck_proc = nn.Sequential(
+            nn.ConvTranspose2d(z_ch + text_channels_in, bottleneck_ch, kernel_size=(self.initial_h, 1), stride=1, padding=0),
+            nn.BatchNorm2d(bottleneck_ch), nn.ReLU(inplace=True))
+        c = bottleneck_ch
+        for i, s in enumerate((skip_chans[2], skip_chans[1], skip_chans[0]), start=1):
+            setattr(self, f"up_tconv{i}", nn.ConvTranspose2d(c, s, kernel_size=2, stride=2))
+            setattr(self, f"spatial_film{i}", SpatialFiLMLayer(text_channels_in, 2 * s))
+            setattr(self, f"conv_block{i}", _double_conv(2 * s, s))
+            c = s
+        self.final_image_conv = nn.Conv2d(skip_chans[0], out_ch_image, kernel_size=1)
+        self.output_activation_fn = nn.Sigmoid()
+
+    def decode(self, z, text_nhwc, skips):
+        """z: fp32 [B,zc]; text_nhwc: NHWC [B,4,W/16,T]; skips: [s1, s2, s3] NHWC."""
+        b = z.shape[0]
+        t0 = L.Upsample2DFn.apply(text_nhwc, 1, self.initial_w)                 # F.interpolate(..., size=(1, W/8))
+        zc = L.ZTextCatFn.apply(z, t0)
+        x = run_convT(self.bottleneck_proc[0], zc, (self.initial_h, self.initial_w))
+        x, _ = run_bn_relu(self.bottleneck_proc[1], x)
+        h, w = self.initial_h, self.initial_w
+        for i in (1, 2, 3):
+            h, w = h * 2, w * 2
+            skip = skips[3 - i]
+            cu = skip.shape[3]
+            buf = torch.empty((b, h, w, 2 * cu), dtype=ops.act_dtype(), device=z.device)
+            up = run_convT(getattr(self, f"up_tconv{i}"), x, (h, w), out=buf[..., :cu])
+            gated = self.skip_gates[i - 1](skip, out=buf[..., cu:])
+            xc = L.CatSlicesFn.apply(up, gated, buf)
+            xm = getattr(self, f"spatial_film{i}")(xc, text_nhwc)
+            x, _ = run_double_conv(getattr(self, f"conv_block{i}"), xm)
+        pre = L.SmallOutConvFn.apply(x, self.final_image_conv.weight, self.final_image_conv.bias, 0)
+        return L.SigmoidOutFn.apply(pre)
+
+    def forward(self, z_latents, spatial_text_features_base, skips_list):
+        _require_cuda(z_latents)
+        t = L.ToNHWCFn.apply(spatial_text_features_base)
+        return self.decode(z_latents.reshape(z_latents.shape[0], -1), t, skips_list)
+
+
+class VAEGAN_UNet_SpatialFiLM_OldV(nn.Module):
+    """vae-gan-oldv.py:323-368 (the script names it ``VAEGAN_UNet_SpatialFiLM`` too; same constructor arguments)."""
+
+    def __init__(self, in_ch_style=4, z_ch_style=Z_CH, out_ch_img=3, alphabet_str_text=ALPHABET_STR,
+                 char_emb_dim_text=CHAR_EMB_DIM, char_rnn_hidden_dim_text=CHAR_RNN_HIDDEN_DIM,
+                 char_rnn_layers_text=CHAR_RNN_LAYERS, patch_shape=None):
+        super().__init__()
+        h, w = _hw(patch_shape)
+        self.text_feature_base_width = w // 16
+        self.char_text_encoder_module = CharacterTokenEncoderOldV(alphabet_str_text, char_emb_dim_text,
+                                                                  char_rnn_hidden_dim_text, char_rnn_layers_text,
+                                                                  self.text_feature_base_width, 4)
+        self.style_vae_encoder_module = VAEEncoderWithSkips3(in_ch=in_ch_style, z_ch=z_ch_style, patch_shape=(w, h))
+        self.image_vae_decoder_module = VAEDecoderWithSpatialFiLM3(
+            z_ch=z_ch_style, text_channels_in=self.char_text_encoder_module.rnn_output_dim, out_ch_image=out_ch_img,
+            patch_h=h, patch_w=w)
+
+    def reparameterize(self, mu, logvar):
+        std = torch.exp(0.5 * logvar)
+        return mu + torch.randn_like(std) * std
+
+    def forward(self, image_for_style_in, mask_for_style_in, texts_batch_list_in):
+        _require_cuda(image_for_style_in)
+        enc = self.style_vae_encoder_module
+        b = image_for_style_in.shape[0]
+        eps = draw_eps(enc, b, enc.mu_head.out_channels, image_for_style_in.device)   # RNG order: eps before GRU dropout
+        _, join = text_features_async(self.char_text_encoder_module, texts_batch_list_in)
+        mu, logvar, z, kl, skips = enc.encode([image_for_style_in, mask_for_style_in], eps=eps)
+        self.__dict__["_last_kl"] = kl
+        t = join()
+        return self.image_vae_decoder_module.decode(z, t, skips), mu, logvar

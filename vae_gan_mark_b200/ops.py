@@ -249,6 +249,38 @@ def upsample_w_bwd(dy, dt):
     _lib.call("vg_upsample_w_bwd", _p(dy), n, h, w, c, w0, _p(dt), dcode(dy), stream())
 
 
+def upsample_h_fwd(t, y):
+    """Bilinear resize along H only: t [n,h0,w,c] -> y [n,h,w,c], both dense."""
+    n, h0, w, c = t.shape
+    assert t.dtype == y.dtype and t.is_contiguous() and y.is_contiguous() and tuple(y.shape) == (n, y.shape[1], w, c)
+    _lib.call("vg_upsample_h_fwd", _p(t), n, h0, w, c, _p(y), y.shape[1], dcode(t), stream())
+
+
+def upsample_h_bwd(dy, dt):
+    """dy [n,h,w,c] dense (bf16 or fp32) -> dt fp32 [n,h0,w,c] (fully written)."""
+    n, h, w, c = dy.shape
+    assert dt.dtype == F32 and dy.is_contiguous() and dt.is_contiguous() and tuple(dt.shape) == (n, dt.shape[1], w, c)
+    _lib.call("vg_upsample_h_bwd", _p(dy), n, h, w, c, dt.shape[1], _p(dt), dcode(dy), stream())
+
+
+def channel_scale_fwd(x, scale, y):
+    """y[..., ch] = x[..., ch] * scale[ch]; x, y NHWC views (y may be a channel slice), scale fp32 [c]."""
+    n, h, w, c = x.shape
+    assert x.dtype == y.dtype and scale.dtype == F32 and scale.is_contiguous() and scale.numel() == c
+    assert nhwc_ok(x) and nhwc_ok(y) and tuple(y.shape) == tuple(x.shape)
+    _lib.call("vg_channel_scale_fwd", _p(x), ld_of(x), _p(scale), _p(y), ld_of(y), 0, C.c_longlong(n * h * w), c,
+              dcode(x), stream())
+
+
+def channel_scale_bwd(x, dy, scale, dx, dscale):
+    """dx = dy * scale, dscale[:c] = sum over pixels of dy * x (dscale: fp32 [2c], second half scratch)."""
+    n, h, w, c = x.shape
+    assert x.dtype == dy.dtype == dx.dtype and dscale.dtype == F32 and dscale.numel() == 2 * c
+    assert nhwc_ok(x) and nhwc_ok(dy) and nhwc_ok(dx)
+    _lib.call("vg_channel_scale_bwd", _p(x), ld_of(x), _p(dy), ld_of(dy), 0, _p(scale), _p(dx), ld_of(dx),
+              C.c_longlong(n * h * w), c, _p(dscale), dcode(x), stream())
+
+
 def im2col(src, c, kh, kw, stride, pad, col):
     n, h, w, _ = src.shape
     assert src.dtype == col.dtype

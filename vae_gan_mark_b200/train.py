@@ -37,9 +37,9 @@ class LossWeights:
 
     @staticmethod
     def for_family(family: str) -> "LossWeights":
-        # vae-gan.py:35-38 ; vae-gan-v2.py:42-45 ; vae-gan-unet.py:43-46
+        # vae-gan.py:35-38 ; vae-gan-v2.py:42-45 ; vae-gan-unet.py:43-46 ; vae-gan-oldv.py:42-45
         return {"base": LossWeights(1.0, 0.005, 0.1), "v2": LossWeights(1.0, 0.001, 0.15),
-                "unet": LossWeights(1.0, 0.001, 0.15)}[family]
+                "unet": LossWeights(1.0, 0.001, 0.15), "oldv": LossWeights(1.0, 0.001, 0.07)}[family]
 
 
 class FusedAdam:
@@ -164,7 +164,7 @@ def weights_channels_last(module: torch.nn.Module) -> int:
     number of tensors converted."""
     count = 0
     for name, p in module.named_parameters():
-        if p.dim() == 4 and not name.endswith("weight_orig") and p.shape[2] * p.shape[3] > 1 and p.shape[1] > 1:
+        if p.dim() == 4 and name.endswith("weight") and p.shape[2] * p.shape[3] > 1 and p.shape[1] > 1:
             if not p.data.is_contiguous(memory_format=torch.channels_last):
                 p.data = p.data.contiguous(memory_format=torch.channels_last)
                 if p.grad is not None:
