@@ -240,6 +240,10 @@ class ConvLinear:
         """Data gradient in bf16 mode: read the forward operand as an MN-major B operand (no transposed weight copy,
         but the tensor pipe runs ~20 % slower on MN-major B -- measured 1478 -> 1170 TFLOP/s on the 128x128x512 3x3
         layer) or make the transposed K-major copy first?  Estimated cost of each in microseconds."""
+        if self.shuffle and self.cin != self.cin_p:
+            # the pixel-shuffle GEMM's columns are (r, q, ci) with ci < cin, but the forward operand's columns are
+            # (r, q, ci_p) zero-padded to 64 per tap: no uniform column map exists (up_tconv3 64 -> 32 of vae-gan-oldv.py)
+            return False
         nk = self.cin * self.cout * self.kh * self.kw
         slowdown_us = 0.4 * gemm_pixels * nk / 1.4e9
         copies = 4 if (self.s == 2 and not self.shuffle) else 1
