@@ -247,6 +247,9 @@ def test_train_step_fp32_matches_oracle(family, h, w, batch, z):
     theirs = sorted(v[1] for v in real.values())
     print(f"gradients vs fp64: ours median {ours[len(ours) // 2]:.1e} max {ours[-1]:.1e} | oracle fp32 median "
           f"{theirs[len(theirs) // 2]:.1e} max {theirs[-1]:.1e}")
+    if os.environ.get("VG_DIAG"):
+        for k, (a, b) in gerr.items():
+            print(f"  {k:75s} ours {a:.1e} oracle32 {b:.1e}")
     assert set(n for n, p in mg.named_parameters() if p.grad is not None) >= set(ref.g_grads), "missing G gradients"
     for k, (a, b) in report.items():
         assert a <= max(STEP_TOL, 2 * b), (k, a, b)

@@ -1,6 +1,8 @@
 """Per-tensor gradient error of one fp32-mode training step against the float64 oracle, listed in backward order
 (dev tool: shows at which layer of the backward pass a precision loss enters).
-usage: python tools/gpu_fp32_grad_diag.py <family> <h> <w> <batch> <z>"""
+usage: python tools/gpu_fp32_grad_diag.py <family> <h> <w> <batch> <z> [dirty]
+``dirty``: first fill 6 GB of the caching allocator's pool with large finite garbage, so that a kernel that reads memory
+it never wrote (and gets zeros from a fresh cudaMalloc in a clean process) shows up."""
 import copy
 import os
 import sys
@@ -25,6 +27,11 @@ def main():
     family = sys.argv[1] if len(sys.argv) > 1 else "oldv"
     h, w, batch, z = (int(v) for v in (sys.argv[2:6] if len(sys.argv) > 5 else (32, 64, 2, 128)))
     vg.set_precision("fp32")
+    if "dirty" in sys.argv:
+        junk = [torch.full((256, 1024, 1024), 1000.0, device="cuda") for _ in range(6)]
+        junk += [torch.full((1 << (10 + k),), 1000.0, device="cuda") for k in range(16) for _ in range(8)]
+        torch.cuda.synchronize()
+        del junk
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     og, od, mg, md = build_pair(family, h, w, z)
     og64, od64 = copy.deepcopy(og).double(), copy.deepcopy(od).double()
