@@ -211,6 +211,16 @@ def test_torch_library_ops_registered_with_fake_impls():
     assert torch.ops.vaegan.conv_transpose2d(x, wt, None, 2, 0, 32, 24, 0).shape == (2, 32, 24, 32)
     yb, mr = torch.ops.vaegan.batch_norm_act(x, torch.empty(64, device="meta"), torch.empty(64, device="meta"), 1e-5, 1)
     assert yb.shape == x.shape and mr.shape == (1, 2, 64) and mr.dtype == torch.float32
+    t = torch.empty(2, 4, 4, 64, dtype=torch.bfloat16, device="meta")
+    assert torch.ops.vaegan.upsample_bilinear2d(t, 8, 16).shape == (2, 8, 16, 64)
+    assert torch.ops.vaegan.channel_gate(t, torch.empty(64, device="meta")).shape == t.shape
+    outs = torch.ops.vaegan.reparam_kl(torch.empty(3, 256, device="meta"), torch.empty(128, device="meta"),
+                                       torch.empty(128, device="meta"), torch.empty(3, 128, device="meta"))
+    assert [tuple(o.shape) for o in outs] == [(3, 128), (3, 128), (3, 128), ()]
+    assert torch.ops.vaegan.l1_loss(torch.empty(2, 3, 8, 8, device="meta"), torch.empty(2, 3, 8, 8, device="meta")).shape == ()
+    assert torch.ops.vaegan.hinge_loss(torch.empty(2, 1, 3, 3, device="meta"), 2).shape == ()
     for name in ("conv2d", "conv2d_dgrad", "conv2d_wgrad", "conv_transpose2d", "batch_norm_act", "batch_norm_act_backward",
-                 "film", "film_backward"):
+                 "film", "film_backward", "upsample_bilinear2d", "upsample_bilinear2d_backward", "channel_gate",
+                 "channel_gate_backward", "reparam_kl", "reparam_kl_backward", "l1_loss", "l1_loss_backward", "hinge_loss",
+                 "hinge_loss_backward"):
         assert hasattr(torch.ops.vaegan, name), name

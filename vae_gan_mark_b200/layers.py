@@ -506,6 +506,38 @@ class UpsampleWFn(Function):
         return out, None, None
 
 
+def upsample2d_fwd(t: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """Separable bilinear resize [n,h0,w0,c] -> [n,h,w,c] (align_corners=False): H pass on the narrow map, then W pass."""
+    n, h0, w0, c = t.shape
+    if not t.is_contiguous():
+        t = ops.dense_nhwc(t)
+    th = t
+    if h != h0:
+        th = torch.empty((n, h, w0, c), dtype=t.dtype, device=t.device)
+        ops.upsample_h_fwd(t, th)
+    y = torch.empty((n, h, w, c), dtype=t.dtype, device=t.device)
+    ops.upsample_w_fwd(th.view(n * h, 1, w0, c), y.view(n * h, 1, w, c))
+    return y
+
+
+def upsample2d_bwd(dy: torch.Tensor, h0: int, w0: int) -> torch.Tensor:
+    """Adjoint of upsample2d_fwd: dy [n,h,w,c] (dense) -> gradient [n,h0,w0,c] in dy's dtype (fp32 accumulation)."""
+    if not dy.is_contiguous():
+        dy = ops.dense_nhwc(dy)
+    n, h, w, c = dy.shape
+    dth = torch.empty((n * h, 1, w0, c), dtype=F32, device=dy.device)
+    ops.upsample_w_bwd(dy.view(n * h, 1, w, c), dth)
+    dt = dth.view(n, h, w0, c)
+    if h != h0:
+        dt = torch.empty((n, h0, w0, c), dtype=F32, device=dy.device)
+        ops.upsample_h_bwd(dth.view(n, h, w0, c), dt)
+    if dy.dtype == F32:
+        return dt
+    out = torch.empty((n, h0, w0, c), dtype=BF16, device=dy.device)
+    ops.strided_copy(dt, out)
+    return out
+
+
 class Upsample2DFn(Function):
     """F.interpolate(t, size=(h, w), mode='bilinear', align_corners=False) of a multi-row NHWC map [n,h0,w0,c]
     (the 4-row text map of vae-gan-oldv.py:165-176 and its (1, W/8) resize at :286-291).  Bilinear interpolation is
@@ -513,36 +545,12 @@ class Upsample2DFn(Function):
 
     @staticmethod
     def forward(ctx, t, h: int, w: int):
-        n, h0, w0, c = t.shape
-        if not t.is_contiguous():
-            t = ops.dense_nhwc(t)
-        th = t
-        if h != h0:
-            th = torch.empty((n, h, w0, c), dtype=t.dtype, device=t.device)
-            ops.upsample_h_fwd(t, th)
-        y = torch.empty((n, h, w, c), dtype=t.dtype, device=t.device)
-        ops.upsample_w_fwd(th.view(n * h, 1, w0, c), y.view(n * h, 1, w, c))
-        ctx.h0, ctx.w0, ctx.dt = h0, w0, t.dtype
-        return y
+        ctx.h0, ctx.w0, ctx.dt = t.shape[1], t.shape[2], t.dtype
+        return upsample2d_fwd(t, h, w)
 
     @staticmethod
     def backward(ctx, dy):
-        dy = grad_in(dy, ctx.dt)
-        if not dy.is_contiguous():
-            dy = ops.dense_nhwc(dy)
-        n, h, w, c = dy.shape
-        h0, w0 = ctx.h0, ctx.w0
-        dth = torch.empty((n * h, 1, w0, c), dtype=F32, device=dy.device)
-        ops.upsample_w_bwd(dy.view(n * h, 1, w, c), dth)
-        dt = dth.view(n, h, w0, c)
-        if h != h0:
-            dt = torch.empty((n, h0, w0, c), dtype=F32, device=dy.device)
-            ops.upsample_h_bwd(dth.view(n, h, w0, c), dt)
-        if ctx.dt == F32:
-            return dt, None, None
-        out = torch.empty((n, h0, w0, c), dtype=BF16, device=dy.device)
-        ops.strided_copy(dt, out)
-        return out, None, None
+        return upsample2d_bwd(grad_in(dy, ctx.dt), ctx.h0, ctx.w0), None, None
 
 
 class ChannelGateFn(Function):

@@ -11,6 +11,10 @@ stateless core of the path as dispatcher ops, for callers that want to build the
     torch.ops.vaegan.batch_norm_act(x, gamma, beta, eps, act) -> (y, mean_rstd)  training-mode statistics
     torch.ops.vaegan.batch_norm_act_backward
     torch.ops.vaegan.film(gb, x)
+    torch.ops.vaegan.upsample_bilinear2d(t, h, w)                               F.interpolate(bilinear) of an NHWC map
+    torch.ops.vaegan.channel_gate(x, scale)                                     x * scale[c] (GatedSkipConnection)
+    torch.ops.vaegan.reparam_kl(heads, bias_mu, bias_lv, eps) -> (mu, logvar, z, kl)
+    torch.ops.vaegan.l1_loss(a, b) / hinge_loss(p, mode)                         fp32 scalars, mode 1 real / 0 fake / 2 G
 
 Activations are NHWC tensors of the package's activation dtype (bf16, or fp32 in the high-accuracy mode); ``act`` is
 0 none / 1 ReLU / 2 LeakyReLU(0.2).  Everything runs on the C ABI of libvaegan_b200.so; there is no CPU implementation
@@ -24,6 +28,7 @@ import torch
 from torch import Tensor
 from torch.library import custom_op, register_autograd
 
+from . import layers as L
 from . import ops
 from .conv import ConvLinear, new_act
 from .ops import F32
@@ -268,3 +273,192 @@ def _film_backward(ctx, dy):
 
 
 register_autograd("vaegan::film", _film_backward, setup_context=_film_setup)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bilinear resize of an NHWC map and the per-channel skip gate (vae-gan-oldv.py:165-176, 226-231)
+# ---------------------------------------------------------------------------------------------------------------
+@custom_op("vaegan::upsample_bilinear2d", mutates_args=())
+def upsample_bilinear2d(t: Tensor, h: int, w: int) -> Tensor:
+    return L.upsample2d_fwd(t, h, w)
+
+
+@upsample_bilinear2d.register_fake
+def _(t, h, w):
+    return t.new_empty((t.shape[0], h, w, t.shape[3]))
+
+
+@custom_op("vaegan::upsample_bilinear2d_backward", mutates_args=())
+def upsample_bilinear2d_backward(dy: Tensor, h0: int, w0: int) -> Tensor:
+    return L.upsample2d_bwd(dy, h0, w0)
+
+
+@upsample_bilinear2d_backward.register_fake
+def _(dy, h0, w0):
+    return dy.new_empty((dy.shape[0], h0, w0, dy.shape[3]))
+
+
+def _up_setup(ctx, inputs, output):
+    ctx.hw0 = (inputs[0].shape[1], inputs[0].shape[2])
+
+
+def _up_backward(ctx, dy):
+    return torch.ops.vaegan.upsample_bilinear2d_backward(dy, ctx.hw0[0], ctx.hw0[1]), None, None
+
+
+register_autograd("vaegan::upsample_bilinear2d", _up_backward, setup_context=_up_setup)
+
+
+@custom_op("vaegan::channel_gate", mutates_args=())
+def channel_gate(x: Tensor, scale: Tensor) -> Tensor:
+    y = new_act(*x.shape, x.device, x.dtype)
+    ops.channel_scale_fwd(x, scale.contiguous(), y)
+    return y
+
+
+@channel_gate.register_fake
+def _(x, scale):
+    return torch.empty_like(x)
+
+
+@custom_op("vaegan::channel_gate_backward", mutates_args=())
+def channel_gate_backward(x: Tensor, scale: Tensor, dy: Tensor) -> Tuple[Tensor, Tensor]:
+    c = x.shape[3]
+    dx = new_act(*x.shape, x.device, x.dtype)
+    ds = torch.empty(2 * c, dtype=F32, device=x.device)
+    ops.channel_scale_bwd(x, L.grad_in(dy, x.dtype), scale.contiguous(), dx, ds)
+    return dx, ds[:c].clone()
+
+
+@channel_gate_backward.register_fake
+def _(x, scale, dy):
+    return torch.empty_like(x), x.new_empty((x.shape[3],), dtype=torch.float32)
+
+
+def _gate_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _gate_backward(ctx, dy):
+    x, scale = ctx.saved_tensors
+    return torch.ops.vaegan.channel_gate_backward(x, scale, dy)
+
+
+register_autograd("vaegan::channel_gate", _gate_backward, setup_context=_gate_setup)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Reparameterisation + KL, L1 and hinge losses (vae-gan.py:133-136, 313-320, 419-420); all fp32
+# ---------------------------------------------------------------------------------------------------------------
+@custom_op("vaegan::reparam_kl", mutates_args=())
+def reparam_kl(heads: Tensor, bias_mu: Tensor, bias_lv: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """heads: fp32 [B, 2z] = (mu | logvar) pre-bias; eps: fp32 [B, z].  Returns mu, logvar, z = mu + eps*exp(logvar/2)
+    (all [B, z]) and kl = mean_b(-0.5 mean_c(1 + logvar - mu^2 - exp(logvar)))."""
+    b = heads.shape[0]
+    return ops.reparam_kl_fwd(heads.reshape(b, -1).contiguous(), bias_mu.contiguous(), bias_lv.contiguous(),
+                              eps.reshape(b, -1).contiguous())
+
+
+@reparam_kl.register_fake
+def _(heads, bias_mu, bias_lv, eps):
+    b, z = heads.shape[0], bias_mu.shape[0]
+    f = dict(dtype=torch.float32)
+    return heads.new_empty((b, z), **f), heads.new_empty((b, z), **f), heads.new_empty((b, z), **f), heads.new_empty((), **f)
+
+
+@custom_op("vaegan::reparam_kl_backward", mutates_args=())
+def reparam_kl_backward(mu: Tensor, lv: Tensor, eps: Tensor, dmu: Tensor, dlv: Tensor, dz: Tensor, dkl: Tensor) -> Tensor:
+    return ops.reparam_kl_bwd(mu, lv, eps.reshape(mu.shape).contiguous(), dz.contiguous(), dmu.contiguous(),
+                              dlv.contiguous(), dkl.contiguous())
+
+
+@reparam_kl_backward.register_fake
+def _(mu, lv, eps, dmu, dlv, dz, dkl):
+    return mu.new_empty((mu.shape[0], 2 * mu.shape[1]))
+
+
+def _rk_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[0], output[1], inputs[3])
+    ctx.heads_shape = inputs[0].shape
+
+
+def _rk_backward(ctx, dmu, dlv, dz, dkl):
+    mu, lv, eps = ctx.saved_tensors
+    dheads = torch.ops.vaegan.reparam_kl_backward(mu, lv, eps, dmu, dlv, dz, dkl)
+    z = mu.shape[1]
+    return dheads.view(ctx.heads_shape), dheads[:, :z].sum(0), dheads[:, z:].sum(0), None
+
+
+register_autograd("vaegan::reparam_kl", _rk_backward, setup_context=_rk_setup)
+
+
+@custom_op("vaegan::l1_loss", mutates_args=())
+def l1_loss(a: Tensor, b: Tensor) -> Tensor:
+    return ops.l1_fwd(a.contiguous(), b.contiguous())
+
+
+@l1_loss.register_fake
+def _(a, b):
+    return a.new_empty((), dtype=torch.float32)
+
+
+@custom_op("vaegan::l1_loss_backward", mutates_args=())
+def l1_loss_backward(a: Tensor, b: Tensor, gout: Tensor) -> Tensor:
+    a = a.contiguous()
+    da = torch.empty_like(a)
+    ops.l1_bwd(a, b.contiguous(), gout.contiguous(), da)
+    return da
+
+
+@l1_loss_backward.register_fake
+def _(a, b, gout):
+    return torch.empty_like(a)
+
+
+def _l1_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _l1_backward(ctx, g):
+    a, b = ctx.saved_tensors
+    return torch.ops.vaegan.l1_loss_backward(a, b, g), None
+
+
+register_autograd("vaegan::l1_loss", _l1_backward, setup_context=_l1_setup)
+
+
+@custom_op("vaegan::hinge_loss", mutates_args=())
+def hinge_loss(p: Tensor, mode: int) -> Tensor:
+    """mode 1: mean(relu(1 - p)) (real), 0: mean(relu(1 + p)) (fake), 2: -mean(p) (generator); vae-gan.py:313-320."""
+    return ops.hinge_fwd(p.contiguous(), mode)
+
+
+@hinge_loss.register_fake
+def _(p, mode):
+    return p.new_empty((), dtype=torch.float32)
+
+
+@custom_op("vaegan::hinge_loss_backward", mutates_args=())
+def hinge_loss_backward(p: Tensor, mode: int, gout: Tensor) -> Tensor:
+    p = p.contiguous()
+    dp = torch.empty_like(p)
+    ops.hinge_bwd(p, mode, gout.contiguous(), dp)
+    return dp
+
+
+@hinge_loss_backward.register_fake
+def _(p, mode, gout):
+    return torch.empty_like(p)
+
+
+def _hinge_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.mode = inputs[1]
+
+
+def _hinge_backward(ctx, g):
+    (p,) = ctx.saved_tensors
+    return torch.ops.vaegan.hinge_loss_backward(p, ctx.mode, g), None
+
+
+register_autograd("vaegan::hinge_loss", _hinge_backward, setup_context=_hinge_setup)
