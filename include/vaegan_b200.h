@@ -282,8 +282,9 @@ int vg_spectral_bwd(const float* g, const float* w_orig, const float* u, const f
  * min(1, max_norm/(sqrt(*gnorm_sq)+1e-6)) when gnorm_sq != NULL and max_norm > 0 */
 int vg_sumsq(const float* g, long long n, float* out, int zero_first, void* stream);
 /* multi-tensor forms: `table` is a DEVICE array of `count` entries (g == NULL entries are skipped); `state` is a
- * device float[4] {step, 1-beta1^step, sqrt(1-beta2^step), -} advanced by vg_adam_prepare, so a captured CUDA graph of
- * the step replays with the right bias corrections */
+ * device float[4] {step, 1-beta1^step, sqrt(1-beta2^step), lr} advanced by vg_adam_prepare, so a captured CUDA graph of
+ * the step replays with the right bias corrections; vg_multi_adam with lr < 0 reads the learning rate from state[3], so
+ * a scheduler (ReduceLROnPlateau of vae-gan-lr-sh.py:751-760, vae-gan-v2.py:944-953) can change it between replays */
 typedef struct VgAdamTensor { float* p; float* g; float* m; float* v; long long n; } VgAdamTensor;
 int vg_adam_prepare(float* state, float beta1, float beta2, void* stream);
 /* deterministic (fixed-order) reduction; scratch: device float[scratch_len], scratch_len >= 1 (use >= 4 x #SMs) */

@@ -224,3 +224,34 @@ def test_torch_library_ops_registered_with_fake_impls():
                  "channel_gate_backward", "reparam_kl", "reparam_kl_backward", "l1_loss", "l1_loss_backward", "hinge_loss",
                  "hinge_loss_backward"):
         assert hasattr(torch.ops.vaegan, name), name
+
+
+def test_plateau_scheduler_matches_torch():
+    """train.ReduceLROnPlateau (host logic over FusedAdam.set_lr) follows torch's scheduler step for step, for the
+    reference's configuration (vae-gan-v2.py:52-56: min, factor 0.95, patience 15, threshold 1e-4, min_lr 1e-7) and a
+    harsher one, and round-trips through state_dict."""
+    import random
+    import torch
+    from vae_gan_mark_b200.train import FusedAdam, ReduceLROnPlateau
+    rng = random.Random(0)
+    for kw in (dict(mode="min", factor=0.95, patience=15, threshold=1e-4, min_lr=1e-7),
+               dict(mode="min", factor=0.5, patience=2, threshold=1e-2, min_lr=3e-5, cooldown=1),
+               dict(mode="max", factor=0.3, patience=0, threshold=0.05, threshold_mode="abs")):
+        p_ref, p_mine = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(3))
+        opt_ref = torch.optim.Adam([p_ref], lr=1e-4, betas=(0.5, 0.999))
+        opt = FusedAdam([p_mine], lr=1e-4)
+        ref, mine = torch.optim.lr_scheduler.ReduceLROnPlateau(opt_ref, **kw), ReduceLROnPlateau(opt, **kw)
+        level = 1.0
+        for epoch in range(120):
+            if epoch == 60:                       # checkpoint / resume in the middle (vae-gan-v2.py:807-808, 974-977)
+                resumed = ReduceLROnPlateau(FusedAdam([p_mine], lr=1e-4), **kw)
+                resumed.load_state_dict(mine.state_dict())
+                mine, opt = resumed, resumed.optimizer
+            level *= rng.choice((0.97, 1.0, 1.0, 1.01, 1.03))
+            metric = level + 0.001 * rng.random()
+            ref.step(metric)
+            mine.step(metric)
+            assert abs(opt.lr - opt_ref.param_groups[0]["lr"]) <= 1e-12 * opt.lr, (kw, epoch)
+            assert float(opt.state[3]) == torch.tensor(opt.lr, dtype=torch.float32).item()
+            assert mine.get_last_lr() == [opt.lr] and opt.param_groups[0]["lr"] == opt.lr
+        assert mine.num_bad_epochs == ref.num_bad_epochs and mine.best == ref.best

@@ -67,3 +67,44 @@ def test_checkpoint_layout_and_resume():
     for k in straight:
         tol = 1e-3 if k == "grad_norm_sq" else 1e-4
         assert abs(straight[k] - resumed[k]) <= tol * max(1.0, abs(straight[k])), (k, straight[k], resumed[k])
+
+
+def test_lr_and_kl_weight_changes_reach_a_captured_graph():
+    """Row f4 plumbing: the learning rates (ReduceLROnPlateau, vae-gan-v2.py:944-953) and the KL weight (annealed per
+    epoch, vae-gan-v2.py:1002-1004) live in device scalars, so a step captured once as a CUDA graph follows them
+    without re-capturing.  bf16 mode (the mode the graph is used in)."""
+    import vae_gan_mark_b200 as vg
+    vg.set_precision("bf16")
+    G, D, tr = build()
+    ru, en, mask, texts = synthetic_batch(4, 32, 64, step=0)
+    tr.capture(ru.cuda(), en.cuda(), mask.cuda(), texts, warmup=2)
+    wg, wd = G.style_vae_encoder_module.e_conv2[0].weight, D.body[2].weight_orig
+    w = tr.w
+
+    def kl_part(out):       # loss_G - recon - gan terms == kl_weight * kl  (vae-gan-v2.py:733-737)
+        return float(out["loss_G"]) - w.recon * float(out["recon"]) - w.gan * float(out["gan"]), float(out["kl"])
+
+    tr.opt_G.set_lr(0.0); tr.opt_D.set_lr(0.0)
+    g0, d0 = wg.detach().clone(), wd.detach().clone()
+    part, kl = kl_part(tr.replay())
+    torch.cuda.synchronize()
+    assert torch.equal(wg, g0) and torch.equal(wd, d0), "lr = 0 must freeze the weights inside the captured graph"
+    assert abs(part - w.kl * kl) <= 1e-5 * max(1.0, abs(kl))
+    tr.opt_G.set_lr(1e-3)
+    tr.replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(wg, g0) and torch.equal(wd, d0)
+    step_g = float((wg - g0).abs().max())
+    assert 1e-5 <= step_g <= 3e-3, step_g             # an Adam step moves a weight by about lr
+    tr.opt_G.set_lr(0.0)
+    for value in (0.0, 0.5):
+        tr.set_kl_weight(value)
+        part, kl = kl_part(tr.replay())
+        assert abs(part - value * kl) <= 1e-5 * max(1.0, abs(kl)), (value, part, kl)
+    sched_metric = [1.0, 1.0, 1.0]
+    from vae_gan_mark_b200.train import ReduceLROnPlateau
+    tr.opt_D.set_lr(1e-4)
+    sch = ReduceLROnPlateau(tr.opt_D, mode="min", factor=0.5, patience=1)
+    for m in sched_metric:
+        sch.step(m)
+    assert abs(tr.opt_D.lr - 5e-5) < 1e-12 and abs(float(tr.opt_D.state[3]) - 5e-5) < 1e-11

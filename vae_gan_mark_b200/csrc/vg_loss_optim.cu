@@ -322,7 +322,7 @@ __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int coun
                                   float max_norm, int write_back_grad) {
   float clip = 1.f;
   if (gnorm_sq != nullptr && max_norm > 0.f) clip = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
-  const float step = lr / state[1];
+  const float step = (lr < 0.f ? state[3] : lr) / state[1];      // lr < 0: the rate lives in the device state block
   const float bc2_sqrt = state[2];
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;

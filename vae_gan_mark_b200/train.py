@@ -55,7 +55,8 @@ class FusedAdam:
         self.exp_avg_sq = [torch.zeros_like(p, dtype=F32) for p in self.params]
         dev = self.params[0].device
         self.norm_sq = torch.zeros((), dtype=F32, device=dev)
-        self.state = torch.zeros(4, dtype=F32, device=dev)          # {step, 1-b1^t, sqrt(1-b2^t), -}
+        self.state = torch.zeros(4, dtype=F32, device=dev)          # {step, 1-b1^t, sqrt(1-b2^t), lr}
+        self.state[3] = lr
         self._norm_scratch = torch.zeros(1024, dtype=F32, device=dev)
         self._table_host = torch.zeros((len(self.params), 5), dtype=torch.int64).pin_memory() if dev.type == "cuda" \
             else torch.zeros((len(self.params), 5), dtype=torch.int64)
@@ -67,6 +68,17 @@ class FusedAdam:
     @property
     def step_count(self) -> int:
         return int(self.state[0].item())
+
+    def set_lr(self, lr: float) -> None:
+        """Change the learning rate.  The kernels read it from the device state block, so this also takes effect in an
+        already captured CUDA graph of the step (LR schedulers of vae-gan-lr-sh.py / vae-gan-v2.py)."""
+        self.lr = float(lr)
+        self.state[3] = self.lr
+
+    @property
+    def param_groups(self):
+        """Read-only torch.optim-style view (one group) for code that inspects ``optimizer.param_groups[0]['lr']``."""
+        return [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "params": self.params}]
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
@@ -113,7 +125,7 @@ class FusedAdam:
         st = ops.stream()
         _lib.call("vg_adam_prepare", C.c_void_p(self.state.data_ptr()), C.c_float(self.betas[0]),
                   C.c_float(self.betas[1]), st)
-        _lib.call("vg_multi_adam", C.c_void_p(self._table.data_ptr()), len(self.params), C.c_float(self.lr),
+        _lib.call("vg_multi_adam", C.c_void_p(self._table.data_ptr()), len(self.params), C.c_float(-1.0),   # lr: state[3]
                   C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
                   C.c_void_p(self.state.data_ptr()), C.c_void_p(self.norm_sq.data_ptr() if max_norm > 0 else 0),
                   C.c_float(max_norm), int(max_norm > 0), st)
@@ -138,7 +150,59 @@ class FusedAdam:
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
         b1, b2 = self.betas
-        self.state.copy_(torch.tensor([float(step), 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5, 0.0]))
+        self.state.copy_(torch.tensor([float(step), 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5, self.lr]))
+
+
+class ReduceLROnPlateau:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau for ``FusedAdam`` (the reference builds one per optimiser:
+    vae-gan-lr-sh.py:751-760, vae-gan-v2.py:944-953, and steps it with the epoch's validation loss, :632-633 / :796-797).
+    Same algorithm, defaults and ``state_dict`` keys as the torch class (threshold_mode 'rel' | 'abs', cooldown, eps), so
+    the reference's ``scheduler_G_state_dict`` checkpoints load; the new rate goes to ``FusedAdam.set_lr`` and therefore
+    into a captured graph without re-capturing."""
+
+    def __init__(self, optimizer: FusedAdam, mode="min", factor=0.1, patience=10, threshold=1e-4, threshold_mode="rel",
+                 cooldown=0, min_lr=0.0, eps=1e-8):
+        assert factor < 1.0 and mode in ("min", "max") and threshold_mode in ("rel", "abs")
+        self.optimizer = optimizer
+        self.mode, self.factor, self.patience, self.threshold, self.threshold_mode = mode, factor, patience, threshold, threshold_mode
+        self.cooldown, self.min_lrs, self.eps = cooldown, [min_lr], eps
+        self.best = float("inf") if mode == "min" else -float("inf")
+        self.num_bad_epochs, self.cooldown_counter, self.last_epoch = 0, 0, 0
+        self._last_lr = [optimizer.lr]
+
+    def _is_better(self, a: float) -> bool:
+        if self.mode == "min":
+            return a < (self.best * (1.0 - self.threshold) if self.threshold_mode == "rel" else self.best - self.threshold)
+        return a > (self.best * (self.threshold + 1.0) if self.threshold_mode == "rel" else self.best + self.threshold)
+
+    def step(self, metrics) -> None:
+        current = float(metrics)
+        self.last_epoch += 1
+        if self._is_better(current):
+            self.best, self.num_bad_epochs = current, 0
+        else:
+            self.num_bad_epochs += 1
+        if self.cooldown_counter > 0:
+            self.cooldown_counter -= 1
+            self.num_bad_epochs = 0
+        if self.num_bad_epochs > self.patience:
+            old = self.optimizer.lr
+            new = max(old * self.factor, self.min_lrs[0])
+            if old - new > self.eps:
+                self.optimizer.set_lr(new)
+            self.cooldown_counter, self.num_bad_epochs = self.cooldown, 0
+        self._last_lr = [self.optimizer.lr]
+
+    def get_last_lr(self):
+        return self._last_lr
+
+    def state_dict(self) -> Dict:
+        return {k: v for k, v in self.__dict__.items() if k != "optimizer"}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.__dict__.update({k: v for k, v in sd.items() if k != "optimizer"})
+        if self._last_lr:
+            self.optimizer.set_lr(self._last_lr[0])
 
 
 @contextlib.contextmanager
@@ -185,12 +249,15 @@ class VAEGANTrainer:
             weights_channels_last(D)
         self.opt_G = FusedAdam(G.parameters(), lr=lr_g)
         self.opt_D = FusedAdam(D.parameters(), lr=lr_d)
+        # KL weight as a device scalar: the reference anneals it per epoch (vae-gan-v2.py:1002-1004); a captured graph
+        # reads the current value, see set_kl_weight
+        self.kl_weight = torch.full((), float(weights.kl), dtype=F32, device=self.opt_G.state.device)
         self.grad_hook = grad_hook        # called as grad_hook("D"|"G", params) after each backward (DP allreduce)
         self._graph = None
 
     def step(self, ru, en, mask, texts, kl_weight: Optional[float] = None) -> Dict[str, torch.Tensor]:
         G, D, w = self.G, self.D, self.w
-        klw = w.kl if kl_weight is None else kl_weight
+        klw = self.kl_weight if kl_weight is None else kl_weight
         fake, mu, logvar = G(ru, mask, texts)
         kl = G.__dict__["_last_kl"]
 
@@ -226,6 +293,11 @@ class VAEGANTrainer:
         if perc is not None:
             out["perc"] = perc.detach()
         return out
+
+    def set_kl_weight(self, value: float) -> None:
+        """KL annealing (vae-gan-v2.py:1002-1004): takes effect in eager steps and in an already captured graph."""
+        self.w.kl = float(value)
+        self.kl_weight.fill_(float(value))
 
     # ------------------------------------------------------------------ checkpoint / resume
     def checkpoint(self, **extra) -> Dict:
