@@ -3,7 +3,8 @@ tests/test_oracle_golden.py).  Runs the drop-in modules of vae_gan_mark_b200 thr
 
 Tolerances.  The CUDA path stores activations in bf16 and feeds bf16 to the tensor cores (fp32 accumulation,
 fp32 master weights); the oracle is fp32.
-  * losses, reconstructed image: relative error <= 2e-2 (north_star's bf16 bound);
+  * losses, reconstructed image: relative error <= 2e-2 (north_star's bf16 bound); the adversarial terms of the tiny
+    test images are means over a handful of patch logits and get 2e-2 x sqrt(64 / n_logits) (see the test body);
   * mu / logvar (10 bf16 conv+BatchNorm layers with batch statistics over as few as 16 samples): <= 6e-2;
   * per-parameter gradients: with random inputs and random weights the true gradients are small residuals of
     heavily cancelling sums, so ANY bf16 evaluation deviates by tens of percent from fp32 -- the reference's own
@@ -120,8 +121,16 @@ def test_train_step_matches_oracle(family, h, w, batch, z):
     print("worst grads:", [(k, f"{v:.2e}") for k, v in worst])
     assert set(n for n, p in mg.named_parameters() if p.grad is not None) >= set(ref.g_grads), "missing G gradients"
     print("median grad err:", f"{sorted(gerr.values())[len(gerr) // 2]:.2e}")
+    # The adversarial scalars are means over only batch x (h/16 - 1) x (w/16 - 1) patch logits (6 at 32x64, batch 2):
+    # independent bf16 rounding errors of the logits average out as 1/sqrt(n), so below 64 logits their bound widens
+    # accordingly (2e-2 is the bound for the 7x7 maps of the 128x128 workload and larger).
+    n_logits = batch * max(1, h // 16 - 1) * max(1, w // 16 - 1)
+    few = max(1.0, (64.0 / n_logits) ** 0.5)
     for k, v in report.items():
-        assert v <= max(LATENT_TOL if k in ("mu", "logvar", "kl", "grad_norm") else ACT_TOL, CAL * cal_rep.get(k, 0.0)), (k, v, cal_rep.get(k))
+        base = LATENT_TOL if k in ("mu", "logvar", "kl", "grad_norm") else ACT_TOL
+        if k in ("d_fake", "d_real", "gan", "loss_D", "loss_G"):
+            base *= few
+        assert v <= max(base, CAL * cal_rep.get(k, 0.0)), (k, v, cal_rep.get(k))
     bad = []
     for k, v in gerr.items():
         # gradients that are exactly-zero-in-theory (conv bias before BatchNorm) are pure rounding noise on both sides
