@@ -1,0 +1,71 @@
+"""The patch-extraction oracle (oracle/warp.py) against OpenCV itself -- the third-party dependency in which the
+reference's ``perspective_crop`` arithmetic lives (vae-gan.py:163-188; opencv-python, requirements.txt:4).  Bit-exact."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from oracle import warp  # noqa: E402
+
+
+def cv_crop(img, bbox, out_shape):
+    w, h = out_shape
+    src = np.array(bbox, dtype=np.float32).reshape(4, 2)
+    dst = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], dtype=np.float32)
+    m = cv2.getPerspectiveTransform(src, dst)
+    return cv2.warpPerspective(img, m, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+
+
+def quads(rng, h, w, n):
+    for i in range(n):
+        cx, cy = rng.uniform(0.2 * w, 0.8 * w), rng.uniform(0.2 * h, 0.8 * h)
+        bw, bh = rng.uniform(0.1 * w, 0.6 * w), rng.uniform(0.05 * h, 0.4 * h)
+        base = np.array([[cx - bw, cy - bh], [cx + bw, cy - bh], [cx + bw, cy + bh], [cx - bw, cy + bh]])
+        jitter = rng.normal(0, 0.06 * min(bw, bh) * (1 + i % 4), (4, 2))
+        ang = rng.uniform(-0.5, 0.5)
+        rot = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+        yield ((base - [cx, cy]) @ rot.T + [cx, cy] + jitter).tolist()
+
+
+@pytest.mark.parametrize("channels", [3, 1])
+@pytest.mark.parametrize("out_shape", [(448, 64), (128, 128), (64, 32), (33, 7)])
+def test_crop_is_bit_exact_against_cv2(channels, out_shape):
+    rng = np.random.default_rng(7 + channels)
+    h, w = 173, 301
+    img = rng.integers(0, 256, size=(h, w, channels) if channels == 3 else (h, w), dtype=np.uint8)
+    for bbox in quads(rng, h, w, 12):                 # several of these leave the image: BORDER_REPLICATE
+        want = cv_crop(img, bbox, out_shape)
+        got = warp.perspective_crop(img, bbox, out_shape)
+        assert got.shape == want.shape and got.dtype == np.uint8
+        assert np.array_equal(got, want), int(np.abs(got.astype(int) - want.astype(int)).max())
+
+
+def test_matrix_and_axis_aligned_cases():
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(80, 120, 3), dtype=np.uint8)
+    # axis-aligned integer box of the output size: the crop is a plain copy
+    box = [[10, 20], [10 + 63, 20], [10 + 63, 20 + 31], [10, 20 + 31]]
+    assert np.array_equal(warp.perspective_crop(img, box, (64, 32)), img[20:52, 10:74])
+    for bbox in quads(rng, 80, 120, 8):
+        src = np.array(bbox, dtype=np.float32).reshape(4, 2)
+        dst = np.array([[0, 0], [447, 0], [447, 63], [0, 63]], dtype=np.float32)
+        m = cv2.getPerspectiveTransform(src, dst)
+        assert np.array_equal(warp.crop_matrix(bbox, (448, 64)), m)                   # bit for bit
+        assert np.array_equal(warp.inverse_map(m), cv2.invert(m)[1])
+    # a quadrilateral far outside the image replicates the border pixel
+    far = [[500, 500], [600, 500], [600, 520], [500, 520]]
+    out = warp.perspective_crop(img, far, (32, 8))
+    assert np.array_equal(out, cv_crop(img, far, (32, 8))) and (out == img[-1, -1]).all()
+
+
+def test_to_tensor_matches_torchvision():
+    import torch
+    T = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    patch = rng.integers(0, 256, size=(16, 24, 3), dtype=np.uint8)
+    want = T.ToTensor()(Image.fromarray(patch)).numpy()
+    assert np.array_equal(warp.to_tensor(patch), want)
+    mask = rng.integers(0, 256, size=(16, 24), dtype=np.uint8)
+    assert np.array_equal(warp.to_tensor(mask), T.ToTensor()(Image.fromarray(mask)).numpy())
+    assert torch.from_numpy(warp.to_tensor(patch)).dtype == torch.float32
