@@ -294,6 +294,19 @@ int vg_multi_adam(const VgAdamTensor* table, int count, float lr, float beta1, f
 int vg_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                  int step, const float* gnorm_sq, float max_norm, int write_back_grad, void* stream);
 
+/* ---- data path: patch extraction (perspective_crop + T.ToTensor, vae-gan.py:163-188,275-281; the same function in every
+ * script).  Restates cv2.getPerspectiveTransform + cv2.warpPerspective(INTER_LINEAR, BORDER_REPLICATE) for 8-bit images
+ * byte for byte (OpenCV's fixed-point arithmetic).  vg_perspective_crop_matrix runs on the HOST: bbox = 4 (x, y) float
+ * pairs, result = the inverse (destination -> source) map, 9 doubles.  vg_warp_perspective_u8: src is a DEVICE uint8
+ * image [src_h][src_w][channels] with src_row_bytes per row, minv the host matrix; writes the uint8 patch
+ * [out_h][out_w][channels] and / or the float32 tensor [channels][out_h][out_w] = value / 255 (either may be NULL). */
+int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_h, double* minv);
+int vg_warp_perspective_u8(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
+                           const double* minv, int out_h, int out_w, unsigned char* dst_u8, float* dst_chw, void* stream);
+/* test hook: the kernel's per-pixel code on HOST buffers (not a fallback; nothing in the package calls it) */
+int vg_debug_warp_perspective_host(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
+                                   const double* minv, int out_h, int out_w, unsigned char* dst_u8, float* dst_chw);
+
 #ifdef __cplusplus
 }
 #endif

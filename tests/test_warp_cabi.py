@@ -1,0 +1,68 @@
+"""Host half of the patch extraction (vg_perspective_crop_matrix in libvaegan_b200.so: cv2.getPerspectiveTransform +
+cv2.invert restated in C++) against the oracle and against OpenCV, bit for bit.  Runs without a GPU."""
+import numpy as np
+import pytest
+
+from oracle import warp
+
+
+def quads(rng, n):
+    for _ in range(n):
+        base = np.array([[40, 30], [260, 40], [270, 120], [35, 130]], dtype=np.float64)
+        yield (base + rng.normal(0, 14, (4, 2))).astype(np.float32).tolist()
+
+
+@pytest.mark.parametrize("out_shape", [(448, 64), (128, 128), (33, 7)])
+def test_crop_matrix_is_bit_exact(out_shape):
+    from vae_gan_mark_b200 import data
+    rng = np.random.default_rng(11)
+    for bbox in quads(rng, 100):
+        got = np.array(list(data.perspective_crop_matrix(bbox, out_shape)), dtype=np.float64).reshape(3, 3)
+        want = warp.inverse_map(warp.crop_matrix(bbox, out_shape))
+        assert np.array_equal(got, want), (bbox, got - want)
+
+
+def test_crop_matrix_against_cv2_and_error_code():
+    cv2 = pytest.importorskip("cv2")
+    from vae_gan_mark_b200 import data
+    from vae_gan_mark_b200._lib import VgError
+    rng = np.random.default_rng(12)
+    w, h = 448, 64
+    dst = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], dtype=np.float32)
+    for bbox in quads(rng, 50):
+        m = cv2.getPerspectiveTransform(np.array(bbox, dtype=np.float32), dst)
+        want = cv2.invert(m)[1]
+        got = np.array(list(data.perspective_crop_matrix(bbox, (w, h)))).reshape(3, 3)
+        assert np.array_equal(got, want)
+    with pytest.raises(VgError):            # four collinear points: no perspective transform exists
+        data.perspective_crop_matrix([[0, 0], [1, 1], [2, 2], [3, 3]], (w, h))
+    with pytest.raises(ValueError):
+        data.perspective_crop_matrix([[0, 0], [1, 1], [2, 2]], (w, h))
+
+
+@pytest.mark.parametrize("channels", [3, 1])
+@pytest.mark.parametrize("out_shape", [(448, 64), (128, 128), (33, 7)])
+def test_kernel_per_pixel_code_on_the_host_is_bit_exact(channels, out_shape):
+    """vg_debug_warp_perspective_host runs the SAME per-pixel function the CUDA kernel runs (vg_warp.cu: warp_pixel) on
+    host buffers: uint8 patch and float tensor must equal the oracle's (which is pinned to cv2) bit for bit, including
+    quadrilaterals that leave the image (BORDER_REPLICATE) and a padded row stride."""
+    import ctypes as C
+    from vae_gan_mark_b200 import _lib, data
+    rng = np.random.default_rng(20 + channels)
+    h, w = 97, 203
+    pitch = w * channels + 5                                        # rows are not densely packed
+    buf = rng.integers(0, 256, size=(h, pitch), dtype=np.uint8)
+    img = buf[:, :w * channels].reshape(h, w, channels)
+    ow, oh = out_shape
+    for k, bbox in enumerate(quads(rng, 10)):
+        if k % 3 == 0:
+            bbox = (np.array(bbox) * 1.6 - 60).tolist()             # partly outside the image
+        minv = data.perspective_crop_matrix(bbox, out_shape)
+        u8 = np.zeros((oh, ow, channels), dtype=np.uint8)
+        chw = np.zeros((channels, oh, ow), dtype=np.float32)
+        _lib.call("vg_debug_warp_perspective_host", buf.ctypes.data_as(C.c_void_p), h, w, channels, C.c_longlong(pitch), minv,
+                  oh, ow, u8.ctypes.data_as(C.c_void_p), chw.ctypes.data_as(C.c_void_p))
+        want = warp.perspective_crop(img if channels == 3 else img[:, :, 0], bbox, out_shape)
+        want3 = want if want.ndim == 3 else want[:, :, None]
+        assert np.array_equal(u8, want3), int(np.abs(u8.astype(int) - want3.astype(int)).max())
+        assert np.array_equal(chw, warp.to_tensor(want))
