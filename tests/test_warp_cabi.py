@@ -66,3 +66,30 @@ def test_kernel_per_pixel_code_on_the_host_is_bit_exact(channels, out_shape):
         want3 = want if want.ndim == 3 else want[:, :, None]
         assert np.array_equal(u8, want3), int(np.abs(u8.astype(int) - want3.astype(int)).max())
         assert np.array_equal(chw, warp.to_tensor(want))
+
+
+def test_python_marshalling_through_the_host_twin():
+    """data._crop builds the argument list of vg_warp_perspective_u8; with ``host_twin`` the identical list (minus the
+    stream) goes to the host twin, so shapes, strides, channel handling and the float layout of the Python wrapper are
+    checked here on CPU tensors exactly as tests/test_warp_gpu.py checks them on the device."""
+    import torch
+    from vae_gan_mark_b200 import data
+    rng = np.random.default_rng(33)
+    page = rng.integers(0, 256, size=(90, 160, 3), dtype=np.uint8)
+    gray = rng.integers(0, 256, size=(90, 160), dtype=np.uint8)
+    for k, bbox in enumerate(quads(rng, 6)):
+        bbox = (np.array(bbox) * 0.5).tolist()
+        want = warp.perspective_crop(page, bbox, (64, 32))
+        assert np.array_equal(data._crop(torch.from_numpy(page), bbox, (64, 32), False, host_twin=True).numpy(), want)
+        assert np.array_equal(data._crop(torch.from_numpy(page), bbox, (64, 32), True, host_twin=True).numpy(), warp.to_tensor(want))
+        wantg = warp.perspective_crop(gray, bbox, (48, 16))
+        gotg = data._crop(torch.from_numpy(gray), bbox, (48, 16), False, host_twin=True)
+        assert tuple(gotg.shape) == (16, 48) and np.array_equal(gotg.numpy(), wantg)
+        assert np.array_equal(data._crop(torch.from_numpy(gray), bbox, (48, 16), True, host_twin=True).numpy(), warp.to_tensor(wantg))
+        view = torch.from_numpy(page)[:, 20:140]                               # row stride > W * C: read in place
+        assert np.array_equal(data._crop(view, bbox, (64, 32), False, host_twin=True).numpy(),
+                              warp.perspective_crop(np.ascontiguousarray(page[:, 20:140]), bbox, (64, 32)))
+        chan_first = torch.from_numpy(np.ascontiguousarray(page.transpose(2, 0, 1))).permute(1, 2, 0)   # not HWC-dense: copied
+        assert np.array_equal(data._crop(chan_first, bbox, (64, 32), False, host_twin=True).numpy(), want)
+    with pytest.raises(RuntimeError):
+        data.perspective_crop(torch.from_numpy(page), quads(rng, 1).__next__(), (64, 32))     # public entry: CUDA only

@@ -32,11 +32,9 @@ def perspective_crop_matrix(bbox, out_shape: Tuple[int, int]):
     return minv
 
 
-def perspective_crop(image_u8: torch.Tensor, bbox, out_shape: Tuple[int, int], to_tensor: bool = True) -> torch.Tensor:
-    """``T.ToTensor()(perspective_crop(image, bbox, out_shape))`` for a CUDA uint8 image (H, W, C) or (H, W):
-    float32 (C, H_out, W_out) in [0, 1]; with ``to_tensor=False`` the uint8 patch (H_out, W_out[, C]) itself."""
-    if not (image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.dim() in (2, 3)):
-        raise RuntimeError("perspective_crop needs a CUDA uint8 image (H, W[, C]); there is no CPU fallback")
+def _crop(image_u8: torch.Tensor, bbox, out_shape: Tuple[int, int], to_tensor: bool, host_twin: bool = False) -> torch.Tensor:
+    """Argument marshalling shared by the CUDA entry point and (tests only, ``host_twin``) the host twin of its per-pixel
+    code, which takes the same arguments minus the stream."""
     img = image_u8 if image_u8.dim() == 3 else image_u8.unsqueeze(2)
     if img.stride(2) != 1 or img.stride(1) != img.shape[2]:
         img = img.contiguous()
@@ -49,11 +47,22 @@ def perspective_crop(image_u8: torch.Tensor, bbox, out_shape: Tuple[int, int], t
     else:
         out = torch.empty((h, w, ch), dtype=torch.uint8, device=img.device)
         u8, chw = C.c_void_p(out.data_ptr()), C.c_void_p(0)
-    _lib.call("vg_warp_perspective_u8", C.c_void_p(img.data_ptr()), sh, sw, ch, C.c_longlong(img.stride(0)), minv, h, w, u8, chw,
-              stream())
+    args = (C.c_void_p(img.data_ptr()), sh, sw, ch, C.c_longlong(img.stride(0)), minv, h, w, u8, chw)
+    if host_twin:
+        _lib.call("vg_debug_warp_perspective_host", *args)
+    else:
+        _lib.call("vg_warp_perspective_u8", *args, stream())
     if not to_tensor and image_u8.dim() == 2:
         out = out[:, :, 0]
     return out
+
+
+def perspective_crop(image_u8: torch.Tensor, bbox, out_shape: Tuple[int, int], to_tensor: bool = True) -> torch.Tensor:
+    """``T.ToTensor()(perspective_crop(image, bbox, out_shape))`` for a CUDA uint8 image (H, W, C) or (H, W):
+    float32 (C, H_out, W_out) in [0, 1]; with ``to_tensor=False`` the uint8 patch (H_out, W_out[, C]) itself."""
+    if not (image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.dim() in (2, 3)):
+        raise RuntimeError("perspective_crop needs a CUDA uint8 image (H, W[, C]); there is no CPU fallback")
+    return _crop(image_u8, bbox, out_shape, to_tensor)
 
 
 def crop_batch(images: Sequence[torch.Tensor], bboxes: Sequence, out_shape: Tuple[int, int]) -> torch.Tensor:
