@@ -247,6 +247,10 @@ def test_plateau_scheduler_matches_torch():
                 resumed = ReduceLROnPlateau(FusedAdam([p_mine], lr=1e-4), **kw)
                 resumed.load_state_dict(mine.state_dict())
                 mine, opt = resumed, resumed.optimizer
+            if epoch == 90:                       # ... and from the reference's own scheduler_G_state_dict (torch's class)
+                resumed = ReduceLROnPlateau(FusedAdam([p_mine], lr=1e-4), **kw)
+                resumed.load_state_dict(ref.state_dict())
+                mine, opt = resumed, resumed.optimizer
             level *= rng.choice((0.97, 1.0, 1.0, 1.01, 1.03))
             metric = level + 0.001 * rng.random()
             ref.step(metric)
