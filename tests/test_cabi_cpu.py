@@ -49,6 +49,14 @@ def test_bad_descriptor_returns_error_code_not_abort(lib):
     assert b"num_taps" in lib.vg_last_error()
     with pytest.raises(_lib.VgError):
         _lib.call("vg_hinge_fwd", None, ctypes.c_longlong(4), 7, None, None)
+    # entry points of the oldv family and of the data path: argument errors come back as codes + messages as well
+    assert lib.vg_upsample_h_fwd(None, 1, 4, 4, 12, None, 8, 0, None) < 0 and b"multiple of 8" in lib.vg_last_error()
+    assert lib.vg_channel_scale_fwd(None, 12, None, None, 16, 0, ctypes.c_longlong(4), 12, 0, None) < 0
+    assert b"vg_channel_scale_fwd" in lib.vg_last_error()
+    buf, m = (ctypes.c_ubyte * 64)(), (ctypes.c_double * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    assert lib.vg_warp_perspective_u8(buf, 4, 4, 5, ctypes.c_longlong(20), m, 2, 2, buf, None, None) < 0     # 5 channels
+    assert b"vg_warp_perspective_u8" in lib.vg_last_error()
+    assert lib.vg_perspective_crop_matrix(None, 8, 8, m) < 0
 
 
 def test_struct_layout_matches_header(lib):
