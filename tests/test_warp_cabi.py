@@ -93,3 +93,29 @@ def test_python_marshalling_through_the_host_twin():
         assert np.array_equal(data._crop(chan_first, bbox, (64, 32), False, host_twin=True).numpy(), want)
     with pytest.raises(RuntimeError):
         data.perspective_crop(torch.from_numpy(page), quads(rng, 1).__next__(), (64, 32))     # public entry: CUDA only
+
+
+def test_full_size_page_properties():
+    """A page-sized image (1500 x 2100 RGB, the scale of the reference's scans) and the reference's patch (448 x 64):
+    size-independent properties -- an axis-aligned box of exactly the patch size is a plain copy, a box flipped left-right
+    mirrors it -- plus oracle equality on boxes that span and that leave the page."""
+    import ctypes as C
+    from vae_gan_mark_b200 import _lib, data
+    rng = np.random.default_rng(50)
+    h, w = 1500, 2100
+    page = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+
+    def run(bbox, out_shape=(448, 64)):
+        ow, oh = out_shape
+        u8 = np.zeros((oh, ow, 3), dtype=np.uint8)
+        _lib.call("vg_debug_warp_perspective_host", page.ctypes.data_as(C.c_void_p), h, w, 3, C.c_longlong(w * 3),
+                  data.perspective_crop_matrix(bbox, out_shape), oh, ow, u8.ctypes.data_as(C.c_void_p), None)
+        return u8
+
+    x0, y0 = 801, 1203
+    box = [[x0, y0], [x0 + 447, y0], [x0 + 447, y0 + 63], [x0, y0 + 63]]
+    assert np.array_equal(run(box), page[y0:y0 + 64, x0:x0 + 448])
+    flipped = [box[1], box[0], box[3], box[2]]
+    assert np.array_equal(run(flipped), page[y0:y0 + 64, x0:x0 + 448][:, ::-1])
+    for bbox in ([[100.3, 50.7], [1900.2, 80.1], [1880.9, 400.4], [90.6, 380.2]], [[-50, -20], [600, 10], [580, 200], [-40, 180]]):
+        assert np.array_equal(run(bbox), warp.perspective_crop(page, bbox, (448, 64)))
