@@ -267,3 +267,46 @@ def test_plateau_scheduler_matches_torch():
             assert float(opt.state[3]) == torch.tensor(opt.lr, dtype=torch.float32).item()
             assert mine.get_last_lr() == [opt.lr] and opt.param_groups[0]["lr"] == opt.lr
         assert mine.num_bad_epochs == ref.num_bad_epochs and mine.best == ref.best
+
+
+def test_checkpoint_dictionary_with_schedulers_round_trips():
+    """The reference's checkpoint dictionary incl. the scheduler entries (vae-gan-lr-sh.py:637-646, vae-gan-v2.py:802-810)
+    written by VAEGANTrainer.checkpoint() and read back by load_checkpoint() -- host logic only, CPU modules."""
+    import io
+    import torch
+    from vae_gan_mark_b200 import modules as M
+    from vae_gan_mark_b200.train import LossWeights, ReduceLROnPlateau, VAEGANTrainer
+
+    def build():
+        torch.manual_seed(0)
+        G = M.VAEGAN(4, 16, 64, 3, patch_shape=(32, 32), text_embedder=lambda t: torch.zeros(len(t), 384))
+        D = M.Discriminator(3)
+        tr = VAEGANTrainer(G, D, LossWeights.for_family("base"))
+        tr.attach_schedulers(ReduceLROnPlateau(tr.opt_G, factor=0.5, patience=0), ReduceLROnPlateau(tr.opt_D, factor=0.5, patience=0))
+        return tr
+
+    a = build()
+    for m in a.opt_G.exp_avg + a.opt_D.exp_avg_sq:
+        m.normal_()
+    a.opt_G.state[0] = 7.0                                   # seven optimiser steps taken
+    for metric in (1.0, 1.1, 1.2):                           # two bad epochs: lr 1e-4 -> 2.5e-5
+        a.sched_G.step(metric)
+    a.sched_D.step(1.0)
+    buf = io.BytesIO()
+    torch.save(a.checkpoint(epoch=3, best_val_loss=0.25), buf)
+    buf.seek(0)
+    ck = torch.load(buf, weights_only=False)
+    assert {"model_state_dict", "disc_state_dict", "opt_G_state_dict", "opt_D_state_dict", "scheduler_G_state_dict",
+            "scheduler_D_state_dict", "epoch", "best_val_loss"} <= set(ck)
+    assert ck["opt_G_state_dict"]["param_groups"][0]["lr"] == 2.5e-5
+    b = build()
+    b.load_checkpoint(ck, strict=True)
+    assert b.opt_G.lr == 2.5e-5 and abs(float(b.opt_G.state[3]) - 2.5e-5) < 1e-12 and b.opt_D.lr == 1e-4
+    assert b.opt_G.step_count == 7 and b.sched_G.num_bad_epochs == a.sched_G.num_bad_epochs and b.sched_G.best == 1.0
+    assert all(torch.equal(x, y) for x, y in zip(a.opt_G.exp_avg, b.opt_G.exp_avg))
+    assert all(torch.equal(x, y) for x, y in zip(a.opt_D.exp_avg_sq, b.opt_D.exp_avg_sq))
+    for (k, v), (k2, v2) in zip(a.G.state_dict().items(), b.G.state_dict().items()):
+        assert k == k2 and torch.equal(v, v2)
+    b.sched_G.step(1.3)                                      # the resumed scheduler keeps counting where the saved one stopped
+    a.sched_G.step(1.3)
+    assert b.opt_G.lr == a.opt_G.lr == 1.25e-5

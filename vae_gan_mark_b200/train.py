@@ -254,6 +254,12 @@ class VAEGANTrainer:
         self.kl_weight = torch.full((), float(weights.kl), dtype=F32, device=self.opt_G.state.device)
         self.grad_hook = grad_hook        # called as grad_hook("D"|"G", params) after each backward (DP allreduce)
         self._graph = None
+        self.sched_G = self.sched_D = None
+
+    def attach_schedulers(self, sched_G: Optional["ReduceLROnPlateau"] = None, sched_D: Optional["ReduceLROnPlateau"] = None):
+        """LR schedulers whose state travels with the checkpoint as ``scheduler_G_state_dict`` / ``scheduler_D_state_dict``
+        (vae-gan-lr-sh.py:643-644,784-787; vae-gan-v2.py:807-808,974-977)."""
+        self.sched_G, self.sched_D = sched_G, sched_D
 
     def step(self, ru, en, mask, texts, kl_weight: Optional[float] = None) -> Dict[str, torch.Tensor]:
         G, D, w = self.G, self.D, self.w
@@ -306,6 +312,10 @@ class VAEGANTrainer:
         through.  Save with ``torch.save``; a checkpoint written by the reference loads with ``load_checkpoint``."""
         ck = {"model_state_dict": self.G.state_dict(), "disc_state_dict": self.D.state_dict(),
               "opt_G_state_dict": self.opt_G.state_dict(), "opt_D_state_dict": self.opt_D.state_dict()}
+        if self.sched_G is not None:
+            ck["scheduler_G_state_dict"] = self.sched_G.state_dict()
+        if self.sched_D is not None:
+            ck["scheduler_D_state_dict"] = self.sched_D.state_dict()
         ck.update(extra)
         return ck
 
@@ -321,6 +331,11 @@ class VAEGANTrainer:
             self.opt_G.load_state_dict(opt_g)
         if opt_d is not None:
             self.opt_D.load_state_dict(opt_d)
+        # like the reference, the schedulers are restored after the optimisers (their last rate wins)
+        if self.sched_G is not None and "scheduler_G_state_dict" in ck:
+            self.sched_G.load_state_dict(ck["scheduler_G_state_dict"])
+        if self.sched_D is not None and "scheduler_D_state_dict" in ck:
+            self.sched_D.load_state_dict(ck["scheduler_D_state_dict"])
         L.bump_weight_epoch()
         self._graph = None
 
