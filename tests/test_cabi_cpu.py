@@ -310,3 +310,12 @@ def test_checkpoint_dictionary_with_schedulers_round_trips():
     b.sched_G.step(1.3)                                      # the resumed scheduler keeps counting where the saved one stopped
     a.sched_G.step(1.3)
     assert b.opt_G.lr == a.opt_G.lr == 1.25e-5
+
+
+def test_kl_anneal_schedule():
+    from vae_gan_mark_b200.train import kl_anneal_weight
+    start, target, n = 1e-7, 0.001, 20                      # vae-gan-v2.py:44,48-49
+    want = [start + (target - start) * (e / max(1, n - 1)) if e < n else target for e in range(30)]
+    assert [kl_anneal_weight(e, start, target, n) for e in range(30)] == want
+    assert kl_anneal_weight(0) == start and kl_anneal_weight(19) == target and kl_anneal_weight(500) == target
+    assert kl_anneal_weight(0, anneal_epochs=1) == start and kl_anneal_weight(1, anneal_epochs=1) == target

@@ -205,6 +205,14 @@ class ReduceLROnPlateau:
             self.optimizer.set_lr(self._last_lr[0])
 
 
+def kl_anneal_weight(epoch: int, start: float = 1e-7, target: float = 0.001, anneal_epochs: int = 20) -> float:
+    """KL weight of an epoch (vae-gan-v2.py:48-49,1001-1004; vae-gan-oldv.py:1043-1045): linear from ``start`` to
+    ``target`` over ``anneal_epochs`` epochs, then ``target``.  Feed it to ``VAEGANTrainer.set_kl_weight``."""
+    if epoch < anneal_epochs:
+        return start + (target - start) * (epoch / max(1, anneal_epochs - 1))
+    return target
+
+
 @contextlib.contextmanager
 def frozen(module: torch.nn.Module):
     """Temporarily stop gradient computation for a module's parameters (D during the G step)."""
