@@ -141,3 +141,15 @@ def to_tensor(patch: np.ndarray) -> np.ndarray:
     """T.ToTensor() (vae-gan.py:280-281): uint8 HWC -> float32 CHW in [0, 1] (a float32 division by 255)."""
     p = patch if patch.ndim == 3 else patch[:, :, None]
     return (p.transpose(2, 0, 1).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+def fixture_inputs():
+    """Deterministic page / mask images and quadrilaterals of tests/golden/warp_crop.npz (outputs of the reference's own
+    ``perspective_crop`` + ``T.ToTensor()``, recorded by tests/golden/make_golden.py); inputs are re-derived, not stored."""
+    rng = np.random.default_rng(2024)
+    page = rng.integers(0, 256, size=(96, 160, 3), dtype=np.uint8)
+    mask = rng.integers(0, 256, size=(96, 160), dtype=np.uint8)
+    boxes = [[[10, 12], [140, 8], [150, 70], [6, 80]], [[30.5, 20.25], [120.75, 30.5], [110.25, 60.5], [25.5, 55.75]],
+             [[-20, -10], [100, 5], [90, 50], [-15, 60]], [[60, 40], [200, 30], [210, 120], [55, 110]],
+             [[5, 5], [68, 5], [68, 36], [5, 36]], [[150, 10], [20, 15], [25, 85], [155, 90]]]
+    return page, mask, boxes

@@ -130,8 +130,29 @@ def run_case(name):
           os.path.getsize(os.path.join(HERE, name + ".pt")) // 1024, "KiB")
 
 
+def run_warp_case():
+    """The reference's own ``perspective_crop`` + ``T.ToTensor()`` (vae-gan.py:163-188, 275-281) on PIL images."""
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as T
+    mod = ref_loader.load("base", (448, 64))
+    from oracle.warp import fixture_inputs
+    page, mask, boxes = fixture_inputs()
+    gold = {}
+    for shape in ((448, 64), (64, 32)):
+        for i, box in enumerate(boxes):
+            ru = T.ToTensor()(mod.perspective_crop(Image.fromarray(page).convert("RGB"), box, shape))
+            mk = T.ToTensor()(mod.perspective_crop(Image.fromarray(mask).convert("L"), box, shape))
+            gold[f"{shape[0]}x{shape[1]}_{i}_rgb"] = (ru * 255).round().to(torch.uint8).numpy()
+            gold[f"{shape[0]}x{shape[1]}_{i}_mask"] = (mk * 255).round().to(torch.uint8).numpy()
+            assert torch.equal(ru, torch.from_numpy(gold[f"{shape[0]}x{shape[1]}_{i}_rgb"]).float() / 255)   # ToTensor is exactly u8 / 255
+    np.savez_compressed(os.path.join(HERE, "warp_crop.npz"), **gold)
+    print("warp_crop", len(gold), "patches", os.path.getsize(os.path.join(HERE, "warp_crop.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     torch.set_num_threads(8)
-    for n in (sys.argv[1:] or CASES):
-        run_case(n)
+    names = sys.argv[1:] or list(CASES) + ["warp_crop"]
+    for n in names:
+        run_warp_case() if n == "warp_crop" else run_case(n)

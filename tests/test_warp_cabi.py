@@ -119,3 +119,18 @@ def test_full_size_page_properties():
     assert np.array_equal(run(flipped), page[y0:y0 + 64, x0:x0 + 448][:, ::-1])
     for bbox in ([[100.3, 50.7], [1900.2, 80.1], [1880.9, 400.4], [90.6, 380.2]], [[-50, -20], [600, 10], [580, 200], [-40, 180]]):
         assert np.array_equal(run(bbox), warp.perspective_crop(page, bbox, (448, 64)))
+
+
+def test_host_twin_reproduces_the_reference_fixture():
+    """The library's per-pixel code against the outputs of the reference's own perspective_crop (tests/golden/warp_crop.npz)."""
+    import os
+    import torch
+    from vae_gan_mark_b200 import data
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_crop.npz"))
+    page, mask, boxes = warp.fixture_inputs()
+    for shape in ((448, 64), (64, 32)):
+        for i, box in enumerate(boxes):
+            got = data._crop(torch.from_numpy(page), box, shape, True, host_twin=True).numpy()
+            assert np.array_equal(got, gold[f"{shape[0]}x{shape[1]}_{i}_rgb"].astype(np.float32) / np.float32(255))
+            gotm = data._crop(torch.from_numpy(mask), box, shape, False, host_twin=True).numpy()
+            assert np.array_equal(gotm[None], gold[f"{shape[0]}x{shape[1]}_{i}_mask"])

@@ -53,3 +53,18 @@ def test_crop_batch_and_strided_source():
     assert np.array_equal(got, warp.perspective_crop(view.cpu().numpy().copy(), box, (64, 32)))
     with pytest.raises(RuntimeError):
         data.perspective_crop(wide.cpu(), box, (64, 32))
+
+
+def test_gpu_reproduces_the_reference_fixture():
+    """The CUDA path against the outputs of the reference's own perspective_crop + T.ToTensor() (tests/golden/warp_crop.npz)."""
+    import os
+    from vae_gan_mark_b200 import data
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_crop.npz"))
+    page, mask, boxes = warp.fixture_inputs()
+    dpage, dmask = torch.from_numpy(page).cuda(), torch.from_numpy(mask).cuda()
+    for shape in ((448, 64), (64, 32)):
+        for i, box in enumerate(boxes):
+            got = data.perspective_crop(dpage, box, shape).cpu().numpy()
+            assert np.array_equal(got, gold[f"{shape[0]}x{shape[1]}_{i}_rgb"].astype(np.float32) / np.float32(255))
+            gotm = data.perspective_crop(dmask, box, shape, to_tensor=False).cpu().numpy()
+            assert np.array_equal(gotm[None], gold[f"{shape[0]}x{shape[1]}_{i}_mask"])

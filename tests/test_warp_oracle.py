@@ -69,3 +69,18 @@ def test_to_tensor_matches_torchvision():
     mask = rng.integers(0, 256, size=(16, 24), dtype=np.uint8)
     assert np.array_equal(warp.to_tensor(mask), T.ToTensor()(Image.fromarray(mask)).numpy())
     assert torch.from_numpy(warp.to_tensor(patch)).dtype == torch.float32
+
+
+def test_oracle_reproduces_the_reference_fixture():
+    """tests/golden/warp_crop.npz holds what the REFERENCE's own perspective_crop + T.ToTensor() returned for the
+    deterministic inputs of oracle.warp.fixture_inputs() (PIL in, PIL out, vae-gan.py:163-188, 275-281)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_crop.npz"))
+    page, mask, boxes = warp.fixture_inputs()
+    assert len(gold.files) == 24
+    for shape in ((448, 64), (64, 32)):
+        for i, box in enumerate(boxes):
+            rgb = gold[f"{shape[0]}x{shape[1]}_{i}_rgb"]            # uint8 view of the ToTensor() output, (3, H, W)
+            assert np.array_equal(warp.perspective_crop(page, box, shape).transpose(2, 0, 1), rgb)
+            assert np.array_equal(warp.to_tensor(warp.perspective_crop(page, box, shape)), rgb.astype(np.float32) / np.float32(255))
+            assert np.array_equal(warp.perspective_crop(mask, box, shape)[None], gold[f"{shape[0]}x{shape[1]}_{i}_mask"])
