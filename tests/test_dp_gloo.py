@@ -101,3 +101,49 @@ def test_two_rank_gradient_average_matches_global_batch():
     torch.nn.functional.mse_loss(net(x_all), y_all).backward()
     for p, a in zip(net.parameters(), g0):
         assert torch.allclose(p.grad, a, atol=1e-6)
+
+
+def _worker_model_params(rank, world, port, ret):
+    """The real parameter sets of the drop-in models (oldv generator incl. the (1,C,1,1) gates, the 4-D positional
+    encoding and the Conv1d weight; the discriminator with its spectral-norm weights), conv weights in channels_last
+    memory order as VAEGANTrainer keeps them, gradients in the layouts the backward produces."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vae_gan_mark_b200 import modules as M
+    from vae_gan_mark_b200.parallel import DataParallelReducer
+    from vae_gan_mark_b200.train import weights_channels_last
+    torch.manual_seed(3)
+    G = M.VAEGAN_UNet_SpatialFiLM_OldV(4, 32, patch_shape=(64, 32))
+    D = M.Discriminator(3)
+    converted = weights_channels_last(G) + weights_channels_last(D)
+    ok, n_cl, n_buckets = True, 0, 0
+    for which, params in (("G", list(G.parameters())), ("D", list(D.parameters()))):
+        red = DataParallelReducer(world, bucket_bytes=1 << 20)
+        n_buckets += len(red.make_buckets(params))
+        bases = []
+        for k, p in enumerate(params):
+            base = torch.randn(p.shape, generator=torch.Generator().manual_seed(1000 + k))
+            bases.append(base)
+            if k % 3 == 0:
+                p.grad = (base * (rank + 1)).contiguous()                    # a fresh contiguous gradient
+            else:
+                p.grad = torch.empty_like(p).copy_(base * (rank + 1))        # the parameter's own memory order
+            n_cl += int(p.dim() == 4 and not p.grad.is_contiguous())
+        strides = [p.grad.stride() for p in params]
+        red.hook(which, params)
+        for p, base, st in zip(params, bases, strides):
+            ok = ok and torch.allclose(p.grad, base * 1.5, rtol=1e-6, atol=1e-6) and p.grad.stride() == st
+    ret[rank] = (ok, converted, n_cl, n_buckets)
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_over_the_real_parameter_sets():
+    world, port = 2, 33000 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_model_params, args=(world, port, ret), nprocs=world, join=True)
+    for rank in range(world):
+        ok, converted, n_cl, n_buckets = ret[rank]
+        assert ok, "averaged gradients (or their memory layout) are wrong for some parameter"
+        assert converted > 20 and n_cl > 10 and n_buckets > 4
