@@ -115,6 +115,18 @@ def test_conv_tap_geometry():
             assert 2 * dh + sh == r - p and 2 * dw + cb // ld == q - p and cb % ld == 0
     op = ConvLinear(64, 128, 4, 4, 2, (1, 1))
     assert op.out_hw(64, 448) == (32, 224)
+    # Conv1d(k=3, p=1) of the oldv text encoder as a 1 x 3 convolution over [B, 1, L, C] (vae-gan-oldv.py:118-121)
+    c1 = ConvLinear(512, 512, 1, 3, 1, (0, 1), (1, 60))
+    assert conv_taps(1, 3, 1, 0, 1, 512) == [(0, -1, 0, 0), (0, 0, 0, 0), (0, 1, 0, 0)]
+    assert c1.out_hw(1, 60) == (1, 60) and not (c1.flat or c1.column or c1.shuffle)
+    # pixel-shuffle data gradients (ConvT 2x2 stride 2): the MN-major operand needs a column map (r, q, ci) -> (r, q, ci_p)
+    # that is uniform only when cin is a multiple of 64; up_tconv3 of the oldv decoder (64 -> 32) must take the K-major path
+    up3 = ConvLinear(32, 64, 2, 2, 2, (0, 0), (64, 448))
+    assert up3.shuffle and up3.cin_p == 64 and not up3.prefer_mn(16)
+    up_v2 = ConvLinear(64, 128, 2, 2, 2, (0, 0), (16, 16))
+    assert up_v2.shuffle and up_v2.prefer_mn(16)                   # small GEMM, cin % 64 == 0: MN-major is allowed
+    bottleneck = ConvLinear(256, 640, 4, 1, 1, (0, 0), (4, 8))     # ConvT(640 -> 256, k = (H/8, 1)): column kernel
+    assert bottleneck.column and bottleneck.shuffle
 
 
 def _plan_copy(src: "np.ndarray", dst_shape, perm):
