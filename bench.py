@@ -259,7 +259,7 @@ def run_ours(args, wl):
     reducer = DataParallelReducer(world) if world > 1 else None
     if reducer is not None:
         reducer.broadcast_parameters(list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()))
-    wts = LossWeights.for_family(wl["family"])
+    wts = LossWeights.for_family(wl["family"], perceptual=bool(args.perceptual))
     perceptual = None
     if args.perceptual:
         # the reference's VGG16 features[:16] perceptual term (vae-gan.py:300-311,422).  Pretrained
@@ -272,7 +272,6 @@ def run_ours(args, wl):
                 p_.data.copy_(torch.randn(p_.shape, generator=gen_w) * (2.0 / (p_.shape[1] * 9)) ** 0.5)
             else:
                 p_.data.zero_()
-        wts.perc = {"base": 0.05}.get(wl["family"], 0.1)      # vae-gan.py:38, vae-gan-v2.py:45, vae-gan-unet.py:46
     trainer = VAEGANTrainer(G, D, wts, grad_hook=reducer.hook if reducer else None, perceptual=perceptual)
     if reducer is not None and not args.no_overlap:
         reducer.install_hooks(trainer.opt_G.params, trainer.opt_D.params)   # all-reduces issued during the backward

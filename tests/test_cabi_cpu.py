@@ -293,7 +293,7 @@ def test_checkpoint_dictionary_with_schedulers_round_trips():
         torch.manual_seed(0)
         G = M.VAEGAN(4, 16, 64, 3, patch_shape=(32, 32), text_embedder=lambda t: torch.zeros(len(t), 384))
         D = M.Discriminator(3)
-        tr = VAEGANTrainer(G, D, LossWeights.for_family("base"))
+        tr = VAEGANTrainer(G, D, LossWeights.for_family("base", perceptual=False))
         tr.attach_schedulers(ReduceLROnPlateau(tr.opt_G, factor=0.5, patience=0), ReduceLROnPlateau(tr.opt_D, factor=0.5, patience=0))
         return tr
 

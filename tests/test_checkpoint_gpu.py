@@ -22,7 +22,7 @@ def build():
     D = M.Discriminator(3).cuda().train()
     G.load_state_dict(deterministic_state(G, 5)); D.load_state_dict(deterministic_state(D, 6))
     G.char_text_encoder_module.rnn.dropout = 0.0
-    return G, D, VAEGANTrainer(G, D, LossWeights.for_family("v2"))
+    return G, D, VAEGANTrainer(G, D, LossWeights.for_family("v2", perceptual=False))
 
 
 def run_step(tr, G, step):

@@ -100,7 +100,7 @@ def test_whole_step_dedup_equals_literal_fp32():
             ru, en, mask, texts = synthetic_batch(2, 32, 64, step=0)
             eps = torch.randn(2, 32, 1, 1, generator=torch.Generator().manual_seed(3))
             G.style_vae_encoder_module.eps_fn = lambda shape: eps
-            tr = VAEGANTrainer(G, D, LossWeights.for_family("v2"))
+            tr = VAEGANTrainer(G, D, LossWeights.for_family("v2", perceptual=False))
             M.FILM_ROW_DEDUP = dedup
             out = tr.step(ru.cuda(), en.cuda(), mask.cuda(), texts)
             M.FILM_ROW_DEDUP = False

@@ -19,7 +19,7 @@ def main():
         M.FILM_ROW_DEDUP = True
     dev = torch.device("cuda", 0)
     G, D = bench.build_models(wl, dev)
-    tr = VAEGANTrainer(G, D, LossWeights.for_family(wl["family"]))
+    tr = VAEGANTrainer(G, D, LossWeights.for_family(wl["family"], perceptual=False))
     B, h, w = wl["batch"], wl["h"], wl["w"]
     gen = torch.Generator(device=dev).manual_seed(1)
     batch = (torch.rand(B, 3, h, w, device=dev, generator=gen), torch.rand(B, 3, h, w, device=dev, generator=gen),

@@ -19,7 +19,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     G, D = bench.build_models(wl, dev)
-    trainer = VAEGANTrainer(G, D, LossWeights.for_family(wl["family"]))
+    trainer = VAEGANTrainer(G, D, LossWeights.for_family(wl["family"], perceptual=False))
     B, h, w = wl["batch"], wl["h"], wl["w"]
     gen = torch.Generator(device=dev).manual_seed(1)
     batch = (torch.rand(B, 3, h, w, device=dev, generator=gen), torch.rand(B, 3, h, w, device=dev, generator=gen),

@@ -239,6 +239,8 @@ template <> VG_DEVICE float as_stored<float>(float v) { return v; }
 
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+// host: index of the current device, clamped to [0, 64) (tables of per-device state are 64 entries long)
+int current_device();
 // host: number of SMs of the current device (cached)
 int num_sms();
 // SMs the persistent tensor-core kernels may occupy (vg_set_conv_sm_limit leaves the rest to concurrent small kernels)

@@ -568,10 +568,11 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     if (rc) return rc;
   }
   const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + p.w_bytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // per device: function attributes belong to the device's context
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int total_tiles = m_tiles * p.n_tiles * p.ksplit * p.ngroups;
   const int grid = min(total_tiles, sms);

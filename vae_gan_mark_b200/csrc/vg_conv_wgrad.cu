@@ -304,10 +304,11 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
     if (rc) return rc;
   }
   const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + 256 + kWgEpiBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // per device: function attributes belong to the device's context
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     VG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   conv_wgrad_kernel<<<min(total_tiles, sms), kWgThreads, smem, stream>>>(tmap_g, tmap_x, p);

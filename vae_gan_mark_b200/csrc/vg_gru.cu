@@ -343,15 +343,15 @@ static int gru_launch(Kernel kernel, int clusters, int smem, cudaStream_t st, Ar
 }
 
 // smallest batch group whose clusters are all co-resident (one wave); cached per kernel direction
-static int g_gru_max_clusters[2][2] = {{-1, -1}, {-1, -1}};   // [fwd|bwd][BG 8|16]
+static int g_gru_max_clusters[64][2][2];   // [device][fwd|bwd][BG 8|16], 0 = not queried yet (stored as n + 1)
 
 }  // namespace vg
 
 extern "C" int vg_gru_max_active_clusters(int backward, int batch_group) {
   using namespace vg;
   if (batch_group != 8 && batch_group != 16) return -1;
-  int& slot = g_gru_max_clusters[backward ? 1 : 0][batch_group == 16 ? 1 : 0];
-  if (slot < 0) {
+  int& slot = g_gru_max_clusters[current_device()][backward ? 1 : 0][batch_group == 16 ? 1 : 0];
+  if (slot == 0) {
     int n = 0, rc;
     if (!backward)
       rc = batch_group == 8 ? gru_query(gru_seq_fwd_kernel<8>, gru_smem_fwd<8>(), &n)
@@ -360,9 +360,9 @@ extern "C" int vg_gru_max_active_clusters(int backward, int batch_group) {
       rc = batch_group == 8 ? gru_query(gru_seq_bwd_kernel<8>, gru_smem_bwd<8>(), &n)
                             : gru_query(gru_seq_bwd_kernel<16>, gru_smem_bwd<16>(), &n);
     if (rc != 0) return rc;
-    slot = n;
+    slot = n + 1;
   }
-  return slot;
+  return slot - 1;
 }
 
 static int gru_pick_group(int backward, int batch) {

@@ -25,11 +25,15 @@ int conv_sms() {
   return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
-int num_sms() {
-  static int cached[64] = {0};
+int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  const int dev = current_device();
   if (cached[dev] == 0) {
     int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);

@@ -33,13 +33,20 @@ class LossWeights:
     recon: float = 1.0
     kl: float = 0.001
     gan: float = 0.15
-    perc: float = 0.0       # PERC_WEIGHT (0.05 base, 0.1 v2 / unet in the reference); used when a VGGPerceptual is given
+    perc: float = 0.0       # PERC_WEIGHT; needs a VGGPerceptual module (VAEGANTrainer(perceptual=...))
 
     @staticmethod
-    def for_family(family: str) -> "LossWeights":
-        # vae-gan.py:35-38 ; vae-gan-v2.py:42-45 ; vae-gan-unet.py:43-46 ; vae-gan-oldv.py:42-45
-        return {"base": LossWeights(1.0, 0.005, 0.1), "v2": LossWeights(1.0, 0.001, 0.15),
-                "unet": LossWeights(1.0, 0.001, 0.15), "oldv": LossWeights(1.0, 0.001, 0.07)}[family]
+    def for_family(family: str, perceptual: bool = True) -> "LossWeights":
+        """The reference's loss weights incl. PERC_WEIGHT (vae-gan.py:35-38 base 0.05; vae-gan-v2.py:42-45 and
+        vae-gan-unet.py:43-46: 0.1; vae-gan-oldv.py:42-45: 0.2).  ``perceptual=False`` drops the VGG term (weight 0) --
+        the configuration every parity test and the headline bench use, because the ImageNet weights of the reference's
+        VGG16 cannot be obtained offline.  VAEGANTrainer refuses a non-zero ``perc`` without a VGGPerceptual module and
+        a VGGPerceptual module with ``perc == 0``, so the term can never be dropped or added silently."""
+        w = {"base": LossWeights(1.0, 0.005, 0.1, 0.05), "v2": LossWeights(1.0, 0.001, 0.15, 0.1),
+             "unet": LossWeights(1.0, 0.001, 0.15, 0.1), "oldv": LossWeights(1.0, 0.001, 0.07, 0.2)}[family]
+        if not perceptual:
+            w.perc = 0.0
+        return w
 
 
 class FusedAdam:
@@ -252,6 +259,13 @@ class VAEGANTrainer:
         ``weights.perc`` (vae-gan.py:422-423)."""
         self.G, self.D, self.w, self.clip_norm = G, D, weights, clip_norm
         self.perceptual = perceptual
+        if perceptual is None and weights.perc != 0.0:
+            raise ValueError(f"LossWeights.perc = {weights.perc} but no VGGPerceptual module was given: pass "
+                             "perceptual=modules.VGGPerceptual() (with the VGG16 weights loaded) or use "
+                             "LossWeights.for_family(family, perceptual=False)")
+        if perceptual is not None and weights.perc == 0.0:
+            raise ValueError("a VGGPerceptual module was given but LossWeights.perc is 0: the perceptual term would be "
+                             "dropped silently (reference PERC_WEIGHT: 0.05 base, 0.1 v2 / unet, 0.2 oldv)")
         if channels_last_weights:
             weights_channels_last(G)
             weights_channels_last(D)
@@ -391,4 +405,7 @@ class VAEGANTrainer:
             if src is not None and src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        # the captured Adam kernels write the weights through raw pointers (no autograd version bump): cached bf16
+        # operands of an eager forward before this replay (a validation pass) are stale from here on
+        L.bump_weight_epoch()
         return self._static_out
