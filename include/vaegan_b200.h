@@ -88,6 +88,11 @@ typedef struct VgConvFprop {
   int halo_mode;            /* 0 = auto (3x3 stride-1 tap sets with n_gemm <= 64 and >= 64K pixels load each 18 x 10
                                activation halo once and address the nine taps as shifted UMMA descriptors; the weights
                                stay resident in shared memory when they fit); -1 = never; 1 = force (testing) */
+  float* stats;             /* optional fp32 [2][cout_per_sub], zeroed by the call: per-destination-channel sum and sum of
+                               squares of the values as stored (after bias / activation, rounded to the output type) over
+                               all valid pixels -- the batch statistics of the BatchNorm2d that follows the convolution
+                               (vae-gan-v2.py:172-177, vae-gan.py:52-55,77-80), produced by the epilogue instead of a
+                               separate pass over the tensor.  Needs out_kind 0/1, no split-K, an aligned destination */
 } VgConvFprop;
 int vg_conv_fprop(const VgConvFprop* desc /*host*/, void* stream);
 
@@ -108,8 +113,13 @@ typedef struct VgConvWgrad {
   int dw_ld;
   int ksplit;               /* 0 = auto */
   int force_bn;             /* 0 = auto; 64/128/192/256 */
+  void* workspace;          /* optional scratch for a DETERMINISTIC split reduction: each split stores its partial tile
+                               here and a second kernel adds them in a fixed order (bit-identical results from run to run);
+                               NULL: the splits are combined with fp32 atomics in whatever order they finish */
+  long long workspace_bytes; /* >= vg_conv_wgrad_workspace(desc) */
 } VgConvWgrad;
 int vg_conv_wgrad(const VgConvWgrad* desc /*host*/, void* stream);
+long long vg_conv_wgrad_workspace(const VgConvWgrad* desc /*host*/);   /* bytes; 0 if the launch does not split; < 0 bad desc */
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -31,7 +31,11 @@ CASES = {
     "v2_32x32_b3_z32": ("v2", 32, 32, 3, 32),
     "unet_32x32_b2": ("unet", 32, 32, 2, 128),
     "oldv_32x64_b2": ("oldv", 32, 64, 2, 128),         # vae-gan-oldv.py: 3-level U-Net, gated skips, 4-row text map
+    # the benchmark's own shapes (BASELINE.json configs[1] / configs[2] at a batch the CPU finishes in seconds): one step
+    "v2_128x128_b8": ("v2", 128, 128, 8, 128),
+    "unet_256x256_b2": ("unet", 256, 256, 2, 128),
 }
+ONE_STEP = {"v2_128x128_b8", "unet_256x256_b2"}
 
 
 def summarize(t: torch.Tensor, n: int = 6) -> torch.Tensor:
@@ -80,7 +84,7 @@ def run_case(name):
         except RuntimeError as e:
             gold["shipped_forward_error"] = str(e)[:80]
 
-    for step in range(2):
+    for step in range(1 if name in ONE_STEP else 2):
         ru, en, mask, texts = synthetic_batch(batch, h, w, step=step)
         torch.manual_seed(10_000 + step)
         # ---- step body, vae-gan.py:404-424 / vae-gan-v2.py:707-740 (perceptual weight 0) ----

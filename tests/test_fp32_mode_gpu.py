@@ -182,7 +182,7 @@ def test_heads_image_small_fp32():
     convc = nn.Conv2d(4, 64, 3, 1, 1).cuda()
     convc.load_state_dict(conv.state_dict())
     cimgs = [t.cuda().requires_grad_(True) for t in imgs]
-    y = L.ImageConvFn.apply(convc.weight, convc.bias, (3, 3, 1, 1), L.WeightCache(), 2, None, *cimgs)
+    y = L.ImageConvFn.apply(convc.weight, convc.bias, (3, 3, 1, 1), L.WeightCache(), 2, None, None, *cimgs)
     y.backward(nhwc(g).detach())
     check("img y", nchw(y), y_ref)
     check("img dw", convc.weight.grad, conv.weight.grad)

@@ -24,24 +24,31 @@ pytestmark = pytest.mark.gpu
 STEPS = 100
 
 
-def test_loss_curves_track_for_100_steps():
+@pytest.mark.parametrize("family,h,w,batch", [("base", 32, 32, 4), ("v2", 64, 64, 4)])
+def test_loss_curves_track_for_100_steps(family, h, w, batch):
+    """base: vae-gan.py:399-428; v2: the U-Net + FiLM generator of the benchmark workload (vae-gan-v2.py:696-748)."""
     from vae_gan_mark_b200 import modules as M
     from vae_gan_mark_b200.train import LossWeights, VAEGANTrainer
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    h = w = 32
-    batch = 4
-    og, od = om.VAEGAN(4, 128, 64, 3, patch_hw=(h, w)), om.Discriminator(3)
+    if family == "base":
+        og = om.VAEGAN(4, 128, 64, 3, patch_hw=(h, w))
+        mg = M.VAEGAN(4, 128, 64, 3, patch_shape=(w, h), text_embedder=om.hash_sentence_embedding)
+    else:
+        og = om.VAEGAN_UNet_SpatialFiLM(4, 128, patch_hw=(h, w))
+        mg = M.VAEGAN_UNet_SpatialFiLM(4, 128, patch_shape=(w, h))
+        for g in (og, mg):
+            g.char_text_encoder_module.rnn.dropout = 0.0   # GRU dropout draws from different RNGs on CPU and CUDA
+    od = om.Discriminator(3)
     sg, sd = deterministic_state(og, 1234), deterministic_state(od, 4321)
     og.load_state_dict(sg); od.load_state_dict(sd)
-    mg = M.VAEGAN(4, 128, 64, 3, patch_shape=(w, h), text_embedder=om.hash_sentence_embedding)
     md = M.Discriminator(3)
     mg.load_state_dict(sg); md.load_state_dict(sd)
     mg, md = mg.cuda().train(), md.cuda().train()
     og.train(); od.train()
-    wts = OLW.for_family("base")
+    wts = OLW.for_family(family)
     opt_g, opt_d = make_optimizers(og, od)
     trainer = VAEGANTrainer(mg, md, LossWeights(wts.recon, wts.kl, wts.gan))
-    mg.encoder.__dict__["eps_fn"] = lambda shape: torch.randn(shape)
+    (getattr(mg, "style_vae_encoder_module", None) or mg.encoder).__dict__["eps_fn"] = lambda shape: torch.randn(shape)
     keys = ("loss_G", "loss_D", "recon", "kl", "gan")
     ref_curve, got_curve = [], []
     for step in range(STEPS):
@@ -64,7 +71,13 @@ def test_loss_curves_track_for_100_steps():
         rms = float(((g - r) ** 2).mean().sqrt())
         corr = float(torch.corrcoef(torch.stack([r, g]))[0, 1])
         report[k] = {"range": round(rng, 4), "rms_over_range": round(rms / max(rng, 1e-9), 4), "corr": round(corr, 4)}
-    print("tracking:", report)
+    print("tracking:", family, report)
+    if os.environ.get("VG_CURVE_LOG"):
+        with open(os.environ["VG_CURVE_LOG"], "a") as f:
+            f.write(f"{family} {h}x{w} b{batch}: 100 steps, oracle/ours at steps 0,1,2,5,10,25,50,75,99\n")
+            for s_ in (0, 1, 2, 5, 10, 25, 50, 75, 99):
+                f.write(f"{s_:4d}   " + "  ".join(f"{keys[i]} {ref_t[s_, i]:8.5f}/{got_t[s_, i]:8.5f}" for i in range(len(keys))) + "\n")
+            f.write(f"tracking: {report}\n")
     for k in ("loss_D", "recon", "kl"):        # first step: identical weights, no dependence on the updated D
         i = keys.index(k)
         assert abs(float(got_t[0, i] - ref_t[0, i])) <= 2e-2 * abs(float(ref_t[0, i])), (k, got_t[0, i], ref_t[0, i])

@@ -261,7 +261,7 @@ def test_image_conv(k, s, p, act, cin):
     y_ref.backward(g)
     conv = conv.cuda()
     cimgs = [t.cuda().requires_grad_(True) for t in imgs]
-    y = L.ImageConvFn.apply(conv.weight, conv.bias, (k, k, s, p), L.WeightCache(), act, None, *cimgs)
+    y = L.ImageConvFn.apply(conv.weight, conv.bias, (k, k, s, p), L.WeightCache(), act, None, None, *cimgs)
     y.backward(nhwc(g).detach())
     check("y", nchw(y), y_ref)
     check("dw", conv.weight.grad, wr.grad)

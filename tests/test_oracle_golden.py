@@ -12,7 +12,8 @@ from oracle import models as om
 from oracle.step import LossWeights, deterministic_state, make_optimizers, synthetic_batch, train_step
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["base_32x32_b4", "base_64x64_b16", "v2_32x64_b2", "v2_32x32_b3_z32", "unet_32x32_b2", "oldv_32x64_b2"]
+CASES = ["base_32x32_b4", "base_64x64_b16", "v2_32x64_b2", "v2_32x32_b3_z32", "unet_32x32_b2", "oldv_32x64_b2",
+         "v2_128x128_b8", "unet_256x256_b2"]      # the last two: the benchmark's own image sizes, one step each
 
 
 def summarize(t, n=6):

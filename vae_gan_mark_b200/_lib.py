@@ -30,7 +30,7 @@ class VgConvFprop(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("ksplit", C.c_int), ("force_bn", C.c_int),
         ("b_mn_major", C.c_int), ("w_rows", C.c_int),
         ("num_groups", C.c_int), ("group_ntaps", C.c_int * 4), ("group_sub", (C.c_int * 2) * 4),
-        ("halo_mode", C.c_int),
+        ("halo_mode", C.c_int), ("stats", C.c_void_p),
     ]
 
 
@@ -42,6 +42,7 @@ class VgConvWgrad(C.Structure):
         ("cin", C.c_int), ("num_taps", C.c_int), ("taps", (C.c_int * 4) * VG_MAX_TAPS),
         ("num_combos", C.c_int), ("combo_g", C.c_int * 8), ("combo_x", C.c_int * 8),
         ("dw", C.c_void_p), ("dw_ld", C.c_int), ("ksplit", C.c_int), ("force_bn", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
     ]
 
 
@@ -83,6 +84,7 @@ def lib() -> C.CDLL:
         _lib.vg_last_error.restype = C.c_char_p
         _lib.vg_version.restype = C.c_int
         _lib.vg_launch_count.restype = C.c_ulonglong
+        _lib.vg_conv_wgrad_workspace.restype = C.c_longlong
     return _lib
 
 

@@ -63,6 +63,10 @@ def _chk(t: torch.Tensor, what: str):
 
 
 HALO_MODE = 0      # VgConvFprop.halo_mode: 0 auto, -1 never, 1 force (tests)
+# Deterministic split reductions (bf16 mode): the weight-gradient kernel stores each pixel split's partial tile into a
+# scratch buffer and adds them in a fixed order (two-stage reduce) instead of fp32 atomics, and split-K forward launches
+# (the 2z-wide heads GEMM) run unsplit.  Results are then bit-identical from run to run; costs a few percent.
+DETERMINISTIC = False
 
 
 def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torch.Tensor, n_gemm: int,
@@ -70,11 +74,13 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
           sub0: Tuple[int, int] = (0, 0), cout_per_sub: Optional[int] = None, bias: Optional[torch.Tensor] = None,
           act: int = 0, ksplit: int = 0, force_bn: int = 0, wk: Optional[Sequence[int]] = None,
           b_mn_major: bool = False, groups: Optional[Sequence[Tuple[int, Tuple[int, int]]]] = None,
-          halo_mode: Optional[int] = None) -> None:
+          halo_mode: Optional[int] = None, stats: Optional[torch.Tensor] = None) -> None:
     """out[pixel, n] = sum_{tap, c<cin} x[pixel@tap, c] * w[n, wk[tap] + c]  (wk[tap] = tap*cin by default).
     ``out`` is an NHWC view ([N, OH, OW, C']); ``x`` and ``w`` are bf16.
     ``b_mn_major``: w is [K rows (c), columns] and out[pixel, n] = sum x[pixel@tap, c] * w[c, wk[tap] + n].
-    ``groups``: [(number of taps, (sub_h0, sub_w0)), ...] -- up to 4 problems in one launch, taps listed group by group."""
+    ``groups``: [(number of taps, (sub_h0, sub_w0)), ...] -- up to 4 problems in one launch, taps listed group by group.
+    ``stats``: fp32 [1, 2, channels] that receives the per-channel sum / sum of squares of the stored output (the batch
+    statistics of a following BatchNorm2d), computed in the epilogue."""
     _chk(x, "fprop x")
     assert w.dtype == BF16 and w.stride(1) == 1 and out.stride(3) == 1
     assert len(taps) <= _lib.VG_MAX_FPROP_TAPS, f"{len(taps)} taps > {_lib.VG_MAX_FPROP_TAPS}"
@@ -98,9 +104,14 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
     d.sub_h0, d.sub_w0 = sub0
     d.cout_per_sub = cout_per_sub or n_gemm
     d.bias = bias.data_ptr() if bias is not None else None
+    if DETERMINISTIC and out_kind == 2 and ksplit == 0 and x.dtype == BF16:
+        ksplit = 1      # one split adds into the zeroed destination exactly once: order-independent
     d.act, d.ksplit, d.force_bn = act, ksplit, force_bn
     d.b_mn_major, d.w_rows = int(b_mn_major), w.shape[0]
     d.halo_mode = HALO_MODE if halo_mode is None else halo_mode
+    if stats is not None:
+        assert stats.dtype == F32 and stats.is_contiguous() and stats.numel() == 2 * d.cout_per_sub and out_kind != 2
+        d.stats = stats.data_ptr()
     if groups is not None:
         assert 2 <= len(groups) <= 4 and sum(g[0] for g in groups) == len(taps) and ksplit in (0, 1)
         d.num_groups = len(groups)
@@ -134,6 +145,12 @@ def wgrad(g: torch.Tensor, cout: int, x: torch.Tensor, taps: Sequence[Tap], x_st
             d.combo_g[i], d.combo_x[i] = int(a), int(b)
     d.dw, d.dw_ld = dw.data_ptr(), dw.stride(0)
     d.ksplit, d.force_bn = ksplit, force_bn
+    if DETERMINISTIC:
+        need = int(_lib.lib().vg_conv_wgrad_workspace(C.byref(d)))
+        assert need >= 0, "vg_conv_wgrad_workspace rejected the descriptor"
+        if need > 0:
+            ws = torch.empty(need // 4, dtype=F32, device=dw.device)      # lives until the stream has consumed it (caching allocator)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), need
     e0 = _prof_begin()
     _lib.call("vg_conv_wgrad", C.byref(d), ops.stream())
     _prof_end(e0, "wgrad", (m, cout, len(taps) * cin),
@@ -302,9 +319,11 @@ class ConvLinear:
 
     # ---------------------------------------------------------------- primitives
     def forward(self, x: torch.Tensor, wf: torch.Tensor, bias=None, act: int = 0, out: Optional[torch.Tensor] = None,
-                out_kind: Optional[int] = None) -> torch.Tensor:
+                out_kind: Optional[int] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``stats`` (bf16 mode only): see :func:`fprop`."""
         n, h, w, _ = x.shape
         hi = x.dtype == F32
+        assert stats is None or (not hi and not self.flat)
         oh, ow = self.out_hw(h, w)
         if out_kind is None:
             out_kind = 1 if hi else 0
@@ -328,14 +347,18 @@ class ConvLinear:
         if hi:
             _hi_launch(xs, vt, self.s, self.cin_p, wf, self.cout, (n, oh, ow), out, wk, bias, act)
         else:
-            fprop(xs, vt, self.s, self.cin_p, wf, self.cout, (n, oh, ow), out, out_kind=out_kind, bias=bias, act=act, wk=wk)
+            fprop(xs, vt, self.s, self.cin_p, wf, self.cout, (n, oh, ow), out, out_kind=out_kind, bias=bias, act=act, wk=wk,
+                  stats=stats)
         return out
 
     def backward_data(self, dy: torch.Tensor, wb: Dict, in_hw: Tuple[int, int], bias=None, act: int = 0,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``stats`` (bf16 mode, single-launch variants only): see :func:`fprop` -- used when this primitive is the
+        FORWARD of a ConvTranspose2d that feeds a BatchNorm2d."""
         n, oh, ow, _ = dy.shape
         h, w = in_hw
         hi = dy.dtype == F32
+        assert stats is None or (not hi and "parity" not in wb)
         kind = 1 if hi else 0
         if out is None:
             out = new_act(n, h, w, self.cin, dy.device, dy.dtype)
@@ -347,23 +370,23 @@ class ConvLinear:
             wf = wb["mn"]
             if self.shuffle:
                 fprop(g, [(0, 0, 0, 0)], 1, self.cout_p, wf, self.kh * self.kw * self.cin, (n, oh, ow), out, out_kind=kind,
-                      su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act, wk=[0], b_mn_major=True)
+                      su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act, wk=[0], b_mn_major=True, stats=stats)
             elif self.s == 1:
                 taps = [(0, self.pw - q, 0, self.ph - r) for r in range(self.kh) for q in range(self.kw)]
                 wk = [(r * self.kw + q) * self.cin_p for r in range(self.kh) for q in range(self.kw)]
                 fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h, w), out, out_kind=kind, bias=bias, act=act, wk=wk,
-                      b_mn_major=True)
+                      b_mn_major=True, stats=stats)
             else:
                 taps, wk, groups = self._parity_taps(self.cin_p)
                 fprop(g, taps, 1, self.cout_p, wf, self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2),
-                      cout_per_sub=self.cin, bias=bias, act=act, wk=wk, b_mn_major=True, groups=groups)
+                      cout_per_sub=self.cin, bias=bias, act=act, wk=wk, b_mn_major=True, groups=groups, stats=stats)
             return out
         if "parity_k" in wb:
             # K-major operand [cin][(r, q)][cout_p] holding every tap; the four output-parity classes are the four
             # groups of ONE launch, each reading its own taps through the column offsets
             taps, wk, groups = self._parity_taps(self.cout_p)
             fprop(g, taps, 1, self.cout_p, wb["parity_k"], self.cin, (n, h // 2, w // 2), out, out_kind=kind, su=(2, 2),
-                  cout_per_sub=self.cin, bias=bias, act=act, wk=wk, groups=groups)
+                  cout_per_sub=self.cin, bias=bias, act=act, wk=wk, groups=groups, stats=stats)
             return out
         if "shuffle" in wb:
             # pixel shuffle: GEMM column (r, q, ci) of input pixel (oh, ow) lands at output pixel (oh*kh + r, ow*kw + q).
@@ -374,7 +397,7 @@ class ConvLinear:
                            su=(self.kh, self.kw), cout_per_sub=self.cin)
             else:
                 fprop(g, vt, 1, self.cout_p, wb["shuffle"], self.kh * self.kw * self.cin, (n, oh, ow), out, out_kind=kind,
-                      su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act, wk=wk)
+                      su=(self.kh, self.kw), cout_per_sub=self.cin, bias=bias, act=act, wk=wk, stats=stats)
             return out
         if "s1" in wb:
             taps = [(0, self.pw - q, 0, self.ph - r) for r in range(self.kh) for q in range(self.kw)]
@@ -382,7 +405,8 @@ class ConvLinear:
             if hi:
                 _hi_launch(g, vt, 1, self.cout_p, wb["s1"], self.cin, (n, h, w), out, wk, bias, act)
             else:
-                fprop(g, vt, 1, self.cout_p, wb["s1"], self.cin, (n, h, w), out, out_kind=kind, bias=bias, act=act, wk=wk)
+                fprop(g, vt, 1, self.cout_p, wb["s1"], self.cin, (n, h, w), out, out_kind=kind, bias=bias, act=act, wk=wk,
+                      stats=stats)
             return out
         if hi:
             out.zero_()

@@ -72,9 +72,43 @@ struct FpropParams {
                                 // bound by the MMA -> epilogue -> MMA round trip per accumulator, not by the tensor pipe)
   int w_bytes;                  // halo mode with resident weights: all 9 x (cin/64) weight tiles live in shared memory for
                                 // the whole kernel (loaded once per CTA), the stages hold only the activation halos
+  float* stats;                 // optional fp32 [2][cout_per_sub]: per-channel sum and sum of squares of the values as
+                                // stored (after bias / activation, rounded to the output type), over all valid pixels --
+                                // the BatchNorm batch statistics of the layer that follows, taken from the epilogue
+                                // instead of re-reading the tensor (vae-gan-v2.py:172-177: Conv -> BN -> ReLU)
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
   int wk[kMaxTaps];             // first weight column of each tap
 };
+
+// Flush one warp's per-lane column statistics (8 floats, see the epilogue) of N tile `n_t` into p.stats.
+VG_DEVICE void stats_flush(const FpropParams& p, float (&st)[8], int n_t, int lane, int c_first, int c_step, int esz) {
+  const int c2 = p.cout_per_sub;
+  if (esz == 2) {
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+      const int col = n_t * p.bn + c_first + slot * c_step + 2 * lane;
+      if (c_first + slot * c_step < p.bn && col < p.n_gemm) {      // n_gemm % 8 == 0 on this path: col + 1 is valid too
+        const int ch = col % c2;
+        atomicAdd(p.stats + ch, st[slot * 4 + 0]);
+        atomicAdd(p.stats + ch + 1, st[slot * 4 + 1]);
+        atomicAdd(p.stats + c2 + ch, st[slot * 4 + 2]);
+        atomicAdd(p.stats + c2 + ch + 1, st[slot * 4 + 3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int slot = 0; slot < 4; ++slot) {
+      const int col = n_t * p.bn + c_first + slot * c_step + lane;
+      if (c_first + slot * c_step < p.bn && col < p.n_gemm) {
+        const int ch = col % c2;
+        atomicAdd(p.stats + ch, st[slot * 2 + 0]);
+        atomicAdd(p.stats + c2 + ch, st[slot * 2 + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st[i] = 0.f;
+}
 
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -287,6 +321,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // the same tile and split its column chunks.
     const bool split = p.nacc == 4;
     const int c_first = split ? 0 : colhalf * chunk_cols, c_step = split ? chunk_cols : 2 * chunk_cols;
+    // fused BatchNorm statistics: per-lane partial sums of the columns this lane owns in each chunk slot of the tile
+    // (bf16 output: 2 slots x 2 columns x {sum, sum of squares}; fp32 output: 4 slots x 1 column), kept in registers
+    // across the tiles of this CTA as long as they belong to the same N tile, then flushed with one atomic each
+    float st[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st[i] = 0.f;
+    int st_nt = -1;
     int seq = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++seq) {
       if (split && (seq & 1) != colhalf) continue;
@@ -304,6 +345,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const bool row_ok = (ow < p.m_w) && (oh < p.m_h) && (n < p.m_n);
       const long long my_base =
           row_ok ? ((static_cast<long long>(n) * p.out_h + oh * p.su_h) * p.out_w + ow * p.su_w) * p.out_ld : -1;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, row_ok);
+      if (p.stats != nullptr && n_t != st_nt) {
+        if (st_nt >= 0) stats_flush(p, st, st_nt, lane, c_first, c_step, esz);
+        st_nt = n_t;
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -384,6 +430,40 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               *reinterpret_cast<uint4*>(gout + base * esz) = v;
             }
           }
+          if (p.stats != nullptr) {
+            // column sums over the valid rows, read back from the staged tile (= the values as stored): lane owns the
+            // 4-byte word `lane` of every 128-byte row -- two bf16 columns or one fp32 column; conflict-free
+            const int wseg = lane >> 2, woff = (lane & 3) * 4;
+            float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if ((vmask >> rr) & 1u) {
+                const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + rr * 128 + ((wseg ^ (rr & 7)) << 4) + woff);
+                if (esz == 2) {
+                  const float2 f = unpack_bf16x2(wv);
+                  a0 += f.x; a1 += f.y; q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                } else {
+                  const float f = __uint_as_float(wv);
+                  a0 += f; q0 = fmaf(f, f, q0);
+                }
+              }
+            }
+            const int slot = (c - c_first) / c_step;
+            if (esz == 2) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const bool on = slot == j;
+                st[j * 4 + 0] += on ? a0 : 0.f; st[j * 4 + 1] += on ? a1 : 0.f;
+                st[j * 4 + 2] += on ? q0 : 0.f; st[j * 4 + 3] += on ? q1 : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool on = slot == j;
+                st[j * 2 + 0] += on ? a0 : 0.f; st[j * 2 + 1] += on ? q0 : 0.f;
+              }
+            }
+          }
           __syncwarp();
         }
       } else if (split || colhalf == 0) {
@@ -417,6 +497,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.stats != nullptr && st_nt >= 0) stats_flush(p, st, st_nt, lane, c_first, c_step, esz);
   }
 
   tc_fence_before();
@@ -542,6 +623,14 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
     p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((static_cast<long long>(d->out_ld) * esz) % 16 == 0) &&
                ((d->out_coff * esz) % 16 == 0) && ((d->cout_per_sub * esz) % 16 == 0) && (d->n_gemm % 8 == 0) &&
                (d->su_h * d->su_w == 1 || d->cout_per_sub % 32 == 0);
+  }
+  p.stats = d->stats;
+  if (d->stats != nullptr) {
+    VG_CHECK(p.vec_ok && d->out_kind != 2 && ksplit == 1, -1,
+             "vg_conv_fprop: fused statistics need the vectorised store path (aligned destination, n_gemm %% 8 == 0), "
+             "a plain (non-atomic) output and no split-K");
+    VG_CHECK(d->cout_per_sub % 2 == 0, -1, "vg_conv_fprop: fused statistics need an even channel count");
+    VG_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * d->cout_per_sub, stream));
   }
   for (int i = 0; i < d->num_taps; ++i) {
     p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);

@@ -11,6 +11,8 @@
 //
 // Serves Conv2d wgrad and (with the operand roles swapped by the caller) ConvTranspose2d wgrad of
 // the reference layers (vae-gan.py:52-60,76-81,153-157; vae-gan-v2.py:123-127,168-176,199-241).
+#include <algorithm>
+
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
 
@@ -35,6 +37,9 @@ struct WgradParams {
   float* dw;                      // [cout][num_taps*cin] fp32
   int dw_ld;
   int atomic;
+  long long split_stride;         // deterministic mode: split s stores its partial tile at dw + s * split_stride (a
+                                  // workspace of ksplit x cout x dw_ld floats) and wgrad_reduce_kernel adds the splits in
+                                  // a fixed order; 0 otherwise
   int4 taps[VG_MAX_TAPS];         // {c_base, dw, sh, dh}
   int ncombos;                    // split-precision operand pairs per pixel tile (1 = plain bf16)
   int combo_g[8], combo_x[8];     // channel offsets of the pair's planes
@@ -176,6 +181,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile % p.n_tiles;
       const int m_t = (tile / p.n_tiles) % p.m_tiles;
+      const long long split_off = static_cast<long long>(tile / (p.n_tiles * p.m_tiles)) * p.split_stride;
       const int co_warp = m_t * kWgBM + quad * 32;           // first output channel handled by this warp
       const int ncols = min(p.bn, p.blocks_total * 64 - n_t * p.bn);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -195,7 +201,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
           const int rr = it * 4 + rsub;
           if (co_warp + rr < p.cout) {
             const float4 v = *reinterpret_cast<const float4*>(stg + rr * kWgEpiPitch + seg * 16);
-            float* o = p.dw + static_cast<long long>(co_warp + rr) * p.dw_ld + n_t * p.bn + c + seg * 4;
+            float* o = p.dw + split_off + static_cast<long long>(co_warp + rr) * p.dw_ld + n_t * p.bn + c + seg * 4;
             if (p.atomic) {
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                            : "memory");
@@ -219,6 +225,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// deterministic split-K: dw[i] = ws[0][i] + ws[1][i] + ... in this order, whatever order the splits finished in
+__global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ dw, long long n4, int ksplit) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 a = ws[i];
+    for (int s = 1; s < ksplit; ++s) {
+      const float4 b = ws[static_cast<long long>(s) * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dw[i] = a;
+  }
+}
+
+// split factor of a launch: the largest split with tiles * ksplit <= #SMs wastes the least of the last wave (a second,
+// partial wave costs a full tile time); keep >= ~8 K steps per split so the pipeline fills
+static int wgrad_auto_split(int tiles, int pix_tiles, int sms) {
+  const int max_split = max(1, min(64, pix_tiles / 8));
+  double best = -1.0;
+  int ksplit = 1;
+  for (int s = 1; s <= max_split; ++s) {
+    const long long work = static_cast<long long>(tiles) * s;
+    const double eff = static_cast<double>(work) / (static_cast<double>((work + sms - 1) / sms) * sms);
+    if (eff > best + 1e-9) { best = eff; ksplit = s; }
+  }
+  return ksplit;
 }
 
 }  // namespace vg
@@ -260,31 +293,31 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   p.nb = nb; p.bn = nb * 64;
   p.n_tiles = cdiv(p.blocks_total, nb);
   int ksplit = d->ksplit;
-  if (ksplit <= 0) {
-    // fill one wave: the largest split with tiles*ksplit <= #SMs (a second, partial wave costs a full tile time)
-    const int tiles = p.m_tiles * p.n_tiles;
-    // choose the split that wastes the least of the last wave; keep >= ~8 K steps per split so the pipeline fills
-    const int max_split = max(1, min(64, pix_tiles / 8));
-    double best = -1.0;
-    ksplit = 1;
-    for (int s = 1; s <= max_split; ++s) {
-      const long long work = static_cast<long long>(tiles) * s;
-      const double eff = static_cast<double>(work) / (static_cast<double>((work + sms - 1) / sms) * sms);
-      if (eff > best + 1e-9) { best = eff; ksplit = s; }
-    }
-  }
+  if (ksplit <= 0) ksplit = wgrad_auto_split(p.m_tiles * p.n_tiles, pix_tiles, sms);
   VG_CHECK(ksplit <= pix_tiles, -1, "vg_conv_wgrad: ksplit %d > pixel tiles %d", ksplit, pix_tiles);
   p.ksplit = ksplit;
   p.atomic = ksplit > 1 ? 1 : 0;
+  const size_t dw_floats = static_cast<size_t>(d->cout) * d->dw_ld;
+  const bool two_stage = ksplit > 1 && d->workspace != nullptr;
+  if (two_stage) {
+    VG_CHECK(d->workspace_bytes >= static_cast<long long>(ksplit * dw_floats * sizeof(float)), -1,
+             "vg_conv_wgrad: workspace of %lld bytes is too small for %d splits of %zu floats (vg_conv_wgrad_workspace)",
+             d->workspace_bytes, ksplit, dw_floats);
+    VG_CHECK(dw_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->dw) & 15) == 0, -1, "vg_conv_wgrad: workspace / dw must be 16-byte aligned");
+    p.atomic = 0;
+    p.split_stride = static_cast<long long>(dw_floats);
+  }
   const int stage_bytes = (2 + nb) * kWgBoxBytes;
   p.stages = min(8, (227 * 1024 - 1024 - 256 - kWgEpiBytes) / stage_bytes);
-  p.dw = d->dw; p.dw_ld = d->dw_ld;
+  p.dw = two_stage ? static_cast<float*>(d->workspace) : d->dw;
+  p.dw_ld = d->dw_ld;
   for (int i = 0; i < d->num_taps; ++i) {
     p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
     VG_CHECK(d->taps[i][2] >= 0 && d->taps[i][2] < d->x_stride, -1, "vg_conv_wgrad: tap %d row parity out of range", i);
   }
   if (p.atomic)
-    VG_CUDA(cudaMemsetAsync(d->dw, 0, static_cast<size_t>(d->cout) * d->dw_ld * sizeof(float), stream));
+    VG_CUDA(cudaMemsetAsync(d->dw, 0, dw_floats * sizeof(float), stream));
 
   CUtensorMap tmap_g, tmap_x;
   const uint32_t box[5] = {64, static_cast<uint32_t>(p.tw), 1, static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.tn)};
@@ -313,5 +346,31 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   conv_wgrad_kernel<<<min(total_tiles, sms), kWgThreads, smem, stream>>>(tmap_g, tmap_x, p);
   VG_LAUNCH_OK();
+  if (two_stage) {
+    const long long n4 = static_cast<long long>(dw_floats / 4);
+    const int grid = static_cast<int>(std::min<long long>((n4 + 255) / 256, static_cast<long long>(num_sms()) * 8));
+    wgrad_reduce_kernel<<<std::max(grid, 1), 256, 0, stream>>>(static_cast<const float4*>(d->workspace),
+                                                             reinterpret_cast<float4*>(d->dw), n4, ksplit);
+    VG_LAUNCH_OK();
+  }
   return 0;
+}
+
+/* Bytes of scratch a deterministic (two-stage) launch of this descriptor needs: ksplit x cout x dw_ld floats, 0 when the
+ * launch does not split.  Same split rule as vg_conv_wgrad. */
+extern "C" long long vg_conv_wgrad_workspace(const VgConvWgrad* d) {
+  if (d == nullptr || d->cin <= 0 || d->cin % 64 != 0 || d->cout < 1) return -1;
+  int w = 1;
+  while (w < d->m_w && w < kWgPix) w <<= 1;
+  int h = 1;
+  while (h < d->m_h && w * h < kWgPix) h <<= 1;
+  const int tn = kWgPix / (w * h);
+  const int ncombos = d->num_combos > 1 ? d->num_combos : 1;
+  const int pix_tiles = cdiv(d->m_n, tn) * cdiv(d->m_h, h) * cdiv(d->m_w, w) * ncombos;
+  const int blocks_total = d->num_taps * (d->cin / 64);
+  int nb = min(4, blocks_total);
+  if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
+  const int tiles = cdiv(d->cout, kWgBM) * cdiv(blocks_total, nb);
+  const int ksplit = d->ksplit > 0 ? d->ksplit : wgrad_auto_split(tiles, pix_tiles, conv_sms());
+  return ksplit > 1 ? static_cast<long long>(ksplit) * d->cout * d->dw_ld * static_cast<long long>(sizeof(float)) : 0;
 }

@@ -80,12 +80,13 @@ class Conv2dFn(Function):
     """y = act(conv2d(x, w) + b).  Replaces nn.Conv2d forward/backward (cuDNN) of the reference layers."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_kind: int, sn):
+    def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_kind: int, sn, stats=None):
+        """``stats``: optional fp32 [1,2,cout] filled by the epilogue with the batch statistics of y (bf16 mode)."""
         scale = sn.sigma if sn is not None else None
         hi = x.dtype == F32
         wf = (cache.get("fwd_hi" if hi else "fwd", weight, lambda: op.prep_fwd(weight.detach(), scale, hi)) if sn is None
               else op.prep_fwd(weight.detach(), scale, hi))
-        y = op.forward(x, wf, bias.detach() if bias is not None else None, act, out, out_kind)
+        y = op.forward(x, wf, bias.detach() if bias is not None else None, act, out, out_kind, stats=stats)
         ctx.op, ctx.cache, ctx.act, ctx.sn, ctx.has_bias = op, cache, act, sn, bias is not None
         ctx.wf = wf if (sn is not None and not hi) else None     # W / sigma of THIS call, reused by its data gradient
         ctx.in_hw = (x.shape[1], x.shape[2])
@@ -121,7 +122,7 @@ class Conv2dFn(Function):
                 dw = sn.backward(dw, weight.detach())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 class ConvTranspose2dFn(Function):
@@ -129,13 +130,13 @@ class ConvTranspose2dFn(Function):
     (cin(op) = C_out of the transpose, cout(op) = C_in of the transpose; the IOHW weight is op's OIHW)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_hw):
+    def forward(ctx, x, weight, bias, op: ConvLinear, cache: WeightCache, act: int, out, out_hw, stats=None):
         hi = x.dtype == F32
         if not hi and op.prefer_mn(x.shape[0] * x.shape[1] * x.shape[2]):
             wb = {"mn": cache.get("fwd", weight, lambda: op.prep_fwd(weight.detach(), None, False))}
         else:
             wb = cache.get("bwd_hi" if hi else "bwd", weight, lambda: op.prep_bwd(weight.detach(), None, hi))
-        y = op.backward_data(x, wb, out_hw, bias.detach() if bias is not None else None, act, out)
+        y = op.backward_data(x, wb, out_hw, bias.detach() if bias is not None else None, act, out, stats=stats)
         ctx.op, ctx.cache, ctx.act, ctx.has_bias = op, cache, act, bias is not None
         ctx.save_for_backward(x, weight, y if act else None)
         return y
@@ -158,7 +159,7 @@ class ConvTranspose2dFn(Function):
             dw = _write_param_grad(op.backward_weight(x, dy), weight)     # operands swapped: [cout(op)=C_in][cin(op)=C_out]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 class HeadsFn(Function):
@@ -231,7 +232,7 @@ class ImageConvFn(Function):
     im2col into a [pixels][64] matrix, then a plain tensor-core GEMM with bias/activation fused."""
 
     @staticmethod
-    def forward(ctx, weight, bias, geom, cache: WeightCache, act: int, sn, *images):
+    def forward(ctx, weight, bias, geom, cache: WeightCache, act: int, sn, stats, *images):
         kh, kw, stride, pad = geom
         n, _, h, w = images[0].shape
         cin = sum(t.shape[1] for t in images)
@@ -261,7 +262,7 @@ class ImageConvFn(Function):
         if hi:
             _hi_launch(ops.split3(col), vt, 1, kpad, wf, cout, (n, oh, ow), y, wk, b_, act)
         else:
-            fprop(col, vt, 1, kpad, wf, cout, (n, oh, ow), y, bias=b_, act=act)
+            fprop(col, vt, 1, kpad, wf, cout, (n, oh, ow), y, bias=b_, act=act, stats=stats)
         ctx.geom, ctx.act, ctx.sn, ctx.cin, ctx.kpad, ctx.has_bias = geom, act, sn, cin, kpad, bias is not None
         ctx.img_shapes = [tuple(t.shape) for t in images]
         ctx.save_for_backward(col, weight, y if act else None)
@@ -296,7 +297,7 @@ class ImageConvFn(Function):
         if ctx.has_bias and ctx.needs_input_grad[1]:
             db = _bias_grad(dy)
         dimgs = [None] * len(ctx.img_shapes)
-        if any(ctx.needs_input_grad[6:]):
+        if any(ctx.needs_input_grad[7:]):
             scale = sn.sigma if sn is not None else None
             tmp = torch.zeros((kpad, cout), dtype=F32, device=dy.device)                 # rows (r, q, ci), zero padded
             ops.strided_copy(weight.detach().permute(2, 3, 1, 0), tmp[:k].view(kh, kw, cin, cout), scale,
@@ -313,10 +314,10 @@ class ImageConvFn(Function):
             ops.col2im(dcol, n_, h, w, cin, kh, kw, stride, pad, dsrc)
             c0 = 0
             for i, shp in enumerate(ctx.img_shapes):
-                if ctx.needs_input_grad[6 + i]:
+                if ctx.needs_input_grad[7 + i]:
                     dimgs[i] = dsrc[:, c0:c0 + shp[1]]
                 c0 += shp[1]
-        return (dw, db, None, None, None, None, *dimgs)
+        return (dw, db, None, None, None, None, None, *dimgs)
 
 
 class SmallOutConvFn(Function):
@@ -363,9 +364,11 @@ class NormActFn(Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, per_sample: bool, act: int, pool: bool, out, eps: float, bn_state, pool_out=None,
-                virt_h: int = 0):
+                virt_h: int = 0, sums=None):
         """``virt_h`` > 0: the h (= 3) rows of x stand for virt_h rows whose interior rows are all equal (row-class
-        FiLM maps); the statistics weight them accordingly and the backward expects per-class gradient sums."""
+        FiLM maps); the statistics weight them accordingly and the backward expects per-class gradient sums.
+        ``sums``: fp32 [1,2,c] batch statistics of x already produced by the epilogue of the convolution that wrote x
+        (``stats`` of Conv2dFn / ConvTranspose2dFn): the statistics pass over x is skipped."""
         n, h, w, c = x.shape
         ctx.virt_h = virt_h
         g, b = (gamma.detach() if gamma is not None else None), (beta.detach() if beta is not None else None)
@@ -373,7 +376,8 @@ class NormActFn(Function):
             mr = torch.stack([bn_state["running_mean"], torch.rsqrt(bn_state["running_var"] + eps)]).unsqueeze(0).contiguous()
             ctx.eval_mode = True
         else:
-            sums = ops.norm_stats_rows(x, virt_h) if virt_h else ops.norm_stats(x, per_sample)
+            if sums is None or virt_h or per_sample:
+                sums = ops.norm_stats_rows(x, virt_h) if virt_h else ops.norm_stats(x, per_sample)
             rows = h * w if per_sample else n * (virt_h or h) * w
             rm = rv = nbt = None
             if bn_state is not None:
@@ -403,7 +407,7 @@ class NormActFn(Function):
         if ctx.virt_h and not dy.is_contiguous():
             dy = ops.dense_nhwc(dy)
         ops.norm_backward(x, dy, dpool, mr, ctx.per_sample, gamma, beta, ctx.act, dx, dgamma, dbeta, virt_h=ctx.virt_h)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

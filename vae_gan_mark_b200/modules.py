@@ -64,38 +64,67 @@ def _bn_state(bn: nn.BatchNorm2d):
             "num_batches_tracked": bn.num_batches_tracked}
 
 
-def run_conv(conv: nn.Conv2d, x, act=0, out=None, in_hw=None, sn=None, weight=None):
-    """nn.Conv2d on the tensor pipe; ``x`` NHWC bf16."""
+def run_conv(conv: nn.Conv2d, x, act=0, out=None, in_hw=None, sn=None, weight=None, stats=None):
+    """nn.Conv2d on the tensor pipe; ``x`` NHWC bf16.  ``stats``: see ``bn_stats_buffer``."""
     w = conv.weight if weight is None else weight
     st = _state(conv, lambda: (ConvLinear(conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.kernel_size[1],
                                           conv.stride[0], tuple(conv.padding), in_hw), L.WeightCache()))
-    return L.Conv2dFn.apply(x, w, conv.bias, st[0], st[1], act, out, None, sn)
+    return L.Conv2dFn.apply(x, w, conv.bias, st[0], st[1], act, out, None, sn, stats)
 
 
-def run_convT(ct: nn.ConvTranspose2d, x, out_hw, act=0, out=None):
+def run_convT(ct: nn.ConvTranspose2d, x, out_hw, act=0, out=None, stats=None):
     """nn.ConvTranspose2d as the data-gradient of its adjoint conv; ``x`` NHWC bf16."""
     st = _state(ct, lambda: (ConvLinear(ct.out_channels, ct.in_channels, ct.kernel_size[0], ct.kernel_size[1],
                                         ct.stride[0], tuple(ct.padding), tuple(out_hw)), L.WeightCache()))
-    return L.ConvTranspose2dFn.apply(x, ct.weight, ct.bias, st[0], st[1], act, out, tuple(out_hw))
+    return L.ConvTranspose2dFn.apply(x, ct.weight, ct.bias, st[0], st[1], act, out, tuple(out_hw), stats)
 
 
-def run_bn_relu(bn: nn.BatchNorm2d, x, pool=False, out=None, pool_out=None, virt_h=0):
-    return L.NormActFn.apply(x, bn.weight, bn.bias, False, RELU, pool, out, bn.eps, _bn_state(bn), pool_out, virt_h)
+# BatchNorm batch statistics from the epilogue of the producing convolution (north_star: "BatchNorm ... fused into the
+# epilogues"): the tensor-core kernel adds each stored tile's per-channel sum / sum of squares into a [1,2,C] buffer, so
+# the separate statistics pass over the conv output (one full read of the tensor) disappears.  bf16 mode only: the
+# high-accuracy mode accumulates its split-K partial tiles with atomics and keeps the separate pass.
+FUSE_BN_STATS = True
 
 
-def run_image_conv(conv: nn.Conv2d, images: Sequence[torch.Tensor], act=0, sn=None, weight=None):
+def bn_stats_buffer(bn: nn.BatchNorm2d, device):
+    """The [1,2,C] fp32 buffer handed to the conv (``stats=``) and then to ``run_bn_relu`` (``sums=``), or None when the
+    statistics have to come from the separate pass (eval mode, high-accuracy mode, odd channel counts)."""
+    c = bn.num_features
+    if not (FUSE_BN_STATS and bn.training and ops.act_dtype() == BF16 and c % 32 == 0):
+        return None
+    return torch.empty((1, 2, c), dtype=F32, device=device)      # zeroed by vg_conv_fprop
+
+
+def run_bn_relu(bn: nn.BatchNorm2d, x, pool=False, out=None, pool_out=None, virt_h=0, sums=None):
+    return L.NormActFn.apply(x, bn.weight, bn.bias, False, RELU, pool, out, bn.eps, _bn_state(bn), pool_out, virt_h, sums)
+
+
+def run_image_conv(conv: nn.Conv2d, images: Sequence[torch.Tensor], act=0, sn=None, weight=None, stats=None):
     w = conv.weight if weight is None else weight
     st = _state(conv, lambda: L.WeightCache())
     geom = (conv.kernel_size[0], conv.kernel_size[1], conv.stride[0], conv.padding[0])
-    return L.ImageConvFn.apply(w, conv.bias, geom, st, act, sn, *images)
+    return L.ImageConvFn.apply(w, conv.bias, geom, st, act, sn, stats, *images)
+
+
+def run_conv_bn_relu(conv: nn.Conv2d, bn: nn.BatchNorm2d, x, images=None, pool=False, out=None, pool_out=None):
+    """Conv2d -> BatchNorm2d -> ReLU (+ fused MaxPool2d(2)); batch statistics from the conv epilogue."""
+    dev = images[0].device if images is not None else x.device
+    sums = bn_stats_buffer(bn, dev)
+    raw = run_image_conv(conv, images, stats=sums) if images is not None else run_conv(conv, x, stats=sums)
+    return run_bn_relu(bn, raw, pool=pool, out=out, pool_out=pool_out, sums=sums)
+
+
+def run_convT_bn_relu(ct: nn.ConvTranspose2d, bn: nn.BatchNorm2d, x, out_hw, out=None):
+    """ConvTranspose2d -> BatchNorm2d -> ReLU; batch statistics from the epilogue of the transposed conv."""
+    sums = bn_stats_buffer(bn, x.device)
+    raw = run_convT(ct, x, out_hw, stats=sums)
+    return run_bn_relu(bn, raw, out=out, sums=sums)
 
 
 def run_double_conv(seq: nn.Sequential, x, images=None, pool=False, out=None, pool_out=None):
     """[Conv3x3 -> BN -> ReLU] x2 (+ fused MaxPool2d(2)); the first conv may take raw NCHW images."""
-    raw = run_image_conv(seq[0], images) if images is not None else run_conv(seq[0], x)
-    y, _ = run_bn_relu(seq[1], raw)
-    raw = run_conv(seq[3], y)
-    return run_bn_relu(seq[4], raw, pool=pool, out=out, pool_out=pool_out)
+    y, _ = run_conv_bn_relu(seq[0], seq[1], x, images=images)
+    return run_conv_bn_relu(seq[3], seq[4], y, pool=pool, out=out, pool_out=pool_out)
 
 
 class _SNCall:
@@ -399,11 +428,9 @@ class VAEEncoder(nn.Module):
         self.logvar_head = nn.Conv2d(1024, z_ch, kernel_size=(h // 16, w // 16))
 
     def features(self, images: Sequence[torch.Tensor]):
-        x = run_image_conv(self.feat[0], images)
-        x, _ = run_bn_relu(self.feat[1], x)
+        x, _ = run_conv_bn_relu(self.feat[0], self.feat[1], None, images=images)
         for i in (3, 6, 9):
-            x = run_conv(self.feat[i], x)
-            x, _ = run_bn_relu(self.feat[i + 1], x)
+            x, _ = run_conv_bn_relu(self.feat[i], self.feat[i + 1], x)
         return x
 
     def encode(self, images):
@@ -434,12 +461,10 @@ class VAEDecoder(nn.Module):
         """zc: NHWC bf16 [B,1,1,z+text]."""
         d = self.decode
         hw = self.start_hw
-        x = run_convT(d[0], zc, hw)
-        x, _ = run_bn_relu(d[1], x)
+        x, _ = run_convT_bn_relu(d[0], d[1], zc, hw)
         for i in (3, 6, 9, 12):
             hw = (hw[0] * 2, hw[1] * 2)
-            x = run_convT(d[i], x, hw)
-            x, _ = run_bn_relu(d[i + 1], x)
+            x, _ = run_convT_bn_relu(d[i], d[i + 1], x, hw)
         pre = L.SmallOutConvFn.apply(x, d[15].weight, d[15].bias, 1)
         return L.SigmoidOutFn.apply(pre)
 
@@ -567,8 +592,7 @@ class SpatialFiLMLayer(nn.Module):
         pp = self.param_predictor
         if text_base_nhwc.shape[1] != 1:
             t = L.Upsample2DFn.apply(text_base_nhwc, h, w)
-            raw = run_conv(pp[0], t)
-            y, _ = run_bn_relu(pp[1], raw)
+            y, _ = run_conv_bn_relu(pp[0], pp[1], t)
             gb = run_conv(pp[3], y)
             return L.FiLMFn.apply(gb, x_main)
         if FILM_ROW_DEDUP and h >= 3:
@@ -582,8 +606,7 @@ class SpatialFiLMLayer(nn.Module):
             gb3 = run_conv(pp[3], y3)
             return L.FiLMRowsFn.apply(gb3, x_main)
         t = L.UpsampleWFn.apply(text_base_nhwc, h, w)
-        raw = run_conv(pp[0], t)
-        y, _ = run_bn_relu(pp[1], raw)
+        y, _ = run_conv_bn_relu(pp[0], pp[1], t)
         gb = run_conv(pp[3], y)
         return L.FiLMFn.apply(gb, x_main)
 
@@ -622,8 +645,7 @@ class VAEDecoderWithSpatialFiLM(nn.Module):
         if bufs is None:
             bufs = self.concat_buffers(b, z.device)
         zc = L.ZTextCatFn.apply(z, text_nhwc)
-        x = run_convT(self.bottleneck_proc[0], zc, (self.initial_h, self.initial_w))
-        x, _ = run_bn_relu(self.bottleneck_proc[1], x)
+        x, _ = run_convT_bn_relu(self.bottleneck_proc[0], self.bottleneck_proc[1], zc, (self.initial_h, self.initial_w))
         h, w = self.initial_h, self.initial_w
         for i in (1, 2, 3, 4):
             h, w = h * 2, w * 2
@@ -720,8 +742,7 @@ class VAEDecoderWithSkips(nn.Module):
             bufs = self.concat_buffers(b, z.device)
         zc = L.ZTextCatFn.apply(z, text_nhwc_1x1)
         h, w, c = self.initial_h, self.initial_w, 1024
-        raw = run_convT(self.bottleneck_upsample[0], zc, (h, w))
-        x, _ = run_bn_relu(self.bottleneck_upsample[1], raw, out=bufs[0][..., :c])
+        x, _ = run_convT_bn_relu(self.bottleneck_upsample[0], self.bottleneck_upsample[1], zc, (h, w), out=bufs[0][..., :c])
         for i in (1, 2, 3, 4):
             buf, skip = bufs[i - 1], pooled[4 - i]
             if skip.data_ptr() != buf.data_ptr() + buf.element_size() * c:
@@ -729,12 +750,9 @@ class VAEDecoderWithSkips(nn.Module):
             xc = L.CatSlicesFn.apply(x, skip, buf)
             blk = getattr(self, f"d_upconv{i}")
             h, w, c = h * 2, w * 2, c // 2
-            raw = run_convT(blk[0], xc, (h, w))
-            y, _ = run_bn_relu(blk[1], raw)
-            raw = run_conv(blk[3], y)
-            y, _ = run_bn_relu(blk[4], raw)
-            raw = run_conv(blk[6], y)
-            x, _ = run_bn_relu(blk[7], raw, out=bufs[i][..., :c] if i < 4 else None)
+            y, _ = run_convT_bn_relu(blk[0], blk[1], xc, (h, w))
+            y, _ = run_conv_bn_relu(blk[3], blk[4], y)
+            x, _ = run_conv_bn_relu(blk[6], blk[7], y, out=bufs[i][..., :c] if i < 4 else None)
         pre = L.SmallOutConvFn.apply(x, self.final_image_conv.weight, self.final_image_conv.bias, 0)
         return L.SigmoidOutFn.apply(pre)
 
@@ -860,8 +878,7 @@ class VAEDecoderWithSpatialFiLM3(nn.Module):
         b = z.shape[0]
         t0 = L.Upsample2DFn.apply(text_nhwc, 1, self.initial_w)                 # F.interpolate(..., size=(1, W/8))
         zc = L.ZTextCatFn.apply(z, t0)
-        x = run_convT(self.bottleneck_proc[0], zc, (self.initial_h, self.initial_w))
-        x, _ = run_bn_relu(self.bottleneck_proc[1], x)
+        x, _ = run_convT_bn_relu(self.bottleneck_proc[0], self.bottleneck_proc[1], zc, (self.initial_h, self.initial_w))
         h, w = self.initial_h, self.initial_w
         for i in (1, 2, 3):
             h, w = h * 2, w * 2
