@@ -261,7 +261,8 @@ def run_ours(args, wl):
         with torch.no_grad():
             frozen = enc([TEXTS[i % len(TEXTS)] for i in range(wl["batch"])]).detach().clone()
         enc.forward = lambda texts: frozen
-    reducer = DataParallelReducer(world) if world > 1 else None
+    reducer = DataParallelReducer(world, bucket_bytes=args.bucket_mb << 20,
+                                  grad_dtype=torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32) if world > 1 else None
     if reducer is not None:
         reducer.broadcast_parameters(list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()))
     wts = LossWeights.for_family(wl["family"], perceptual=bool(args.perceptual))
@@ -280,6 +281,8 @@ def run_ours(args, wl):
     trainer = VAEGANTrainer(G, D, wts, grad_hook=reducer.hook if reducer else None, perceptual=perceptual)
     if reducer is not None and not args.no_overlap:
         reducer.install_hooks(trainer.opt_G.params, trainer.opt_D.params)   # all-reduces issued during the backward
+    if reducer is not None and args.nccl_sms > 0:
+        trainer.backward_sm_limit = torch.cuda.get_device_properties(dev).multi_processor_count - args.nccl_sms
 
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     pool = 2
@@ -478,7 +481,9 @@ def run_ours(args, wl):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "image": [h, w],
                        "cpu_sample_batch": (4 if h >= 128 else B) if cpu is not None else None,
-                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "precision": "bf16 storage + tcgen05 bf16 MMA, fp32 accumulate, fp32 master weights",
+                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
+                       "dp": ({"grad_dtype": args.grad_dtype, "bucket_mb": args.bucket_mb, "overlap": not args.no_overlap,
+                               "sms_left_to_nccl_during_backward": args.nccl_sms} if world > 1 else None), "precision": "bf16 storage + tcgen05 bf16 MMA, fp32 accumulate, fp32 master weights",
                        "l2": "per-step working set (activations >> 1 GB) far exceeds the 126 MB L2; 2 input batches cycled",
                        "perceptual_term": ("included: VGG16 features[:16] with seeded random weights (pretrained weights "
                                            "unavailable offline), weight %.2f" % wts.perc) if args.perceptual
@@ -541,6 +546,11 @@ def main():
     ap.add_argument("--diag-freeze-text", action="store_true",
                     help="diagnostic: cache the text encoder output (result is tagged, not a bench value)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="DP: dtype of the gradient buckets on the wire (bf16 halves the all-reduce bytes)")
+    ap.add_argument("--bucket-mb", type=int, default=32, help="DP: gradient bucket size")
+    ap.add_argument("--nccl-sms", type=int, default=0,
+                    help="DP: SMs kept out of the persistent conv grids during loss_G.backward() so NCCL can run beside them")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra objects of the line (stock_gpu: stock PyTorch/cuDNN on this GPU; fp32_mode)")
     args = ap.parse_args()

@@ -263,6 +263,26 @@ int vg_gru_seq_bwd(const float* dout, const float* out, const float* gates, cons
  * batch_group = 8 or 16 rows per cluster; the launchers use the smallest group that runs in a single wave. */
 int vg_gru_max_active_clusters(int backward, int batch_group);
 
+/* Front end of CharacterTokenEncoder on the device (vae-gan-v2.py:65-114; the reference tokenises with a Python loop and a
+ * dict lookup per character on the host, :89-100, and goes through ATen's embedding / adaptive_avg_pool1d kernels):
+ *   vg_tokenize       idx[i] = lut[codepoints[i]] (0 = padding for code points >= lut_size); codepoints are the UTF-32
+ *                     code units of the strings, zero padded to max_len (uint32 [n]); idx int64 [n]
+ *   vg_embedding_fwd  out[t][:] = weight[idx[t]][:]            (fp32 [vocab][dim] -> fp32 [n][dim])
+ *   vg_embedding_bwd  dw[r][:] = sum_{t: idx[t] == r} g[t][:], row padding_idx = 0; fixed summation order (deterministic),
+ *                     every row of dw written
+ *   vg_seqpool_fwd    adaptive average pooling of a sequence [b][l][c] (row stride in_ld) along l into [b][w][c] (row
+ *                     stride out_ld) -- i.e. the NHWC text map [b][1][w][c]; bins as torch.nn.AdaptiveAvgPool1d
+ *   vg_seqpool_bwd    its adjoint: dy [b][w][c] -> dseq [b][l][c] (fully written)
+ * dtype codes: 0 = bf16, 1 = fp32. */
+int vg_tokenize(const uint32_t* codepoints, long long n, const int* lut, int lut_size, long long* idx, void* stream);
+int vg_embedding_fwd(const long long* idx, long long n, const float* weight, int vocab, int dim, float* out, void* stream);
+int vg_embedding_bwd(const long long* idx, long long n, const float* g, int vocab, int dim, int padding_idx, float* dw,
+                     void* stream);
+int vg_seqpool_fwd(const void* seq, int in_dtype, int in_ld, int b, int l, int c, int w, void* out, int out_dtype,
+                   int out_ld, void* stream);
+int vg_seqpool_bwd(const void* dy, int dy_dtype, int dy_ld, int b, int l, int c, int w, void* dseq, int out_dtype,
+                   int out_ld, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Losses, reparameterisation, spectral norm, optimiser (fp32)
  * ------------------------------------------------------------------------------------------- */

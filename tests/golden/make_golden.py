@@ -70,10 +70,15 @@ def run_case(name):
     G.load_state_dict(deterministic_state(G, 1234), strict=True)
     D.load_state_dict(deterministic_state(D, 4321), strict=True)
     G.train(); D.train()
+    if name in ONE_STEP:
+        # the big fixtures are what the GPU step tests are held to directly; CPU and CUDA dropout masks cannot be lined
+        # up, so the reference's GRU is run with its inter-layer dropout (0.1) switched off for them
+        G.char_text_encoder_module.rnn.dropout = 0.0
     wts = LossWeights.for_family(family)
     opt_G = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.5, 0.999))   # vae-gan.py:541
     opt_D = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.5, 0.999))   # vae-gan.py:542
-    gold = {"case": name, "family": family, "h": h, "w": w, "batch": batch, "z": z, "steps": []}
+    gold = {"case": name, "family": family, "h": h, "w": w, "batch": batch, "z": z, "steps": [],
+            "gru_dropout": 0.0 if name in ONE_STEP else None}
 
     fwd = (lambda a, b, c: unet_repaired_forward(G, a, b, c)) if family == "unet" else G
     if family == "unet":   # record that the shipped forward cannot run (row U)

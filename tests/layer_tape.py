@@ -192,7 +192,7 @@ def ref_unit(u: Unit, G: nn.Module, D: nn.Module, round_bf16: bool):
     Returns {"y": ..., "pool": ..., "dx": ..., "dx2": ..., "grads": {param name: grad}}.
     ``round_bf16``: the recorded tensors are first rounded to bf16 (the CUDA path stores activations in bf16; both sides
     then see identical inputs)."""
-    r = (lambda t: t.bfloat16().float()) if round_bf16 else (lambda t: t)
+    r = (lambda t: t.detach().bfloat16().float()) if round_bf16 else (lambda t: t.detach().clone())
     net = G if u.net == "G" else D
     out: dict = {"grads": {}}
     if u.kind == "conv":
@@ -249,6 +249,18 @@ def fresh_oracle(family, h, w, z, sg, sd):
     G.load_state_dict(sg, strict=True)
     D.load_state_dict(sd, strict=True)
     return G, D
+
+
+def act_ambiguity_mask(u: Unit, G: nn.Module, D: nn.Module, rel_band: float = 1e-2) -> torch.Tensor:
+    """For a conv unit whose activation is fused into the conv (D's first layer: SN conv -> LeakyReLU): boolean mask of
+    the output elements whose pre-activation lies within ``rel_band`` x rms of zero.  The CUDA path rounds the weight
+    operand W / sigma to bf16, which moves every pre-activation by ~1e-3 of its rms; elements that close to zero can land on
+    either side, so their activation slope (1 vs 0.2) is ambiguous at bf16 resolution.  The test zeroes the incoming
+    gradient there (for both sides), which removes them from every gradient of the unit."""
+    net = G if u.net == "G" else D
+    with torch.no_grad():
+        pre = copy.deepcopy(net.get_submodule(u.name)).train()(u.x.detach().clone())
+    return pre.abs() < rel_band * pre.pow(2).mean().sqrt()
 
 
 def pool_tie_mask(y: torch.Tensor) -> torch.Tensor:

@@ -147,3 +147,34 @@ def test_two_rank_reduction_over_the_real_parameter_sets():
         ok, converted, n_cl, n_buckets = ret[rank]
         assert ok, "averaged gradients (or their memory layout) are wrong for some parameter"
         assert converted > 20 and n_cl > 10 and n_buckets > 4
+
+
+def _worker_bf16(rank, world, port, ret):
+    """bf16 gradient buckets (the option for the 568 M-parameter configuration): averaged in bf16 on the wire, cast back
+    into the fp32 gradients, whose shape and memory order are kept; every rank ends up with the SAME values."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vae_gan_mark_b200.parallel import DataParallelReducer
+    torch.manual_seed(9)
+    params = [torch.nn.Parameter(torch.zeros(64, 32, 3, 3).contiguous(memory_format=torch.channels_last)),
+              torch.nn.Parameter(torch.zeros(64)), torch.nn.Parameter(torch.zeros(10, 7))]
+    bases = [torch.randn(p.shape, generator=torch.Generator().manual_seed(50 + k)) for k, p in enumerate(params)]
+    for p, b in zip(params, bases):
+        p.grad = torch.empty_like(p).copy_(b * (rank + 1))
+    red = DataParallelReducer(world, bucket_bytes=4096, grad_dtype=torch.bfloat16)
+    red.hook("G", params)
+    ok = all(p.grad.dtype == torch.float32 and p.grad.stride() == p.stride() and
+             torch.allclose(p.grad, b * 1.5, rtol=2e-2, atol=1e-3) for p, b in zip(params, bases))
+    ret[rank] = (ok, [p.grad.clone() for p in params])
+    dist.destroy_process_group()
+
+
+def test_two_rank_bf16_buckets():
+    world, port = 2, 35000 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_bf16, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] and ret[1][0], "bf16-bucket average is off or changed the gradient layout"
+    for a, b in zip(ret[0][1], ret[1][1]):
+        assert torch.equal(a, b), "ranks must hold bit-identical gradients after the exchange"

@@ -51,6 +51,8 @@ def test_eval_forward_matches_reference_fixture(case):
     od, md = om.Discriminator(3), M.Discriminator(3)
     og.load_state_dict(deterministic_state(og, 1234)); od.load_state_dict(deterministic_state(od, 4321))
     og.train(); od.train()
+    if gold.get("gru_dropout") is not None:
+        og.char_text_encoder_module.rnn.dropout = gold["gru_dropout"]
     opt_g, opt_d = make_optimizers(og, od)
     wts = OLW.for_family(family)
     for step in range(len(gold["steps"])):          # the training steps the reference had taken when "eval" was recorded

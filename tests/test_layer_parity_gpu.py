@@ -18,6 +18,9 @@ Tolerances (relative L2 per tensor; asserted below, observed values in profiles/
   * max-pool windows whose two largest values coincide at bf16 resolution route the pooled gradient ambiguously (either
     routing is a valid sub-gradient): they are excluded from the input-gradient comparison and must stay below 3 % of
     the windows.
+  * D's first layer fuses LeakyReLU into the conv epilogue: output elements whose pre-activation is within 1 % of its rms
+    of zero can fall on either side once the weight operand is rounded to bf16, so their slope is ambiguous; the incoming
+    gradient is zeroed there for both sides (must stay below 3 % of the elements).
   * conv biases in front of a BatchNorm have a gradient that is zero in exact arithmetic (the incoming gradient sums to
     zero over the batch): compared in absolute terms against sum |gy|.
 """
@@ -78,7 +81,7 @@ def build_ours(family, h, w, z, sg, sd):
 def to_act(t_nchw, need_grad=True):
     """NCHW fp32 (CPU) -> (NCHW fp32 CUDA leaf, NHWC activation of the package's dtype derived from it)."""
     from vae_gan_mark_b200 import layers as L
-    leaf = t_nchw.cuda().contiguous().requires_grad_(need_grad)
+    leaf = t_nchw.detach().cuda().contiguous().requires_grad_(need_grad)
     return leaf, L.ToNHWCFn.apply(leaf)
 
 
@@ -144,7 +147,7 @@ def run_ours(u, mg, md):
         y.backward(L.ToNHWCFn.apply(u.gy.cuda()))
         out.update(y=nchw(y), dx=leaf.grad)
     elif m.in_channels <= 4:                                        # image-side conv: NCHW fp32 in
-        leaf = u.x.cuda().contiguous().requires_grad_()
+        leaf = u.x.detach().cuda().contiguous().requires_grad_()
         y = M.run_image_conv(m, [leaf], act=u.act, sn=sn, weight=weight)
         y.backward(L.ToNHWCFn.apply(u.gy.cuda()))
         out.update(y=nchw(y), dx=leaf.grad)
@@ -223,6 +226,12 @@ def test_layers_match_oracle_on_real_step_tensors(family, h, w, batch, z, precis
 
         for u in units:
             tag = f"{u.net}.{u.name}[{u.kind}]"
+            if u.kind == "conv" and u.act and rb:
+                amb = lt.act_ambiguity_mask(u, ref_G, ref_D)
+                frac = float(amb.float().mean())
+                report.append((tag, "ambiguous activation slopes", frac))
+                assert frac < 0.03, (tag, frac)
+                u.gy = u.gy * (~amb)
             want = lt.ref_unit(u, ref_G, ref_D, rb)
             if u.kind == "film":
                 u.meta["gb"] = want["gb"]
@@ -233,7 +242,8 @@ def test_layers_match_oracle_on_real_step_tensors(family, h, w, batch, z, precis
             check(tag, "y", got["y"], want["y"])
             if "pool" in want:
                 check(tag, "pool", got["pool"], want["pool"])
-            if "dx" in want and want["dx"] is not None and got.get("dx") is not None:
+            if "dx" in want and want["dx"] is not None:
+                assert got.get("dx") is not None, (tag, "no input gradient from the CUDA path")
                 mask = None
                 if u.pool:
                     tie = lt.pool_tie_mask(want["y"])
@@ -259,7 +269,7 @@ def test_layers_match_oracle_on_real_step_tensors(family, h, w, batch, z, precis
             check("G.heads", "d" + k, got["grads"][k], g)
     finally:
         vg.set_precision("bf16")
-    worst = sorted(report, key=lambda t: -t[2] if t[1] != "ambiguous pool windows" else 0)[:12]
+    worst = sorted(report, key=lambda t: -t[2] if not t[1].startswith("ambiguous") else 0)[:12]
     print(f"{family} {h}x{w} b{batch} {precision}: {len(report)} comparisons over {len(units)} units; worst:",
           [(a, b, f"{c:.2e}") for a, b, c in worst])
     if os.environ.get("VG_LAYER_LOG"):

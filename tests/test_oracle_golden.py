@@ -51,6 +51,8 @@ def test_oracle_matches_reference_golden(case):
     G.load_state_dict(deterministic_state(G, 1234), strict=True)
     D.load_state_dict(deterministic_state(D, 4321), strict=True)
     G.train(); D.train()
+    if gold.get("gru_dropout") is not None:
+        G.char_text_encoder_module.rnn.dropout = gold["gru_dropout"]
     opt_G, opt_D = make_optimizers(G, D)
     wts = LossWeights.for_family(family)
     for step, rec in enumerate(gold["steps"]):

@@ -582,65 +582,103 @@ class ChannelGateFn(Function):
         return dx, ds[:c], None
 
 
-class _gru_gemm_precision:
-    """The time-parallel GEMMs of the GRU layer run through cuBLAS.  In bf16 mode they may use TF32 tensor cores, which
-    is what the reference's cuDNN GRU does by default (torch.backends.cudnn.allow_tf32 = True); the high-accuracy
-    mode keeps them in full fp32."""
+class EmbeddingFn(Function):
+    """nn.Embedding(padding_idx) lookup (vae-gan-v2.py:83,104): a row gather forward; backward = per-vocabulary-row sum of
+    the token gradients in a fixed order (no index sort, no atomics), padding row zero."""
 
-    def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = ops.act_dtype() == BF16
-        return self
+    @staticmethod
+    def forward(ctx, idx, weight, padding_idx: int):
+        idx = idx.contiguous()
+        ctx.save_for_backward(idx)
+        ctx.vocab, ctx.pad = weight.shape[0], padding_idx
+        return ops.embedding_fwd(idx, weight.detach().contiguous())
 
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
-        return False
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return None, ops.embedding_bwd(idx, g.float(), ctx.vocab, ctx.pad), None
+
+
+class SeqPoolFn(Function):
+    """nn.AdaptiveAvgPool1d(w) over the time axis of a sequence (B, L, C) -- or of an NHWC activation [B,1,L,C] -- written
+    as the NHWC text map [B,1,w,C] (vae-gan-v2.py:107-113: adaptive_pool(out.permute(0,2,1)).unsqueeze(2), plus the change
+    to this package's activation layout, in one pass).  ``out_dtype`` None = the activation dtype."""
+
+    @staticmethod
+    def forward(ctx, seq, w: int, out_dtype=None):
+        b, l, c = seq.shape[0], seq.shape[-2], seq.shape[-1]
+        src = seq.detach()
+        if src.stride(-1) != 1 or src.stride(0) != l * src.stride(-2):
+            src = src.contiguous()
+        out = new_act(b, 1, w, c, seq.device, out_dtype or ops.act_dtype())
+        ops.seqpool_fwd(src, out)
+        ctx.shape, ctx.dt = tuple(seq.shape), seq.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = grad_in(dy, dy.dtype if dy.dtype in (BF16, F32) else None)
+        dseq = torch.empty(ctx.shape, dtype=ctx.dt, device=dy.device)
+        ops.seqpool_bwd(dy, dseq)
+        return dseq, None, None
 
 
 class GRULayerFn(Function):
     """One bidirectional, batch_first GRU layer with hidden size 256 (torch.nn.GRU semantics; the text encoder of
-    vae-gan-v2.py:84-89,105).  The input projections of all time steps and the weight / input gradients are
-    time-parallel library GEMMs; the recurrence itself -- the part that costs the stock path ~1000 launches per
-    training step -- is one cluster kernel per direction pair (vg_gru.cu)."""
+    vae-gan-v2.py:84-89,105).  The recurrence -- the part that costs the stock path ~1000 launches per training step --
+    is one cluster kernel per direction pair (vg_gru.cu).  The time-parallel GEMMs around it (x W_ih^T for all t, dx,
+    dW_ih, dW_hh) run on the tcgen05 implicit-GEMM kernels as 1x1 convolutions over the [B,1,T,C] view of the sequence,
+    always with split-bf16 operands (three bf16 planes per fp32 value, fp32 accumulation: ~1e-6 relative, tighter than
+    the TF32 GEMMs cuDNN's GRU uses) -- they are ~1 GFLOP, so the 6x tensor work is free and no library GEMM is left
+    on the path."""
 
     @staticmethod
-    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+    def forward(ctx, x, cache, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         b, t, i = x.shape
         h = w_hh_f.shape[1]
-        w_ih = torch.cat([w_ih_f.detach(), w_ih_r.detach()], 0)          # [6H, I]
-        b_ih = torch.cat([b_ih_f.detach(), b_ih_r.detach()], 0)
-        w_hh = torch.stack([w_hh_f.detach(), w_hh_r.detach()], 0)        # [2, 3H, H]
-        b_hh = torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0)
-        xm = x.detach().reshape(b * t, i).float()
-        with _gru_gemm_precision():
-            xproj = torch.addmm(b_ih, xm, w_ih.t())                      # [B*T, 6H] == [B, T, 2, 3H]
+        op = ConvLinear(i, 6 * h, 1, 1)
+
+        def build():
+            w_ih = torch.cat([w_ih_f.detach(), w_ih_r.detach()], 0).contiguous()       # [6H, I]
+            w4 = w_ih.view(6 * h, i, 1, 1)
+            return {"wf": op.prep_fwd(w4, None, True), "wb": op.prep_bwd(w4, None, True),
+                    "b_ih": torch.cat([b_ih_f.detach(), b_ih_r.detach()], 0).contiguous(),
+                    "w_hh": torch.stack([w_hh_f.detach(), w_hh_r.detach()], 0).contiguous(),   # [2, 3H, H]
+                    "b_hh": torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0).contiguous()}
+        pk = cache.get("gru", (w_ih_f, w_ih_r, b_ih_f, b_ih_r, w_hh_f, w_hh_r, b_hh_f, b_hh_r), build)
+        x4 = x.detach().float().reshape(b, 1, t, i).contiguous()
+        xproj = op.forward(x4, pk["wf"], pk["b_ih"])                    # fp32 [B,1,T,6H] == [B, T, 2, 3H]
         out = torch.empty((b, t, 2 * h), dtype=F32, device=x.device)
         gates = torch.empty((2, b, t, 4, h), dtype=F32, device=x.device)
-        ops.gru_seq_fwd(xproj, w_hh, b_hh, out, gates)
-        ctx.save_for_backward(xm, w_ih, w_hh, out, gates)
-        ctx.dims = (b, t, i, h)
+        ops.gru_seq_fwd(xproj.view(b, t, 2, 3 * h), pk["w_hh"], pk["b_hh"], out, gates)
+        ctx.save_for_backward(x4, pk["w_hh"], out, gates)
+        ctx.op, ctx.wb, ctx.dims = op, pk["wb"], (b, t, i, h)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xm, w_ih, w_hh, out, gates = ctx.saved_tensors
+        x4, w_hh, out, gates = ctx.saved_tensors
         b, t, i, h = ctx.dims
+        op: ConvLinear = ctx.op
         dout = dout.contiguous().float()
         dgx = torch.empty((b, t, 2, 3 * h), dtype=F32, device=dout.device)
         dgh = torch.empty((2, b, t, 3 * h), dtype=F32, device=dout.device)
         ops.gru_seq_bwd(dout, out, gates, w_hh, dgx, dgh)
-        dgx_m = dgx.view(b * t, 6 * h)
+        dgx4 = dgx.view(b, 1, t, 6 * h)
         hprev = torch.zeros((2, b, t, h), dtype=F32, device=dout.device)  # h_{t-1} of each direction's recurrence
         hprev[0, :, 1:] = out[:, :-1, :h]
         hprev[1, :, :-1] = out[:, 1:, h:]
-        dgh_m = dgh.view(2, b * t, 3 * h)
-        with _gru_gemm_precision():
-            dx = (dgx_m @ w_ih).view(b, t, i) if ctx.needs_input_grad[0] else None
-            dw_ih = dgx_m.t() @ xm                                            # [6H, I]
-            dw_hh = torch.bmm(dgh_m.transpose(1, 2), hprev.view(2, b * t, h))  # [2, 3H, H]
-        db_ih = dgx_m.sum(0)
-        db_hh = dgh_m.sum(1)
-        return (dx, dw_ih[:3 * h], dw_hh[0], db_ih[:3 * h], db_hh[0], dw_ih[3 * h:], dw_hh[1], db_ih[3 * h:], db_hh[1])
+        dx = op.backward_data(dgx4, ctx.wb, (1, t)).view(b, t, i) if ctx.needs_input_grad[0] else None
+        dw_ih = op.backward_weight(dgx4, x4).reshape(6 * h, i)                                # [6H, I]
+        op_hh = ConvLinear(h, 3 * h, 1, 1)
+        dw_hh = [op_hh.backward_weight(dgh[d].view(b, 1, t, 3 * h), hprev[d].view(b, 1, t, h)).reshape(3 * h, h)
+                 for d in (0, 1)]
+        db_ih = torch.empty(6 * h, dtype=F32, device=dout.device)
+        ops.colsum_f32(dgx.view(b * t, 6 * h), db_ih)
+        db_hh = torch.empty((2, 3 * h), dtype=F32, device=dout.device)
+        for d in (0, 1):
+            ops.colsum_f32(dgh[d].view(b * t, 3 * h), db_hh[d])
+        return (dx, None, dw_ih[:3 * h], dw_hh[0], db_ih[:3 * h], db_hh[0], dw_ih[3 * h:], dw_hh[1], db_ih[3 * h:], db_hh[1])
 
 
 class ToNHWCFn(Function):

@@ -149,8 +149,12 @@ class _SNCall:
 # text encoders
 # ------------------------------------------------------------------------------------------------
 class CharacterTokenEncoder(nn.Module):
-    """vae-gan-v2.py:65-114.  Embedding + biGRU (cluster-kernel recurrence, layers.GRULayerFn) + adaptive pool;
-    output (B, 2*hid, 1, W/16) fp32.  ``self.rnn`` is a stock nn.GRU used as the parameter container."""
+    """vae-gan-v2.py:65-114.  Tokenisation table + Embedding + biGRU + adaptive pool, all on the device: the strings are
+    turned into UTF-32 code units on the host (one C-level ``str.encode`` per string, no per-character Python loop), a
+    lookup-table kernel maps them to vocabulary indices, the embedding is a gather kernel, the GRU recurrence a cluster
+    kernel with its time-parallel GEMMs on the tensor-core kernels (layers.GRULayerFn), and the pooling writes the NHWC
+    text map directly (layers.SeqPoolFn).  Output of ``forward``: (B, 2*hid, 1, W/16) fp32 like the reference.
+    ``self.rnn`` (a stock nn.GRU), ``self.embedding`` and ``self.adaptive_pool`` are parameter / API containers."""
 
     def __init__(self, alphabet_str, emb_dim, rnn_hidden_dim, rnn_layers, target_feature_width):
         super().__init__()
@@ -164,8 +168,16 @@ class CharacterTokenEncoder(nn.Module):
         self.rnn_output_dim = rnn_hidden_dim * 2
         self.target_feature_width = target_feature_width
         self.adaptive_pool = nn.AdaptiveAvgPool1d(target_feature_width)
+        # code point -> index table of the device tokeniser (not part of the state_dict: it restates ``alphabet_str``)
+        lut = torch.zeros(max(ord(ch) for ch in alphabet_str) + 1 if alphabet_str else 1, dtype=torch.int32)
+        for ch, i in self.char_to_idx.items():
+            lut[ord(ch)] = i
+        self.register_buffer("_lut", lut, persistent=False)
+        self.__dict__["_gru_caches"] = [L.WeightCache() for _ in range(rnn_layers)]
 
     def tokens_to_indices(self, text_list, max_len_chars):
+        """The reference's host tokeniser (vae-gan-v2.py:89-100), kept for API compatibility and as the tests' oracle of
+        the device tokeniser; the forward path uses ``codepoints`` + the lookup-table kernel instead."""
         idx = torch.zeros(len(text_list), max_len_chars, dtype=torch.long)
         for r, text in enumerate(text_list):
             ids = [self.char_to_idx.get(ch, self.pad_idx) for ch in text][:max_len_chars]
@@ -173,30 +185,62 @@ class CharacterTokenEncoder(nn.Module):
                 idx[r, :len(ids)] = torch.tensor(ids, dtype=torch.long)
         return idx
 
+    @staticmethod
+    def codepoints(text_list, max_len_chars=60, pin: bool = False) -> torch.Tensor:
+        """Host half of the device tokeniser: int32 [B, max_len] holding the UTF-32 code units of each string (zero
+        padded / truncated to max_len characters)."""
+        import numpy as np
+        buf = np.zeros((len(text_list), max_len_chars), dtype=np.uint32)
+        for r, text in enumerate(text_list):
+            s = text[:max_len_chars]
+            if s:
+                cp = np.frombuffer(s.encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
+                buf[r, :cp.shape[0]] = cp
+        t = torch.from_numpy(buf.view(np.int32))
+        return t.pin_memory() if pin else t
+
+    def indices(self, texts_batch, max_len_chars=60) -> torch.Tensor:
+        """int64 [B, max_len] vocabulary indices on the module's device, from strings, code points (int32) or indices."""
+        dev = self.embedding.weight.device
+        if torch.is_tensor(texts_batch):
+            if texts_batch.dtype == torch.long:          # already tokenised
+                return texts_batch.to(dev)
+            cps = texts_batch
+        else:
+            cps = self.codepoints(texts_batch, max_len_chars, pin=dev.type == "cuda")
+        return ops.tokenize(cps.to(dev, non_blocking=True).contiguous(), self._lut)
+
     def rnn_outputs(self, texts_batch, max_len_chars_for_tokenization=60):
         """Embedding + biGRU: (B, L, 2*hid) fp32."""
-        if torch.is_tensor(texts_batch):      # already tokenised (B, max_len) indices, e.g. a CUDA-graph static input
-            idx = texts_batch
-        else:
-            idx = self.tokens_to_indices(texts_batch, max_len_chars_for_tokenization).to(self.embedding.weight.device)
-        emb = self.embedding(idx)
+        idx = self.indices(texts_batch, max_len_chars_for_tokenization)
         rnn = self.rnn
-        if emb.is_cuda and rnn.hidden_size == 256 and rnn.bidirectional and rnn.batch_first and rnn.bias:
-            # cluster-kernel recurrence (vg_gru.cu); self.rnn is only the parameter container
-            out = emb
+        if idx.is_cuda and rnn.hidden_size == 256 and rnn.bidirectional and rnn.batch_first and rnn.bias:
+            out = L.EmbeddingFn.apply(idx, self.embedding.weight, self.pad_idx)
+            caches = self.__dict__["_gru_caches"]
             for layer in range(rnn.num_layers):
                 params = [getattr(rnn, f"{name}_l{layer}{suffix}") for suffix in ("", "_reverse")
                           for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-                out = L.GRULayerFn.apply(out, *params)
+                out = L.GRULayerFn.apply(out, caches[layer], *params)
                 if layer < rnn.num_layers - 1 and rnn.dropout > 0 and self.training:
                     out = torch.nn.functional.dropout(out, rnn.dropout, True)
         else:                                   # other hidden sizes: stock cuDNN recurrence
-            out, _ = rnn(emb)
+            out, _ = rnn(self.embedding(idx))
         return out
+
+    def nhwc_features(self, texts_batch, max_len_chars_for_tokenization=60, reduce_width: bool = False):
+        """The text map in this package's activation layout, NHWC [B,1,W/16,2*hid] (``reduce_width``: its mean over the
+        width, [B,1,1,2*hid] -- the row-U repair of vae-gan-unet.py)."""
+        out = self.rnn_outputs(texts_batch, max_len_chars_for_tokenization)
+        if reduce_width:
+            t = L.SeqPoolFn.apply(out, self.target_feature_width, F32)
+            return L.ToNHWCFn.apply(t.permute(0, 3, 1, 2).mean(dim=3, keepdim=True))
+        return L.SeqPoolFn.apply(out, self.target_feature_width)
 
     def forward(self, texts_batch, max_len_chars_for_tokenization=60):
         out = self.rnn_outputs(texts_batch, max_len_chars_for_tokenization)
-        return self.adaptive_pool(out.permute(0, 2, 1)).unsqueeze(2)
+        if not out.is_cuda:
+            return self.adaptive_pool(out.permute(0, 2, 1)).unsqueeze(2)
+        return L.SeqPoolFn.apply(out, self.target_feature_width, F32).permute(0, 3, 1, 2)     # (B, C, 1, W/16) fp32
 
 
 class _SeqToNHWCFn(torch.autograd.Function):
@@ -238,8 +282,8 @@ class CharacterTokenEncoderOldV(CharacterTokenEncoder):
         c1 = self.conv1d
         st = _state(c1, lambda: (ConvLinear(c, c, 1, 3, 1, (0, 1), (1, l)), L.WeightCache()))
         y = L.Conv2dFn.apply(_SeqToNHWCFn.apply(out), c1.weight.unsqueeze(2), c1.bias, st[0], st[1], 0, None, None, None)
-        x = torch.nn.functional.adaptive_avg_pool1d(y.view(b, l, c).float().permute(0, 2, 1), self.target_feature_width)
-        return x.unsqueeze(2).expand(-1, -1, self.target_feature_height, -1) + self.pos_enc
+        x = L.SeqPoolFn.apply(y, self.target_feature_width, F32).permute(0, 3, 1, 2)          # (B, C, 1, W/16) fp32
+        return x.expand(-1, -1, self.target_feature_height, -1) + self.pos_enc
 
 
 class TransformerTextEncoder(nn.Module):
@@ -354,6 +398,9 @@ def text_features_async(module: nn.Module, texts, reduce_width: bool = False):
     stream, where it overlaps with the style encoder's backward.  Returns (NHWC bf16 text map, join) -- call join()
     before consuming the map on the current stream."""
     if not TEXT_SIDE_STREAM:
+        if type(module).forward is CharacterTokenEncoder.forward:      # pooled straight into the NHWC text map
+            t = module.nhwc_features(texts, reduce_width=reduce_width)
+            return t, (lambda: t)
         text = module(texts)
         if reduce_width:
             text = text.mean(dim=3, keepdim=True)

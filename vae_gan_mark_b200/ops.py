@@ -395,6 +395,49 @@ def gru_seq_bwd(dout, out, gates, w_hh, dgx, dgh):
     _lib.call("vg_gru_seq_bwd", _p(dout), _p(out), _p(gates), _p(w_hh), _p(dgx), _p(dgh), b, t, h, stream())
 
 
+# ----------------------------------------------------------------------------------------------
+# text front end: tokenisation, embedding, sequence pooling
+# ----------------------------------------------------------------------------------------------
+def tokenize(codepoints: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    """codepoints: int32 device tensor holding uint32 UTF-32 code units (any shape); lut: int32 [lut_size].  -> int64 indices."""
+    assert codepoints.dtype == torch.int32 and lut.dtype == torch.int32 and codepoints.is_contiguous() and lut.is_contiguous()
+    idx = torch.empty(codepoints.shape, dtype=torch.long, device=codepoints.device)
+    _lib.call("vg_tokenize", _p(codepoints), C.c_longlong(codepoints.numel()), _p(lut), lut.numel(), _p(idx), stream())
+    return idx
+
+
+def embedding_fwd(idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    assert idx.dtype == torch.long and idx.is_contiguous() and weight.dtype == F32 and weight.is_contiguous()
+    out = torch.empty(tuple(idx.shape) + (weight.shape[1],), dtype=F32, device=weight.device)
+    _lib.call("vg_embedding_fwd", _p(idx), C.c_longlong(idx.numel()), _p(weight), weight.shape[0], weight.shape[1], _p(out),
+              stream())
+    return out
+
+
+def embedding_bwd(idx: torch.Tensor, g: torch.Tensor, vocab: int, padding_idx: int) -> torch.Tensor:
+    g = g.contiguous()
+    assert g.dtype == F32
+    dw = torch.empty((vocab, g.shape[-1]), dtype=F32, device=g.device)
+    _lib.call("vg_embedding_bwd", _p(idx), C.c_longlong(idx.numel()), _p(g), vocab, g.shape[-1], padding_idx, _p(dw), stream())
+    return dw
+
+
+def seqpool_fwd(seq: torch.Tensor, out: torch.Tensor) -> None:
+    """seq: [b,l,c] (or NHWC [b,1,l,c]) rows of stride seq.stride(-2); out: NHWC [b,1,w,c]."""
+    b, l, c = seq.shape[0], seq.shape[-2], seq.shape[-1]
+    w = out.shape[2]
+    assert seq.stride(-1) == 1 and out.stride(3) == 1 and seq.stride(0) == l * seq.stride(-2) and out.stride(0) == w * out.stride(2)
+    _lib.call("vg_seqpool_fwd", _p(seq), dcode(seq), seq.stride(-2), b, l, c, w, _p(out), dcode(out), out.stride(2), stream())
+
+
+def seqpool_bwd(dy: torch.Tensor, dseq: torch.Tensor) -> None:
+    """dy: NHWC [b,1,w,c]; dseq: [b,l,c] (or NHWC [b,1,l,c]), fully written."""
+    b, l, c = dseq.shape[0], dseq.shape[-2], dseq.shape[-1]
+    w = dy.shape[2]
+    assert dy.stride(3) == 1 and dseq.stride(-1) == 1 and dy.stride(0) == w * dy.stride(2) and dseq.stride(0) == l * dseq.stride(-2)
+    _lib.call("vg_seqpool_bwd", _p(dy), dcode(dy), dy.stride(2), b, l, c, w, _p(dseq), dcode(dseq), dseq.stride(-2), stream())
+
+
 def sumsq(g, out, zero_first=True):
     _lib.call("vg_sumsq", _p(g), C.c_longlong(g.numel()), _p(out), int(zero_first), stream())
 

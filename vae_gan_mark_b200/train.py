@@ -275,6 +275,10 @@ class VAEGANTrainer:
         # reads the current value, see set_kl_weight
         self.kl_weight = torch.full((), float(weights.kl), dtype=F32, device=self.opt_G.state.device)
         self.grad_hook = grad_hook        # called as grad_hook("D"|"G", params) after each backward (DP allreduce)
+        # data parallel: SMs the persistent tensor-core grids may occupy during loss_G.backward() (0 = all).  The conv
+        # grids otherwise own every SM, so NCCL's CTAs only get in at kernel boundaries; leaving a few SMs free lets the
+        # bucketed all-reduces of the big generator run concurrently with the rest of the backward pass
+        self.backward_sm_limit = 0
         self._graph = None
         self.sched_G = self.sched_D = None
 
@@ -310,6 +314,8 @@ class VAEGANTrainer:
             if self.perceptual is not None and w.perc != 0.0:
                 perc = self.perceptual(fake, en)
                 loss_g = loss_g + w.perc * perc
+            if self.backward_sm_limit:
+                _lib.call("vg_set_conv_sm_limit", int(self.backward_sm_limit))
             loss_g.backward()
         _lib.call("vg_set_conv_sm_limit", 0)      # (only ever raised by the optional side-stream text path)
         if self.grad_hook is not None:
@@ -391,13 +397,16 @@ class VAEGANTrainer:
             return texts
         enc = getattr(G, "char_text_encoder_module", None)
         if enc is not None:
-            return enc.tokens_to_indices(texts, 60).to(next(G.parameters()).device)
+            # UTF-32 code units (host, C speed); the lookup-table tokeniser kernel runs inside the step / the graph
+            dev = next(G.parameters()).device
+            return enc.codepoints(texts, 60, pin=dev.type == "cuda").to(dev, non_blocking=True)
         te = G.text_encoder
         with torch.no_grad():
             return te._embed(texts).to(next(G.parameters()).device, F32).clone()
 
     def set_texts(self, texts):
-        self._static_text.copy_(self._encode_texts(texts))
+        """New strings for the next replays: host -> code units -> one pinned H2D copy into the graph's static buffer."""
+        self._static_text.copy_(self._encode_texts(texts), non_blocking=True)
 
     def replay(self, ru=None, en=None, mask=None) -> Dict[str, torch.Tensor]:
         """Run one captured step; new inputs (device or pinned-host tensors) are copied into the graph's static buffers."""
