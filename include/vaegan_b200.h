@@ -315,7 +315,10 @@ int vg_sumsq(const float* g, long long n, float* out, int zero_first, void* stre
  * device float[4] {step, 1-beta1^step, sqrt(1-beta2^step), lr} advanced by vg_adam_prepare, so a captured CUDA graph of
  * the step replays with the right bias corrections; vg_multi_adam with lr < 0 reads the learning rate from state[3], so
  * a scheduler (ReduceLROnPlateau of vae-gan-lr-sh.py:751-760, vae-gan-v2.py:944-953) can change it between replays */
-typedef struct VgAdamTensor { float* p; float* g; float* m; float* v; long long n; } VgAdamTensor;
+/* shadow (nullable): bf16 [n] in the memory order of p, rewritten by vg_multi_adam with the updated values -- for conv
+ * weights kept in [Cout][kh][kw][Cin] order it IS the tensor-core operand of the next step's forward, so the per-step
+ * fp32 -> bf16 operand conversion disappears */
+typedef struct VgAdamTensor { float* p; float* g; float* m; float* v; long long n; void* shadow; } VgAdamTensor;
 int vg_adam_prepare(float* state, float beta1, float beta2, void* stream);
 /* deterministic (fixed-order) reduction; scratch: device float[scratch_len], scratch_len >= 1 (use >= 4 x #SMs) */
 int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, float* scratch, int scratch_len, void* stream);

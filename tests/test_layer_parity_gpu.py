@@ -21,8 +21,9 @@ Tolerances (relative L2 per tensor; asserted below, observed values in profiles/
   * D's first layer fuses LeakyReLU into the conv epilogue: output elements whose pre-activation is within 1 % of its rms
     of zero can fall on either side once the weight operand is rounded to bf16, so their slope is ambiguous; the incoming
     gradient is zeroed there for both sides (must stay below 3 % of the elements).
-  * conv biases in front of a BatchNorm have a gradient that is zero in exact arithmetic (the incoming gradient sums to
-    zero over the batch): compared in absolute terms against sum |gy|.
+  * bias / shift gradients are sums of the incoming gradient over all pixels; where those terms cancel (a conv bias in
+    front of a BatchNorm has a gradient that is zero in exact arithmetic; the first BatchNorm's shift at 128x128 sums
+    131 072 mixed-sign terms) the error is measured against 1e-2 x sum |gy| instead of the small result.
 """
 import os
 import sys
@@ -257,8 +258,11 @@ def test_layers_match_oracle_on_real_step_tensors(family, h, w, batch, z, precis
             for k, g in want["grads"].items():
                 assert k in got["grads"], (tag, k, "no gradient from the CUDA path")
                 gg = got["grads"][k]
-                if k == "bias" and u.kind == "conv" and float(g.norm()) < 1e-3 * float(u.gy.abs().sum(dim=(0, 2, 3)).norm()):
-                    check(tag, "d" + k + " (cancelling)", gg, g, abs_scale=float(u.gy.abs().sum(dim=(0, 2, 3)).norm()))
+                # per-channel sums over all pixels (conv bias, BatchNorm / InstanceNorm shift): when the terms cancel, the
+                # attainable accuracy of an fp32 sum is set by sum |gy|, not by the (small) result
+                cancel = float(u.gy.abs().sum(dim=(0, 2, 3)).norm()) if (k == "bias" and u.kind in ("conv", "norm")) else 0.0
+                if cancel and float(g.norm()) < 1e-2 * cancel:
+                    check(tag, "d" + k + " (cancelling)", gg, g, abs_scale=1e-2 * cancel)
                 else:
                     check(tag, "d" + k, gg, g)
         # the two full-kernel heads as our fused pair

@@ -507,7 +507,8 @@ def test_text_front_end_kernels():
     # whole module on strings == on the host-tokenised indices; gradient reaches the embedding
     y1 = enc(texts)
     y2 = enc(enc.tokens_to_indices(texts, 60).cuda())
-    assert tuple(y1.shape) == (len(texts), 512, 1, 28) and torch.equal(y1, y2)
+    assert tuple(y1.shape) == (len(texts), 512, 1, 28)
+    check("strings vs host-tokenised indices", y1, y2, 1e-6)       # (not bit-equal: split-K partial tiles meet in atomics)
     y1.sum().backward()
     assert enc.embedding.weight.grad is not None and float(enc.embedding.weight.grad.abs().max()) > 0
     t = enc.nhwc_features(texts)

@@ -195,13 +195,23 @@ def _operand(view: torch.Tensor, kp: int, hi: bool, scale=None) -> torch.Tensor:
 HI_STEPS_PER_SPLIT = 16   # high-accuracy mode: K steps (of 64) accumulated in TMEM before an fp32 (RN) add in L2
 
 
+# K steps one TMEM accumulation may run in a high-accuracy launch; None = HI_STEPS_PER_SPLIT.  The GRU's time-parallel GEMMs
+# (layers.GRULayerFn) raise it in bf16 mode: their ~1e-5 truncation bias is far below the bf16 noise of everything around
+# them, and an unsplit launch stores its tile directly instead of combining partial tiles with atomics.
+HI_MAX_STEPS = None
+
+
 def _hi_launch(x, vt, stride, cin, w, n_gemm, m, out, wk, bias, act, **kw):
     """High-accuracy launch: the tensor core's fp32 accumulator truncates on every MMA, which biases long K sums by
-    ~1e-4; so K is cut into short splits whose partial sums are combined with round-to-nearest fp32 atomics."""
+    ~1e-4; so K is cut into short splits whose partial sums are combined with round-to-nearest fp32 atomics.  A launch
+    short enough for ONE accumulation stores its tile directly (bias / activation fused, no zero-fill, no atomics)."""
     ksteps = len(vt) * (cin // 64)
+    ksplit = max(1, -(-ksteps // (HI_MAX_STEPS or HI_STEPS_PER_SPLIT)))
+    if ksplit == 1 and out.dtype == F32 and not kw.get("groups"):
+        fprop(x, vt, stride, cin, w, n_gemm, m, out, out_kind=1, bias=bias, act=act, wk=wk, ksplit=1, **kw)
+        return
     out.zero_()
-    fprop(x, vt, stride, cin, w, n_gemm, m, out, out_kind=2, bias=bias, act=0, wk=wk,
-          ksplit=max(1, -(-ksteps // HI_STEPS_PER_SPLIT)), **kw)
+    fprop(x, vt, stride, cin, w, n_gemm, m, out, out_kind=2, bias=bias, act=0, wk=wk, ksplit=ksplit, **kw)
     if act:
         ops.act_fwd_(out, act)
 

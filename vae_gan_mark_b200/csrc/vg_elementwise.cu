@@ -456,11 +456,24 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int 
       float colsum[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) colsum[k] = 0.f;
-      for (int i = i_begin; i < i_end; ++i) {
-        float d[8];
-        load8(dy + ((static_cast<long long>(b) * h + i) * w + j) * c + ch, d);
+      // all rows of the run are loaded before any is consumed: 8 independent 16-byte loads in flight per thread
+      // (one dependent load per row left the kernel latency-bound at 0.46 of the copy bandwidth)
+      const T* col = dy + ((static_cast<long long>(b) * h + i_begin) * w + j) * c + ch;
+      const long long rstride = static_cast<long long>(w) * c;
+      for (int i0 = i_begin; i0 < i_end; i0 += 8) {
+        Raw8<T> v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) colsum[k] += d[k];
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u < i_end) v[u] = Raw8<T>::load(col + (i0 - i_begin + u) * rstride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + u < i_end) {
+            float d[8];
+            v[u].unpack(d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) colsum[k] += d[k];
+          }
+        }
       }
       const int s0 = j0 - base, s1 = j1 - base;          // 0..2 by construction of jlen
 #pragma unroll

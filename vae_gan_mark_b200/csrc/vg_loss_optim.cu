@@ -328,11 +328,12 @@ __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int coun
   const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
   for (int t = 0; t < count; ++t) {
     float* p = tab[t].p; float* g = tab[t].g; float* m = tab[t].m; float* v = tab[t].v;
+    __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(tab[t].shadow);
     const long long n = tab[t].n;
     if (g == nullptr) continue;
     long long done = 0;
     if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-          reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+          reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(sh) & 7) == 0) {
       const long long n4 = n / 4;
       float4* p4 = reinterpret_cast<float4*>(p); float4* g4 = reinterpret_cast<float4*>(g);
       float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
@@ -349,6 +350,8 @@ __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int coun
         }
         p4[i] = pv; m4[i] = mv; v4[i] = vv;
         if (write_back_grad) g4[i] = gv;
+        if (sh != nullptr)      // bf16 copy of the updated weights = the tensor core's operand of the next step
+          reinterpret_cast<uint2*>(sh)[i] = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
       }
       done = n4 * 4;
     }
@@ -358,7 +361,9 @@ __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int coun
       const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
       m[i] = mi;
       v[i] = vi;
-      p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+      const float pn = p[i] - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+      p[i] = pn;
+      if (sh != nullptr) sh[i] = __float2bfloat16(pn);
       if (write_back_grad) g[i] = gi;
     }
   }

@@ -34,18 +34,43 @@ __global__ void embedding_fwd_kernel(const long long* __restrict__ idx, long lon
   }
 }
 
-// dw[r][k] = sum over tokens t with idx[t] == r of g[t][k]; row padding_idx stays zero.  One block per vocabulary row,
-// one thread per embedding column (strided when d > blockDim): the token loop reads idx as a broadcast.
+// dw[r][k] = sum over tokens t with idx[t] == r of g[t][k]; row padding_idx stays zero.  One block per vocabulary row.
+// Phase 1: all threads scan the tokens and mark the matches in a shared-memory bitmap (order-independent); phase 2:
+// thread k walks the set bits in ascending token order and sums column k -- a fixed summation order, so the result is
+// deterministic, without a sort and without atomics on the gradient.
+constexpr int kEmbChunk = 8192;      // tokens per bitmap pass (1 KB of shared memory)
 __global__ void embedding_bwd_kernel(const long long* __restrict__ idx, long long n, const float* __restrict__ g, int d,
                                      int padding_idx, float* __restrict__ dw) {
+  __shared__ unsigned bits[kEmbChunk / 32];
   const int r = blockIdx.x;
-  for (int k = threadIdx.x; k < d; k += blockDim.x) {
-    float a = 0.f;
-    if (r != padding_idx) {
-      for (long long t = 0; t < n; ++t)
-        if (idx[t] == r) a += g[t * d + k];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};      // columns threadIdx.x + j * blockDim.x (d <= 4 * blockDim.x)
+  if (r != padding_idx) {
+    for (long long t0 = 0; t0 < n; t0 += kEmbChunk) {
+      const int len = static_cast<int>(min(static_cast<long long>(kEmbChunk), n - t0));
+      for (int w = threadIdx.x; w < kEmbChunk / 32; w += blockDim.x) bits[w] = 0u;
+      __syncthreads();
+      for (int t = threadIdx.x; t < len; t += blockDim.x)
+        if (idx[t0 + t] == r) atomicOr(&bits[t >> 5], 1u << (t & 31));
+      __syncthreads();
+      for (int w = 0; w < (len + 31) / 32; ++w) {
+        unsigned m = bits[w];
+        while (m) {
+          const int t = (w << 5) + __ffs(m) - 1;
+          m &= m - 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = threadIdx.x + j * blockDim.x;
+            if (k < d) acc[j] += g[(t0 + t) * d + k];
+          }
+        }
+      }
+      __syncthreads();
     }
-    dw[static_cast<long long>(r) * d + k] = a;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = threadIdx.x + j * blockDim.x;
+    if (k < d) dw[static_cast<long long>(r) * d + k] = acc[j];
   }
 }
 
@@ -125,8 +150,8 @@ extern "C" int vg_embedding_fwd(const long long* idx, long long n, const float* 
 extern "C" int vg_embedding_bwd(const long long* idx, long long n, const float* g, int vocab, int dim, int padding_idx,
                                 float* dw, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  VG_CHECK(n >= 0 && vocab >= 1 && dim >= 1, -1, "vg_embedding_bwd: bad sizes");
-  embedding_bwd_kernel<<<vocab, dim < 256 ? ((dim + 31) / 32) * 32 : 256, 0, st>>>(idx, n, g, dim, padding_idx, dw);
+  VG_CHECK(n >= 0 && vocab >= 1 && dim >= 1 && dim <= 1024, -1, "vg_embedding_bwd: bad sizes (dim <= 1024)");
+  embedding_bwd_kernel<<<vocab, 256, 0, st>>>(idx, n, g, dim, padding_idx, dw);
   VG_LAUNCH_OK();
   return 0;
 }

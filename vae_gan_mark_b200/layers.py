@@ -4,6 +4,7 @@ PyTorch layouts so that state_dicts match the reference modules (SURVEY.md secti
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -22,6 +23,65 @@ def bump_weight_epoch() -> None:
     _WEIGHT_EPOCH += 1
 
 
+# bf16 operand shadows maintained by the optimiser (train.FusedAdam writes them in the same kernel that updates the fp32
+# master weights): {data_ptr of the parameter (or tuple of data_ptrs): [bf16 operand, parameter(s), version at last sync]}.
+# The forward operand of a conv whose weight lives in [Cout][kh][kw][Cin] order with Cin % 64 == 0 is exactly the bf16
+# copy of that memory, so ``WeightCache.get("fwd", ...)`` returns the shadow instead of converting the weight every step.
+SHADOWS: Dict[object, list] = {}
+
+
+def shadow_eligible(p: torch.Tensor) -> bool:
+    """A 4-D weight whose memory order is [O][kh][kw][I] (channels_last, or any order when the kernel is 1x1) with
+    I % 64 == 0: its forward operand is the plain bf16 copy of its memory."""
+    if p.dim() != 4 or p.shape[1] % 64 != 0 or p.dtype != F32:
+        return False
+    if p.shape[2] * p.shape[3] == 1:
+        return p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
+    return p.is_contiguous(memory_format=torch.channels_last)
+
+
+def register_shadow(params, operand: torch.Tensor) -> None:
+    """``params``: one parameter, or the (mu_head, logvar_head) pair whose operands are the two halves of ``operand``."""
+    ps = params if isinstance(params, (tuple, list)) else (params,)
+    for k in [k for k, e in SHADOWS.items() if any(r() is None for r in e[1])]:      # parameters that no longer exist
+        del SHADOWS[k]
+    key = ps[0].data_ptr() if len(ps) == 1 else tuple(q.data_ptr() for q in ps)
+    SHADOWS[key] = [operand, tuple(weakref.ref(q) for q in ps), None]
+    sync_shadow(key)
+
+
+def sync_all_shadows() -> None:
+    """After parameters were written behind autograd's back (``p.data`` broadcasts of the data-parallel setup)."""
+    for key in list(SHADOWS):
+        if all(r() is not None for r in SHADOWS[key][1]):
+            sync_shadow(key)
+
+
+def sync_shadow(key) -> None:
+    """(Re)fill a shadow from its fp32 parameter(s) -- at registration and whenever a parameter was modified by anything
+    other than the optimiser kernel (load_state_dict, an eager copy_: both bump the tensor's version counter)."""
+    operand, refs, _ = SHADOWS[key]
+    ps = tuple(r() for r in refs)
+    rows = 0
+    for q in ps:
+        o, i, kh, kw = q.shape
+        ops.strided_copy(q.detach().permute(0, 2, 3, 1), operand[rows:rows + o].view(o, kh, kw, i))
+        rows += o
+    SHADOWS[key][2] = tuple(q._version for q in ps)
+
+
+def _shadow_for(params) -> Optional[torch.Tensor]:
+    if not SHADOWS or ops.act_dtype() != BF16:
+        return None
+    key = params[0].data_ptr() if len(params) == 1 else tuple(q.data_ptr() for q in params)
+    ent = SHADOWS.get(key)
+    if ent is None or any(r() is not b for r, b in zip(ent[1], params)):
+        return None
+    if ent[2] != tuple(q._version for q in params):
+        sync_shadow(key)
+    return ent[0]
+
+
 class WeightCache:
     """bf16 GEMM layouts of one fp32 parameter, rebuilt only when the parameter changed."""
 
@@ -31,6 +91,10 @@ class WeightCache:
 
     def get(self, name: str, param, build):
         params = param if isinstance(param, (tuple, list)) else (param,)
+        if name == "fwd":
+            sh = _shadow_for(params)
+            if sh is not None:
+                return sh
         key = tuple((p.data_ptr(), p._version) for p in params) + (_WEIGHT_EPOCH,)
         if key != self.key:
             self.key, self.store = key, {}
@@ -623,6 +687,22 @@ class SeqPoolFn(Function):
         return dseq, None, None
 
 
+class _gru_gemm_steps:
+    """bf16 mode: let the GRU's split-bf16 GEMMs accumulate their whole K extent (<= 48 steps) in one TMEM pass."""
+
+    def __enter__(self):
+        from . import conv
+        self.prev = conv.HI_MAX_STEPS
+        if ops.act_dtype() == BF16:
+            conv.HI_MAX_STEPS = 64
+        return self
+
+    def __exit__(self, *exc):
+        from . import conv
+        conv.HI_MAX_STEPS = self.prev
+        return False
+
+
 class GRULayerFn(Function):
     """One bidirectional, batch_first GRU layer with hidden size 256 (torch.nn.GRU semantics; the text encoder of
     vae-gan-v2.py:84-89,105).  The recurrence -- the part that costs the stock path ~1000 launches per training step --
@@ -647,7 +727,8 @@ class GRULayerFn(Function):
                     "b_hh": torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0).contiguous()}
         pk = cache.get("gru", (w_ih_f, w_ih_r, b_ih_f, b_ih_r, w_hh_f, w_hh_r, b_hh_f, b_hh_r), build)
         x4 = x.detach().float().reshape(b, 1, t, i).contiguous()
-        xproj = op.forward(x4, pk["wf"], pk["b_ih"])                    # fp32 [B,1,T,6H] == [B, T, 2, 3H]
+        with _gru_gemm_steps():
+            xproj = op.forward(x4, pk["wf"], pk["b_ih"])                # fp32 [B,1,T,6H] == [B, T, 2, 3H]
         out = torch.empty((b, t, 2 * h), dtype=F32, device=x.device)
         gates = torch.empty((2, b, t, 4, h), dtype=F32, device=x.device)
         ops.gru_seq_fwd(xproj.view(b, t, 2, 3 * h), pk["w_hh"], pk["b_hh"], out, gates)
@@ -668,16 +749,15 @@ class GRULayerFn(Function):
         hprev = torch.zeros((2, b, t, h), dtype=F32, device=dout.device)  # h_{t-1} of each direction's recurrence
         hprev[0, :, 1:] = out[:, :-1, :h]
         hprev[1, :, :-1] = out[:, 1:, h:]
-        dx = op.backward_data(dgx4, ctx.wb, (1, t)).view(b, t, i) if ctx.needs_input_grad[0] else None
+        with _gru_gemm_steps():
+            dx = op.backward_data(dgx4, ctx.wb, (1, t)).view(b, t, i) if ctx.needs_input_grad[0] else None
         dw_ih = op.backward_weight(dgx4, x4).reshape(6 * h, i)                                # [6H, I]
         op_hh = ConvLinear(h, 3 * h, 1, 1)
         dw_hh = [op_hh.backward_weight(dgh[d].view(b, 1, t, 3 * h), hprev[d].view(b, 1, t, h)).reshape(3 * h, h)
                  for d in (0, 1)]
-        db_ih = torch.empty(6 * h, dtype=F32, device=dout.device)
-        ops.colsum_f32(dgx.view(b * t, 6 * h), db_ih)
-        db_hh = torch.empty((2, 3 * h), dtype=F32, device=dout.device)
-        for d in (0, 1):
-            ops.colsum_f32(dgh[d].view(b * t, 3 * h), db_hh[d])
+        # bias gradients = column sums over all (batch, time) rows: the row-parallel statistics kernel
+        db_ih = ops.norm_stats(dgx4, per_sample=False)[0, 0]
+        db_hh = [ops.norm_stats(dgh[d].view(b, 1, t, 3 * h), per_sample=False)[0, 0] for d in (0, 1)]
         return (dx, None, dw_ih[:3 * h], dw_hh[0], db_ih[:3 * h], db_hh[0], dw_ih[3 * h:], dw_hh[1], db_ih[3 * h:], db_hh[1])
 
 

@@ -42,6 +42,9 @@ class DataParallelReducer:
             return
         for t in tensors:
             dist.broadcast(t.data if t.is_floating_point() or t.dtype == torch.int64 else t, src, group=self.group)
+        if any(t.is_cuda for t in tensors):
+            from . import layers as L      # (p.data writes do not bump version counters: refresh the bf16 operand shadows)
+            L.sync_all_shadows()
 
     def make_buckets(self, params: Sequence[torch.nn.Parameter]) -> List[List[torch.nn.Parameter]]:
         """Reverse parameter order, ~bucket_bytes each."""

@@ -65,12 +65,43 @@ class FusedAdam:
         self.state = torch.zeros(4, dtype=F32, device=dev)          # {step, 1-b1^t, sqrt(1-b2^t), lr}
         self.state[3] = lr
         self._norm_scratch = torch.zeros(1024, dtype=F32, device=dev)
-        self._table_host = torch.zeros((len(self.params), 5), dtype=torch.int64).pin_memory() if dev.type == "cuda" \
-            else torch.zeros((len(self.params), 5), dtype=torch.int64)
+        self.shadows: List[Optional[torch.Tensor]] = [None] * len(self.params)   # bf16 operand copies the update keeps current
+        self._table_host = torch.zeros((len(self.params), 6), dtype=torch.int64).pin_memory() if dev.type == "cuda" \
+            else torch.zeros((len(self.params), 6), dtype=torch.int64)
         self._table_host_graph = torch.zeros_like(self._table_host)
         if dev.type == "cuda":
             self._table_host_graph = self._table_host_graph.pin_memory()
-        self._table = torch.zeros((len(self.params), 5), dtype=torch.int64, device=dev)
+        self._table = torch.zeros((len(self.params), 6), dtype=torch.int64, device=dev)
+
+    def attach_operand_shadows(self) -> int:
+        """Give every eligible conv / conv-transpose weight (memory order [O][kh][kw][I], I % 64 == 0; the two full-kernel
+        heads as one [2z][K] operand) a bf16 shadow that ``vg_multi_adam`` rewrites together with the fp32 master weight:
+        the next step's forward finds its tensor-core operand ready instead of converting the weight again.  Returns the
+        number of shadowed tensors."""
+        count = 0
+        for i, p in enumerate(self.params):
+            if self.shadows[i] is None and L.shadow_eligible(p):
+                o, c, kh, kw = p.shape
+                sh = torch.empty((o, kh * kw * c), dtype=torch.bfloat16, device=p.device)
+                L.register_shadow(p, sh)
+                self.shadows[i] = sh
+                count += 1
+        return count
+
+    def attach_heads_shadow(self, w_mu: torch.nn.Parameter, w_lv: torch.nn.Parameter) -> bool:
+        """mu_head / logvar_head run as ONE GEMM with N = 2z: their operand is one [2z][kh*kw*C] matrix, so their two
+        shadows are the halves of one buffer."""
+        idx = {id(p): i for i, p in enumerate(self.params)}
+        if id(w_mu) not in idx or id(w_lv) not in idx or not (L.shadow_eligible(w_mu) and L.shadow_eligible(w_lv)):
+            return False
+        z, c, kh, kw = w_mu.shape
+        buf = torch.empty((2 * z, kh * kw * c), dtype=torch.bfloat16, device=w_mu.device)
+        # the pair's entry serves HeadsFn; the single-tensor entries created by attach_operand_shadows (if any) are replaced
+        L.SHADOWS.pop(w_mu.data_ptr(), None)
+        L.SHADOWS.pop(w_lv.data_ptr(), None)
+        L.register_shadow((w_mu, w_lv), buf)
+        self.shadows[idx[id(w_mu)]], self.shadows[idx[id(w_lv)]] = buf[:z], buf[z:]
+        return True
 
     @property
     def step_count(self) -> int:
@@ -110,6 +141,7 @@ class FusedAdam:
                 p.grad = g
             t[i, 0], t[i, 1] = p.data_ptr(), (g.data_ptr() if g is not None else 0)
             t[i, 2], t[i, 3], t[i, 4] = m.data_ptr(), v.data_ptr(), p.numel()
+            t[i, 5] = self.shadows[i].data_ptr() if self.shadows[i] is not None else 0
         self._table.copy_(t, non_blocking=True)
         if not torch.cuda.is_current_stream_capturing():
             self._table_event = torch.cuda.Event()
@@ -271,6 +303,14 @@ class VAEGANTrainer:
             weights_channels_last(D)
         self.opt_G = FusedAdam(G.parameters(), lr=lr_g)
         self.opt_D = FusedAdam(D.parameters(), lr=lr_d)
+        if channels_last_weights and next(G.parameters()).is_cuda:
+            # bf16 operand shadows written by the Adam kernel (generator only: D's convs are spectrally normalised, their
+            # operand W / sigma changes with every call)
+            for m in G.modules():
+                mu, lv = getattr(m, "mu_head", None), getattr(m, "logvar_head", None)
+                if mu is not None and lv is not None:
+                    self.opt_G.attach_heads_shadow(mu.weight, lv.weight)
+            self.opt_G.attach_operand_shadows()
         # KL weight as a device scalar: the reference anneals it per epoch (vae-gan-v2.py:1002-1004); a captured graph
         # reads the current value, see set_kl_weight
         self.kl_weight = torch.full((), float(weights.kl), dtype=F32, device=self.opt_G.state.device)
@@ -390,8 +430,8 @@ class VAEGANTrainer:
         self.launches_per_step = int(_lib.lib().vg_launch_count() - n0)   # our kernels recorded in the graph
         return self._static_out
 
-    def _encode_texts(self, texts):
-        """Host-side part of the text path (tokenisation / sentence embedding), hoisted out of the graph."""
+    def _encode_texts(self, texts, to_device: bool = True):
+        """Host-side part of the text path (code units of the strings / sentence embedding), hoisted out of the graph."""
         G = self.G
         if torch.is_tensor(texts):
             return texts
@@ -399,14 +439,15 @@ class VAEGANTrainer:
         if enc is not None:
             # UTF-32 code units (host, C speed); the lookup-table tokeniser kernel runs inside the step / the graph
             dev = next(G.parameters()).device
-            return enc.codepoints(texts, 60, pin=dev.type == "cuda").to(dev, non_blocking=True)
+            host = enc.codepoints(texts, 60, pin=dev.type == "cuda")
+            return host.to(dev, non_blocking=True) if to_device else host
         te = G.text_encoder
         with torch.no_grad():
             return te._embed(texts).to(next(G.parameters()).device, F32).clone()
 
     def set_texts(self, texts):
         """New strings for the next replays: host -> code units -> one pinned H2D copy into the graph's static buffer."""
-        self._static_text.copy_(self._encode_texts(texts), non_blocking=True)
+        self._static_text.copy_(self._encode_texts(texts, to_device=False), non_blocking=True)
 
     def replay(self, ru=None, en=None, mask=None) -> Dict[str, torch.Tensor]:
         """Run one captured step; new inputs (device or pinned-host tensors) are copied into the graph's static buffers."""
