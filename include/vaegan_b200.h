@@ -119,6 +119,8 @@ typedef struct VgConvWgrad {
   long long workspace_bytes; /* >= vg_conv_wgrad_workspace(desc) */
 } VgConvWgrad;
 int vg_conv_wgrad(const VgConvWgrad* desc /*host*/, void* stream);
+/* CTA-pair (tcgen05 cta_group::2, clusters of two CTAs) variant of the weight-gradient kernel on (default) / off */
+int vg_set_cta_pairs(int wgrad_on);
 long long vg_conv_wgrad_workspace(const VgConvWgrad* desc /*host*/);   /* bytes; 0 if the launch does not split; < 0 bad desc */
 
 

@@ -154,3 +154,32 @@ def test_wgrad_two_stage_reduction_is_deterministic_and_equal():
     assert e < 1e-5
     ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (256, 128, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
     assert rel(outs[True][0], ref) < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,n,h,w", [(512, 512, 3, 1, 1, 4, 32, 32), (128, 256, 3, 1, 1, 8, 32, 32),
+                                                  (512, 1024, 1, 1, 0, 8, 32, 32), (1024, 384, 3, 1, 1, 8, 16, 16),
+                                                  (128, 256, 3, 2, 1, 8, 64, 64), (192, 320, 3, 1, 1, 4, 24, 40)])
+def test_wgrad_cta_pair_kernel_equals_single_cta_kernel(cin, cout, k, s, p, n, h, w):
+    """conv_wgrad_kernel<true> (clusters of two CTAs, tcgen05.mma.cta_group::2 with M = 256, each CTA staging half of the
+    X tile) against the single-CTA kernel (same products, same fp32 accumulation, only the split of the work differs) and
+    against torch: odd numbers of 128-channel tiles (cout 384 / 320: the pair's second CTA idles or is partly masked),
+    partial N tiles, stride 2, 1x1."""
+    from vae_gan_mark_b200 import _lib
+    from vae_gan_mark_b200.conv import ConvLinear
+    op = ConvLinear(cin, cout, k, k, s, (p, p))
+    x = act(n, h, w, cin, 31)
+    oh, ow = op.out_hw(h, w)
+    dy = act(n, oh, ow, cout, 32)
+    res = {}
+    try:
+        for pairs in (0, 1):
+            _lib.lib().vg_set_cta_pairs(pairs)
+            res[pairs] = op.backward_weight(dy, x).contiguous().clone()
+    finally:
+        _lib.lib().vg_set_cta_pairs(1)
+    torch.cuda.synchronize()
+    e = rel(res[1], res[0])
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
+                                      stride=s, padding=p)
+    print(f"pair vs single {e:.2e}, pair vs torch {rel(res[1], ref):.2e}")
+    assert e < 1e-5 and rel(res[1], ref) < 2e-3

@@ -45,13 +45,19 @@ struct WgradParams {
   int combo_g[8], combo_x[8];     // channel offsets of the pair's planes
 };
 
+// k2 = true: CTA-pair variant (cta_group::2).  A cluster of two CTAs computes a 256 x bn tile of dW with ONE stream of
+// tcgen05.mma of M = 256: CTA r stages the dY boxes of ITS 128 output channels and HALF of the X blocks (nb / 2 boxes) in
+// its own shared memory -- 32 KB per stage instead of 48 KB (6 stages instead of 4) and half the X bytes through L2 and
+// shared memory per CTA, which is what bounds the MN-major operand path -- and drains its own 128 TMEM lanes.
+template <bool k2>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                   const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = 2 * kWgBoxBytes;
-  const uint32_t stage_bytes = a_bytes + p.nb * kWgBoxBytes;
+  const int nb_cta = k2 ? p.nb / 2 : p.nb;                 // X boxes this CTA stages per K step
+  const uint32_t stage_bytes = a_bytes + nb_cta * kWgBoxBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
@@ -62,6 +68,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = k2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_g);
@@ -72,23 +79,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], k2 ? 256 : 128);           // the leader's barrier collects the epilogues of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_base_slot, 512);
-    tmem_relinquish();
+    if (k2) { tmem_alloc_2cta(tmem_base_slot, 512); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_base_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   // K steps: (pixel tile, operand pair) with the pair index fastest
   const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.ncombos;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  const int m_units = k2 ? (p.m_tiles + 1) / 2 : p.m_tiles;      // 256-channel pairs of M tiles, or single M tiles
+  const int total_tiles = m_units * p.n_tiles * p.ksplit;
   const int cchunks = p.cin / 64;
+  const int worker = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nworkers = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -96,21 +106,32 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     // six copies run in parallel lanes instead of serially in one thread, which otherwise starves the tensor pipe.
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += nworkers) {
       const int n_t = tile % p.n_tiles;
-      const int m_t = (tile / p.n_tiles) % p.m_tiles;
-      const int split = tile / (p.n_tiles * p.m_tiles);
+      const int m_u = (tile / p.n_tiles) % m_units;
+      const int m_t = k2 ? 2 * m_u + static_cast<int>(rank) : m_u;
+      const int split = tile / (p.n_tiles * m_units);
       const int k_begin = static_cast<int>((static_cast<long long>(pix_tiles) * split) / p.ksplit);
       const int k_end = static_cast<int>((static_cast<long long>(pix_tiles) * (split + 1)) / p.ksplit);
-      const int nblk = min(p.nb, p.blocks_total - n_t * p.nb);
-      const int aboxes = min(2, (p.cout - m_t * kWgBM + 63) / 64);
-      // this lane's box: lanes [0, aboxes) load dY, lanes [2, 2 + nblk) load X
+      const int nblk = min(p.nb, p.blocks_total - n_t * p.nb);          // X blocks of this N tile that exist
+      const int aboxes = max(0, min(2, (p.cout - m_t * kWgBM + 63) / 64));
+      // X blocks staged by this CTA: the pair splits the N tile in halves [0, nb/2) | [nb/2, nb)
+      const int b0 = k2 ? static_cast<int>(rank) * nb_cta : 0;
+      const int myb = max(0, min(nb_cta, nblk - b0));
+      uint32_t tx_bytes = static_cast<uint32_t>(aboxes + myb) * kWgBoxBytes;
+      if (k2) {      // the leader's barrier also receives the peer's boxes
+        const int ab1 = max(0, min(2, (p.cout - (2 * m_u + 1) * kWgBM + 63) / 64));
+        const int ab0 = max(0, min(2, (p.cout - (2 * m_u) * kWgBM + 63) / 64));
+        const int nb0 = max(0, min(nb_cta, nblk)), nb1 = max(0, min(nb_cta, nblk - nb_cta));
+        tx_bytes = static_cast<uint32_t>(ab0 + ab1 + nb0 + nb1) * kWgBoxBytes;
+      }
+      // this lane's box: lanes [0, aboxes) load dY, lanes [2, 2 + myb) load X
       const bool is_a = lane < aboxes;
-      const bool is_b = lane >= 2 && lane < 2 + nblk;
+      const bool is_b = lane >= 2 && lane < 2 + myb;
       int c0 = 0, dwv = 0, shv = 0, dhv = 0;
       if (is_a) c0 = p.g_coff + m_t * kWgBM + lane * 64;
       if (is_b) {
-        const int b = n_t * p.nb + (lane - 2);
+        const int b = n_t * p.nb + b0 + (lane - 2);
         const int4 t = p.taps[b / cchunks];
         c0 = t.x + (b % cchunks) * 64; dwv = t.y; shv = t.z; dhv = t.w;
       }
@@ -122,14 +143,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
       for (int k = k_begin; k < k_end; ++k) {
         if (lane == 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], (aboxes + nblk) * kWgBoxBytes);
+          if (!k2 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         }
         __syncwarp();
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
-        if (is_a) tma_load_5d(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0 + p.combo_g[combo], ow0, 0, oh0, n0);
-        if (is_b) tma_load_5d(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0 + p.combo_x[combo],
-                              ow0 + dwv, shv, oh0 + dhv, n0);
+        if (k2) {
+          if (is_a) tma_load_5d_2cta(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0 + p.combo_g[combo], ow0, 0, oh0, n0);
+          if (is_b) tma_load_5d_2cta(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0 + p.combo_x[combo],
+                                     ow0 + dwv, shv, oh0 + dhv, n0);
+        } else {
+          if (is_a) tma_load_5d(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0 + p.combo_g[combo], ow0, 0, oh0, n0);
+          if (is_b) tma_load_5d(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0 + p.combo_x[combo],
+                                ow0 + dwv, shv, oh0 + dhv, n0);
+        }
         if (++combo == p.ncombos) {
           combo = 0;
           if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
@@ -137,15 +164,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(kWgBM, p.bn, 1, 1);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only in the pair variant) =====================
+    const uint32_t idesc = umma_idesc_bf16(k2 ? 2 * kWgBM : kWgBM, p.bn, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = tile / (p.n_tiles * p.m_tiles);
+    for (int tile = worker; tile < total_tiles; tile += nworkers) {
+      const int split = tile / (p.n_tiles * m_units);
       const int k_begin = static_cast<int>((static_cast<long long>(pix_tiles) * split) / p.ksplit);
       const int k_end = static_cast<int>((static_cast<long long>(pix_tiles) * (split + 1)) / p.ksplit);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -161,12 +188,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
           // 16 pixels (= 2 groups of 8 rows, SBO apart) per MMA; 64-channel groups LBO (= one box) apart
           const uint64_t da = umma_smem_desc_sw128(sa + j * 16 * 128, kWgBoxBytes, 1024);
           const uint64_t db = umma_smem_desc_sw128(sb + j * 16 * 128, kWgBoxBytes, 1024);
-          umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+          if (k2) umma_bf16_2cta(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+          else umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);
+        if (k2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tmem_full[acc]);
+      if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -174,14 +202,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     // TMEM -> registers (thread = one output-channel row, 32 fp32 columns at a time) -> per-warp staging tile in
     // shared memory -> coalesced 16-byte stores / vector reductions (8 lanes cover 128 contiguous bytes of a dW row).
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
     uint8_t* stg = epi_smem + quad * (32 * kWgEpiPitch);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += nworkers) {
       const int n_t = tile % p.n_tiles;
-      const int m_t = (tile / p.n_tiles) % p.m_tiles;
-      const long long split_off = static_cast<long long>(tile / (p.n_tiles * p.m_tiles)) * p.split_stride;
+      const int m_u = (tile / p.n_tiles) % m_units;
+      const int m_t = k2 ? 2 * m_u + static_cast<int>(rank) : m_u;
+      const long long split_off = static_cast<long long>(tile / (p.n_tiles * m_units)) * p.split_stride;
       const int co_warp = m_t * kWgBM + quad * 32;           // first output channel handled by this warp
       const int ncols = min(p.bn, p.blocks_total * 64 - n_t * p.bn);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -213,17 +241,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if (k2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    (void)row;
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (k2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -239,6 +266,10 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, float4* __res
     dw[i] = a;
   }
 }
+
+// CTA-pair (cta_group::2) variant on / off (vg_set_cta_pairs; on by default)
+static int g_wgrad_pairs = 1;
+static bool wgrad_pairs_enabled() { return g_wgrad_pairs != 0; }
 
 // split factor of a launch: the largest split with tiles * ksplit <= #SMs wastes the least of the last wave (a second,
 // partial wave costs a full tile time); keep >= ~8 K steps per split so the pipeline fills
@@ -292,8 +323,13 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
   p.nb = nb; p.bn = nb * 64;
   p.n_tiles = cdiv(p.blocks_total, nb);
+  // CTA pairs: at least two 128-channel M tiles to pair up and an N tile that splits in halves
+  // (tiny problems are launch-latency bound and gain nothing from the cluster launch)
+  const bool pair = wgrad_pairs_enabled() && p.m_tiles >= 2 && (nb == 2 || nb == 4) && pix_tiles >= 128;
+  const int workers = pair ? sms / 2 : sms;
+  const int m_units = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
   int ksplit = d->ksplit;
-  if (ksplit <= 0) ksplit = wgrad_auto_split(p.m_tiles * p.n_tiles, pix_tiles, sms);
+  if (ksplit <= 0) ksplit = wgrad_auto_split(m_units * p.n_tiles, pix_tiles, workers);
   VG_CHECK(ksplit <= pix_tiles, -1, "vg_conv_wgrad: ksplit %d > pixel tiles %d", ksplit, pix_tiles);
   p.ksplit = ksplit;
   p.atomic = ksplit > 1 ? 1 : 0;
@@ -308,7 +344,7 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
     p.atomic = 0;
     p.split_stride = static_cast<long long>(dw_floats);
   }
-  const int stage_bytes = (2 + nb) * kWgBoxBytes;
+  const int stage_bytes = (2 + (pair ? nb / 2 : nb)) * kWgBoxBytes;
   p.stages = min(8, (227 * 1024 - 1024 - 256 - kWgEpiBytes) / stage_bytes);
   p.dw = two_stage ? static_cast<float*>(d->workspace) : d->dw;
   p.dw_ld = d->dw_ld;
@@ -340,11 +376,26 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   static bool attr_set[64] = {false};      // per device: function attributes belong to the device's context
   const int dev = current_device();
   if (!attr_set[dev]) {
-    VG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
-  conv_wgrad_kernel<<<min(total_tiles, sms), kWgThreads, smem, stream>>>(tmap_g, tmap_x, p);
+  const int total_tiles = m_units * p.n_tiles * p.ksplit;
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * min(total_tiles, workers)), 1, 1);
+    cfg.blockDim = dim3(kWgThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VG_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, tmap_g, tmap_x, p));
+  } else {
+    conv_wgrad_kernel<false><<<min(total_tiles, sms), kWgThreads, smem, stream>>>(tmap_g, tmap_x, p);
+  }
   VG_LAUNCH_OK();
   if (two_stage) {
     const long long n4 = static_cast<long long>(dw_floats / 4);
@@ -353,6 +404,11 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
                                                              reinterpret_cast<float4*>(d->dw), n4, ksplit);
     VG_LAUNCH_OK();
   }
+  return 0;
+}
+
+extern "C" int vg_set_cta_pairs(int wgrad_on) {
+  g_wgrad_pairs = wgrad_on;
   return 0;
 }
 
@@ -370,7 +426,9 @@ extern "C" long long vg_conv_wgrad_workspace(const VgConvWgrad* d) {
   const int blocks_total = d->num_taps * (d->cin / 64);
   int nb = min(4, blocks_total);
   if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
-  const int tiles = cdiv(d->cout, kWgBM) * cdiv(blocks_total, nb);
-  const int ksplit = d->ksplit > 0 ? d->ksplit : wgrad_auto_split(tiles, pix_tiles, conv_sms());
+  const int m_tiles = cdiv(d->cout, kWgBM);
+  const bool pair = wgrad_pairs_enabled() && m_tiles >= 2 && (nb == 2 || nb == 4) && pix_tiles >= 128;
+  const int tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * cdiv(blocks_total, nb);
+  const int ksplit = d->ksplit > 0 ? d->ksplit : wgrad_auto_split(tiles, pix_tiles, pair ? conv_sms() / 2 : conv_sms());
   return ksplit > 1 ? static_cast<long long>(ksplit) * d->cout * d->dw_ld * static_cast<long long>(sizeof(float)) : 0;
 }
