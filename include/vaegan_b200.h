@@ -95,6 +95,9 @@ typedef struct VgConvFprop {
                                separate pass over the tensor.  Needs out_kind 0/1, no split-K, an aligned destination */
 } VgConvFprop;
 int vg_conv_fprop(const VgConvFprop* desc /*host*/, void* stream);
+/* CTA-pair (tcgen05 cta_group::2, clusters of two CTAs, M = 256 MMAs, half the weight tile per CTA) variant of the
+ * forward kernel for wide layers (256-column N tiles, K-major weights) on (default) / off */
+int vg_set_fprop_cta_pairs(int on);
 
 /* dw[co][tap*cin + ci] = sum_pixels g[pixel][co] * x[pixel@tap][ci]      (fp32 result)
  * Replaces Conv2d / ConvTranspose2d weight-gradient dispatches to cuDNN (same call sites, backward). */

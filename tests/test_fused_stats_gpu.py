@@ -183,3 +183,42 @@ def test_wgrad_cta_pair_kernel_equals_single_cta_kernel(cin, cout, k, s, p, n, h
                                       stride=s, padding=p)
     print(f"pair vs single {e:.2e}, pair vs torch {rel(res[1], ref):.2e}")
     assert e < 1e-5 and rel(res[1], ref) < 2e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,n,h,w,bias", [(512, 512, 3, 1, 1, 8, 64, 64, False), (256, 512, 3, 1, 1, 37, 16, 16, True),
+                                                       (512, 1024, 1, 1, 0, 16, 32, 32, True), (128, 256, 3, 2, 1, 64, 64, 64, True),
+                                                       (512, 384, 3, 1, 1, 33, 24, 20, False)])
+def test_fprop_cta_pair_kernel_is_bit_equal_to_single_cta_kernel(cin, cout, k, s, p, n, h, w, bias):
+    """conv_fprop_kernel<true> (clusters of two CTAs, one stream of M = 256 tcgen05.mma.cta_group::2, each CTA staging its own
+    128-pixel box and half of the weight tile) must reproduce the single-CTA kernel bit for bit -- same products, same
+    K order, same fp32 accumulator: forward (+ fused ReLU, bias, BatchNorm statistics), data gradient, and the pixel-shuffle
+    epilogue of a 2x2 stride-2 transposed conv; odd pixel-tile counts (n = 37 / 33) leave the last pair half empty."""
+    from vae_gan_mark_b200 import _lib, layers as L
+    from vae_gan_mark_b200.conv import ConvLinear
+    torch.manual_seed(8)
+    op = ConvLinear(cin, cout, k, k, s, (p, p))
+    x = act(n, h, w, cin, 41)
+    wt = (torch.randn(cout, cin, k, k) * (cin * k * k) ** -0.5).cuda()
+    b = torch.randn(cout).cuda() if bias else None
+    oh, ow = op.out_hw(h, w)
+    dy = act(n, oh, ow, cout, 42)
+    wf, wb = op.prep_fwd(wt), op.prep_bwd(wt)
+    ct = nn.ConvTranspose2d(cout, 128, 2, 2).cuda()
+    opt = ConvLinear(128, cout, 2, 2, 2, (0, 0), (2 * oh, 2 * ow))
+    res = {}
+    try:
+        for pairs in (0, 1):
+            _lib.lib().vg_set_fprop_cta_pairs(pairs)
+            stats = torch.empty((1, 2, cout), device="cuda")
+            y = op.forward(x, wf, b, 1, stats=stats)
+            dx = op.backward_data(dy, wb, (h, w))
+            with torch.no_grad():
+                up = L.ConvTranspose2dFn.apply(dy, ct.weight, ct.bias, opt, L.WeightCache(), 0, None, (2 * oh, 2 * ow))
+            res[pairs] = (y.clone(), dx.clone(), up.clone(), stats.clone())
+    finally:
+        _lib.lib().vg_set_fprop_cta_pairs(1)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert rel(res[1][3], res[0][3]) < 1e-5
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), b, stride=s, padding=p))
+    assert rel(res[1][0].float().permute(0, 3, 1, 2), ref) < 1e-2

@@ -110,6 +110,12 @@ VG_DEVICE void stats_flush(const FpropParams& p, float (&st)[8], int n_t, int la
   for (int i = 0; i < 8; ++i) st[i] = 0.f;
 }
 
+// k2 = true: CTA-pair variant (cta_group::2; plain K-major mode with 256-wide N tiles only).  A cluster of two CTAs
+// computes a 256-pixel x 256-column tile with ONE stream of M = 256 MMAs issued by the leader: each CTA stages its own
+// 128-pixel activation box and HALF of the weight tile (128 columns), i.e. 32 KB per stage instead of 48 KB -- six
+// pipeline stages instead of four in the same shared memory, and half the weight bytes from L2 per CTA -- and drains
+// its own 128 TMEM lanes through the unchanged epilogue.
+template <bool k2>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ FpropParams p) {
@@ -131,6 +137,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = k2 ? cluster_ctarank() : 0u;        // 0 = leader of the pair (issues the MMAs)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -141,24 +148,38 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], p.nacc == 4 ? 128 : 256);
+      mbar_init(&tmem_empty[i], (p.nacc == 4 ? 128 : 256) * (k2 ? 2 : 1));   // pair: the leader's barrier collects both epilogues
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_base_slot, 512);
-    tmem_relinquish();
+    if (k2) { tmem_alloc_2cta(tmem_base_slot, 512); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_base_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  // pair variant (one group, no split-K): work item = (pair of adjacent pixel tiles, N tile); this CTA's pixel tile is
+  // m_t = 2 * unit + rank, expressed below as a virtual tile index in the single-CTA enumeration (n_t fastest); an odd
+  // tile count leaves the last pair's second CTA with a tile beyond the grid: its loads are zero-filled, its rows masked
+  const int m_tiles_real = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int m_tiles = k2 ? 2 * ((m_tiles_real + 1) / 2) : m_tiles_real;
   const int tiles_per_group = m_tiles * p.n_tiles * p.ksplit;
   const int total_tiles = tiles_per_group * p.ngroups;
   const int cchunks_all = p.cin / kBK;
+  // single CTA: tiles blockIdx.x, + gridDim.x, ...   pair: units (blockIdx.x / 2), + gridDim.x / 2, ... each unit being the
+  // two consecutive virtual tiles {2u * n_tiles + n_t + rank * n_tiles}
+  const int worker = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nworkers = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_work = k2 ? total_tiles / 2 : total_tiles;
+  auto tile_of = [&](int work) -> int {
+    if (!k2) return work;
+    const int n_t = work % p.n_tiles, unit = work / p.n_tiles;
+    return (2 * unit + static_cast<int>(rank)) * p.n_tiles + n_t;
+  };
 
   // Producer: in the plain K-major mode ONE thread issues both loads of a stage (measured 2-7 % faster than a
   // warp-wide loop with a __syncwarp per stage); the MN-major and halo modes have up to 10 boxes per stage and use one
@@ -169,14 +190,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int b_boxes = p.b_mn ? p.bn / 64 : 1;
     int stage = 0;
     uint32_t phase = 0;
-    if (p.w_bytes > 0 && blockIdx.x < total_tiles) {
+    if (p.w_bytes > 0 && worker < total_work) {
       // resident weights: tile (cc, tap) at wres + (cc*9 + tap) * bn*128; one barrier for all of them
       if (lane == 0) mbar_arrive_expect_tx(w_bar, p.w_bytes);
       __syncwarp();
       for (int i = lane; i < 9 * cchunks_all; i += 32)
         tma_load_2d(wres + static_cast<size_t>(i) * (p.bn * 128), &tmap_b, w_bar, p.wk[i % 9] + (i / 9) * kBK, 0);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = worker; work < total_work; work += nworkers) {
+      const int tile = tile_of(work);
       const int grp = tile / tiles_per_group;
       const int tl = tile - grp * tiles_per_group;
       const int n_t = tl % p.n_tiles;
@@ -214,12 +236,19 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int k = k_begin; k < k_end; ++k) {
         if (lane == 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          if (!k2) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          else if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);      // both CTAs' boxes land on the leader's barrier
         }
         if (wide_producer) __syncwarp();
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        if (lane == 0) {
+        if (k2) {
+          if (lane == 0) {
+            const int4 t = p.taps[tap];
+            tma_load_5d_2cta(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
+            tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn + static_cast<int>(rank) * (p.bn / 2));
+          }
+        } else if (lane == 0) {
           const int4 t = p.taps[tap];
           tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
           if (!p.b_mn) tma_load_2d(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn);
@@ -232,21 +261,22 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(kBM, p.bn, 0, p.b_mn);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only in the pair variant) =====================
+    const uint32_t idesc = umma_idesc_bf16(k2 ? 2 * kBM : kBM, p.bn, 0, p.b_mn);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (p.w_bytes > 0 && blockIdx.x < total_tiles) {
+    if (p.w_bytes > 0 && worker < total_work) {
       mbar_wait(w_bar, 0);
       tc_fence_after();
     }
     uint32_t halo_a16[9];      // start of each tap's view inside the halo buffer, in 16-byte units
 #pragma unroll
     for (int t = 0; t < 9; ++t) halo_a16[t] = static_cast<uint32_t>(((p.taps[t].w + 1) * kHaloW + (p.taps[t].y + 1)) * 128) >> 4;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = worker; work < total_work; work += nworkers) {
+      const int tile = tile_of(work);
       const int grp = tile / tiles_per_group;
       const int split = ((tile - grp * tiles_per_group) / p.n_tiles) / m_tiles;
       const int ksteps = p.g_ntaps[grp] * cchunks_all;
@@ -290,12 +320,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint64_t db0 = p.b_mn ? umma_smem_desc_sw128(sb, 64 * 128, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
         const uint32_t b_step16 = p.b_mn ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
 #pragma unroll
-        for (int j = 0; j < kBK / kUmmaK; ++j)
-          umma_bf16(d_tmem, da0 + 2 * j, db0 + j * b_step16, idesc, (k > k_begin || j > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+        for (int j = 0; j < kBK / kUmmaK; ++j) {
+          if (k2) umma_bf16_2cta(d_tmem, da0 + 2 * j, db0 + j * b_step16, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+          else umma_bf16(d_tmem, da0 + 2 * j, db0 + j * b_step16, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+        }
+        // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+        if (k2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+      // accumulator complete -> epilogue (of both CTAs)
+      if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -329,7 +363,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int i = 0; i < 8; ++i) st[i] = 0.f;
     int st_nt = -1;
     int seq = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++seq) {
+    for (int work = worker; work < total_work; work += nworkers, ++seq) {
+      const int tile = tile_of(work);
       if (split && (seq & 1) != colhalf) continue;
       const int acc = seq % p.nacc;
       const uint32_t acc_phase = static_cast<uint32_t>(seq / p.nacc) & 1u;
@@ -495,18 +530,20 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if (k2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
     }
     if (p.stats != nullptr && st_nt >= 0) stats_flush(p, st, st_nt, lane, c_first, c_step, esz);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (k2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
+
+static int g_fprop_pairs = 1;      // CTA-pair variant on / off (vg_set_cta_pairs)
 
 static int pick_pixel_tile(int m_n, int m_h, int m_w, int total, int* tn, int* th, int* tw) {
   // tw = largest power of two <= min(m_w rounded up to pow2, total); th likewise; tn = rest
@@ -523,6 +560,11 @@ static int pick_pixel_tile(int m_n, int m_h, int m_w, int total, int* tn, int* t
 }  // namespace vg
 
 using namespace vg;
+
+extern "C" int vg_set_fprop_cta_pairs(int on) {
+  g_fprop_pairs = on;
+  return 0;
+}
 
 extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -587,8 +629,12 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   p.ksplit = ksplit;
   p.nacc = bn <= 128 ? 4 : 2;
   p.acc_cols = 512 / p.nacc;
+  // CTA pairs: the plain K-major mode with 256-wide N tiles, one group, no split-K, and enough pixel tiles that pairing
+  // them does not leave SMs without work
+  const bool pair = g_fprop_pairs != 0 && !halo && !d->b_mn_major && bn == 256 && ksplit == 1 && d->num_groups <= 1 &&
+                    (m_tiles / 2) * p.n_tiles >= sms / 2 && sms % 2 == 0;
   p.a_bytes = halo ? kHaloBytes : kBM * kBK * 2;
-  p.b_bytes = halo ? 9 * bn * kBK * 2 : bn * kBK * 2;
+  p.b_bytes = halo ? 9 * bn * kBK * 2 : (pair ? bn / 2 : bn) * kBK * 2;
   const int smem_budget = 227 * 1024 - 1024 - 256 - kEpiBytes;
   if (halo && p.n_tiles == 1) {
     // weights resident when they leave room for at least two halo stages
@@ -652,7 +698,7 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   {
     uint64_t dims[2] = {static_cast<uint64_t>(d->w_ld), static_cast<uint64_t>(p.b_mn ? d->w_rows : d->n_gemm)};
     uint64_t strides[2] = {1, static_cast<uint64_t>(d->w_ld)};
-    uint32_t box[2] = {kBK, static_cast<uint32_t>(p.b_mn ? 64 : bn)};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(p.b_mn ? 64 : (pair ? bn / 2 : bn))};
     int rc = encode_tmap_bf16(&tmap_b, d->w, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -660,12 +706,28 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   static bool attr_set[64] = {false};      // per device: function attributes belong to the device's context
   const int dev = current_device();
   if (!attr_set[dev]) {
-    VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
   const int total_tiles = m_tiles * p.n_tiles * p.ksplit * p.ngroups;
-  const int grid = min(total_tiles, sms);
-  conv_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tmap_a, tmap_b, p);
+  if (pair) {
+    const int units = ((m_tiles + 1) / 2) * p.n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * min(units, sms / 2)), 1, 1);
+    cfg.blockDim = dim3(kFpropThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VG_CUDA(cudaLaunchKernelEx(&cfg, conv_fprop_kernel<true>, tmap_a, tmap_b, p));
+  } else {
+    const int grid = min(total_tiles, sms);
+    conv_fprop_kernel<false><<<grid, kFpropThreads, smem, stream>>>(tmap_a, tmap_b, p);
+  }
   VG_LAUNCH_OK();
   return 0;
 }
