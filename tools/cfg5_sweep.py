@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--nccl-sms", type=int, default=16)
     ap.add_argument("--bucket-mb", type=int, default=64)
+    ap.add_argument("--plan", default="", help='per-batch variant lists, e.g. "8:nocomm,fp32,bf16,bf16+sms;16:nocomm,bf16+sms" '
+                                               "(overrides --batches / --variants)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -64,8 +66,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    variants = [v for v in args.variants.split(",") if world > 1 or v == "nocomm"]
-    for B in [int(b) for b in args.batches.split(",")]:
+    if args.plan:
+        plan = [(int(item.split(":")[0]), item.split(":")[1].split(",")) for item in args.plan.split(";") if item]
+    else:
+        plan = [(int(b), args.variants.split(",")) for b in args.batches.split(",")]
+    for B, variants in plan:
+        variants = [v for v in variants if world > 1 or v == "nocomm"]
         gen = torch.Generator(device=dev).manual_seed(4321 + rank)
         data = [(torch.rand(B, 3, h, w, device=dev, generator=gen), torch.rand(B, 3, h, w, device=dev, generator=gen),
                  (torch.rand(B, 1, h, w, device=dev, generator=gen) > 0.5).float()) for _ in range(2)]
