@@ -406,7 +406,7 @@ def run_ours(args, wl):
     pk = peaks()
     traffic = None       # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             traffic = json.load(f).get(f"conv_{tkind}_kernel{tkey}", {}).get("traffic_bytes_per_launch")
     except Exception:
         pass

@@ -259,8 +259,10 @@ struct BwdParams {
   int virt_h;                                         // > 0: the h rows stand for virt_h rows (row classes, see above)
 };
 
+// (the pooled variants would take 172-180 registers = one 256-thread block per SM; capped at 128 they spill a few hundred
+// bytes to L1 but run two blocks per SM, which is what a latency-bound streaming kernel needs)
 template <typename T, bool kApply, bool kPool>
-__global__ void __launch_bounds__(kNT) bwd_kernel(const BwdParams<T> p) {
+__global__ void __launch_bounds__(kNT, kPool ? 2 : 1) bwd_kernel(const BwdParams<T> p) {
   const RowMap m = row_map(p.c);
   const int tid = threadIdx.x;
   const int rl = tid / m.cvl, cvi = tid % m.cvl;
