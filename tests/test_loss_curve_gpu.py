@@ -15,7 +15,8 @@ orders do not.  The test therefore requires, per loss term over the 100 steps,
     reference drifts from the fp32 one is the intrinsic sensitivity of the GAN game to bf16 rounding; where it drifts
     further than the fixed bounds above (v2 64x64: smoothed loss_G correlation 0.77 for our path), our path only has to
     track as well as it does: rms <= max(0.25 x range, 1.5 x its rms), correlation >= min(0.85, its correlation - 0.05),
-  * the reconstruction loss within 3% pointwise,
+  * the reconstruction loss within 3% pointwise -- or, where the autocast trajectory itself leaves that band (v2 64x64
+    reaches 3-4 % late in the run, after ~80 chaotic steps of the adversarial game), within 1.5 x ITS worst deviation,
 and the first step (identical weights) within 2e-2 for every term that does not depend on the updated D.
 A kernel bug shows up as a diverging or flat curve.
 """
@@ -113,7 +114,11 @@ def test_loss_curves_track_for_100_steps(family, h, w, batch):
         i = keys.index(k)
         assert abs(float(got_t[0, i] - ref_t[0, i])) <= 2e-2 * abs(float(ref_t[0, i])), (k, got_t[0, i], ref_t[0, i])
     i = keys.index("recon")
-    assert float(((got_t[:, i] - ref_t[:, i]).abs() / ref_t[:, i].abs()).max()) <= 3e-2
+    recon_dev = float(((got_t[:, i] - ref_t[:, i]).abs() / ref_t[:, i].abs()).max())
+    recon_cal = float(((cal_t[:, i] - ref_t[:, i]).abs() / ref_t[:, i].abs()).max())
+    print(f"recon: worst pointwise deviation {recon_dev:.4f} (autocast trajectory {recon_cal:.4f})")
+    assert recon_dev <= max(3e-2, 1.5 * recon_cal), (recon_dev, recon_cal)
+    assert float(((got_t[:20, i] - ref_t[:20, i]).abs() / ref_t[:20, i].abs()).max()) <= 3e-2     # before the game amplifies rounding
     for k, v in report.items():
         if v["range"] > 0.05:
             assert v["rms_over_range"] <= max(0.25, 1.5 * v["autocast_rms_over_range"]), (k, v)
