@@ -348,6 +348,13 @@ class ConvLinear:
             vt, wk = _vtaps([(0, 0, 0, 0)], k, k, hi)
             if hi:
                 _hi_launch(xs, vt, 1, k, wf, self.cout, (n, 1, 1), out, wk, bias, act)
+            elif out_kind == 0 and bias is None and act == 0 and k >= 64 * 256:
+                # a handful of output tiles against a very long K axis (the data gradient of the bottleneck
+                # ConvTranspose2d, vae-gan-unet.py:194: K = 16*16*1024): without split-K three to five CTAs would stream
+                # the whole weight (1.26 ms at 256x256); accumulate the K splits in fp32 and round once
+                acc = torch.zeros((n, 1, 1, self.cout), dtype=F32, device=x.device)
+                fprop(xs, vt, 1, k, wf, self.cout, (n, 1, 1), acc, out_kind=2, wk=wk)
+                ops.strided_copy(acc, out)
             else:
                 fprop(xs, vt, 1, k, wf, self.cout, (n, 1, 1), out, out_kind=out_kind, bias=bias, act=act, wk=wk)
             return out

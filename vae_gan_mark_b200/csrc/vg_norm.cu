@@ -14,6 +14,7 @@
 // and it walks rows with several independent loads in flight.  Reductions: registers -> shared memory across
 // the rows of a block -> one fp32 atomic per (block, channel); grids are kept small (<= 2 blocks per SM per
 // group) so that the atomics on one address do not serialise.
+#include <stdlib.h>
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
 
@@ -259,10 +260,18 @@ struct BwdParams {
   int virt_h;                                         // > 0: the h rows stand for virt_h rows (row classes, see above)
 };
 
-// (the pooled variants would take 172-180 registers = one 256-thread block per SM; capped at 128 they spill a few hundred
-// bytes to L1 but run two blocks per SM, which is what a latency-bound streaming kernel needs)
+// Register budget is what decides the bandwidth of these passes: a thread keeps four per-channel constants for its 8
+// channels (32 registers) and, while walking rows, U independent (x, dy) row pairs in flight.  Two 256-thread blocks per SM
+// (<= 128 registers) x 8 sixteen-byte loads per thread = 64 KB in flight per SM, enough to cover HBM latency at full
+// bandwidth; the first version of this kernel kept six constants per channel, took 148 registers = ONE block per SM with
+// four loads per thread, and ran at 0.45-0.75 of the copy bandwidth (0.35 for the pooled variant, which spilled).
+//   pre  = x * sc + sh                      (sc = gamma * rstd, sh = beta - mean * sc)      -> activation mask
+//   xhat = x * ca + cb                      (reduce pass: ca = rstd, cb = -mean * rstd)
+//   dx   = sc * g - wt * (x * ca + cb)      (apply pass:  ca = sc * k2 * rstd, cb = sc * (k1 - k2 * mean * rstd);
+//                                            k1 = mean(g), k2 = mean(g * xhat); wt = 1 except for row classes)
 template <typename T, bool kApply, bool kPool>
-__global__ void __launch_bounds__(kNT, kPool ? 2 : 1) bwd_kernel(const BwdParams<T> p) {
+__global__ void __launch_bounds__(kNT, 2) bwd_kernel(const BwdParams<T> p) {
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;           // rows in flight per thread (non-pooled walk)
   const RowMap m = row_map(p.c);
   const int tid = threadIdx.x;
   const int rl = tid / m.cvl, cvi = tid % m.cvl;
@@ -272,8 +281,10 @@ __global__ void __launch_bounds__(kNT, kPool ? 2 : 1) bwd_kernel(const BwdParams
   const long long cells = static_cast<long long>(n_count) * ph * pw;
   const long long stride = static_cast<long long>(gridDim.x) * m.rows_par;
   const float inv_rows = 1.f / (static_cast<float>(n_count) * (p.virt_h > 0 ? p.virt_h : p.h) * p.w);
+  const bool virt = kApply && p.virt_h > 0;
   const float wmid = p.virt_h > 0 ? static_cast<float>(p.virt_h - 2) / static_cast<float>(p.h - 2) : 1.f;
   const long long pix0 = static_cast<long long>(p.per_sample ? grp : 0) * p.h * p.w;
+  const float neg_slope = p.act == 1 ? 0.f : (p.act == 2 ? 0.2f : 1.f);      // act'(pre) for pre <= 0
   __shared__ float red[kApply ? 1 : kNT][17];
   for (int cv0 = 0; cv0 < m.cv; cv0 += m.cvl) {
     const int cvec = cv0 + cvi;
@@ -284,61 +295,63 @@ __global__ void __launch_bounds__(kNT, kPool ? 2 : 1) bwd_kernel(const BwdParams
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     if (active) {
       const float* mr = p.mean_rstd + static_cast<long long>(grp) * 2 * p.c;
-      float mean[8], rstd[8], sc[8], sh[8], k1[8], k2[8];
+      float sc[8], sh[8], ca[8], cb[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float ga = p.gamma ? p.gamma[ch + i] : 1.f, be = p.beta ? p.beta[ch + i] : 0.f;
-        mean[i] = mr[ch + i];
-        rstd[i] = mr[p.c + ch + i];
-        sc[i] = ga * rstd[i];
-        sh[i] = be - mean[i] * sc[i];
+        const float mean = mr[ch + i], rstd = mr[p.c + ch + i];
+        sc[i] = ga * rstd;
+        sh[i] = be - mean * sc[i];
         if (kApply) {
           const float* sm = p.sums + static_cast<long long>(grp) * 2 * p.c;
-          k1[i] = sm[ch + i] * inv_rows;
-          k2[i] = sm[p.c + ch + i] * inv_rows;
+          const float k1 = sm[ch + i] * inv_rows, k2 = sm[p.c + ch + i] * inv_rows;
+          ca[i] = sc[i] * k2 * rstd;
+          cb[i] = sc[i] * (k1 - k2 * mean * rstd);
+        } else {
+          ca[i] = rstd;
+          cb[i] = -mean * rstd;
         }
       }
       const T* xb = p.x + p.x_coff + ch;
       const T* gb = p.dy ? p.dy + p.dy_coff + ch : nullptr;
       T* ob = kApply ? p.dx + p.dx_coff + ch : nullptr;
 
-      // one pixel: g = dyv * act'(pre); accumulate or emit dx
-      auto pixel = [&](const Raw8<T>& xv, const float (&dyv)[8], long long pix) {
-        float f[8], o[8];
+      // one pixel: g = d * act'(pre); accumulate (reduce pass) or emit dx (apply pass)
+      auto pixel = [&](const Raw8<T>& xv, float (&d)[8], long long pix) {
+        float f[8];
         xv.unpack(f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (f[i] - mean[i]) * rstd[i];
-          const float g = dyv[i] * act_grad(fmaf(f[i], sc[i], sh[i]), p.act);
-          if (kApply) o[i] = sc[i] * (g - k1[i] - xh * k2[i]);
-          else { s[i] += g; q[i] = fmaf(g, xh, q[i]); }
-        }
         if (kApply) {
-          if (p.virt_h > 0) {
-            // g is already the sum over the rows of this class; the mean terms enter once per represented row
-            const float wt = row_class_weight(pix, p.w, p.h, wmid);
+          const float wt = virt ? row_class_weight(pix, p.w, p.h, wmid) : 1.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float xh = (f[i] - mean[i]) * rstd[i];
-              const float g = dyv[i] * act_grad(fmaf(f[i], sc[i], sh[i]), p.act);
-              o[i] = sc[i] * (g - wt * (k1[i] + xh * k2[i]));
-            }
+          for (int i = 0; i < 8; ++i) {
+            const float g = d[i] * (fmaf(f[i], sc[i], sh[i]) > 0.f ? 1.f : neg_slope);
+            d[i] = fmaf(sc[i], g, -wt * fmaf(f[i], ca[i], cb[i]));
           }
-          store8(ob + pix * p.dx_ld, o);
+          store8(ob + pix * p.dx_ld, d);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = d[i] * (fmaf(f[i], sc[i], sh[i]) > 0.f ? 1.f : neg_slope);
+            s[i] += g;
+            q[i] = fmaf(g, fmaf(f[i], ca[i], cb[i]), q[i]);
+          }
         }
       };
 
       if (!kPool) {
         long long r = static_cast<long long>(blockIdx.x) * m.rows_par + rl;
-        for (; r + stride < cells; r += 2 * stride) {
-          const long long pa = pix0 + r, pb = pix0 + r + stride;
-          const Raw8<T> xa = Raw8<T>::load(xb + pa * p.x_ld), xc = Raw8<T>::load(xb + pb * p.x_ld);
-          const Raw8<T> da = Raw8<T>::load(gb + pa * p.dy_ld), dc = Raw8<T>::load(gb + pb * p.dy_ld);
-          float d[8];
-          da.unpack(d);
-          pixel(xa, d, pa);
-          dc.unpack(d);
-          pixel(xc, d, pb);
+        for (; r + (U - 1) * stride < cells; r += U * stride) {
+          Raw8<T> xa[U], da[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) xa[u] = Raw8<T>::load(xb + (pix0 + r + u * stride) * p.x_ld);
+#pragma unroll
+          for (int u = 0; u < U; ++u) da[u] = Raw8<T>::load(gb + (pix0 + r + u * stride) * p.dy_ld);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float d[8];
+            da[u].unpack(d);
+            pixel(xa[u], d, pix0 + r + u * stride);
+          }
         }
         for (; r < cells; r += stride) {
           const long long pa = pix0 + r;
@@ -352,32 +365,34 @@ __global__ void __launch_bounds__(kNT, kPool ? 2 : 1) bwd_kernel(const BwdParams
           const int pi = static_cast<int>((cell / pw) % ph);
           const long long nn = (p.per_sample ? grp : cell / (static_cast<long long>(pw) * ph));
           const long long row0 = (nn * p.h + 2 * pi) * p.w + 2 * pj;
-          long long pix[4] = {row0, row0 + 1, row0 + p.w, row0 + p.w + 1};
           Raw8<T> xv[4], dv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) xv[u] = Raw8<T>::load(xb + pix[u] * p.x_ld);
+          for (int u = 0; u < 4; ++u) xv[u] = Raw8<T>::load(xb + (row0 + (u >> 1) * p.w + (u & 1)) * p.x_ld);
           if (gb != nullptr) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dv[u] = Raw8<T>::load(gb + pix[u] * p.dy_ld);
+            for (int u = 0; u < 4; ++u) dv[u] = Raw8<T>::load(gb + (row0 + (u >> 1) * p.w + (u & 1)) * p.dy_ld);
           }
           const long long ppix = (nn * ph + pi) * pw + pj;
-          float dp[8];
-          Raw8<T>::load(p.dpool + ppix * p.dp_ld + p.dp_coff + ch).unpack(dp);
-          // first maximum of the (bf16-rounded) activations of the window, per channel
-          int best[8];
-          float bv[8];
+          const Raw8<T> dpv = Raw8<T>::load(p.dpool + ppix * p.dp_ld + p.dp_coff + ch);
+          // first maximum of the (storage-rounded) activations of the window, per channel: 2 bits per channel
+          unsigned best = 0;
+          {
+            float bv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { best[i] = 0; bv[i] = -INFINITY; }
+            for (int i = 0; i < 8; ++i) bv[i] = -INFINITY;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float f[8];
-            xv[u].unpack(f);
+            for (int u = 0; u < 4; ++u) {
+              float f[8];
+              xv[u].unpack(f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float yv = as_stored<T>(act_fwd(fmaf(f[i], sc[i], sh[i]), p.act));
-              if (yv > bv[i]) { bv[i] = yv; best[i] = u; }
+              for (int i = 0; i < 8; ++i) {
+                const float yv = as_stored<T>(act_fwd(fmaf(f[i], sc[i], sh[i]), p.act));
+                if (yv > bv[i]) { bv[i] = yv; best = (best & ~(3u << (2 * i))) | (static_cast<unsigned>(u) << (2 * i)); }
+              }
             }
           }
+          float dp[8];
+          dpv.unpack(dp);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float d[8];
@@ -387,8 +402,8 @@ __global__ void __launch_bounds__(kNT, kPool ? 2 : 1) bwd_kernel(const BwdParams
               for (int i = 0; i < 8; ++i) d[i] = 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] += (best[i] == u) ? dp[i] : 0.f;
-            pixel(xv[u], d, pix[u]);
+            for (int i = 0; i < 8; ++i) d[i] += (((best >> (2 * i)) & 3u) == static_cast<unsigned>(u)) ? dp[i] : 0.f;
+            pixel(xv[u], d, row0 + (u >> 1) * p.w + (u & 1));
           }
         }
       }
@@ -570,8 +585,10 @@ static int norm_backward_impl(const VgNormBackward* d, cudaStream_t st) {
   const bool pool = d->dpool != nullptr;
   const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (pool ? d->h / 2 : d->h) *
                           (pool ? d->w / 2 : d->w);
-  const dim3 g_red(row_grid(cells, m.rows_par, groups, 4, pool ? 2 : 8), groups);
-  const dim3 g_app(row_grid(cells, m.rows_par, groups, 8, pool ? 2 : 8), groups);
+  static const int red_per_sm = getenv("VG_NORM_RED_PER_SM") ? atoi(getenv("VG_NORM_RED_PER_SM")) : 4;
+  static const int app_per_sm = getenv("VG_NORM_APP_PER_SM") ? atoi(getenv("VG_NORM_APP_PER_SM")) : 8;
+  const dim3 g_red(row_grid(cells, m.rows_par, groups, red_per_sm, pool ? 2 : 8), groups);
+  const dim3 g_app(row_grid(cells, m.rows_par, groups, app_per_sm, pool ? 2 : 8), groups);
   if (pool) {
     bwd_kernel<T, false, true><<<g_red, kNT, 0, st>>>(p);
     VG_LAUNCH_OK();

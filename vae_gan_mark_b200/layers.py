@@ -248,6 +248,7 @@ class HeadsFn(Function):
             feat = ops.dense_nhwc(feat)
         y = op.forward(feat, wf, None, 0, None, 2)
         ctx.op, ctx.cache_b = op, cache_b
+        ctx.wf = wf if (op.shuffle and not hi and 2 * z == op.cout_p) else None
         ctx.save_for_backward(feat, w_mu, w_lv)
         return y
 
@@ -265,7 +266,12 @@ class HeadsFn(Function):
                 ops.strided_copy(w_mu.detach().permute(2, 3, 1, 0), tmp[..., :z])
                 ops.strided_copy(w_lv.detach().permute(2, 3, 1, 0), tmp[..., z:])
                 return {"shuffle": _operand(tmp.view(kh * kw * c, 1, 2 * z), op.cout_p, hi)}
-            wb = ctx.cache_b.get("bwd_hi" if hi else "bwd", (w_mu, w_lv), build)
+            if not hi and ctx.wf is not None and op.prefer_mn(feat.shape[0]):
+                # a handful of pixels against a (2z x h*w*c) weight: the forward operand doubles as the MN-major operand of
+                # the data gradient -- no transposed copy of the two head weights per step (2 x 134 MB at 256x256)
+                wb = {"mn": ctx.wf}
+            else:
+                wb = ctx.cache_b.get("bwd_hi" if hi else "bwd", (w_mu, w_lv), build)
             dx = op.backward_data(dy, wb, (feat.shape[1], feat.shape[2]))
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             g = op.backward_weight(dy, feat)                 # view [2z, c, kh, kw]
