@@ -116,6 +116,21 @@ VG_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp that
 VG_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 VG_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp (the same lane every time for a given membermask).  The MMA-issuing warp runs its
+// loop with all 32 lanes so that descriptors and addresses stay in UNIFORM registers, and only the tcgen05 instructions
+// themselves sit under this predicate: inside an `if (lane == 0)` region the compiler treats every operand as divergent and
+// wraps each tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall loop (~21 instructions, ~135 cycles per MMA -- longer than a
+// 128 x 64 x 16 or 128 x 128 x 16 MMA occupies the tensor pipe).
+VG_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate; issued by ONE thread.
 VG_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -123,6 +138,20 @@ VG_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, with the two shared-memory descriptors given as (low, high) 32-bit halves: the high half (SBO, version, layout) is
+// constant per operand and the low half (start address | LBO << 16) moves by small offsets, so the per-MMA address
+// arithmetic is 32-bit and stays in the uniform datapath.
+VG_DEVICE void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed
@@ -180,6 +209,18 @@ VG_DEVICE void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+VG_DEVICE void umma_bf16_2cta_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                   uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(z)
       : "memory");
 }
 // arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of this thread have completed

@@ -135,9 +135,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 256;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // broadcast: provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = k2 ? cluster_ctarank() : 0u;        // 0 = leader of the pair (issues the MMAs)
+  // 0 = leader of the pair (issues the MMAs); clusters are (2, 1, 1), so the rank is the parity of blockIdx.x (uniform)
+  const uint32_t rank = k2 ? (blockIdx.x & 1u) : 0u;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -181,21 +182,24 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     return (2 * unit + static_cast<int>(rank)) * p.n_tiles + n_t;
   };
 
-  // Producer: in the plain K-major mode ONE thread issues both loads of a stage (measured 2-7 % faster than a
-  // warp-wide loop with a __syncwarp per stage); the MN-major and halo modes have up to 10 boxes per stage and use one
-  // lane per box (a single issuing thread left the tensor pipe idle there, cf. the wgrad kernel).
-  const bool wide_producer = p.b_mn || p.halo;
-  if (warp == 0 && (lane == 0 || wide_producer)) {
+  // Producer: the whole warp walks the K loop with uniform control flow, and ONE elected lane issues the copies of a
+  // stage (2 in the plain mode, up to 5 with an MN-major B operand, up to 10 in the halo mode) one after the other with
+  // warp-uniform coordinates -- a few uniform-datapath instructions per copy.  (Issued from inside a per-lane region every
+  // copy sits in an ELECT / R2UR waterfall loop of ~20 instructions; see the MMA issuer below.)
+  if (warp == 0) {
     // ===================== TMA producer =====================
+    const bool leader = elect_one();
     const int b_boxes = p.b_mn ? p.bn / 64 : 1;
     int stage = 0;
     uint32_t phase = 0;
     if (p.w_bytes > 0 && worker < total_work) {
       // resident weights: tile (cc, tap) at wres + (cc*9 + tap) * bn*128; one barrier for all of them
-      if (lane == 0) mbar_arrive_expect_tx(w_bar, p.w_bytes);
-      __syncwarp();
-      for (int i = lane; i < 9 * cchunks_all; i += 32)
-        tma_load_2d(wres + static_cast<size_t>(i) * (p.bn * 128), &tmap_b, w_bar, p.wk[i % 9] + (i / 9) * kBK, 0);
+      if (leader) mbar_arrive_expect_tx(w_bar, p.w_bytes);
+      for (int cc = 0; cc < cchunks_all; ++cc) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          if (leader) tma_load_2d(wres + static_cast<size_t>(cc * 9 + t) * (p.bn * 128), &tmap_b, w_bar, p.wk[t] + cc * kBK, 0);
+      }
     }
     for (int work = worker; work < total_work; work += nworkers) {
       const int tile = tile_of(work);
@@ -214,19 +218,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int k_begin = static_cast<int>((static_cast<long long>(ksteps) * split) / p.ksplit);
       const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
       if (p.halo) {
-        // one stage per 64-channel chunk: the halo (lane 0) and the nine weight tiles (lanes 1..9)
+        // one stage per 64-channel chunk: the halo and (unless they are resident) the nine weight tiles
         for (int cc = 0; cc < cchunks; ++cc) {
-          if (lane == 0) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kHaloRows * 128 + (p.w_bytes > 0 ? 0 : 9 * p.bn * 128));
-          }
-          __syncwarp();
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], kHaloRows * 128 + (p.w_bytes > 0 ? 0 : 9 * p.bn * 128));
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          if (lane == 0)
-            tma_load_5d(sa, &tmap_a, &full_bar[stage], p.taps[0].x + cc * kBK, ow0 - 1, 0, oh0 - 1, n0);
-          else if (lane <= 9 && p.w_bytes == 0)
-            tma_load_2d(sa + a_bytes + (lane - 1) * (p.bn * 128), &tmap_b, &full_bar[stage], p.wk[lane - 1] + cc * kBK,
-                        n_t * p.bn);
+          if (leader) tma_load_5d(sa, &tmap_a, &full_bar[stage], p.taps[0].x + cc * kBK, ow0 - 1, 0, oh0 - 1, n0);
+          if (p.w_bytes == 0) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+              if (leader) tma_load_2d(sa + a_bytes + t * (p.bn * 128), &tmap_b, &full_bar[stage], p.wk[t] + cc * kBK, n_t * p.bn);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         continue;
@@ -234,35 +236,45 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int tap = p.g_tap0[grp] + k_begin / cchunks;
       int cc = k_begin % cchunks;
       for (int k = k_begin; k < k_end; ++k) {
-        if (lane == 0) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
           if (!k2) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           else if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);      // both CTAs' boxes land on the leader's barrier
         }
-        if (wide_producer) __syncwarp();
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         uint8_t* sb = sa + a_bytes;
+        const int4 t = p.taps[tap];
+        const int wk = p.wk[tap];
         if (k2) {
-          if (lane == 0) {
-            const int4 t = p.taps[tap];
-            tma_load_5d_2cta(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
-            tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn + static_cast<int>(rank) * (p.bn / 2));
+          if (leader) tma_load_5d_2cta(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
+          if (leader) tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], wk + cc * kBK, n_t * p.bn + static_cast<int>(rank) * (p.bn / 2));
+        } else {
+          if (leader) tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
+          if (!p.b_mn) {
+            if (leader) tma_load_2d(sb, &tmap_b, &full_bar[stage], wk + cc * kBK, n_t * p.bn);
+          } else {
+            // MN-major boxes: N columns [n_t*bn + 64*i, +64) of this tap, K rows [cc*64, +64)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < b_boxes) {
+                if (leader) tma_load_2d(sb + i * (64 * 128), &tmap_b, &full_bar[stage], wk + n_t * p.bn + i * 64, cc * kBK);
+              }
           }
-        } else if (lane == 0) {
-          const int4 t = p.taps[tap];
-          tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
-          if (!p.b_mn) tma_load_2d(sb, &tmap_b, &full_bar[stage], p.wk[tap] + cc * kBK, n_t * p.bn);
-        } else if (lane <= b_boxes) {
-          // MN-major box (lane-1): N columns [n_t*bn + 64*(lane-1), +64) of this tap, K rows [cc*64, +64)
-          tma_load_2d(sb + (lane - 1) * (64 * 128), &tmap_b, &full_bar[stage], p.wk[tap] + n_t * p.bn + (lane - 1) * 64,
-                      cc * kBK);
         }
         if (++cc == cchunks) { cc = 0; ++tap; }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+    __syncwarp();
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader CTA only in the pair variant) =====================
+    // The WHOLE warp runs this loop (waits included) so that every address and descriptor is warp-uniform and lives in
+    // uniform registers; only the tcgen05 instructions are predicated on one elected lane (see elect_one()).  Issued from
+    // inside an `if (lane == 0)` region the same loop cost ~135 cycles per MMA, more than a 128 x 64 x 16 (32 cycles) or
+    // 128 x 128 x 16 (64 cycles) MMA occupies the tensor pipe: the narrow layers ran at 0.25-0.5 of the tensor peak because
+    // of the issue loop, not because of the tensor pipe (tools/mma_issue_bench.cu: 50 / 64 / 128 cycles per MMA at N = 64 /
+    // 128 / 256 once the issue loop is lean, shifted halo views and MN-major operands included).
+    const bool leader = elect_one();
     const uint32_t idesc = umma_idesc_bf16(k2 ? 2 * kBM : kBM, p.bn, 0, p.b_mn);
     int stage = 0;
     uint32_t phase = 0;
@@ -272,9 +284,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(w_bar, 0);
       tc_fence_after();
     }
+    // descriptor halves: the high word (SBO, version, swizzle) is constant per operand kind; the low word is the start
+    // address (16-byte units) | LBO << 16
+    const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, p.halo ? kHaloW * 128 : 1024) >> 32);
+    const uint64_t b_proto = p.b_mn ? umma_smem_desc_sw128(0, 64 * 128, 1024) : umma_smem_desc_sw128(0, 16, 1024);
+    const uint32_t b_hi = static_cast<uint32_t>(b_proto >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, 1024));          // LBO field only
+    const uint32_t b_lo0 = static_cast<uint32_t>(b_proto);
+    const uint32_t b_step16 = p.b_mn ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
     uint32_t halo_a16[9];      // start of each tap's view inside the halo buffer, in 16-byte units
 #pragma unroll
     for (int t = 0; t < 9; ++t) halo_a16[t] = static_cast<uint32_t>(((p.taps[t].w + 1) * kHaloW + (p.taps[t].y + 1)) * 128) >> 4;
+    const uint32_t b_tap16 = static_cast<uint32_t>(p.bn * 128) >> 4;
     for (int work = worker; work < total_work; work += nworkers) {
       const int tile = tile_of(work);
       const int grp = tile / tiles_per_group;
@@ -286,27 +307,26 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
       if (p.halo) {
-        // Issue cost matters here: an N = 64 MMA occupies the tensor pipe for ~20 cycles, so the issuing thread must
-        // not spend more than that per MMA.  The descriptors of one stage differ only in their start-address field:
-        // build one per operand and ADD the (precomputed, 16-byte unit) tap and K offsets.
-        const uint32_t b_tap16 = static_cast<uint32_t>(p.bn * 128) >> 4;
+        // the descriptors of one stage differ only in their start-address field: one base per operand plus the
+        // (precomputed, 16-byte unit) tap and K offsets
         for (int cc = 0; cc < cchunks_all; ++cc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = p.w_bytes > 0 ? smem_u32(wres) + static_cast<uint32_t>(cc * 9 * p.bn * 128) : sa + a_bytes;
-          const uint64_t da0 = umma_smem_desc_sw128(sa, 16, kHaloW * 128);
-          const uint64_t db0 = umma_smem_desc_sw128(sb, 16, 1024);
+          const uint32_t a_lo = a_lo0 + (sa >> 4), b_lo = b_lo0 + (sb >> 4);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
 #pragma unroll
             for (int j = 0; j < kBK / kUmmaK; ++j)
-              umma_bf16(d_tmem, da0 + halo_a16[t] + 2 * j, db0 + t * b_tap16 + 2 * j, idesc, (cc > 0 || t > 0 || j > 0) ? 1u : 0u);
+              if (leader)
+                umma_bf16_lohi(d_tmem, a_lo + halo_a16[t] + 2 * j, a_hi, b_lo + t * b_tap16 + 2 * j, b_hi, idesc,
+                               (cc > 0 || t > 0 || j > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (leader) umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (leader) umma_commit(&tmem_full[acc]);
         if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
         continue;
       }
@@ -315,23 +335,25 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
         const uint32_t sb = sa + a_bytes;
-        const uint64_t da0 = umma_smem_desc_sw128(sa, 16, 1024);
         // MN-major B: 16 K rows = 2 groups of 8 rows (SBO = 1024 B apart); 64-column N groups one box (8 KB) apart
-        const uint64_t db0 = p.b_mn ? umma_smem_desc_sw128(sb, 64 * 128, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
-        const uint32_t b_step16 = p.b_mn ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
+        const uint32_t a_lo = a_lo0 + (sa >> 4), b_lo = b_lo0 + (sb >> 4);
 #pragma unroll
         for (int j = 0; j < kBK / kUmmaK; ++j) {
-          if (k2) umma_bf16_2cta(d_tmem, da0 + 2 * j, db0 + j * b_step16, idesc, (k > k_begin || j > 0) ? 1u : 0u);
-          else umma_bf16(d_tmem, da0 + 2 * j, db0 + j * b_step16, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+          const uint32_t accum = (k > k_begin || j > 0) ? 1u : 0u;
+          if (leader) {
+            if (k2) umma_bf16_2cta_lohi(d_tmem, a_lo + 2 * j, a_hi, b_lo + j * b_step16, b_hi, idesc, accum);
+            else umma_bf16_lohi(d_tmem, a_lo + 2 * j, a_hi, b_lo + j * b_step16, b_hi, idesc, accum);
+          }
         }
         // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-        if (k2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+        if (leader) { if (k2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]); }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       // accumulator complete -> epilogue (of both CTAs)
-      if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+      if (leader) { if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
     // TMEM -> registers (thread = one pixel row, 64 bf16 / 32 fp32 columns = 128 bytes per round) -> bias/activation

@@ -66,9 +66,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 256;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // broadcast: provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = k2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
+  const uint32_t rank = k2 ? (blockIdx.x & 1u) : 0u;       // 0 = leader (issues the MMAs); clusters are (2, 1, 1)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_g);
@@ -102,8 +102,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // One lane per TMA box (2 dY boxes + up to 4 X boxes per stage): the coordinate arithmetic and the issue of the
-    // six copies run in parallel lanes instead of serially in one thread, which otherwise starves the tensor pipe.
+    // The whole warp walks the K loop with uniform control flow; the up to six copies of a stage (2 dY boxes + up to 4 X
+    // boxes) are issued one after the other by ONE elected lane with warp-uniform coordinates (a few uniform-datapath
+    // instructions each).  Issued from inside a per-lane region -- one thread, or one lane per box -- every copy sits in
+    // an ELECT / R2UR waterfall loop of ~20 instructions, which starved the tensor pipe.
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = worker; tile < total_tiles; tile += nworkers) {
@@ -125,15 +128,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         const int nb0 = max(0, min(nb_cta, nblk)), nb1 = max(0, min(nb_cta, nblk - nb_cta));
         tx_bytes = static_cast<uint32_t>(ab0 + ab1 + nb0 + nb1) * kWgBoxBytes;
       }
-      // this lane's box: lanes [0, aboxes) load dY, lanes [2, 2 + myb) load X
-      const bool is_a = lane < aboxes;
-      const bool is_b = lane >= 2 && lane < 2 + myb;
-      int c0 = 0, dwv = 0, shv = 0, dhv = 0;
-      if (is_a) c0 = p.g_coff + m_t * kWgBM + lane * 64;
-      if (is_b) {
-        const int b = n_t * p.nb + b0 + (lane - 2);
-        const int4 t = p.taps[b / cchunks];
-        c0 = t.x + (b % cchunks) * 64; dwv = t.y; shv = t.z; dhv = t.w;
+      // box coordinates that do not change along K: dY boxes i < aboxes, X boxes j < myb
+      const int ca0 = p.g_coff + m_t * kWgBM;
+      int cb[4], dwv[4], shv[4], dhv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int blk = min(n_t * p.nb + b0 + j, p.blocks_total - 1);
+        const int4 t = p.taps[blk / cchunks];
+        cb[j] = t.x + (blk % cchunks) * 64; dwv[j] = t.y; shv[j] = t.z; dhv[j] = t.w;
       }
       int combo = k_begin % p.ncombos;
       const int pt0 = k_begin / p.ncombos;
@@ -141,21 +143,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
       int th_i = (pt0 / p.tiles_w) % p.tiles_h;
       int tn_i = pt0 / (p.tiles_w * p.tiles_h);
       for (int k = k_begin; k < k_end; ++k) {
-        if (lane == 0) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (!k2 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-        }
-        __syncwarp();
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader && (!k2 || rank == 0)) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
         const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
-        if (k2) {
-          if (is_a) tma_load_5d_2cta(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0 + p.combo_g[combo], ow0, 0, oh0, n0);
-          if (is_b) tma_load_5d_2cta(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0 + p.combo_x[combo],
-                                     ow0 + dwv, shv, oh0 + dhv, n0);
-        } else {
-          if (is_a) tma_load_5d(sa + lane * kWgBoxBytes, &tmap_g, &full_bar[stage], c0 + p.combo_g[combo], ow0, 0, oh0, n0);
-          if (is_b) tma_load_5d(sa + a_bytes + (lane - 2) * kWgBoxBytes, &tmap_x, &full_bar[stage], c0 + p.combo_x[combo],
-                                ow0 + dwv, shv, oh0 + dhv, n0);
+        const int cg = ca0 + p.combo_g[combo], cx = p.combo_x[combo];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (i < aboxes) {
+            if (leader) {
+              if (k2) tma_load_5d_2cta(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], cg + i * 64, ow0, 0, oh0, n0);
+              else tma_load_5d(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], cg + i * 64, ow0, 0, oh0, n0);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < myb) {
+            if (leader) {
+              if (k2) tma_load_5d_2cta(sa + a_bytes + j * kWgBoxBytes, &tmap_x, &full_bar[stage], cb[j] + cx, ow0 + dwv[j], shv[j],
+                                       oh0 + dhv[j], n0);
+              else tma_load_5d(sa + a_bytes + j * kWgBoxBytes, &tmap_x, &full_bar[stage], cb[j] + cx, ow0 + dwv[j], shv[j],
+                               oh0 + dhv[j], n0);
+            }
+          }
         }
         if (++combo == p.ncombos) {
           combo = 0;
@@ -164,9 +175,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+    __syncwarp();
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader CTA only in the pair variant) =====================
+    // whole warp, uniform control flow and addresses; only the tcgen05 instructions sit under the elected lane (see the
+    // forward kernel and elect_one(): an `if (lane == 0)` region costs ~135 cycles of issue overhead per MMA)
+    const bool leader = elect_one();
     const uint32_t idesc = umma_idesc_bf16(k2 ? 2 * kWgBM : kWgBM, p.bn, 1, 1);
+    const uint64_t proto = umma_smem_desc_sw128(0, kWgBoxBytes, 1024);
+    const uint32_t d_hi = static_cast<uint32_t>(proto >> 32), d_lo0 = static_cast<uint32_t>(proto);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -183,20 +200,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
         const uint32_t sb = sa + a_bytes;
+        const uint32_t a_lo = d_lo0 + (sa >> 4), b_lo = d_lo0 + (sb >> 4);
 #pragma unroll
         for (int j = 0; j < kWgPix / 16; ++j) {
           // 16 pixels (= 2 groups of 8 rows, SBO apart) per MMA; 64-channel groups LBO (= one box) apart
-          const uint64_t da = umma_smem_desc_sw128(sa + j * 16 * 128, kWgBoxBytes, 1024);
-          const uint64_t db = umma_smem_desc_sw128(sb + j * 16 * 128, kWgBoxBytes, 1024);
-          if (k2) umma_bf16_2cta(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
-          else umma_bf16(d_tmem, da, db, idesc, (k > k_begin || j > 0) ? 1u : 0u);
+          const uint32_t accum = (k > k_begin || j > 0) ? 1u : 0u;
+          if (leader) {
+            if (k2) umma_bf16_2cta_lohi(d_tmem, a_lo + j * (16 * 128 >> 4), d_hi, b_lo + j * (16 * 128 >> 4), d_hi, idesc, accum);
+            else umma_bf16_lohi(d_tmem, a_lo + j * (16 * 128 >> 4), d_hi, b_lo + j * (16 * 128 >> 4), d_hi, idesc, accum);
+          }
         }
-        if (k2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+        if (leader) { if (k2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]); }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+      if (leader) { if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // TMEM -> registers (thread = one output-channel row, 32 fp32 columns at a time) -> per-warp staging tile in

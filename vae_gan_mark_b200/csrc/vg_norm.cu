@@ -585,8 +585,8 @@ static int norm_backward_impl(const VgNormBackward* d, cudaStream_t st) {
   const bool pool = d->dpool != nullptr;
   const long long cells = static_cast<long long>(d->per_sample ? 1 : d->n) * (pool ? d->h / 2 : d->h) *
                           (pool ? d->w / 2 : d->w);
-  static const int red_per_sm = getenv("VG_NORM_RED_PER_SM") ? atoi(getenv("VG_NORM_RED_PER_SM")) : 4;
-  static const int app_per_sm = getenv("VG_NORM_APP_PER_SM") ? atoi(getenv("VG_NORM_APP_PER_SM")) : 8;
+  static const int red_per_sm = getenv("VG_NORM_RED_PER_SM") ? atoi(getenv("VG_NORM_RED_PER_SM")) : 2;
+  static const int app_per_sm = getenv("VG_NORM_APP_PER_SM") ? atoi(getenv("VG_NORM_APP_PER_SM")) : 2;
   const dim3 g_red(row_grid(cells, m.rows_par, groups, red_per_sm, pool ? 2 : 8), groups);
   const dim3 g_app(row_grid(cells, m.rows_par, groups, app_per_sm, pool ? 2 : 8), groups);
   if (pool) {
