@@ -341,9 +341,32 @@ int vg_adam_step(float* p, float* g, float* m, float* v, long long n, float lr, 
 int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_h, double* minv);
 int vg_warp_perspective_u8(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
                            const double* minv, int out_h, int out_w, unsigned char* dst_u8, float* dst_chw, void* stream);
-/* test hook: the kernel's per-pixel code on HOST buffers (not a fallback; nothing in the package calls it) */
+/* general form: inverse (destination -> source) map of cv2.getPerspectiveTransform(src_quad -> dst_quad), HOST */
+int vg_perspective_matrix(const float* src_quad, const float* dst_quad, double* minv);
+/* perspective_unwarp (vae-gan.py:190-200): the generated patch pasted back into the page.  vg_perspective_unwarp_matrix
+ * (HOST): patch rectangle [0, patch_w - 1] x [0, patch_h - 1] -> bbox.  vg_warp_perspective_u8_transparent: the warp with
+ * borderMode = BORDER_TRANSPARENT into the caller's DEVICE canvas [out_h][out_w][channels] uint8 (the reference zero-fills
+ * it first): only destination pixels whose source coordinate falls inside the patch are written (cv2 4.13 semantics). */
+int vg_perspective_unwarp_matrix(const float* bbox, int patch_w, int patch_h, double* minv);
+int vg_warp_perspective_u8_transparent(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
+                                       const double* minv, int out_h, int out_w, unsigned char* canvas_u8, void* stream);
+/* a whole batch of warps (the patches of one training batch: vae-gan.py:268-283 runs perspective_crop three times per
+ * sample) in ONE launch, one grid row per job.  The caller owns the table: `jobs_host` (validated here) and an identical
+ * copy `jobs_device` in device memory, made on `stream` before the call. */
+typedef struct VgWarpJob {
+  const unsigned char* src; int src_h, src_w, channels; long long src_row_bytes;
+  double minv[9];
+  int out_h, out_w;
+  unsigned char* dst_u8; float* dst_chw;      /* either may be NULL (not both) */
+  int transparent;                            /* 0: BORDER_REPLICATE (crop), 1: BORDER_TRANSPARENT into dst_u8 (unwarp) */
+} VgWarpJob;
+int vg_warp_perspective_u8_batch(const VgWarpJob* jobs_host, const VgWarpJob* jobs_device, int count, void* stream);
+/* test hooks: the kernel's per-pixel code on HOST buffers (not a fallback; nothing in the package calls them) */
 int vg_debug_warp_perspective_host(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
                                    const double* minv, int out_h, int out_w, unsigned char* dst_u8, float* dst_chw);
+int vg_debug_warp_perspective_transparent_host(const unsigned char* src, int src_h, int src_w, int channels,
+                                               long long src_row_bytes, const double* minv, int out_h, int out_w,
+                                               unsigned char* canvas_u8);
 
 #ifdef __cplusplus
 }

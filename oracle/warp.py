@@ -109,8 +109,12 @@ def warp_coords(minv: np.ndarray, out_w: int, out_h: int):
     return np.rint(fx).astype(np.int64), np.rint(fy).astype(np.int64)      # cvRound: half to even
 
 
-def warp_perspective_u8(img: np.ndarray, m: np.ndarray, out_shape) -> np.ndarray:
-    """cv2.warpPerspective(img, m, (W, H), flags=INTER_LINEAR, borderMode=BORDER_REPLICATE) for uint8 images."""
+def warp_perspective_u8(img: np.ndarray, m: np.ndarray, out_shape, transparent_into: np.ndarray = None) -> np.ndarray:
+    """cv2.warpPerspective(img, m, (W, H), flags=INTER_LINEAR, borderMode=BORDER_REPLICATE) for uint8 images.
+    ``transparent_into`` = a (H, W[, C]) uint8 canvas: borderMode=BORDER_TRANSPARENT with ``dst=canvas`` instead.
+    Pinned against cv2 4.13 (tests/test_warp_oracle.py): a destination pixel is written iff the integer part of its source
+    coordinate lies inside the source (0 <= sx <= sw - 1 and 0 <= sy <= sh - 1), with the same value BORDER_REPLICATE
+    gives (the +1 neighbours of the last row / column are clamped); every other canvas pixel is left untouched."""
     assert img.dtype == np.uint8
     out_w, out_h = out_shape
     src = img if img.ndim == 3 else img[:, :, None]
@@ -129,12 +133,33 @@ def warp_perspective_u8(img: np.ndarray, m: np.ndarray, out_shape) -> np.ndarray
     p = src.astype(np.int64)
     acc = p[y0, x0] * w00 + p[y0, x1] * w01 + p[y1, x0] * w10 + p[y1, x1] * w11
     out = ((acc * 32 + (1 << 14)) >> 15).astype(np.uint8)
+    if transparent_into is not None:
+        canvas = transparent_into if transparent_into.ndim == 3 else transparent_into[:, :, None]
+        assert canvas.shape == out.shape and canvas.dtype == np.uint8
+        inside = (sx >= 0) & (sx <= sw - 1) & (sy >= 0) & (sy <= sh - 1)
+        out = np.where(inside[..., None], out, canvas)
     return out if img.ndim == 3 else out[:, :, 0]
 
 
 def perspective_crop(img: np.ndarray, bbox, out_shape) -> np.ndarray:
     """vae-gan.py:163-188 on a uint8 array (H, W[, C]); out_shape = (W, H).  Returns the uint8 patch."""
     return warp_perspective_u8(img, crop_matrix(bbox, out_shape), out_shape)
+
+
+def unwarp_matrix(bbox, patch_shape) -> np.ndarray:
+    """The matrix ``perspective_unwarp`` hands to warpPerspective (vae-gan.py:193-196): patch rectangle -> bbox;
+    patch_shape = (W, H) of the patch."""
+    w, h = patch_shape
+    src = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], dtype=np.float32)
+    return get_perspective_transform(src, np.asarray(bbox, dtype=np.float32).reshape(4, 2))
+
+
+def perspective_unwarp(patch: np.ndarray, bbox, canvas_shape) -> np.ndarray:
+    """vae-gan.py:190-200: paste a (generated) uint8 patch (h, w[, C]) back into a zero canvas of ``canvas_shape`` =
+    (H, W[, C]) through the inverse perspective map, borderMode=BORDER_TRANSPARENT."""
+    canvas = np.zeros(canvas_shape, dtype=np.uint8)
+    h, w = patch.shape[:2]
+    return warp_perspective_u8(patch, unwarp_matrix(bbox, (w, h)), (canvas_shape[1], canvas_shape[0]), transparent_into=canvas)
 
 
 def to_tensor(patch: np.ndarray) -> np.ndarray:
@@ -153,3 +178,30 @@ def fixture_inputs():
              [[-20, -10], [100, 5], [90, 50], [-15, 60]], [[60, 40], [200, 30], [210, 120], [55, 110]],
              [[5, 5], [68, 5], [68, 36], [5, 36]], [[150, 10], [20, 15], [25, 85], [155, 90]]]
     return page, mask, boxes
+
+
+def unwarp_fixture_patches():
+    """Deterministic patches of tests/golden/warp_unwarp.npz (outputs of the reference's own ``perspective_unwarp`` on the
+    quadrilaterals of ``fixture_inputs``, recorded by tests/golden/make_golden.py warp_unwarp)."""
+    rng = np.random.default_rng(2025)
+    return {"rgb_64x448": rng.integers(0, 256, size=(64, 448, 3), dtype=np.uint8),
+            "gray_32x64": rng.integers(0, 256, size=(32, 64), dtype=np.uint8)}
+
+
+def unwarp_cases(rng, n):
+    """(patch, bbox, canvas_shape): 1-4 channel patches down to 2 x 2, quadrilaterals partly off the canvas, rotated corner
+    order (mirrored pastes)."""
+    for trial in range(n):
+        ch = [None, 3, 1, 3, 4, 2][trial % 6]
+        h, w = int(rng.integers(2, 70)), int(rng.integers(2, 200))
+        patch = rng.integers(0, 256, size=(h, w) if ch is None else (h, w, ch), dtype=np.uint8)
+        H, W = int(rng.integers(60, 200)), int(rng.integers(80, 300))
+        cx, cy = rng.uniform(20, W - 20), rng.uniform(20, H - 20)
+        sx, sy = rng.uniform(10, W / 2), rng.uniform(8, H / 2)
+        bbox = (np.array([[cx - sx, cy - sy], [cx + sx, cy - sy], [cx + sx, cy + sy], [cx - sx, cy + sy]], dtype=np.float32)
+                + rng.uniform(-6, 6, size=(4, 2)).astype(np.float32))
+        if trial % 5 == 0:
+            bbox -= 30
+        if trial % 7 == 0:
+            bbox = bbox[[1, 2, 3, 0]]
+        yield patch, bbox, ((H, W) if ch is None else (H, W, ch))

@@ -159,9 +159,28 @@ def run_warp_case():
     print("warp_crop", len(gold), "patches", os.path.getsize(os.path.join(HERE, "warp_crop.npz")) // 1024, "KiB")
 
 
+def run_unwarp_case():
+    """The reference's own ``perspective_unwarp`` (vae-gan.py:190-200) on PIL patches: a generated patch pasted back into
+    a zero canvas of the page's shape."""
+    import numpy as np
+    from PIL import Image
+    mod = ref_loader.load("base", (448, 64))
+    from oracle.warp import fixture_inputs, unwarp_fixture_patches
+    page, mask, boxes = fixture_inputs()
+    gold = {}
+    for name, patch in unwarp_fixture_patches().items():
+        for i, box in enumerate(boxes):
+            shape = page.shape if patch.ndim == 3 else mask.shape
+            out = mod.perspective_unwarp(Image.fromarray(patch), box, shape)
+            assert out.dtype == np.uint8 and out.shape == shape
+            gold[f"{name}_{i}"] = out
+    np.savez_compressed(os.path.join(HERE, "warp_unwarp.npz"), **gold)
+    print("warp_unwarp", len(gold), "canvases", os.path.getsize(os.path.join(HERE, "warp_unwarp.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     torch.set_num_threads(8)
-    names = sys.argv[1:] or list(CASES) + ["warp_crop"]
+    names = sys.argv[1:] or list(CASES) + ["warp_crop", "warp_unwarp"]
     for n in names:
-        run_warp_case() if n == "warp_crop" else run_case(n)
+        run_warp_case() if n == "warp_crop" else (run_unwarp_case() if n == "warp_unwarp" else run_case(n))

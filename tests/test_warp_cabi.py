@@ -134,3 +134,26 @@ def test_host_twin_reproduces_the_reference_fixture():
             assert np.array_equal(got, gold[f"{shape[0]}x{shape[1]}_{i}_rgb"].astype(np.float32) / np.float32(255))
             gotm = data._crop(torch.from_numpy(mask), box, shape, False, host_twin=True).numpy()
             assert np.array_equal(gotm[None], gold[f"{shape[0]}x{shape[1]}_{i}_mask"])
+
+
+def test_unwarp_host_half_and_per_pixel_code_are_bit_exact():
+    """perspective_unwarp (vae-gan.py:190-200): vg_perspective_unwarp_matrix against the oracle's matrix, and the kernel's
+    per-pixel code in BORDER_TRANSPARENT mode (host twin, through data.perspective_unwarp's own marshalling) against the
+    oracle, which tests/test_warp_oracle.py pins to cv2 -- incl. pasting into a non-zero canvas."""
+    import torch
+    from vae_gan_mark_b200 import data
+    rng = np.random.default_rng(6)
+    for k, (patch, bbox, cshape) in enumerate(warp.unwarp_cases(rng, 36)):
+        h, w = patch.shape[:2]
+        got_m = np.array(list(data.perspective_unwarp_matrix(bbox.tolist(), (w, h)))).reshape(3, 3)
+        assert np.array_equal(got_m, warp.inverse_map(warp.unwarp_matrix(bbox, (w, h))))
+        if patch.ndim == 3 and patch.shape[2] == 2:
+            continue                                  # the oracle handles any channel count; keep the twin to 1 / 3 / 4
+        got = data.perspective_unwarp(torch.from_numpy(patch), bbox.tolist(), cshape, host_twin=True).numpy()
+        assert np.array_equal(got, warp.perspective_unwarp(patch, bbox, cshape)), k
+        if k % 4 == 0:
+            page = rng.integers(0, 256, size=cshape, dtype=np.uint8)
+            want = warp.warp_perspective_u8(patch, warp.unwarp_matrix(bbox, (w, h)), (cshape[1], cshape[0]), transparent_into=page)
+            got = data.perspective_unwarp(torch.from_numpy(patch), bbox.tolist(), cshape, canvas=torch.from_numpy(page.copy()),
+                                          host_twin=True).numpy()
+            assert np.array_equal(got, want)

@@ -68,3 +68,67 @@ def test_gpu_reproduces_the_reference_fixture():
             assert np.array_equal(got, gold[f"{shape[0]}x{shape[1]}_{i}_rgb"].astype(np.float32) / np.float32(255))
             gotm = data.perspective_crop(dmask, box, shape, to_tensor=False).cpu().numpy()
             assert np.array_equal(gotm[None], gold[f"{shape[0]}x{shape[1]}_{i}_mask"])
+
+
+def test_perspective_unwarp_is_bit_exact():
+    """The inverse direction (vae-gan.py:190-200) on the device against the cv2-pinned oracle: BORDER_TRANSPARENT paste of
+    1-, 3- and 4-channel patches into a zero canvas and into an existing page."""
+    from vae_gan_mark_b200 import data
+    rng = np.random.default_rng(8)
+    n = 0
+    for k, (patch, bbox, cshape) in enumerate(warp.unwarp_cases(rng, 48)):
+        if patch.ndim == 3 and patch.shape[2] == 2:
+            continue
+        h, w = patch.shape[:2]
+        got = data.perspective_unwarp(torch.from_numpy(patch).cuda(), bbox.tolist(), cshape).cpu().numpy()
+        assert np.array_equal(got, warp.perspective_unwarp(patch, bbox, cshape)), k
+        if k % 3 == 0:
+            page = rng.integers(0, 256, size=cshape, dtype=np.uint8)
+            want = warp.warp_perspective_u8(patch, warp.unwarp_matrix(bbox, (w, h)), (cshape[1], cshape[0]), transparent_into=page)
+            got = data.perspective_unwarp(torch.from_numpy(patch).cuda(), bbox.tolist(), cshape,
+                                          canvas=torch.from_numpy(page.copy()).cuda()).cpu().numpy()
+            assert np.array_equal(got, want)
+        n += 1
+    assert n >= 30
+    # crop -> unwarp round trip at the reference's patch shape: inside the quadrilateral the page comes back within the
+    # two bilinear resamplings' smoothing, outside it the canvas stays zero
+    page = np.kron(rng.integers(0, 256, size=(30, 50, 3), dtype=np.uint8), np.ones((8, 8, 1), dtype=np.uint8))      # 240 x 400, blocky
+    box = [[60.0, 50.0], [340.0, 60.0], [330.0, 180.0], [70.0, 170.0]]
+    dev = torch.from_numpy(page).cuda()
+    patch = data.perspective_crop(dev, box, (448, 64), to_tensor=False)
+    back = data.perspective_unwarp(patch, box, page.shape).cpu().numpy()
+    inside = back.any(axis=2)
+    assert 0.2 < inside.mean() < 0.5
+    diff = np.abs(back.astype(int) - page.astype(int))[inside]
+    assert np.median(diff) <= 2, float(np.median(diff))
+
+
+def test_crop_batch_is_one_launch():
+    from vae_gan_mark_b200 import _lib, data
+    rng = np.random.default_rng(41)
+    pages = [torch.from_numpy(rng.integers(0, 256, size=(100 + 3 * i, 180 + 5 * i, 3), dtype=np.uint8)).cuda() for i in range(16)]
+    boxes = [next(quads(rng, p.shape[0], p.shape[1], 1)) for p in pages]
+    n0 = _lib.lib().vg_launch_count()
+    batch = data.crop_batch(pages, boxes, (128, 128))
+    assert _lib.lib().vg_launch_count() - n0 == 1
+    for i in range(16):
+        assert np.array_equal(batch[i].cpu().numpy(), warp.to_tensor(warp.perspective_crop(pages[i].cpu().numpy(), boxes[i], (128, 128))))
+    # gray masks batch, and the C ABI rejects a bad job instead of launching
+    masks = [p[:, :, 0].contiguous() for p in pages[:3]]
+    mb = data.crop_batch(masks, boxes[:3], (64, 32))
+    assert tuple(mb.shape) == (3, 1, 32, 64)
+    for i in range(3):
+        assert np.array_equal(mb[i].cpu().numpy(), warp.to_tensor(warp.perspective_crop(masks[i].cpu().numpy(), boxes[i], (64, 32))))
+
+
+def test_gpu_reproduces_the_reference_unwarp_fixture():
+    """The CUDA path against canvases returned by the reference's own perspective_unwarp (tests/golden/warp_unwarp.npz)."""
+    import os
+    from vae_gan_mark_b200 import data
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_unwarp.npz"))
+    page, mask, boxes = warp.fixture_inputs()
+    for name, patch in warp.unwarp_fixture_patches().items():
+        for i, box in enumerate(boxes):
+            shape = page.shape if patch.ndim == 3 else mask.shape
+            got = data.perspective_unwarp(torch.from_numpy(patch).cuda(), box, shape).cpu().numpy()
+            assert np.array_equal(got, gold[f"{name}_{i}"]), (name, i)

@@ -1,5 +1,6 @@
 """The patch-extraction oracle (oracle/warp.py) against OpenCV itself -- the third-party dependency in which the
 reference's ``perspective_crop`` arithmetic lives (vae-gan.py:163-188; opencv-python, requirements.txt:4).  Bit-exact."""
+import os
 import numpy as np
 import pytest
 
@@ -84,3 +85,32 @@ def test_oracle_reproduces_the_reference_fixture():
             assert np.array_equal(warp.perspective_crop(page, box, shape).transpose(2, 0, 1), rgb)
             assert np.array_equal(warp.to_tensor(warp.perspective_crop(page, box, shape)), rgb.astype(np.float32) / np.float32(255))
             assert np.array_equal(warp.perspective_crop(mask, box, shape)[None], gold[f"{shape[0]}x{shape[1]}_{i}_mask"])
+
+
+def test_unwarp_is_bit_exact_against_cv2():
+    """perspective_unwarp (vae-gan.py:190-200), statement for statement with cv2 itself: getPerspectiveTransform(patch
+    rectangle -> bbox) + warpPerspective(dst=zero canvas, INTER_LINEAR, BORDER_TRANSPARENT).  Pins which destination
+    pixels BORDER_TRANSPARENT writes in the opencv-python of this image (4.13) and their values."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for patch, bbox, cshape in warp.unwarp_cases(rng, 90):
+        h, w = patch.shape[:2]
+        m = cv2.getPerspectiveTransform(np.float32([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]]), np.float32(bbox).reshape(4, 2))
+        canvas = np.zeros(cshape, dtype=np.uint8)
+        cv2.warpPerspective(patch, m, (cshape[1], cshape[0]), dst=canvas, borderMode=cv2.BORDER_TRANSPARENT, flags=cv2.INTER_LINEAR)
+        got = warp.perspective_unwarp(patch, bbox, cshape)
+        assert np.array_equal(got, canvas), (patch.shape, cshape, int((got != canvas).sum()))
+        assert np.array_equal(warp.unwarp_matrix(bbox, (w, h)), m)
+
+
+def test_oracle_reproduces_the_reference_unwarp_fixture():
+    """tests/golden/warp_unwarp.npz: canvases returned by the reference's own ``perspective_unwarp`` (vae-gan.py:190-200)."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_unwarp.npz"))
+    page, mask, boxes = warp.fixture_inputs()
+    n = 0
+    for name, patch in warp.unwarp_fixture_patches().items():
+        for i, box in enumerate(boxes):
+            shape = page.shape if patch.ndim == 3 else mask.shape
+            assert np.array_equal(warp.perspective_unwarp(patch, box, shape), gold[f"{name}_{i}"]), (name, i)
+            n += 1
+    assert n == len(gold.files) == 12

@@ -70,6 +70,14 @@ class VgNormBackward(C.Structure):
     ]
 
 
+class VgWarpJob(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_h", C.c_int), ("src_w", C.c_int), ("channels", C.c_int), ("src_row_bytes", C.c_longlong),
+        ("minv", C.c_double * 9), ("out_h", C.c_int), ("out_w", C.c_int),
+        ("dst_u8", C.c_void_p), ("dst_chw", C.c_void_p), ("transparent", C.c_int),
+    ]
+
+
 _lib = None
 
 

@@ -1,5 +1,8 @@
 // Patch extraction of the data path: perspective_crop + T.ToTensor of the reference (vae-gan.py:163-188, 275-281),
 // i.e. cv2.getPerspectiveTransform + cv2.warpPerspective(INTER_LINEAR, BORDER_REPLICATE) on 8-bit images.
+// Also the inverse direction, perspective_unwarp (vae-gan.py:190-200): the same warp with borderMode=BORDER_TRANSPARENT into
+// a caller-provided canvas, and a batched launch over a device table of jobs (one grid row per patch) for a whole training
+// batch of crops.
 // Integer / byte work: the arithmetic below restates OpenCV's (imgwarp.cpp: fixed-point coordinates with 5 fractional
 // bits, 15-bit bilinear weights, blocks of 64 destination columns) so that the bytes are identical; oracle/warp.py is
 // the numpy restatement pinned against cv2, tests/test_warp_*.py hold this file to it.
@@ -57,7 +60,8 @@ VG_HD float to_unit(int v) {          // T.ToTensor(): float32(v) / 255, IEEE di
 // One destination pixel.  Source coordinate in 1/32 pixel units in OpenCV's operation order: X0 = M0*bx + M1*y + M2 per
 // 64-column block, then X = cvRound((X0 + M0*x1) * (32 / (W0 + M6*x1))) clamped to int; bilinear blend with 15-bit weights.
 VG_HD void warp_pixel(const unsigned char* __restrict__ src, int sh, int sw, int ch, long long row_bytes, const WarpMat& m,
-                      int oh, int ow, int x, int y, unsigned char* __restrict__ dst_u8, float* __restrict__ dst_chw) {
+                      int oh, int ow, int x, int y, unsigned char* __restrict__ dst_u8, float* __restrict__ dst_chw,
+                      int transparent = 0) {
   const int bx = (x / kWarpBlockW) * kWarpBlockW;
   const double dbx = static_cast<double>(bx), dy = static_cast<double>(y), dx1 = static_cast<double>(x - bx);
   const double X0 = dadd(dadd(dmul(m.v[0], dbx), dmul(m.v[1], dy)), m.v[2]);
@@ -71,6 +75,9 @@ VG_HD void warp_pixel(const unsigned char* __restrict__ src, int sh, int sw, int
   int sx = X >> 5, sy = Y >> 5;                                                     // arithmetic shifts
   sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);                            // stored as short
   sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+  // BORDER_TRANSPARENT (cv2 4.13, pinned in tests/test_warp_oracle.py): the destination pixel is written iff the integer
+  // part of its source coordinate lies inside the source; its value is the BORDER_REPLICATE one
+  if (transparent && (sx < 0 || sx > sw - 1 || sy < 0 || sy > sh - 1)) return;
   const int ax = X & 31, ay = Y & 31;
   const int x0 = sx < 0 ? 0 : (sx > sw - 1 ? sw - 1 : sx), x1 = sx + 1 < 0 ? 0 : (sx + 1 > sw - 1 ? sw - 1 : sx + 1);   // BORDER_REPLICATE
   const int y0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy), y1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
@@ -88,11 +95,25 @@ VG_HD void warp_pixel(const unsigned char* __restrict__ src, int sh, int sw, int
 
 __global__ void warp_perspective_u8_kernel(const unsigned char* __restrict__ src, int sh, int sw, int ch, long long row_bytes,
                                            const WarpMat m, int oh, int ow, unsigned char* __restrict__ dst_u8,
-                                           float* __restrict__ dst_chw) {
+                                           float* __restrict__ dst_chw, int transparent) {
   const int total = oh * ow;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int y = idx / ow;
-    warp_pixel(src, sh, sw, ch, row_bytes, m, oh, ow, idx - y * ow, y, dst_u8, dst_chw);
+    warp_pixel(src, sh, sw, ch, row_bytes, m, oh, ow, idx - y * ow, y, dst_u8, dst_chw, transparent);
+  }
+}
+
+// one grid row (blockIdx.y) per job of a device-resident table: a whole batch of patches in ONE launch
+__global__ void warp_perspective_u8_batch_kernel(const VgWarpJob* __restrict__ jobs) {
+  const VgWarpJob& j = jobs[blockIdx.y];
+  WarpMat m;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m.v[i] = j.minv[i];
+  const int total = j.out_h * j.out_w;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int y = idx / j.out_w;
+    warp_pixel(j.src, j.src_h, j.src_w, j.channels, j.src_row_bytes, m, j.out_h, j.out_w, idx - y * j.out_w, y, j.dst_u8, j.dst_chw,
+               j.transparent);
   }
 }
 
@@ -103,14 +124,13 @@ using namespace vg;
 // cv::getPerspectiveTransform(bbox -> output rectangle) followed by cv::invert, on the host, operation for operation:
 // the products of the system matrix are float32 products (Point2f members), the 8x8 system is solved by Gaussian
 // elimination with partial pivoting (hal::LU64f), the 3x3 inverse is cofactors times the reciprocal determinant.
-extern "C" int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_h, double* minv) {
-  VG_CHECK(bbox != nullptr && minv != nullptr && out_w >= 1 && out_h >= 1, -1, "vg_perspective_crop_matrix: bad arguments");
-  const float dst[4][2] = {{0.f, 0.f}, {static_cast<float>(out_w - 1), 0.f},
-                           {static_cast<float>(out_w - 1), static_cast<float>(out_h - 1)}, {0.f, static_cast<float>(out_h - 1)}};
+// Inverse (destination -> source) map of cv::getPerspectiveTransform(src_quad -> dst_quad): 4 (x, y) float pairs each.
+extern "C" int vg_perspective_matrix(const float* src_quad, const float* dst_quad, double* minv) {
+  VG_CHECK(src_quad != nullptr && dst_quad != nullptr && minv != nullptr, -1, "vg_perspective_matrix: bad arguments");
   double a[8][8], b[8];
   for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) a[i][j] = 0.0;
   for (int i = 0; i < 4; ++i) {
-    const float sx = bbox[2 * i], sy = bbox[2 * i + 1], dx = dst[i][0], dy = dst[i][1];
+    const float sx = src_quad[2 * i], sy = src_quad[2 * i + 1], dx = dst_quad[2 * i], dy = dst_quad[2 * i + 1];
     a[i][0] = a[i + 4][3] = sx;
     a[i][1] = a[i + 4][4] = sy;
     a[i][2] = a[i + 4][5] = 1.0;
@@ -123,7 +143,7 @@ extern "C" int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_
     int k = i;
     for (int j = i + 1; j < n; ++j)
       if (std::fabs(a[j][i]) > std::fabs(a[k][i])) k = j;
-    VG_CHECK(std::fabs(a[k][i]) >= 2.220446049250313e-16 * 100, -4, "vg_perspective_crop_matrix: degenerate quadrilateral");
+    VG_CHECK(std::fabs(a[k][i]) >= 2.220446049250313e-16 * 100, -4, "vg_perspective_matrix: degenerate quadrilateral");
     if (k != i) {
       for (int j = i; j < n; ++j) { const double t = a[i][j]; a[i][j] = a[k][j]; a[k][j] = t; }
       const double t = b[i]; b[i] = b[k]; b[k] = t;
@@ -148,7 +168,7 @@ extern "C" int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_
   const double det = mul(S(0, 0), mul(S(1, 1), S(2, 2)) - mul(S(1, 2), S(2, 1))) -
                      mul(S(0, 1), mul(S(1, 0), S(2, 2)) - mul(S(1, 2), S(2, 0))) +
                      mul(S(0, 2), mul(S(1, 0), S(2, 1)) - mul(S(1, 1), S(2, 0)));
-  VG_CHECK(det != 0.0, -4, "vg_perspective_crop_matrix: singular transform");
+  VG_CHECK(det != 0.0, -4, "vg_perspective_matrix: singular transform");
   const double d = 1.0 / det;
   minv[0] = mul(mul(S(1, 1), S(2, 2)) - mul(S(1, 2), S(2, 1)), d);
   minv[1] = mul(mul(S(0, 2), S(2, 1)) - mul(S(0, 1), S(2, 2)), d);
@@ -163,21 +183,78 @@ extern "C" int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_
   return 0;
 }
 
-extern "C" int vg_warp_perspective_u8(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
-                                      const double* minv, int out_h, int out_w, unsigned char* dst_u8, float* dst_chw,
-                                      void* stream_) {
-  VG_CHECK(src != nullptr && minv != nullptr && (dst_u8 != nullptr || dst_chw != nullptr), -1,
-           "vg_warp_perspective_u8: null pointer");
+// perspective_crop (vae-gan.py:176-178): bbox -> the output rectangle [0, W-1] x [0, H-1]
+extern "C" int vg_perspective_crop_matrix(const float* bbox, int out_w, int out_h, double* minv) {
+  VG_CHECK(bbox != nullptr && minv != nullptr && out_w >= 1 && out_h >= 1, -1, "vg_perspective_crop_matrix: bad arguments");
+  const float rect[8] = {0.f, 0.f, static_cast<float>(out_w - 1), 0.f, static_cast<float>(out_w - 1), static_cast<float>(out_h - 1),
+                         0.f, static_cast<float>(out_h - 1)};
+  return vg_perspective_matrix(bbox, rect, minv);
+}
+// perspective_unwarp (vae-gan.py:193-196): the patch rectangle [0, w-1] x [0, h-1] -> bbox on the canvas
+extern "C" int vg_perspective_unwarp_matrix(const float* bbox, int patch_w, int patch_h, double* minv) {
+  VG_CHECK(bbox != nullptr && minv != nullptr && patch_w >= 1 && patch_h >= 1, -1, "vg_perspective_unwarp_matrix: bad arguments");
+  const float rect[8] = {0.f, 0.f, static_cast<float>(patch_w - 1), 0.f, static_cast<float>(patch_w - 1),
+                         static_cast<float>(patch_h - 1), 0.f, static_cast<float>(patch_h - 1)};
+  return vg_perspective_matrix(rect, bbox, minv);
+}
+
+static int warp_check(const char* who, const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
+                      const double* minv, int out_h, int out_w) {
+  VG_CHECK(src != nullptr && minv != nullptr, -1, "%s: null pointer", who);
   VG_CHECK(src_h >= 1 && src_w >= 1 && src_h <= 32767 && src_w <= 32767 && channels >= 1 && channels <= 4 && out_h >= 1 &&
                out_w >= 1 && src_row_bytes >= static_cast<long long>(src_w) * channels,
-           -1, "vg_warp_perspective_u8: sizes (source up to 32767 x 32767, 1..4 channels)");
-  VG_CHECK(static_cast<long long>(out_h) * out_w < (1LL << 31), -1, "vg_warp_perspective_u8: output too large");
+           -1, "%s: sizes (source up to 32767 x 32767, 1..4 channels)", who);
+  VG_CHECK(static_cast<long long>(out_h) * out_w < (1LL << 31), -1, "%s: output too large", who);
+  return 0;
+}
+
+static int warp_launch(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes, const double* minv,
+                       int out_h, int out_w, unsigned char* dst_u8, float* dst_chw, int transparent, void* stream_) {
   WarpMat m;
   for (int i = 0; i < 9; ++i) m.v[i] = minv[i];
   const int total = out_h * out_w;
   const int grid = std::max(1, std::min((total + 255) / 256, num_sms() * 8));
   warp_perspective_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(src, src_h, src_w, channels, src_row_bytes, m,
-                                                                                  out_h, out_w, dst_u8, dst_chw);
+                                                                                  out_h, out_w, dst_u8, dst_chw, transparent);
+  VG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vg_warp_perspective_u8(const unsigned char* src, int src_h, int src_w, int channels, long long src_row_bytes,
+                                      const double* minv, int out_h, int out_w, unsigned char* dst_u8, float* dst_chw,
+                                      void* stream_) {
+  VG_CHECK(dst_u8 != nullptr || dst_chw != nullptr, -1, "vg_warp_perspective_u8: null pointer");
+  if (int rc = warp_check("vg_warp_perspective_u8", src, src_h, src_w, channels, src_row_bytes, minv, out_h, out_w)) return rc;
+  return warp_launch(src, src_h, src_w, channels, src_row_bytes, minv, out_h, out_w, dst_u8, dst_chw, 0, stream_);
+}
+
+// perspective_unwarp's warp: BORDER_TRANSPARENT into the caller's canvas (out_h x out_w x channels uint8, modified in place)
+extern "C" int vg_warp_perspective_u8_transparent(const unsigned char* src, int src_h, int src_w, int channels,
+                                                  long long src_row_bytes, const double* minv, int out_h, int out_w,
+                                                  unsigned char* canvas_u8, void* stream_) {
+  VG_CHECK(canvas_u8 != nullptr, -1, "vg_warp_perspective_u8_transparent: null pointer");
+  if (int rc = warp_check("vg_warp_perspective_u8_transparent", src, src_h, src_w, channels, src_row_bytes, minv, out_h, out_w))
+    return rc;
+  return warp_launch(src, src_h, src_w, channels, src_row_bytes, minv, out_h, out_w, canvas_u8, nullptr, 1, stream_);
+}
+
+// A batch of warps in one launch.  `jobs_host` is validated here; `jobs_device` is the same table in device memory (the
+// caller copies it on `stream` before this call -- the library never allocates or copies on its own).
+extern "C" int vg_warp_perspective_u8_batch(const VgWarpJob* jobs_host, const VgWarpJob* jobs_device, int count, void* stream_) {
+  VG_CHECK(jobs_host != nullptr && jobs_device != nullptr && count >= 1 && count <= 65535, -1,
+           "vg_warp_perspective_u8_batch: bad table (1..65535 jobs)");
+  int max_total = 1;
+  for (int i = 0; i < count; ++i) {
+    const VgWarpJob& j = jobs_host[i];
+    VG_CHECK(j.dst_u8 != nullptr || j.dst_chw != nullptr, -1, "vg_warp_perspective_u8_batch: job %d has no destination", i);
+    VG_CHECK(!j.transparent || j.dst_chw == nullptr, -1, "vg_warp_perspective_u8_batch: job %d: transparent jobs write a uint8 canvas", i);
+    if (int rc = warp_check("vg_warp_perspective_u8_batch", j.src, j.src_h, j.src_w, j.channels, j.src_row_bytes, j.minv, j.out_h,
+                            j.out_w))
+      return rc;
+    max_total = std::max(max_total, j.out_h * j.out_w);
+  }
+  const int gx = std::max(1, std::min((max_total + 255) / 256, std::max(1, num_sms() * 8 / count)));
+  warp_perspective_u8_batch_kernel<<<dim3(gx, count), 256, 0, static_cast<cudaStream_t>(stream_)>>>(jobs_device);
   VG_LAUNCH_OK();
   return 0;
 }
@@ -192,5 +269,16 @@ extern "C" int vg_debug_warp_perspective_host(const unsigned char* src, int src_
   for (int i = 0; i < 9; ++i) m.v[i] = minv[i];
   for (int y = 0; y < out_h; ++y)
     for (int x = 0; x < out_w; ++x) warp_pixel(src, src_h, src_w, channels, src_row_bytes, m, out_h, out_w, x, y, dst_u8, dst_chw);
+  return 0;
+}
+extern "C" int vg_debug_warp_perspective_transparent_host(const unsigned char* src, int src_h, int src_w, int channels,
+                                                          long long src_row_bytes, const double* minv, int out_h, int out_w,
+                                                          unsigned char* canvas_u8) {
+  VG_CHECK(src != nullptr && minv != nullptr && canvas_u8 != nullptr && channels >= 1 && channels <= 4, -1,
+           "vg_debug_warp_perspective_transparent_host: arguments");
+  WarpMat m;
+  for (int i = 0; i < 9; ++i) m.v[i] = minv[i];
+  for (int y = 0; y < out_h; ++y)
+    for (int x = 0; x < out_w; ++x) warp_pixel(src, src_h, src_w, channels, src_row_bytes, m, out_h, out_w, x, y, canvas_u8, nullptr, 1);
   return 0;
 }
