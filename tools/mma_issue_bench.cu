@@ -18,20 +18,23 @@ unsigned long long g_launches = 0;
 using namespace vg;
 
 struct Cfg {
-  int n, nacc, shifted, mn_major, iters, mmas_per_commit, ctas_busy;
+  int n, nacc, shifted, mn_major, iters, mmas_per_commit, ctas_busy, vary_b, commits;
 };
 
 __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[2];
   __shared__ uint32_t tmem_slot;
   // A: 48 KB region (enough for the shifted halo views), B: 32 KB
   uint8_t* sa = smem;
-  uint8_t* sb = smem + 48 * 1024;
-  for (int i = threadIdx.x; i < 80 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
+  uint8_t* sb = smem + 48 * 1024;      // up to 9 x 16 KB of weight tiles
+  for (int i = threadIdx.x; i < 190 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2[0], 1 << 20);
+    mbar_init(&bar2[1], 1 << 20);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
@@ -63,7 +66,13 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* cycles)
         for (int j = 0; j < 36; ++j) {
           const int t = j / 4;
           const uint32_t shift = c.shifted ? static_cast<uint32_t>(((t / 3) * 10 + t % 3) * 128) >> 4 : 0u;
-          if (leader) umma_bf16_lohi(tmem + acc * acc_cols, a_lo + shift + kstep * (j % 4), a_hi, b_lo + kstep * (j % 4), b_hi, idesc, 1u);
+          const uint32_t bshift = c.vary_b ? static_cast<uint32_t>(t * c.n * 128) >> 4 : 0u;      // a different weight tile per tap
+          if (leader) umma_bf16_lohi(tmem + acc * acc_cols, a_lo + shift + kstep * (j % 4), a_hi, b_lo + bshift + kstep * (j % 4), b_hi, idesc, j > 0 ? 1u : 0u);
+          if (c.commits == 0) { if (++acc == c.nacc) acc = 0; }
+        }
+        if (c.commits) {      // the forward kernel's pattern: one accumulator per 36 MMAs, two commits after them
+          if (leader) umma_commit(&bar2[0]);
+          if (leader) umma_commit(&bar2[1]);
           if (++acc == c.nacc) acc = 0;
         }
       }
@@ -82,23 +91,25 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* cycles)
 int main() {
   long long* d;
   cudaMalloc(&d, sizeof(long long) * 256);
-  cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   printf("%5s %5s %8s %9s %6s | %12s %8s\n", "N", "nacc", "shifted", "mn_major", "ctas", "cyc/MMA", "floor");
-  for (int ctas : {1, 148}) {
-    for (int mn = 0; mn < 2; ++mn) {
+  printf("%5s %5s %8s %9s %6s %7s %8s | %12s %8s\n", "N", "nacc", "shifted", "mn_major", "ctas", "vary_b", "commits", "cyc/MMA", "floor");
+  for (int commits = 0; commits < 2; ++commits) {
+    for (int vary_b = 0; vary_b < 2; ++vary_b) {
       for (int n : {64, 128, 256}) {
-        for (int shifted = 0; shifted < (mn ? 1 : 2); ++shifted) {
-          for (int nacc : {1, 2, 4}) {
+        for (int shifted = 0; shifted < 2; ++shifted) {
+          for (int nacc : {1, 4}) {
             if (n * nacc > 512) continue;
-            Cfg c{n, nacc, shifted, mn, 200, 36, ctas};
-            bench_kernel<<<ctas, 128, 100 * 1024>>>(c, d);
+            if (vary_b && n > 128) continue;      // 9 tiles of 32 KB do not fit
+            Cfg c{n, nacc, shifted, 0, 200, 36, 148, vary_b, commits};
+            bench_kernel<<<148, 128, 200 * 1024>>>(c, d);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
-            std::vector<long long> h(ctas);
-            cudaMemcpy(h.data(), d, sizeof(long long) * ctas, cudaMemcpyDeviceToHost);
+            std::vector<long long> h(148);
+            cudaMemcpy(h.data(), d, sizeof(long long) * 148, cudaMemcpyDeviceToHost);
             long long mx = 0;
             for (long long v : h) mx = v > mx ? v : mx;
-            printf("%5d %5d %8d %9d %6d | %12.1f %8d\n", n, nacc, shifted, mn, ctas, double(mx) / (200.0 * 36), n / 2);
+            printf("%5d %5d %8d %9d %6d %7d %8d | %12.1f %8d\n", n, nacc, shifted, 0, 148, vary_b, commits, double(mx) / (200.0 * 36), n / 2);
           }
         }
       }

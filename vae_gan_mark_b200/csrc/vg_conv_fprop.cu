@@ -26,6 +26,7 @@
 // This one kernel serves Conv2d fprop, Conv2d dgrad (flipped weights), ConvTranspose2d fprop/dgrad and the
 // GEMM-shaped layers (1x1 convs, full-kernel heads, bottleneck ConvT) of the reference models
 // (vae-gan.py:52-60,76-81,153-157; vae-gan-v2.py:123-127,168-176,199-241).
+#include <stdlib.h>
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
 
@@ -76,6 +77,7 @@ struct FpropParams {
                                 // stored (after bias / activation, rounded to the output type), over all valid pixels --
                                 // the BatchNorm batch statistics of the layer that follows, taken from the epilogue
                                 // instead of re-reading the tensor (vae-gan-v2.py:172-177: Conv -> BN -> ReLU)
+  int dbg;                      // development only (VG_FPROP_DBG): 1 = the epilogue skips its work (what bounds the MMA side?)
   int4 taps[kMaxTaps];          // {c_base, dw, sh, dh}
   int wk[kMaxTaps];             // first weight column of each tap
 };
@@ -108,6 +110,29 @@ VG_DEVICE void stats_flush(const FpropParams& p, float (&st)[8], int n_t, int la
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) st[i] = 0.f;
+}
+
+// Per-tile bookkeeping, kept cheap: the narrow layers have short tiles (K = 576: ~1800 cycles of MMAs), and the generic
+// decode (three 32-bit divisions plus two 64-bit ones for the split-K range) cost ~1300 cycles per tile in EACH warp role --
+// 40 % of such a tile in the MMA warp.  One group / one N tile / no split-K, the common case, needs no division here.
+struct TileId { int grp, n_t, m_t, split; };
+VG_DEVICE TileId decode_tile(const FpropParams& p, int tile, int tiles_per_group, int m_tiles) {
+  TileId t;
+  int tl = tile;
+  if (p.ngroups == 1) t.grp = 0;
+  else { t.grp = tile / tiles_per_group; tl = tile - t.grp * tiles_per_group; }
+  int rest = tl;
+  if (p.n_tiles == 1) t.n_t = 0;
+  else { rest = tl / p.n_tiles; t.n_t = tl - rest * p.n_tiles; }
+  if (p.ksplit == 1) { t.m_t = rest; t.split = 0; }
+  else { t.split = rest / m_tiles; t.m_t = rest - t.split * m_tiles; }
+  return t;
+}
+VG_DEVICE void k_range(int ksteps, int split, int ksplit, int& k_begin, int& k_end) {
+  if (ksplit == 1) { k_begin = 0; k_end = ksteps; return; }
+  // ksteps * ksplit stays far below 2^32 (ksteps <= 96 taps x 4096 channel chunks, ksplit <= #SMs)
+  k_begin = static_cast<int>(static_cast<unsigned>(ksteps) * static_cast<unsigned>(split) / static_cast<unsigned>(ksplit));
+  k_end = static_cast<int>(static_cast<unsigned>(ksteps) * static_cast<unsigned>(split + 1) / static_cast<unsigned>(ksplit));
 }
 
 // k2 = true: CTA-pair variant (cta_group::2; plain K-major mode with 256-wide N tiles only).  A cluster of two CTAs
@@ -178,7 +203,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int total_work = k2 ? total_tiles / 2 : total_tiles;
   auto tile_of = [&](int work) -> int {
     if (!k2) return work;
-    const int n_t = work % p.n_tiles, unit = work / p.n_tiles;
+    if (p.n_tiles == 1) return 2 * work + static_cast<int>(rank);
+    const int unit = work / p.n_tiles, n_t = work - unit * p.n_tiles;
     return (2 * unit + static_cast<int>(rank)) * p.n_tiles + n_t;
   };
 
@@ -203,20 +229,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int work = worker; work < total_work; work += nworkers) {
       const int tile = tile_of(work);
-      const int grp = tile / tiles_per_group;
-      const int tl = tile - grp * tiles_per_group;
-      const int n_t = tl % p.n_tiles;
-      int rest = tl / p.n_tiles;
-      const int m_t = rest % m_tiles;
-      const int split = rest / m_tiles;
-      const int tw_i = m_t % p.tiles_w;
-      const int th_i = (m_t / p.tiles_w) % p.tiles_h;
-      const int tn_i = m_t / (p.tiles_w * p.tiles_h);
+      const TileId tid = decode_tile(p, tile, tiles_per_group, m_tiles);
+      const int grp = tid.grp, n_t = tid.n_t, m_t = tid.m_t, split = tid.split;
+      const int q1 = m_t / p.tiles_w, tw_i = m_t - q1 * p.tiles_w;
+      const int tn_i = q1 / p.tiles_h, th_i = q1 - tn_i * p.tiles_h;
       const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
       const int cchunks = cchunks_all;
       const int ksteps = p.g_ntaps[grp] * cchunks;
-      const int k_begin = static_cast<int>((static_cast<long long>(ksteps) * split) / p.ksplit);
-      const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
+      int k_begin, k_end;
+      k_range(ksteps, split, p.ksplit, k_begin, k_end);
       if (p.halo) {
         // one stage per 64-channel chunk: the halo and (unless they are resident) the nine weight tiles
         for (int cc = 0; cc < cchunks; ++cc) {
@@ -233,8 +254,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         continue;
       }
-      int tap = p.g_tap0[grp] + k_begin / cchunks;
-      int cc = k_begin % cchunks;
+      int tap = p.g_tap0[grp], cc = 0;
+      if (k_begin > 0) { tap += k_begin / cchunks; cc = k_begin % cchunks; }
       for (int k = k_begin; k < k_end; ++k) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
@@ -296,22 +317,32 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
     for (int t = 0; t < 9; ++t) halo_a16[t] = static_cast<uint32_t>(((p.taps[t].w + 1) * kHaloW + (p.taps[t].y + 1)) * 128) >> 4;
     const uint32_t b_tap16 = static_cast<uint32_t>(p.bn * 128) >> 4;
+    long long dbg_t[4] = {0, 0, 0, 0};      // development (VG_FPROP_DBG=4): cycles in tmem_empty wait, full wait, issue; tiles
+    const long long dbg_start = clock64();
     for (int work = worker; work < total_work; work += nworkers) {
       const int tile = tile_of(work);
-      const int grp = tile / tiles_per_group;
-      const int split = ((tile - grp * tiles_per_group) / p.n_tiles) / m_tiles;
+      int grp = 0, split = 0;
+      if (p.ngroups > 1 || p.ksplit > 1) {
+        const TileId tid = decode_tile(p, tile, tiles_per_group, m_tiles);
+        grp = tid.grp; split = tid.split;
+      }
       const int ksteps = p.g_ntaps[grp] * cchunks_all;
-      const int k_begin = static_cast<int>((static_cast<long long>(ksteps) * split) / p.ksplit);
-      const int k_end = static_cast<int>((static_cast<long long>(ksteps) * (split + 1)) / p.ksplit);
+      int k_begin, k_end;
+      k_range(ksteps, split, p.ksplit, k_begin, k_end);
+      const long long c0 = p.dbg == 4 ? clock64() : 0;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      if (p.dbg == 4) dbg_t[0] += clock64() - c0;
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
       if (p.halo) {
         // the descriptors of one stage differ only in their start-address field: one base per operand plus the
         // (precomputed, 16-byte unit) tap and K offsets
         for (int cc = 0; cc < cchunks_all; ++cc) {
+          const long long c1 = p.dbg == 4 ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          const long long c2 = p.dbg == 4 ? clock64() : 0;
+          if (p.dbg == 4) dbg_t[1] += c2 - c1;
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = p.w_bytes > 0 ? smem_u32(wres) + static_cast<uint32_t>(cc * 9 * p.bn * 128) : sa + a_bytes;
           const uint32_t a_lo = a_lo0 + (sa >> 4), b_lo = b_lo0 + (sb >> 4);
@@ -324,10 +355,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                (cc > 0 || t > 0 || j > 0) ? 1u : 0u);
           }
           if (leader) umma_commit(&empty_bar[stage]);
+          if (p.dbg == 4) dbg_t[2] += clock64() - c2;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (leader) umma_commit(&tmem_full[acc]);
         if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
+        if (p.dbg == 4) ++dbg_t[3];
         continue;
       }
       for (int k = k_begin; k < k_end; ++k) {
@@ -353,6 +386,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (leader) { if (k2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.dbg == 4 && leader && blockIdx.x == 0)
+      printf("fprop dbg: tiles %lld total %lld cyc | tmem_empty wait %lld  full wait %lld  issue %lld\n", dbg_t[3],
+             clock64() - dbg_start, dbg_t[0], dbg_t[1], dbg_t[2]);
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
@@ -390,14 +426,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (split && (seq & 1) != colhalf) continue;
       const int acc = seq % p.nacc;
       const uint32_t acc_phase = static_cast<uint32_t>(seq / p.nacc) & 1u;
-      const int grp = tile / tiles_per_group;
-      const int tl = tile - grp * tiles_per_group;
+      const TileId tid = decode_tile(p, tile, tiles_per_group, m_tiles);
+      const int grp = tid.grp, n_t = tid.n_t, m_t = tid.m_t;
       const int sub_h0 = p.g_sub_h0[grp], sub_w0 = p.g_sub_w0[grp];
-      const int n_t = tl % p.n_tiles;
-      const int m_t = (tl / p.n_tiles) % m_tiles;
-      const int tw_i = m_t % p.tiles_w;
-      const int th_i = (m_t / p.tiles_w) % p.tiles_h;
-      const int tn_i = m_t / (p.tiles_w * p.tiles_h);
+      const int q1 = m_t / p.tiles_w, tw_i = m_t - q1 * p.tiles_w;
+      const int tn_i = q1 / p.tiles_h, th_i = q1 - tn_i * p.tiles_h;
       const int ow = tw_i * p.tw + r_w, oh = th_i * p.th + r_h, n = tn_i * p.tn + r_n;
       const bool row_ok = (ow < p.m_w) && (oh < p.m_h) && (n < p.m_n);
       const long long my_base =
@@ -411,7 +444,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * p.acc_cols);
-      if (p.vec_ok && p.out_kind != 2) {
+      if (p.dbg == 1) {
+      } else if (p.vec_ok && p.out_kind != 2) {
         for (int c = c_first; c < p.bn; c += c_step) {
           const int ng0 = n_t * p.bn + c;        // first GEMM column of this chunk
           if (ng0 >= p.n_gemm) break;
@@ -448,6 +482,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               }
             }
           }
+          if (p.dbg == 2) { if (r[0] == 0x7fc12345u) reinterpret_cast<uint32_t*>(p.out)[0] = r[63]; continue; }      // development: no staging, no stores
           // stage: 16-byte segment s of row `lane` goes to slot (s ^ (lane & 7)) -> conflict-free both ways
           uint8_t* dst = stg + lane * 128;
           if (esz == 2) {
@@ -484,7 +519,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const long long base = __shfl_sync(0xffffffffu, my_base, rr);
             if (seg_ok && base >= 0) {
               const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((seg ^ (rr & 7)) << 4));
-              *reinterpret_cast<uint4*>(gout + base * esz) = v;
+              if (p.dbg != 3 || v.x == 0x7fc12345u) *reinterpret_cast<uint4*>(gout + base * esz) = v;      // dbg 3: staging, no global stores
             }
           }
           if (p.stats != nullptr) {
@@ -540,7 +575,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int j = 0; j < 32; ++j) {
               if (j < nvalid) {
                 float x = __uint_as_float(r[j]);
-                if (p.bias != nullptr && (p.out_kind != 2 || tl / (p.n_tiles * m_tiles) == 0)) x += __ldg(p.bias + ch0 + j);   // split-K: bias once
+                if (p.bias != nullptr && (p.out_kind != 2 || tid.split == 0)) x += __ldg(p.bias + ch0 + j);   // split-K: bias once
                 if (p.act == 1) x = fmaxf(x, 0.f);
                 else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
                 if (p.out_kind == 0) reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16(x);
@@ -692,6 +727,8 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
                ((d->out_coff * esz) % 16 == 0) && ((d->cout_per_sub * esz) % 16 == 0) && (d->n_gemm % 8 == 0) &&
                (d->su_h * d->su_w == 1 || d->cout_per_sub % 32 == 0);
   }
+  static const int dbg_env = getenv("VG_FPROP_DBG") ? atoi(getenv("VG_FPROP_DBG")) : 0;
+  p.dbg = dbg_env;
   p.stats = d->stats;
   if (d->stats != nullptr) {
     VG_CHECK(p.vec_ok && d->out_kind != 2 && ksplit == 1, -1,
