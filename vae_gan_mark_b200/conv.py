@@ -62,6 +62,8 @@ def _chk(t: torch.Tensor, what: str):
     assert t.dtype == BF16 and ops.nhwc_ok(t), f"{what}: not an NHWC bf16 view {tuple(t.shape)} {t.stride()}"
 
 
+import os as _os
+_PREFER_MN_MODE = _os.environ.get("VG_PREFER_MN", "")
 HALO_MODE = 0      # VgConvFprop.halo_mode: 0 auto, -1 never, 1 force (tests)
 # Deterministic split reductions (bf16 mode): the weight-gradient kernel stores each pixel split's partial tile into a
 # scratch buffer and adds them in a fixed order (two-stage reduce) instead of fp32 atomics, and split-K forward launches
@@ -264,17 +266,25 @@ class ConvLinear:
         assert stride in (1, 2)
 
     def prefer_mn(self, gemm_pixels: int) -> bool:
-        """Data gradient in bf16 mode: read the forward operand as an MN-major B operand (no transposed weight copy,
-        but the tensor pipe runs ~20 % slower on MN-major B -- measured 1478 -> 1170 TFLOP/s on the 128x128x512 3x3
-        layer) or make the transposed K-major copy first?  Estimated cost of each in microseconds."""
+        """Data gradient in bf16 mode: read the forward operand as an MN-major B operand (no transposed weight copy per
+        step) or make the transposed K-major copy first?  With the warp-uniform issue loops and CTA pairs on both paths
+        the MN-major operand costs nothing up to 64x64x64 pixels (tools/gpu_mn_vs_k.py: 1618 vs 1610 TFLOP/s on the
+        512 -> 512 3x3 layer) and ~7 % on the largest launches (1510 vs 1624 at 128x128x64: two boxes per CTA and K step
+        instead of one); the copy costs ~5 us of launch plus the weight at ~0.8 TB/s.  K-major also keeps the halo mode
+        of the narrow 3x3 layers (data gradient with <= 64 input channels), which the MN-major path does not have."""
         if self.shuffle and self.cin != self.cin_p:
             # the pixel-shuffle GEMM's columns are (r, q, ci) with ci < cin, but the forward operand's columns are
             # (r, q, ci_p) zero-padded to 64 per tap: no uniform column map exists (up_tconv3 64 -> 32 of vae-gan-oldv.py)
             return False
+        if self.s == 1 and (self.kh, self.kw) == (3, 3) and self.cin <= 64 and gemm_pixels >= 65536:
+            return False                                   # halo mode (K-major weights only): 892 vs 671 TFLOP/s
         nk = self.cin * self.cout * self.kh * self.kw
-        slowdown_us = 0.4 * gemm_pixels * nk / 1.4e9
+        if _PREFER_MN_MODE == "old":       # development A/B: the mid-round cost model (MN-major assumed 40 % slower)
+            return 0.4 * gemm_pixels * nk / 1.4e9 < 5.0 * (4 if (self.s == 2 and not self.shuffle) else 1) + nk * 6 / 1e6
+        gemm_us = 2.0 * gemm_pixels * nk / 1.5e9
+        slowdown_us = 0.07 * gemm_us if gemm_pixels >= (1 << 19) else 0.0
         copies = 4 if (self.s == 2 and not self.shuffle) else 1
-        copy_us = 5.0 * copies + nk * 6 / 1e6
+        copy_us = 5.0 * copies + nk * 6 / 0.8e6
         return slowdown_us < copy_us
 
     def _parity_taps(self, col_step: int):

@@ -268,7 +268,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int wk = p.wk[tap];
         if (k2) {
           if (leader) tma_load_5d_2cta(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
-          if (leader) tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], wk + cc * kBK, n_t * p.bn + static_cast<int>(rank) * (p.bn / 2));
+          if (!p.b_mn) {
+            if (leader) tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], wk + cc * kBK, n_t * p.bn + static_cast<int>(rank) * (p.bn / 2));
+          } else {
+            // MN-major operand of a pair: this CTA stages ITS half of the N columns = two {64 N, 64 K} boxes
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if (leader)
+                tma_load_2d_2cta(sb + i * (64 * 128), &tmap_b, &full_bar[stage],
+                                 wk + n_t * p.bn + (static_cast<int>(rank) * 2 + i) * 64, cc * kBK);
+          }
         } else {
           if (leader) tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
           if (!p.b_mn) {
@@ -686,9 +695,10 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   p.ksplit = ksplit;
   p.nacc = bn <= 128 ? 4 : 2;
   p.acc_cols = 512 / p.nacc;
-  // CTA pairs: the plain K-major mode with 256-wide N tiles, one group, no split-K, and enough pixel tiles that pairing
+  // CTA pairs: the plain mode (K-major or MN-major weights) with 256-wide N tiles, one group, no split-K, and enough pixel tiles that pairing
   // them does not leave SMs without work
-  const bool pair = g_fprop_pairs != 0 && !halo && !d->b_mn_major && bn == 256 && ksplit == 1 && d->num_groups <= 1 &&
+  static const int mn_pairs = getenv("VG_FPROP_MN_PAIRS") ? atoi(getenv("VG_FPROP_MN_PAIRS")) : 1;
+  const bool pair = g_fprop_pairs != 0 && !halo && (!d->b_mn_major || mn_pairs) && bn == 256 && ksplit == 1 && d->num_groups <= 1 &&
                     (m_tiles / 2) * p.n_tiles >= sms / 2 && sms % 2 == 0;
   p.a_bytes = halo ? kHaloBytes : kBM * kBK * 2;
   p.b_bytes = halo ? 9 * bn * kBK * 2 : (pair ? bn / 2 : bn) * kBK * 2;
