@@ -22,6 +22,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import VgConvFprop, VgConvWgrad
+from .dispatch import launch_op
 from .ops import BF16, F32, round_up
 
 Tap = Tuple[int, int, int, int]   # (c_base, dw, sh, dh)
@@ -82,81 +83,106 @@ def fprop(x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int, w: torc
     ``b_mn_major``: w is [K rows (c), columns] and out[pixel, n] = sum x[pixel@tap, c] * w[c, wk[tap] + n].
     ``groups``: [(number of taps, (sub_h0, sub_w0)), ...] -- up to 4 problems in one launch, taps listed group by group.
     ``stats``: fp32 [1, 2, channels] that receives the per-channel sum / sum of squares of the stored output (the batch
-    statistics of a following BatchNorm2d), computed in the epilogue."""
+    statistics of a following BatchNorm2d), computed in the epilogue.
+    The launch itself is the dispatcher op ``torch.ops.vaegan.vg_conv_fprop`` (tap / group tables flattened to int[])."""
     _chk(x, "fprop x")
     assert w.dtype == BF16 and w.stride(1) == 1 and out.stride(3) == 1
     assert len(taps) <= _lib.VG_MAX_FPROP_TAPS, f"{len(taps)} taps > {_lib.VG_MAX_FPROP_TAPS}"
     assert wk is not None or w.shape[1] == len(taps) * cin, (w.shape, len(taps), cin)
     assert not b_mn_major or wk is not None
+    if DETERMINISTIC and out_kind == 2 and ksplit == 0 and x.dtype == BF16:
+        ksplit = 1      # one split adds into the zeroed destination exactly once: order-independent
+    flat_groups = None
+    if groups is not None:
+        assert 2 <= len(groups) <= 4 and sum(g[0] for g in groups) == len(taps) and ksplit in (0, 1)
+        flat_groups = [int(v) for nt, (sh, sw) in groups for v in (nt, sh, sw)]
+    e0 = _prof_begin()
+    _fprop_launch(x, [int(v) for t in taps for v in t], x_stride, cin, w, n_gemm, list(m), out, out_kind, list(su), list(sub0),
+                  cout_per_sub or n_gemm, bias, act, ksplit, force_bn, [int(v) for v in wk] if wk is not None else None,
+                  b_mn_major, flat_groups, HALO_MODE if halo_mode is None else halo_mode, stats)
+    _prof_end(e0, "fprop", (m, n_gemm, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * n_gemm * len(taps) * cin)
+
+
+@launch_op("vg_conv_fprop(Tensor x, int[] taps, int x_stride, int cin, Tensor w, int n_gemm, int[] m, Tensor(a!) out, int out_kind, "
+           "int[] su, int[] sub0, int cout_per_sub, Tensor? bias, int act, int ksplit, int force_bn, int[]? wk, bool b_mn_major, "
+           "int[]? groups, int halo_mode, Tensor(b!)? stats) -> ()")
+def _fprop_launch(x, taps, x_stride, cin, w, n_gemm, m, out, out_kind, su, sub0, cout_per_sub, bias, act, ksplit, force_bn, wk,
+                  b_mn_major, groups, halo_mode, stats):
+    """Descriptor marshalling + launch of the forward / data-gradient tensor-core kernel (include/vaegan_b200.h: VgConvFprop)."""
+    ntaps = len(taps) // 4
     d = VgConvFprop()
     d.x, d.x_n, d.x_h, d.x_w, d.x_ld, d.x_stride = x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], x.stride(2), x_stride
     d.m_n, d.m_h, d.m_w = m
-    d.cin, d.num_taps = cin, len(taps)
-    for i, t in enumerate(taps):
+    d.cin, d.num_taps = cin, ntaps
+    for i in range(ntaps):
         for j in range(4):
-            d.taps[i][j] = int(t[j])
+            d.taps[i][j] = taps[4 * i + j]
     if wk is not None:
         d.use_wk = 1
         for i, v in enumerate(wk):
-            d.wk[i] = int(v)
+            d.wk[i] = v
     d.w, d.w_ld, d.n_gemm = w.data_ptr(), w.stride(0), n_gemm
     d.out, d.out_kind = out.data_ptr(), out_kind
     d.out_h, d.out_w, d.out_ld, d.out_coff = out.shape[1], out.shape[2], out.stride(2), 0
     d.su_h, d.su_w = su
     d.sub_h0, d.sub_w0 = sub0
-    d.cout_per_sub = cout_per_sub or n_gemm
+    d.cout_per_sub = cout_per_sub
     d.bias = bias.data_ptr() if bias is not None else None
-    if DETERMINISTIC and out_kind == 2 and ksplit == 0 and x.dtype == BF16:
-        ksplit = 1      # one split adds into the zeroed destination exactly once: order-independent
     d.act, d.ksplit, d.force_bn = act, ksplit, force_bn
     d.b_mn_major, d.w_rows = int(b_mn_major), w.shape[0]
-    d.halo_mode = HALO_MODE if halo_mode is None else halo_mode
+    d.halo_mode = halo_mode
     if stats is not None:
         assert stats.dtype == F32 and stats.is_contiguous() and stats.numel() == 2 * d.cout_per_sub and out_kind != 2
         d.stats = stats.data_ptr()
     if groups is not None:
-        assert 2 <= len(groups) <= 4 and sum(g[0] for g in groups) == len(taps) and ksplit in (0, 1)
-        d.num_groups = len(groups)
-        for i, (nt, (sh, sw)) in enumerate(groups):
-            d.group_ntaps[i] = nt
-            d.group_sub[i][0], d.group_sub[i][1] = sh, sw
-    e0 = _prof_begin()
+        d.num_groups = len(groups) // 3
+        for i in range(d.num_groups):
+            d.group_ntaps[i] = groups[3 * i]
+            d.group_sub[i][0], d.group_sub[i][1] = groups[3 * i + 1], groups[3 * i + 2]
     _lib.call("vg_conv_fprop", C.byref(d), ops.stream())
-    _prof_end(e0, "fprop", (m, n_gemm, len(taps) * cin), 2.0 * m[0] * m[1] * m[2] * n_gemm * len(taps) * cin)
 
 
 def wgrad(g: torch.Tensor, cout: int, x: torch.Tensor, taps: Sequence[Tap], x_stride: int, cin: int,
           m: Tuple[int, int, int], dw: torch.Tensor, ksplit: int = 0, force_bn: int = 0,
           pairs: Optional[Sequence[Tuple[int, int]]] = None) -> None:
     """dw[co, tap*cin + ci] (fp32) = sum_pixels g[pixel, co] * x[pixel@tap, ci]; ``pairs`` = channel offsets (g, x) of
-    split-precision operand planes accumulated into the same dw."""
+    split-precision operand planes accumulated into the same dw.  The launch is ``torch.ops.vaegan.vg_conv_wgrad``."""
     _chk(g, "wgrad g")
     _chk(x, "wgrad x")
     assert dw.dtype == F32 and dw.stride(1) == 1 and len(taps) <= _lib.VG_MAX_TAPS
+    e0 = _prof_begin()
+    _wgrad_launch(g, cout, x, [int(v) for t in taps for v in t], x_stride, cin, list(m), dw, ksplit, force_bn,
+                  [int(v) for ab in pairs for v in ab] if pairs else None, DETERMINISTIC)
+    _prof_end(e0, "wgrad", (m, cout, len(taps) * cin),
+              2.0 * m[0] * m[1] * m[2] * cout * len(taps) * cin * (len(pairs) if pairs else 1))
+
+
+@launch_op("vg_conv_wgrad(Tensor g, int cout, Tensor x, int[] taps, int x_stride, int cin, int[] m, Tensor(a!) dw, int ksplit, "
+           "int force_bn, int[]? pairs, bool deterministic) -> ()")
+def _wgrad_launch(g, cout, x, taps, x_stride, cin, m, dw, ksplit, force_bn, pairs, deterministic):
+    """Descriptor marshalling + launch of the weight-gradient tensor-core kernel (include/vaegan_b200.h: VgConvWgrad)."""
+    ntaps = len(taps) // 4
     d = VgConvWgrad()
     d.g, d.g_ld, d.g_coff, d.cout = g.data_ptr(), g.stride(2), 0, cout
     d.x, d.x_n, d.x_h, d.x_w, d.x_ld, d.x_stride = x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], x.stride(2), x_stride
     d.m_n, d.m_h, d.m_w = m
-    d.cin, d.num_taps = cin, len(taps)
-    for i, t in enumerate(taps):
+    d.cin, d.num_taps = cin, ntaps
+    for i in range(ntaps):
         for j in range(4):
-            d.taps[i][j] = int(t[j])
+            d.taps[i][j] = taps[4 * i + j]
     if pairs:
-        d.num_combos = len(pairs)
-        for i, (a, b) in enumerate(pairs):
-            d.combo_g[i], d.combo_x[i] = int(a), int(b)
+        d.num_combos = len(pairs) // 2
+        for i in range(d.num_combos):
+            d.combo_g[i], d.combo_x[i] = pairs[2 * i], pairs[2 * i + 1]
     d.dw, d.dw_ld = dw.data_ptr(), dw.stride(0)
     d.ksplit, d.force_bn = ksplit, force_bn
-    if DETERMINISTIC:
+    if deterministic:
         need = int(_lib.lib().vg_conv_wgrad_workspace(C.byref(d)))
         assert need >= 0, "vg_conv_wgrad_workspace rejected the descriptor"
         if need > 0:
             ws = torch.empty(need // 4, dtype=F32, device=dw.device)      # lives until the stream has consumed it (caching allocator)
             d.workspace, d.workspace_bytes = ws.data_ptr(), need
-    e0 = _prof_begin()
     _lib.call("vg_conv_wgrad", C.byref(d), ops.stream())
-    _prof_end(e0, "wgrad", (m, cout, len(taps) * cin),
-              2.0 * m[0] * m[1] * m[2] * cout * len(taps) * cin * (len(pairs) if pairs else 1))
 
 
 def pad_channels(t: torch.Tensor, c_pad: int) -> torch.Tensor:

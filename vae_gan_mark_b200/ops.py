@@ -1,7 +1,9 @@
 """Thin Python wrappers over the C ABI (include/vaegan_b200.h): tensors in, kernel launches out.
 
 Everything here enqueues hand-written CUDA kernels on the current torch stream; torch is used only for
-memory (allocation, views).  NHWC bf16 activations are plain torch tensors of shape [N, H, W, C] whose last
+memory (allocation, views).  Every launching function is a ``torch.library`` custom op, registered under the name of the
+C entry point it wraps (``torch.ops.vaegan.vg_norm_apply`` ...; see dispatch.py): calling ``ops.norm_apply(...)`` goes
+through the dispatcher.  NHWC bf16 activations are plain torch tensors of shape [N, H, W, C] whose last
 stride is 1 and whose pixel stride ``ld = stride(2)`` may exceed C (a channel slice of a wider buffer).
 """
 from __future__ import annotations
@@ -12,6 +14,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from .dispatch import launch_op
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -66,6 +69,7 @@ def dense_nhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:
     return out
 
 
+@launch_op("vg_split3(Tensor t) -> Tensor")
 def split3(t: torch.Tensor) -> torch.Tensor:
     """fp32 NHWC view [N,H,W,C] -> bf16 [N,H,W,3*Cp] holding the hi | mid | lo planes (Cp = C rounded up to 64)."""
     assert t.dtype == F32 and t.stride(3) == 1
@@ -84,6 +88,7 @@ def ld_of(t: torch.Tensor) -> int:
 # ----------------------------------------------------------------------------------------------
 # data movement
 # ----------------------------------------------------------------------------------------------
+@launch_op("vg_strided_copy(Tensor src, Tensor(a!) dst, Tensor? scale=None, bool scale_inverse=False, bool accumulate=False) -> ()")
 def strided_copy(src: torch.Tensor, dst: torch.Tensor, scale: Optional[torch.Tensor] = None,
                  scale_inverse: bool = False, accumulate: bool = False) -> None:
     """dst[...] (=|+=) scale * src[...] for two tensors of equal shape (<= 5 dims), any strides, fp32/bf16."""
@@ -102,6 +107,7 @@ def strided_copy(src: torch.Tensor, dst: torch.Tensor, scale: Optional[torch.Ten
 # ----------------------------------------------------------------------------------------------
 # normalisation + activation (+ pool)
 # ----------------------------------------------------------------------------------------------
+@launch_op("vg_norm_stats(Tensor x, bool per_sample) -> Tensor")
 def norm_stats(x: torch.Tensor, per_sample: bool) -> torch.Tensor:
     n, h, w, c = x.shape
     groups = n if per_sample else 1
@@ -111,6 +117,7 @@ def norm_stats(x: torch.Tensor, per_sample: bool) -> torch.Tensor:
     return sums
 
 
+@launch_op("vg_norm_stats_rows(Tensor x, int virt_h) -> Tensor")
 def norm_stats_rows(x: torch.Tensor, virt_h: int) -> torch.Tensor:
     """Batch statistics of a tensor whose h rows stand for ``virt_h`` rows (interior rows all equal)."""
     n, h, w, c = x.shape
@@ -120,6 +127,7 @@ def norm_stats_rows(x: torch.Tensor, virt_h: int) -> torch.Tensor:
     return sums
 
 
+@launch_op("vg_norm_finalize(Tensor sums, int rows, float eps, float momentum=0.1, Tensor(a!)? running_mean=None, Tensor(b!)? running_var=None, Tensor(c!)? num_batches_tracked=None) -> Tensor")
 def norm_finalize(sums: torch.Tensor, rows: int, eps: float, momentum: float = 0.1,
                   running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None,
                   num_batches_tracked: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -130,6 +138,7 @@ def norm_finalize(sums: torch.Tensor, rows: int, eps: float, momentum: float = 0
     return mr
 
 
+@launch_op("vg_norm_apply(Tensor x, Tensor mean_rstd, Tensor? gamma, Tensor? beta, int act, Tensor(a!) y, Tensor(b!)? pool=None) -> ()")
 def norm_apply(x: torch.Tensor, mean_rstd: torch.Tensor, gamma, beta, act: int, y: torch.Tensor,
                pool: Optional[torch.Tensor] = None) -> None:
     n, h, w, c = x.shape
@@ -148,6 +157,7 @@ def norm_apply(x: torch.Tensor, mean_rstd: torch.Tensor, gamma, beta, act: int, 
     _lib.call("vg_norm_apply", C.byref(d), stream())
 
 
+@launch_op("vg_norm_backward(Tensor x, Tensor? dy, Tensor? dpool, Tensor mean_rstd, bool per_sample, Tensor? gamma, Tensor? beta, int act, Tensor(a!) dx, Tensor(b!)? dgamma, Tensor(c!)? dbeta, bool accumulate=False, int virt_h=0) -> ()")
 def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dgamma, dbeta, accumulate=False,
                   virt_h: int = 0):
     n, h, w, c = x.shape
@@ -176,18 +186,21 @@ def norm_backward(x, dy, dpool, mean_rstd, per_sample, gamma, beta, act, dx, dga
     _lib.call("vg_norm_backward", C.byref(d), stream())
 
 
+@launch_op("vg_maxpool2x2_fwd(Tensor x, Tensor(a!) y) -> ()")
 def maxpool_fwd(x, y):
     n, h, w, c = x.shape
     assert x.dtype == y.dtype and y.is_contiguous() and nhwc_ok(x)
     _lib.call("vg_maxpool2x2_fwd", _p(x), ld_of(x), _p(y), n, h, w, c, dcode(x), stream())
 
 
+@launch_op("vg_maxpool2x2_bwd(Tensor x, Tensor dy, Tensor(a!) dx) -> ()")
 def maxpool_bwd(x, dy, dx):
     n, h, w, c = x.shape
     assert x.dtype == dy.dtype == dx.dtype and dy.is_contiguous() and dx.is_contiguous() and nhwc_ok(x)
     _lib.call("vg_maxpool2x2_bwd", _p(x), ld_of(x), _p(dy), _p(dx), n, h, w, c, dcode(x), stream())
 
 
+@launch_op("vg_act_bwd(Tensor y, Tensor dy, Tensor(a!) dx, int act) -> ()")
 def act_bwd(y, dy, dx, act):
     n, h, w, c = y.shape
     assert y.dtype == dy.dtype == dx.dtype
@@ -195,11 +208,13 @@ def act_bwd(y, dy, dx, act):
               dcode(y), stream())
 
 
+@launch_op("vg_act_fwd(Tensor(a!) y, int act) -> ()")
 def act_fwd_(y, act):
     n, h, w, c = y.shape
     _lib.call("vg_act_fwd", _p(y), ld_of(y), C.c_longlong(n * h * w), c, act, dcode(y), stream())
 
 
+@launch_op("vg_colsum_f32(Tensor t2d, Tensor(a!) out, bool accumulate=False) -> ()")
 def colsum_f32(t2d, out, accumulate=False):
     rows, cols = t2d.shape
     _lib.call("vg_colsum_f32", _p(t2d), C.c_longlong(rows), cols, t2d.stride(0), _p(out), int(accumulate), stream())
@@ -208,12 +223,14 @@ def colsum_f32(t2d, out, accumulate=False):
 # ----------------------------------------------------------------------------------------------
 # FiLM / upsample / im2col / small-N convs
 # ----------------------------------------------------------------------------------------------
+@launch_op("vg_film_fwd(Tensor gb, Tensor x, Tensor(a!) y) -> ()")
 def film_fwd(gb, x, y):
     n, h, w, c = x.shape
     assert gb.dtype == x.dtype == y.dtype
     _lib.call("vg_film_fwd", _p(gb), _p(x), ld_of(x), 0, _p(y), C.c_longlong(n * h * w), c, dcode(x), stream())
 
 
+@launch_op("vg_film_bwd(Tensor gb, Tensor x, Tensor dy, Tensor(a!) dgb, Tensor(b!) dx) -> ()")
 def film_bwd(gb, x, dy, dgb, dx):
     n, h, w, c = x.shape
     assert gb.dtype == x.dtype == dy.dtype == dgb.dtype == dx.dtype
@@ -221,6 +238,7 @@ def film_bwd(gb, x, dy, dgb, dx):
               C.c_longlong(n * h * w), c, dcode(x), stream())
 
 
+@launch_op("vg_film_rows_fwd(Tensor gb3, Tensor x, Tensor(a!) y) -> ()")
 def film_rows_fwd(gb3, x, y):
     n, h, w, c = x.shape
     assert gb3.dtype == x.dtype == y.dtype and gb3.is_contiguous() and y.is_contiguous()
@@ -228,6 +246,7 @@ def film_rows_fwd(gb3, x, y):
     _lib.call("vg_film_rows_fwd", _p(gb3), 3, _p(x), ld_of(x), 0, _p(y), n, h, w, c, dcode(x), stream())
 
 
+@launch_op("vg_film_rows_bwd(Tensor gb3, Tensor x, Tensor dy, Tensor(a!) dgb3, Tensor(b!) dx) -> ()")
 def film_rows_bwd(gb3, x, dy, dgb3, dx):
     n, h, w, c = x.shape
     assert gb3.dtype == x.dtype == dy.dtype == dgb3.dtype == dx.dtype
@@ -236,6 +255,7 @@ def film_rows_bwd(gb3, x, dy, dgb3, dx):
               dcode(x), stream())
 
 
+@launch_op("vg_upsample_w_fwd(Tensor t, Tensor(a!) y) -> ()")
 def upsample_w_fwd(t, y):
     n, _, w0, c = t.shape
     _, h, w, _ = y.shape
@@ -243,12 +263,14 @@ def upsample_w_fwd(t, y):
     _lib.call("vg_upsample_w_fwd", _p(t), ld_of(t), 0, n, w0, c, _p(y), h, w, dcode(t), stream())
 
 
+@launch_op("vg_upsample_w_bwd(Tensor dy, Tensor(a!) dt) -> ()")
 def upsample_w_bwd(dy, dt):
     n, h, w, c = dy.shape
     w0 = dt.shape[2]
     _lib.call("vg_upsample_w_bwd", _p(dy), n, h, w, c, w0, _p(dt), dcode(dy), stream())
 
 
+@launch_op("vg_upsample_h_fwd(Tensor t, Tensor(a!) y) -> ()")
 def upsample_h_fwd(t, y):
     """Bilinear resize along H only: t [n,h0,w,c] -> y [n,h,w,c], both dense."""
     n, h0, w, c = t.shape
@@ -256,6 +278,7 @@ def upsample_h_fwd(t, y):
     _lib.call("vg_upsample_h_fwd", _p(t), n, h0, w, c, _p(y), y.shape[1], dcode(t), stream())
 
 
+@launch_op("vg_upsample_h_bwd(Tensor dy, Tensor(a!) dt) -> ()")
 def upsample_h_bwd(dy, dt):
     """dy [n,h,w,c] dense (bf16 or fp32) -> dt fp32 [n,h0,w,c] (fully written)."""
     n, h, w, c = dy.shape
@@ -263,6 +286,7 @@ def upsample_h_bwd(dy, dt):
     _lib.call("vg_upsample_h_bwd", _p(dy), n, h, w, c, dt.shape[1], _p(dt), dcode(dy), stream())
 
 
+@launch_op("vg_channel_scale_fwd(Tensor x, Tensor scale, Tensor(a!) y) -> ()")
 def channel_scale_fwd(x, scale, y):
     """y[..., ch] = x[..., ch] * scale[ch]; x, y NHWC views (y may be a channel slice), scale fp32 [c]."""
     n, h, w, c = x.shape
@@ -272,6 +296,7 @@ def channel_scale_fwd(x, scale, y):
               dcode(x), stream())
 
 
+@launch_op("vg_channel_scale_bwd(Tensor x, Tensor dy, Tensor scale, Tensor(a!) dx, Tensor(b!) dscale) -> ()")
 def channel_scale_bwd(x, dy, scale, dx, dscale):
     """dx = dy * scale, dscale[:c] = sum over pixels of dy * x (dscale: fp32 [2c], second half scratch)."""
     n, h, w, c = x.shape
@@ -281,6 +306,7 @@ def channel_scale_bwd(x, dy, scale, dx, dscale):
               C.c_longlong(n * h * w), c, _p(dscale), dcode(x), stream())
 
 
+@launch_op("vg_im2col(Tensor src, int c, int kh, int kw, int stride, int pad, Tensor(a!) col) -> ()")
 def im2col(src, c, kh, kw, stride, pad, col):
     n, h, w, _ = src.shape
     assert src.dtype == col.dtype
@@ -288,23 +314,27 @@ def im2col(src, c, kh, kw, stride, pad, col):
               stream())
 
 
+@launch_op("vg_col2im(Tensor dcol, int n, int h, int w, int c, int kh, int kw, int stride, int pad, Tensor(a!) dsrc_nchw) -> ()")
 def col2im(dcol, n, h, w, c, kh, kw, stride, pad, dsrc_nchw):
     _lib.call("vg_col2im", _p(dcol), dcol.shape[-1], n, h, w, c, kh, kw, stride, pad, _p(dsrc_nchw), dcode(dcol),
               stream())
 
 
+@launch_op("vg_conv_smalln_fwd(Tensor x, Tensor wt, Tensor? bias, int kh, int kw, int pad, Tensor(a!) out) -> ()")
 def smalln_fwd(x, wt, bias, kh, kw, pad, out):
     n, h, w, cin = x.shape
     _lib.call("vg_conv_smalln_fwd", _p(x), ld_of(x), 0, n, h, w, cin, _p(wt), _p(bias), wt.shape[0], kh, kw, pad,
               _p(out), dcode(x), stream())
 
 
+@launch_op("vg_conv_smalln_dgrad(Tensor dy, Tensor wt, int kh, int kw, int pad, Tensor(a!) dx) -> ()")
 def smalln_dgrad(dy, wt, kh, kw, pad, dx):
     n, h, w, cin = dx.shape
     _lib.call("vg_conv_smalln_dgrad", _p(dy), n, h, w, cin, _p(wt), wt.shape[0], kh, kw, pad, _p(dx), ld_of(dx), 0,
               dcode(dx), stream())
 
 
+@launch_op("vg_conv_smalln_wgrad(Tensor dy, Tensor x, int kh, int kw, int pad, Tensor(a!) dw, Tensor(b!)? dbias) -> ()")
 def smalln_wgrad(dy, x, kh, kw, pad, dw, dbias):
     n, h, w, cin = x.shape
     _lib.call("vg_conv_smalln_wgrad", _p(dy), _p(x), ld_of(x), 0, n, h, w, cin, dw.shape[0], kh, kw, pad, _p(dw),
@@ -314,6 +344,7 @@ def smalln_wgrad(dy, x, kh, kw, pad, dw, dbias):
 # ----------------------------------------------------------------------------------------------
 # losses / reparam / spectral norm / optimiser
 # ----------------------------------------------------------------------------------------------
+@launch_op("vg_reparam_kl_fwd(Tensor heads, Tensor bias_mu, Tensor bias_lv, Tensor eps) -> (Tensor, Tensor, Tensor, Tensor)")
 def reparam_kl_fwd(heads, bias_mu, bias_lv, eps):
     b, z2 = heads.shape
     z = z2 // 2
@@ -324,6 +355,7 @@ def reparam_kl_fwd(heads, bias_mu, bias_lv, eps):
     return mu, lv, zo, kl
 
 
+@launch_op("vg_reparam_kl_bwd(Tensor mu, Tensor lv, Tensor eps, Tensor? dz, Tensor? dmu, Tensor? dlv, Tensor? dkl, Tensor(a!)? dheads_bf16=None) -> Tensor")
 def reparam_kl_bwd(mu, lv, eps, dz, dmu, dlv, dkl, dheads_bf16=None):
     b, z = mu.shape
     dheads = torch.empty(b, 2 * z, dtype=F32, device=mu.device)
@@ -332,36 +364,43 @@ def reparam_kl_bwd(mu, lv, eps, dz, dmu, dlv, dkl, dheads_bf16=None):
     return dheads
 
 
+@launch_op("vg_sigmoid_fwd(Tensor pre_nhwc, Tensor(a!) y_nchw) -> ()")
 def sigmoid_fwd(pre_nhwc, y_nchw):
     n, c, h, w = y_nchw.shape
     _lib.call("vg_sigmoid_fwd", _p(pre_nhwc), n, c, h * w, _p(y_nchw), stream())
 
 
+@launch_op("vg_sigmoid_bwd(Tensor y_nchw, Tensor dy_nchw, Tensor(a!) dpre_nhwc) -> ()")
 def sigmoid_bwd(y_nchw, dy_nchw, dpre_nhwc):
     n, c, h, w = y_nchw.shape
     _lib.call("vg_sigmoid_bwd", _p(y_nchw), _p(dy_nchw), n, c, h * w, _p(dpre_nhwc), stream())
 
 
+@launch_op("vg_l1_fwd(Tensor a, Tensor b) -> Tensor")
 def l1_fwd(a, b):
     out = torch.empty((), dtype=F32, device=a.device)
     _lib.call("vg_l1_fwd", _p(a), _p(b), C.c_longlong(a.numel()), _p(out), stream())
     return out
 
 
+@launch_op("vg_l1_bwd(Tensor a, Tensor b, Tensor gout, Tensor(a!) da, bool accumulate=False) -> ()")
 def l1_bwd(a, b, gout, da, accumulate=False):
     _lib.call("vg_l1_bwd", _p(a), _p(b), C.c_longlong(a.numel()), _p(gout), _p(da), int(accumulate), stream())
 
 
+@launch_op("vg_hinge_fwd(Tensor p, int mode) -> Tensor")
 def hinge_fwd(p, mode):
     out = torch.empty((), dtype=F32, device=p.device)
     _lib.call("vg_hinge_fwd", _p(p), C.c_longlong(p.numel()), mode, _p(out), stream())
     return out
 
 
+@launch_op("vg_hinge_bwd(Tensor p, int mode, Tensor gout, Tensor(a!) dp) -> ()")
 def hinge_bwd(p, mode, gout, dp):
     _lib.call("vg_hinge_bwd", _p(p), C.c_longlong(p.numel()), mode, _p(gout), _p(dp), stream())
 
 
+@launch_op("vg_spectral_sigma(Tensor w2d, Tensor(a!) u, Tensor(b!) v, bool training, float eps=1e-12) -> Tensor")
 def spectral_sigma(w2d, u, v, training, eps=1e-12):
     rows, cols = w2d.shape
     sigma = torch.empty((), dtype=F32, device=w2d.device)
@@ -371,6 +410,7 @@ def spectral_sigma(w2d, u, v, training, eps=1e-12):
     return sigma
 
 
+@launch_op("vg_spectral_bwd(Tensor g2d, Tensor w2d, Tensor u, Tensor v, Tensor sigma, Tensor(a!) dw, bool accumulate=False) -> ()")
 def spectral_bwd(g2d, w2d, u, v, sigma, dw, accumulate=False):
     rows, cols = w2d.shape
     scratch = torch.empty(1, dtype=F32, device=w2d.device)
@@ -378,6 +418,7 @@ def spectral_bwd(g2d, w2d, u, v, sigma, dw, accumulate=False):
               _p(scratch), stream())
 
 
+@launch_op("vg_gru_seq_fwd(Tensor xproj, Tensor w_hh, Tensor b_hh, Tensor(a!) out, Tensor(b!) gates) -> ()")
 def gru_seq_fwd(xproj, w_hh, b_hh, out, gates):
     """Time recurrence of one bidirectional GRU layer; xproj [B,T,2,3H], out [B,T,2H], gates [2,B,T,4,H] (fp32)."""
     b, t = out.shape[0], out.shape[1]
@@ -387,6 +428,7 @@ def gru_seq_fwd(xproj, w_hh, b_hh, out, gates):
     _lib.call("vg_gru_seq_fwd", _p(xproj), _p(w_hh), _p(b_hh), _p(out), _p(gates), b, t, h, stream())
 
 
+@launch_op("vg_gru_seq_bwd(Tensor dout, Tensor out, Tensor gates, Tensor w_hh, Tensor(a!) dgx, Tensor(b!) dgh) -> ()")
 def gru_seq_bwd(dout, out, gates, w_hh, dgx, dgh):
     b, t = out.shape[0], out.shape[1]
     h = w_hh.shape[2]
@@ -398,6 +440,7 @@ def gru_seq_bwd(dout, out, gates, w_hh, dgx, dgh):
 # ----------------------------------------------------------------------------------------------
 # text front end: tokenisation, embedding, sequence pooling
 # ----------------------------------------------------------------------------------------------
+@launch_op("vg_tokenize(Tensor codepoints, Tensor lut) -> Tensor")
 def tokenize(codepoints: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
     """codepoints: int32 device tensor holding uint32 UTF-32 code units (any shape); lut: int32 [lut_size].  -> int64 indices."""
     assert codepoints.dtype == torch.int32 and lut.dtype == torch.int32 and codepoints.is_contiguous() and lut.is_contiguous()
@@ -406,6 +449,7 @@ def tokenize(codepoints: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
     return idx
 
 
+@launch_op("vg_embedding_fwd(Tensor idx, Tensor weight) -> Tensor")
 def embedding_fwd(idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     assert idx.dtype == torch.long and idx.is_contiguous() and weight.dtype == F32 and weight.is_contiguous()
     out = torch.empty(tuple(idx.shape) + (weight.shape[1],), dtype=F32, device=weight.device)
@@ -414,6 +458,7 @@ def embedding_fwd(idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@launch_op("vg_embedding_bwd(Tensor idx, Tensor g, int vocab, int padding_idx) -> Tensor")
 def embedding_bwd(idx: torch.Tensor, g: torch.Tensor, vocab: int, padding_idx: int) -> torch.Tensor:
     g = g.contiguous()
     assert g.dtype == F32
@@ -422,6 +467,7 @@ def embedding_bwd(idx: torch.Tensor, g: torch.Tensor, vocab: int, padding_idx: i
     return dw
 
 
+@launch_op("vg_seqpool_fwd(Tensor seq, Tensor(a!) out) -> ()")
 def seqpool_fwd(seq: torch.Tensor, out: torch.Tensor) -> None:
     """seq: [b,l,c] (or NHWC [b,1,l,c]) rows of stride seq.stride(-2); out: NHWC [b,1,w,c]."""
     b, l, c = seq.shape[0], seq.shape[-2], seq.shape[-1]
@@ -430,6 +476,7 @@ def seqpool_fwd(seq: torch.Tensor, out: torch.Tensor) -> None:
     _lib.call("vg_seqpool_fwd", _p(seq), dcode(seq), seq.stride(-2), b, l, c, w, _p(out), dcode(out), out.stride(2), stream())
 
 
+@launch_op("vg_seqpool_bwd(Tensor dy, Tensor(a!) dseq) -> ()")
 def seqpool_bwd(dy: torch.Tensor, dseq: torch.Tensor) -> None:
     """dy: NHWC [b,1,w,c]; dseq: [b,l,c] (or NHWC [b,1,l,c]), fully written."""
     b, l, c = dseq.shape[0], dseq.shape[-2], dseq.shape[-1]
@@ -438,10 +485,12 @@ def seqpool_bwd(dy: torch.Tensor, dseq: torch.Tensor) -> None:
     _lib.call("vg_seqpool_bwd", _p(dy), dcode(dy), dy.stride(2), b, l, c, w, _p(dseq), dcode(dseq), dseq.stride(-2), stream())
 
 
+@launch_op("vg_sumsq(Tensor g, Tensor(a!) out, bool zero_first=True) -> ()")
 def sumsq(g, out, zero_first=True):
     _lib.call("vg_sumsq", _p(g), C.c_longlong(g.numel()), _p(out), int(zero_first), stream())
 
 
+@launch_op("vg_adam_step(Tensor(a!) p, Tensor(b!) g, Tensor(c!) m, Tensor(d!) v, float lr, float beta1, float beta2, float eps, int step, Tensor? gnorm_sq=None, float max_norm=0.0, bool write_back_grad=False) -> ()")
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, gnorm_sq=None, max_norm=0.0, write_back_grad=False):
     _lib.call("vg_adam_step", _p(p), _p(g), _p(m), _p(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
               C.c_float(beta2), C.c_float(eps), int(step), _p(gnorm_sq), C.c_float(max_norm), int(write_back_grad),

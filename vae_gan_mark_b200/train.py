@@ -23,6 +23,7 @@ from typing import Dict, Iterable, List, Optional
 import torch
 
 from . import _lib
+from .dispatch import launch_op
 from . import layers as L
 from . import ops
 from .ops import F32
@@ -47,6 +48,28 @@ class LossWeights:
         if not perceptual:
             w.perc = 0.0
         return w
+
+
+# The optimiser launches as dispatcher ops (dispatch.py).  ``table`` is the device copy of the VgAdamTensor table: the
+# parameters, gradients, moments and operand shadows a launch reads / writes are reached through the raw pointers in it, so
+# the schema names the table itself as the mutated argument.
+@launch_op("vg_multi_sumsq(Tensor table, int count, Tensor(a!) out, Tensor(b!) scratch) -> ()")
+def _multi_sumsq(table, count, out, scratch):
+    _lib.call("vg_multi_sumsq", C.c_void_p(table.data_ptr()), count, C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+              scratch.numel(), ops.stream())
+
+
+@launch_op("vg_adam_prepare(Tensor(a!) state, float beta1, float beta2) -> ()")
+def _adam_prepare(state, beta1, beta2):
+    _lib.call("vg_adam_prepare", C.c_void_p(state.data_ptr()), C.c_float(beta1), C.c_float(beta2), ops.stream())
+
+
+@launch_op("vg_multi_adam(Tensor(a!) table, int count, float lr, float beta1, float beta2, float eps, Tensor state, "
+           "Tensor? gnorm_sq, float max_norm, bool write_back_grad) -> ()")
+def _multi_adam(table, count, lr, beta1, beta2, eps, state, gnorm_sq, max_norm, write_back_grad):
+    _lib.call("vg_multi_adam", C.c_void_p(table.data_ptr()), count, C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+              C.c_float(eps), C.c_void_p(state.data_ptr()), C.c_void_p(gnorm_sq.data_ptr() if gnorm_sq is not None else 0),
+              C.c_float(max_norm), int(write_back_grad), ops.stream())
 
 
 class FusedAdam:
@@ -149,9 +172,7 @@ class FusedAdam:
 
     def grad_norm_sq(self) -> torch.Tensor:
         self._upload_table()
-        _lib.call("vg_multi_sumsq", C.c_void_p(self._table.data_ptr()), len(self.params),
-                  C.c_void_p(self.norm_sq.data_ptr()), C.c_void_p(self._norm_scratch.data_ptr()),
-                  self._norm_scratch.numel(), ops.stream())
+        _multi_sumsq(self._table, len(self.params), self.norm_sq, self._norm_scratch)
         return self.norm_sq
 
     def step(self, max_norm: float = 0.0):
@@ -161,13 +182,9 @@ class FusedAdam:
             self.grad_norm_sq()
         else:
             self._upload_table()
-        st = ops.stream()
-        _lib.call("vg_adam_prepare", C.c_void_p(self.state.data_ptr()), C.c_float(self.betas[0]),
-                  C.c_float(self.betas[1]), st)
-        _lib.call("vg_multi_adam", C.c_void_p(self._table.data_ptr()), len(self.params), C.c_float(-1.0),   # lr: state[3]
-                  C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                  C.c_void_p(self.state.data_ptr()), C.c_void_p(self.norm_sq.data_ptr() if max_norm > 0 else 0),
-                  C.c_float(max_norm), int(max_norm > 0), st)
+        _adam_prepare(self.state, self.betas[0], self.betas[1])
+        _multi_adam(self._table, len(self.params), -1.0, self.betas[0], self.betas[1], self.eps, self.state,   # lr < 0: state[3]
+                    self.norm_sq if max_norm > 0 else None, max_norm, max_norm > 0)
         L.bump_weight_epoch()
 
     def state_dict(self) -> Dict:
