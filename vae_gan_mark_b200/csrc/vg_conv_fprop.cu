@@ -698,7 +698,9 @@ extern "C" int vg_conv_fprop(const VgConvFprop* d, void* stream_) {
   // CTA pairs: the plain mode (K-major or MN-major weights) with 256-wide N tiles, one group, no split-K, and enough pixel tiles that pairing
   // them does not leave SMs without work
   static const int mn_pairs = getenv("VG_FPROP_MN_PAIRS") ? atoi(getenv("VG_FPROP_MN_PAIRS")) : 1;
-  const bool pair = g_fprop_pairs != 0 && !halo && (!d->b_mn_major || mn_pairs) && bn == 256 && ksplit == 1 && d->num_groups <= 1 &&
+  static const int pair_min_bn = getenv("VG_FPROP_PAIR_MIN_BN") ? atoi(getenv("VG_FPROP_PAIR_MIN_BN")) : 128;
+  const bool pair = g_fprop_pairs != 0 && !halo && (!d->b_mn_major || mn_pairs) && bn >= pair_min_bn && bn >= 128 && ksplit == 1 &&
+                    d->num_groups <= 1 &&
                     (m_tiles / 2) * p.n_tiles >= sms / 2 && sms % 2 == 0;
   p.a_bytes = halo ? kHaloBytes : kBM * kBK * 2;
   p.b_bytes = halo ? 9 * bn * kBK * 2 : (pair ? bn / 2 : bn) * kBK * 2;
