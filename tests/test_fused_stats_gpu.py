@@ -187,7 +187,9 @@ def test_wgrad_cta_pair_kernel_equals_single_cta_kernel(cin, cout, k, s, p, n, h
 
 @pytest.mark.parametrize("cin,cout,k,s,p,n,h,w,bias", [(512, 512, 3, 1, 1, 8, 64, 64, False), (256, 512, 3, 1, 1, 37, 16, 16, True),
                                                        (512, 1024, 1, 1, 0, 16, 32, 32, True), (128, 256, 3, 2, 1, 64, 64, 64, True),
-                                                       (512, 384, 3, 1, 1, 33, 24, 20, False)])
+                                                       (512, 384, 3, 1, 1, 33, 24, 20, False),
+                                                       (128, 128, 3, 1, 1, 16, 64, 64, True),       # 128-wide N tiles in pairs
+                                                       (128, 512, 3, 1, 1, 8, 64, 64, False)])      # ... for the data gradient
 def test_fprop_cta_pair_kernel_is_bit_equal_to_single_cta_kernel(cin, cout, k, s, p, n, h, w, bias):
     """conv_fprop_kernel<true> (clusters of two CTAs, one stream of M = 256 tcgen05.mma.cta_group::2, each CTA staging its own
     128-pixel box and half of the weight tile) must reproduce the single-CTA kernel bit for bit -- same products, same
@@ -212,13 +214,15 @@ def test_fprop_cta_pair_kernel_is_bit_equal_to_single_cta_kernel(cin, cout, k, s
             stats = torch.empty((1, 2, cout), device="cuda")
             y = op.forward(x, wf, b, 1, stats=stats)
             dx = op.backward_data(dy, wb, (h, w))
+            dx_mn = op.backward_data(dy, {"mn": wf}, (h, w))      # the forward operand read MN-major (pairs: half the boxes per CTA)
             with torch.no_grad():
                 up = L.ConvTranspose2dFn.apply(dy, ct.weight, ct.bias, opt, L.WeightCache(), 0, None, (2 * oh, 2 * ow))
-            res[pairs] = (y.clone(), dx.clone(), up.clone(), stats.clone())
+            res[pairs] = (y.clone(), dx.clone(), up.clone(), stats.clone(), dx_mn.clone())
     finally:
         _lib.lib().vg_set_fprop_cta_pairs(1)
     torch.cuda.synchronize()
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert torch.equal(res[0][4], res[1][4]) and rel(res[1][4], res[1][1]) < 1e-6       # MN-major operand: pairs == single == K-major
     assert rel(res[1][3], res[0][3]) < 1e-5
     ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), b, stride=s, padding=p))
     assert rel(res[1][0].float().permute(0, 3, 1, 2), ref) < 1e-2

@@ -271,12 +271,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (!p.b_mn) {
             if (leader) tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], wk + cc * kBK, n_t * p.bn + static_cast<int>(rank) * (p.bn / 2));
           } else {
-            // MN-major operand of a pair: this CTA stages ITS half of the N columns = two {64 N, 64 K} boxes
+            // MN-major operand of a pair: this CTA stages ITS half of the N columns = bn / 128 boxes of {64 N, 64 K}
+            // (two for 256-wide tiles, one for 128-wide ones)
+            const int half_boxes = p.bn / 128;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-              if (leader)
-                tma_load_2d_2cta(sb + i * (64 * 128), &tmap_b, &full_bar[stage],
-                                 wk + n_t * p.bn + (static_cast<int>(rank) * 2 + i) * 64, cc * kBK);
+              if (i < half_boxes) {
+                if (leader)
+                  tma_load_2d_2cta(sb + i * (64 * 128), &tmap_b, &full_bar[stage],
+                                   wk + n_t * p.bn + (static_cast<int>(rank) * half_boxes + i) * 64, cc * kBK);
+              }
           }
         } else {
           if (leader) tma_load_5d(sa, &tmap_a, &full_bar[stage], t.x + cc * kBK, ow0 + t.y, t.z, oh0 + t.w, n0);
