@@ -8,6 +8,7 @@
 //   * direct convolutions with <= 4 output channels (final_image_conv vae-gan-v2.py:232, decode.15
 //     vae-gan.py:81, D's patch head vae-gan.py:157) -- HBM-bound GEMV-like work, kept off the tensor pipe.
 #include <algorithm>
+#include <stdlib.h>
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
 
@@ -425,7 +426,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ t, int t_ld, int t_cof
 // exactly once (each column feeds the two sources it was interpolated from); a run is short enough (<= half the
 // upsampling ratio) to touch at most three consecutive sources, whose partial sums live in registers.
 template <typename T>
-__global__ void upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int w, int c, int w0,
+__global__ void __launch_bounds__(256, 3) upsample_bwd_kernel(const T* __restrict__ dy, int n, int h, int w, int c, int w0,
                                     float* __restrict__ dt, int rows_per_thread, int jlen) {
   const int cv = c / 8;
   const int ichunks = (h + rows_per_thread - 1) / rows_per_thread;
@@ -1247,7 +1248,9 @@ extern "C" int vg_upsample_w_bwd(const void* dy, int n, int h, int w, int c, int
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   VG_CHECK(c % 8 == 0, -1, "vg_upsample_w_bwd: channels must be multiples of 8");
   VG_CUDA(cudaMemsetAsync(dt, 0, sizeof(float) * static_cast<size_t>(n) * w0 * c, st));
-  const int rpt = 8;
+  // rows per thread: the fp32 atomics that flush a thread's partial sums, not the loads, bound this kernel (shorter column runs
+  // or fewer rows per thread = more atomics per byte read: 0.15 ... 0.66 of the copy bandwidth); 32 rows per thread: 0.79 at 128 x 128
+  const int rpt = h >= 64 ? 32 : (h >= 32 ? 16 : 8);
   // a run of jlen columns spans at most jlen * w0 / w < 1 source steps plus the two-tap footprint: <= 3 sources
   const int jlen = std::max(1, w / (2 * w0));
   const long long items = static_cast<long long>(n) * ((w + jlen - 1) / jlen) * (c / 8) * ((h + rpt - 1) / rpt);
