@@ -84,16 +84,16 @@ def run_convT(ct: nn.ConvTranspose2d, x, out_hw, act=0, out=None, stats=None):
 # the separate statistics pass over the conv output (one full read of the tensor) disappears.  bf16 mode only: the
 # high-accuracy mode accumulates its split-K partial tiles with atomics and keeps the separate pass.
 FUSE_BN_STATS = True
-FUSE_BN_STATS_MIN_C = 128
+FUSE_BN_STATS_MIN_C = 64
 
 
 def bn_stats_buffer(bn: nn.BatchNorm2d, device):
     """The [1,2,C] fp32 buffer handed to the conv (``stats=``) and then to ``run_bn_relu`` (``sums=``), or None when the
     statistics have to come from the separate pass (eval mode, high-accuracy mode, odd channel counts)."""
     c = bn.num_features
-    # narrow layers (64 channels: the halo-mode / four-accumulator tiles) are bound by the latency chain of their epilogue;
-    # there the extra shared-memory pass of the statistics costs more (+0.06 ms per launch at 128x128 b64) than the
-    # separate statistics kernel it replaces (0.02 ms), so they keep the separate pass
+    # (mid-round the 64-channel layers kept the separate pass: their epilogue was the bound and the extra shared-memory pass
+    # cost +0.06 ms per launch; with the lean MMA issue loop the epilogue has slack and the fused statistics are free --
+    # unet 256x256: 19.11 -> 18.99 ms per step, v2 128x128 unchanged -- so every BatchNorm with >= 64 channels uses them)
     if not (FUSE_BN_STATS and bn.training and ops.act_dtype() == BF16 and c % 32 == 0 and c >= FUSE_BN_STATS_MIN_C):
         return None
     return torch.empty((1, 2, c), dtype=F32, device=device)      # zeroed by vg_conv_fprop
