@@ -226,3 +226,35 @@ def test_fprop_cta_pair_kernel_is_bit_equal_to_single_cta_kernel(cin, cout, k, s
     assert rel(res[1][3], res[0][3]) < 1e-5
     ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float(), b, stride=s, padding=p))
     assert rel(res[1][0].float().permute(0, 3, 1, 2), ref) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout,n,h,w", [(64, 64, 8, 128, 128), (128, 64, 4, 64, 96), (64, 64, 3, 61, 75), (64, 32, 2, 72, 130),
+                                            (192, 64, 2, 64, 64)])
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_wgrad_dual_shift_mode_matches_torch(cin, cout, n, h, w, deterministic):
+    """Weight gradient of 3x3 stride-1 layers with <= 64 output channels: the kernel fills the second half of its M = 128 rows
+    with dY shifted one pixel column (six X shifts instead of nine taps, vg_conv_wgrad.cu: wgrad_plan).  Against
+    torch.nn.grad.conv2d_weight on the same bf16 inputs, incl. widths / heights that are not multiples of the 8 x 8 pixel
+    tile (the extra tile column that carries the shifted last column) and the deterministic two-stage reduction."""
+    from vae_gan_mark_b200 import conv
+    from vae_gan_mark_b200.conv import ConvLinear
+    op = ConvLinear(cin, cout, 3, 3, 1, (1, 1))
+    x = act(n, h, w, cin, 51)
+    dy = act(n, h, w, cout, 52)
+    old = conv.DETERMINISTIC
+    try:
+        conv.DETERMINISTIC = deterministic
+        got = op.backward_weight(dy, x).contiguous().clone()
+        again = op.backward_weight(dy, x).contiguous().clone()
+    finally:
+        conv.DETERMINISTIC = old
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy[..., :cout].float().permute(0, 3, 1, 2),
+                                      stride=1, padding=1)
+    e = rel(got, ref)
+    print(f"dual-shift wgrad {cin}->{cout} {n}x{h}x{w}: {e:.2e}")
+    assert e < 2e-3
+    for tap in range(9):            # every tap separately: a wrong (row half, block) -> tap map would swap whole taps
+        r, q = divmod(tap, 3)
+        assert rel(got[:, :, r, q], ref[:, :, r, q]) < 4e-3, (tap, rel(got[:, :, r, q], ref[:, :, r, q]))
+    if deterministic:
+        assert torch.equal(got, again)

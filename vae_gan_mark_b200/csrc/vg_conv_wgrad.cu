@@ -12,6 +12,7 @@
 // Serves Conv2d wgrad and (with the operand roles swapped by the caller) ConvTranspose2d wgrad of
 // the reference layers (vae-gan.py:52-60,76-81,153-157; vae-gan-v2.py:123-127,168-176,199-241).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
@@ -41,6 +42,7 @@ struct WgradParams {
                                   // workspace of ksplit x cout x dw_ld floats) and wgrad_reduce_kernel adds the splits in
                                   // a fixed order; 0 otherwise
   int4 taps[VG_MAX_TAPS];         // {c_base, dw, sh, dh}
+  int ds;                         // dual-shift mode for <= 64 output channels (see wgrad_plan): A = dY at two pixel shifts
   int ncombos;                    // split-precision operand pairs per pixel tile (1 = plain bf16)
   int combo_g[8], combo_x[8];     // channel offsets of the pair's planes
 };
@@ -117,7 +119,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
       const int k_begin = static_cast<int>((static_cast<long long>(pix_tiles) * split) / p.ksplit);
       const int k_end = static_cast<int>((static_cast<long long>(pix_tiles) * (split + 1)) / p.ksplit);
       const int nblk = min(p.nb, p.blocks_total - n_t * p.nb);          // X blocks of this N tile that exist
-      const int aboxes = max(0, min(2, (p.cout - m_t * kWgBM + 63) / 64));
+      const int aboxes = p.ds ? 2 : max(0, min(2, (p.cout - m_t * kWgBM + 63) / 64));
       // X blocks staged by this CTA: the pair splits the N tile in halves [0, nb/2) | [nb/2, nb)
       const int b0 = k2 ? static_cast<int>(rank) * nb_cta : 0;
       const int myb = max(0, min(nb_cta, nblk - b0));
@@ -151,9 +153,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           if (i < aboxes) {
+            // dual-shift mode: the second box holds the SAME 64 channels one pixel column to the left (dY[p - (0, 1)])
+            const int ca = p.ds ? cg : cg + i * 64, owa = p.ds ? ow0 - i : ow0;
             if (leader) {
-              if (k2) tma_load_5d_2cta(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], cg + i * 64, ow0, 0, oh0, n0);
-              else tma_load_5d(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], cg + i * 64, ow0, 0, oh0, n0);
+              if (k2) tma_load_5d_2cta(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], ca, owa, 0, oh0, n0);
+              else tma_load_5d(sa + i * kWgBoxBytes, &tmap_g, &full_bar[stage], ca, owa, 0, oh0, n0);
             }
           }
         }
@@ -239,6 +243,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(t_row + c, r);
         tmem_ld_wait();
+        // dual-shift mode: accumulator rows [0, 64) belong to dY[p], rows [64, 128) to dY[p - (0, 1)]; the 64-column block
+        // (dh, x in {-1, 0}, 64-channel chunk) of row half j is tap (dh, x + j): j = 1, x = -1 duplicates j = 0, x = 0
+        int row0 = co_warp, col0 = n_t * p.bn + c;
+        bool skip = false;
+        if (p.ds) {
+          const int j = quad >> 1, blk = n_t * p.nb + (c >> 6);
+          const int t6 = blk / cchunks, cc = blk - t6 * cchunks;
+          const int x = (t6 & 1) - 1;
+          skip = (j == 1 && x == -1);
+          row0 = (quad & 1) * 32;
+          col0 = (((t6 >> 1) * 3) + (x + j + 1)) * p.cin + cc * 64 + (c & 63);
+        }
         uint8_t* dst = stg + lane * kWgEpiPitch;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
@@ -247,9 +263,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + rsub;
-          if (co_warp + rr < p.cout) {
+          if (!skip && row0 + rr < p.cout) {
             const float4 v = *reinterpret_cast<const float4*>(stg + rr * kWgEpiPitch + seg * 16);
-            float* o = p.dw + split_off + static_cast<long long>(co_warp + rr) * p.dw_ld + n_t * p.bn + c + seg * 4;
+            float* o = p.dw + split_off + static_cast<long long>(row0 + rr) * p.dw_ld + col0 + seg * 4;
             if (p.atomic) {
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                            : "memory");
@@ -305,6 +321,57 @@ static int wgrad_auto_split(int tiles, int pix_tiles, int sms) {
   return ksplit;
 }
 
+
+// Tiling decisions of a launch, shared by vg_conv_wgrad and vg_conv_wgrad_workspace.
+//
+// Dual-shift mode (ds): with <= 64 output channels half of the M = 128 rows of every MMA would be empty (the 64 -> 64 3x3
+// layers at full resolution ran the tensor pipe 94 % busy at 0.35 of the peak).  The empty half is filled with the SAME 64
+// channels of dY shifted one pixel column to the left: with A_j[p] = dY[p - (0, j)] and B blocks X[p + (dh, x)], x in {-1, 0},
+//     sum_p A_j[p] X[p + (dh, x)] = sum_p' dY[p'] X[p' + (dh, x + j)] = dW[tap (dh, x + j)],
+// so six X blocks per 64-channel chunk (instead of nine) produce all nine taps ((j, x) = (0,-1), (0,0), (1,0); (1,-1) is a
+// duplicate of (0,0) and is not stored): N = 384 per chunk on full M instead of N = 576 on half of M.  The pixel grid is
+// extended by one column (p' = p - (0,1) must reach column W - 1), which is why the pixel tile is 8 x 8 here (+1 column of
+// 8-wide tiles instead of +1 column of 64-wide ones); everything outside the image is TMA zero-fill on both operands.
+struct WgPlan {
+  int tw, th, tn, tiles_n, tiles_h, tiles_w, ncombos, pix_tiles, blocks_total, nb, m_tiles, m_units, ksplit, ds;
+  bool pair;
+};
+static bool wgrad_plan(const VgConvWgrad* d, WgPlan* q) {
+  static const int ds_env = getenv("VG_WGRAD_DS") ? atoi(getenv("VG_WGRAD_DS")) : 1;
+  q->ncombos = d->num_combos > 1 ? d->num_combos : 1;
+  bool ds = ds_env != 0 && d->cout <= 64 && d->num_taps == 9 && d->x_stride == 1 && q->ncombos == 1 && d->force_bn == 0 &&
+            d->m_w >= 8 && d->m_h >= 8 && d->m_w == d->x_w && d->m_h == d->x_h;
+  for (int i = 0; ds && i < 9; ++i)
+    ds = d->taps[i][0] == d->taps[0][0] && d->taps[i][1] == i % 3 - 1 && d->taps[i][2] == 0 && d->taps[i][3] == i / 3 - 1;
+  if (ds && static_cast<long long>(d->m_n) * d->m_h * d->m_w < 128 * kWgPix) ds = false;      // tiny: launch-latency bound
+  q->ds = ds ? 1 : 0;
+  if (ds) {
+    q->tw = 8; q->th = 8; q->tn = 1;
+    q->tiles_w = cdiv(d->m_w + 1, 8);
+  } else {
+    int w = 1;
+    while (w < d->m_w && w < kWgPix) w <<= 1;
+    int h = 1;
+    while (h < d->m_h && w * h < kWgPix) h <<= 1;
+    q->tw = w; q->th = h; q->tn = kWgPix / (w * h);
+    q->tiles_w = cdiv(d->m_w, q->tw);
+  }
+  q->tiles_n = cdiv(d->m_n, q->tn); q->tiles_h = cdiv(d->m_h, q->th);
+  q->pix_tiles = q->tiles_n * q->tiles_h * q->tiles_w * q->ncombos;
+  q->blocks_total = (ds ? 6 : d->num_taps) * (d->cin / 64);
+  q->m_tiles = ds ? 1 : cdiv(d->cout, kWgBM);
+  int nb = min(4, q->blocks_total);
+  if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
+  q->nb = nb;
+  // CTA pairs: at least two 128-channel M tiles to pair up and an N tile that splits in halves
+  // (tiny problems are launch-latency bound and gain nothing from the cluster launch)
+  q->pair = wgrad_pairs_enabled() && q->m_tiles >= 2 && (nb == 2 || nb == 4) && q->pix_tiles >= 128;
+  q->m_units = q->pair ? (q->m_tiles + 1) / 2 : q->m_tiles;
+  const int workers = q->pair ? conv_sms() / 2 : conv_sms();
+  q->ksplit = d->ksplit > 0 ? d->ksplit : wgrad_auto_split(q->m_units * cdiv(q->blocks_total, nb), q->pix_tiles, workers);
+  return true;
+}
+
 }  // namespace vg
 
 using namespace vg;
@@ -320,36 +387,29 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
   VG_CHECK(d->x_ld % 8 == 0 && d->g_ld % 8 == 0 && d->dw_ld % 4 == 0, -1, "vg_conv_wgrad: leading dims alignment");
   VG_CHECK(d->dw_ld >= d->num_taps * d->cin, -1, "vg_conv_wgrad: dw_ld too small");
 
+  WgPlan q;
+  wgrad_plan(d, &q);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.m_n = d->m_n; p.m_h = d->m_h; p.m_w = d->m_w;
-  {
-    int w = 1;
-    while (w < p.m_w && w < kWgPix) w <<= 1;
-    int h = 1;
-    while (h < p.m_h && w * h < kWgPix) h <<= 1;
-    p.tw = w; p.th = h; p.tn = kWgPix / (w * h);
-  }
-  p.tiles_n = cdiv(p.m_n, p.tn); p.tiles_h = cdiv(p.m_h, p.th); p.tiles_w = cdiv(p.m_w, p.tw);
-  p.ncombos = d->num_combos > 1 ? d->num_combos : 1;
+  p.tw = q.tw; p.th = q.th; p.tn = q.tn;
+  p.tiles_n = q.tiles_n; p.tiles_h = q.tiles_h; p.tiles_w = q.tiles_w;
+  p.ncombos = q.ncombos;
+  p.ds = q.ds;
   VG_CHECK(p.ncombos <= 8, -1, "vg_conv_wgrad: at most 8 operand pairs");
   for (int i = 0; i < 8; ++i) { p.combo_g[i] = d->num_combos > 1 ? d->combo_g[i] : 0; p.combo_x[i] = d->num_combos > 1 ? d->combo_x[i] : 0; }
-  const int pix_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.ncombos;
-  p.cout = d->cout; p.cin = d->cin; p.num_taps = d->num_taps; p.g_coff = d->g_coff;
-  p.blocks_total = d->num_taps * (d->cin / 64);
-  p.m_tiles = cdiv(d->cout, kWgBM);
+  const int pix_tiles = q.pix_tiles;
+  p.cout = d->cout; p.cin = d->cin; p.num_taps = q.ds ? 6 : d->num_taps; p.g_coff = d->g_coff;
+  p.blocks_total = q.blocks_total;
+  p.m_tiles = q.m_tiles;
   const int sms = conv_sms();
-  int nb = min(4, p.blocks_total);
-  if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
+  const int nb = q.nb;
   p.nb = nb; p.bn = nb * 64;
   p.n_tiles = cdiv(p.blocks_total, nb);
-  // CTA pairs: at least two 128-channel M tiles to pair up and an N tile that splits in halves
-  // (tiny problems are launch-latency bound and gain nothing from the cluster launch)
-  const bool pair = wgrad_pairs_enabled() && p.m_tiles >= 2 && (nb == 2 || nb == 4) && pix_tiles >= 128;
+  const bool pair = q.pair;
   const int workers = pair ? sms / 2 : sms;
-  const int m_units = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
-  int ksplit = d->ksplit;
-  if (ksplit <= 0) ksplit = wgrad_auto_split(m_units * p.n_tiles, pix_tiles, workers);
+  const int m_units = q.m_units;
+  const int ksplit = q.ksplit;
   VG_CHECK(ksplit <= pix_tiles, -1, "vg_conv_wgrad: ksplit %d > pixel tiles %d", ksplit, pix_tiles);
   p.ksplit = ksplit;
   p.atomic = ksplit > 1 ? 1 : 0;
@@ -372,6 +432,8 @@ extern "C" int vg_conv_wgrad(const VgConvWgrad* d, void* stream_) {
     p.taps[i] = make_int4(d->taps[i][0], d->taps[i][1], d->taps[i][2], d->taps[i][3]);
     VG_CHECK(d->taps[i][2] >= 0 && d->taps[i][2] < d->x_stride, -1, "vg_conv_wgrad: tap %d row parity out of range", i);
   }
+  if (q.ds)      // the six X shifts (dh, x) of the dual-shift mode, block index t6 = (dh + 1) * 2 + (x + 1)
+    for (int t6 = 0; t6 < 6; ++t6) p.taps[t6] = make_int4(d->taps[0][0], (t6 & 1) - 1, 0, (t6 >> 1) - 1);
   if (p.atomic)
     VG_CUDA(cudaMemsetAsync(d->dw, 0, dw_floats * sizeof(float), stream));
 
@@ -436,19 +498,7 @@ extern "C" int vg_set_cta_pairs(int wgrad_on) {
  * launch does not split.  Same split rule as vg_conv_wgrad. */
 extern "C" long long vg_conv_wgrad_workspace(const VgConvWgrad* d) {
   if (d == nullptr || d->cin <= 0 || d->cin % 64 != 0 || d->cout < 1) return -1;
-  int w = 1;
-  while (w < d->m_w && w < kWgPix) w <<= 1;
-  int h = 1;
-  while (h < d->m_h && w * h < kWgPix) h <<= 1;
-  const int tn = kWgPix / (w * h);
-  const int ncombos = d->num_combos > 1 ? d->num_combos : 1;
-  const int pix_tiles = cdiv(d->m_n, tn) * cdiv(d->m_h, h) * cdiv(d->m_w, w) * ncombos;
-  const int blocks_total = d->num_taps * (d->cin / 64);
-  int nb = min(4, blocks_total);
-  if (d->force_bn == 64 || d->force_bn == 128 || d->force_bn == 192 || d->force_bn == 256) nb = min(nb, d->force_bn / 64);
-  const int m_tiles = cdiv(d->cout, kWgBM);
-  const bool pair = wgrad_pairs_enabled() && m_tiles >= 2 && (nb == 2 || nb == 4) && pix_tiles >= 128;
-  const int tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * cdiv(blocks_total, nb);
-  const int ksplit = d->ksplit > 0 ? d->ksplit : wgrad_auto_split(tiles, pix_tiles, pair ? conv_sms() / 2 : conv_sms());
-  return ksplit > 1 ? static_cast<long long>(ksplit) * d->cout * d->dw_ld * static_cast<long long>(sizeof(float)) : 0;
+  WgPlan q;
+  wgrad_plan(d, &q);
+  return q.ksplit > 1 ? static_cast<long long>(q.ksplit) * d->cout * d->dw_ld * static_cast<long long>(sizeof(float)) : 0;
 }
