@@ -3,6 +3,7 @@
 
     python tools/make_profiles.py ncu   NAME.ncu-rep [...]  -> text summary of the named `ncu --set full` captures on stdout
     python tools/make_profiles.py sass                      -> SASS mnemonic counts + excerpts of the tensor-core kernels
+    python tools/make_profiles.py hbm   NAME.ncu-rep PLAIN.log -> table of the HBM-bound kernels (tools/gpu_ew_once.py capture)
 """
 import csv
 import io
@@ -70,8 +71,46 @@ def sass():
         print()
 
 
+def hbm(path, plain_log):
+    """One line per profiled launch of tools/gpu_ew_once.py: duration, DRAM bytes and achieved DRAM bandwidth under ncu, next
+    to the CUDA-event numbers of the plain run of the same script."""
+    import json
+    try:
+        peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+
+    def val(r, m, scale):
+        i = hdr.index(m)
+        return float(r[i].replace(",", "")) * scale[units[i]]
+    t_s = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9, "s": 1.0, "second": 1.0}
+    b_s = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+    one = {u: 1.0 for u in set(units)}
+    print(f"copy peak of the pool (MEASURED_PEAKS.json hbm_gbs) = {peak:.0f} GB/s; `dram %` is ncu's gpu__dram_throughput against the\n"
+          f"hardware peak (a plain copy reaches ~80 % on that scale); DRAM GB/s = (dram__bytes_read + dram__bytes_write) / duration\n")
+    print(f"{'kernel':44s} {'us':>8s} {'read MB':>9s} {'write MB':>9s} {'DRAM GB/s':>10s} {'of copy':>8s} {'dram %':>7s} {'L2 hit %':>8s} {'regs':>5s} {'grid':>6s}")
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", "").replace("__nv_bfloat16", "bf16")
+        t = val(r, "gpu__time_duration.sum", t_s)
+        rd, wr = val(r, "dram__bytes_read.sum", b_s), val(r, "dram__bytes_write.sum", b_s)
+        gbs = (rd + wr) / t / 1e9
+        print(f"{name:44s} {t * 1e6:8.1f} {rd / 1e6:9.1f} {wr / 1e6:9.1f} {gbs:10.0f} {gbs / peak:8.2f} "
+              f"{val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', one):7.1f} {val(r, 'lts__t_sector_hit_rate.pct', one):8.1f} "
+              f"{int(val(r, 'launch__registers_per_thread', one)):5d} {int(val(r, 'launch__grid_size', one)):6d}")
+    print("\nCUDA events, plain run of the same script (5 back-to-back launches per kernel, warm; algorithmic bytes = every tensor once):")
+    for ln in open(plain_log):
+        if ln.startswith("{"):
+            d = json.loads(ln)
+            print(f"  {d['kernel']:38s} {str(d['shape']):22s} {d['algorithmic_MB']:8.1f} MB {d['ms'] * 1e3:8.1f} us {d['GB/s']:8.0f} GB/s  {d['frac_of_copy_peak']:.2f} of copy peak")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "ncu":
+    if sys.argv[1] == "hbm":
+        hbm(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "ncu":
         fl = 2.0 * 64 * 128 * 128 * 512 * 4608
         for pth in sys.argv[2:]:
             ncu_summary(pth, fl if "film4" in pth else None)
