@@ -372,6 +372,70 @@ def test_fused_adam_and_clip_match_torch():
     check("exp_avg", sd["state"][0]["exp_avg"], ref_sd["state"][0]["exp_avg"], 1e-5)
 
 
+def test_multi_tensor_adam_over_a_long_ragged_parameter_list():
+    """The multi-tensor kernels start tensor t at block (t * 37) mod grid (vg_loss_optim.cu: rotated_tid), so every element
+    of every tensor must still be visited exactly once: 60 tensors from 1 element to 3 M elements (several sweeps of the
+    grid), odd sizes (scalar tails), against torch's clip_grad_norm_ + Adam for two steps."""
+    from vae_gan_mark_b200.train import FusedAdam
+    g = torch.Generator().manual_seed(77)
+    sizes = [1, 3, 4, 5, 255, 256, 257, 1023, 4099, 65537, 151552 * 4, 151552 * 4 + 4, 606211, 1000003, 3000001]
+    sizes = sizes + [int(torch.randint(1, 200000, (1,), generator=g)) for _ in range(45)]
+    ps_ref = [torch.randn(n, generator=g).requires_grad_(True) for n in sizes]
+    ps = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ps_ref]
+    opt_ref = torch.optim.Adam(ps_ref, lr=1e-3, betas=(0.5, 0.999))
+    opt = FusedAdam(ps, lr=1e-3, betas=(0.5, 0.999))
+    for it in range(2):
+        for p, q in zip(ps_ref, ps):
+            gr = torch.randn(p.shape, generator=g) * (0.02 if it == 0 else 1e-4)
+            p.grad = gr.clone()
+            q.grad = gr.clone().cuda()
+        n64 = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in ps_ref))     # torch's own fp32 norm is 2e-5 off at 11 M elements
+        torch.nn.utils.clip_grad_norm_(ps_ref, 1.0)
+        opt_ref.step()
+        opt.step(max_norm=1.0)
+        check(f"norm {it}", opt.norm_sq.sqrt(), n64, 3e-5)
+        for i, (p, q) in enumerate(zip(ps_ref, ps)):
+            assert float((q.detach().cpu() - p.detach()).abs().max()) <= 2e-6, (it, i, sizes[i])
+            check(f"clipped grad {it}.{i}", q.grad, p.grad, 1e-4)      # the two clip coefficients differ by the norms' 2e-5
+            # (1 - beta2) is formed in fp32 by the kernel and in double by torch: 1.3e-5 relative on exp_avg_sq
+            check(f"exp_avg_sq {it}.{i}", opt.exp_avg_sq[i], opt_ref.state[p]["exp_avg_sq"], 2e-4)
+
+
+@pytest.mark.parametrize("n,offset", [(1000003, 0), (4096, 0), (1000003, 1), (7, 0)])
+def test_single_tensor_adam_step_matches_torch(n, offset):
+    """vg_adam_step / vg_sumsq, the flat-buffer entry points of the C ABI: 16-byte accesses when the four arrays are
+    aligned (offset 0), the scalar loop otherwise (views starting one element into their buffers) and for the tail."""
+    from vae_gan_mark_b200 import ops
+    from vae_gan_mark_b200._lib import VgError
+    g = torch.Generator().manual_seed(n + offset)
+    p_ref = torch.randn(n, generator=g).requires_grad_(True)
+    opt_ref = torch.optim.Adam([p_ref], lr=1e-3, betas=(0.5, 0.999))
+    bufs = [torch.zeros(n + offset, device="cuda") for _ in range(4)]
+    p, gr, m, v = (b[offset:] for b in bufs)
+    p.copy_(p_ref.detach())
+    nsq = torch.zeros((), device="cuda")
+    for it in range(1, 3):
+        grad = torch.randn(n, generator=g) * (0.05 if it == 1 else 1e-4)
+        p_ref.grad = grad.clone()
+        gr.copy_(grad)
+        n64 = (grad.double() ** 2).sum().sqrt()
+        torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt_ref.step()
+        if offset:      # vg_sumsq reads 16 bytes at a time and refuses other buffers with an error code
+            with pytest.raises(VgError):
+                ops.sumsq(gr, nsq)
+            nsq.copy_((gr.double() ** 2).sum())
+        else:
+            ops.sumsq(gr, nsq)
+        ops.adam_step(p, gr, m, v, 1e-3, 0.5, 0.999, 1e-8, it, nsq, 1.0, True)
+        check(f"norm {it}", nsq.sqrt(), n64, 3e-5)
+        assert float((p.cpu() - p_ref.detach()).abs().max()) <= 2e-6
+        check(f"clipped grad {it}", gr, p_ref.grad, 1e-4)
+        check(f"exp_avg {it}", m, opt_ref.state[p_ref]["exp_avg"], 1e-4)
+        # (1 - beta2) is formed in fp32 by the kernel and in double by torch: 1.3e-5 relative on exp_avg_sq
+        check(f"exp_avg_sq {it}", v, opt_ref.state[p_ref]["exp_avg_sq"], 2e-4)
+
+
 def test_strided_copy_layouts_exact():
     """vg_strided_copy (tiled through shared memory) against torch for the re-layouts the step uses: weight OIHW ->
     GEMM layouts, gradients back, NCHW <-> NHWC, channel-slice destinations, broadcast sources, scale, accumulate.

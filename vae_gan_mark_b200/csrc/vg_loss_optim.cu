@@ -8,6 +8,7 @@
 //   * clip_grad_norm_ + Adam fused into one pass over flat parameter/gradient/moment buffers
 //     (vae-gan.py:424, :541-542).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "vg_common.cuh"
 #include "../../include/vaegan_b200.h"
@@ -253,20 +254,43 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* ou
   const float s = block_sum(acc);
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
+__device__ __forceinline__ void adam_update(float& p, float& g, float& m, float& v, float clip, float step, float b1, float b2,
+                                            float eps, float bc2_sqrt) {
+  g *= clip;
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  p -= step * m / (sqrtf(v) / bc2_sqrt + eps);
+}
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                             const float* __restrict__ gnorm_sq, float max_norm, int write_back_grad) {
   float clip = 1.f;
   if (gnorm_sq != nullptr && max_norm > 0.f) clip = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
   const float step = lr / bc1;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * clip;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long done = 0;
+  // 16-byte accesses (the scalar loop below ran at 0.46 of the copy bandwidth: profiles/r02_ncu_hbm_bound_kernels.txt)
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    const long long n4 = n / 4;
+    float4* p4 = reinterpret_cast<float4*>(p); float4* g4 = reinterpret_cast<float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = tid; i < n4; i += nth) {
+      float4 pv = p4[i], gv = g4[i], mv = m4[i], vv = v4[i];
+      adam_update(pv.x, gv.x, mv.x, vv.x, clip, step, b1, b2, eps, bc2_sqrt);
+      adam_update(pv.y, gv.y, mv.y, vv.y, clip, step, b1, b2, eps, bc2_sqrt);
+      adam_update(pv.z, gv.z, mv.z, vv.z, clip, step, b1, b2, eps, bc2_sqrt);
+      adam_update(pv.w, gv.w, mv.w, vv.w, clip, step, b1, b2, eps, bc2_sqrt);
+      p4[i] = pv; m4[i] = mv; v4[i] = vv;
+      if (write_back_grad) g4[i] = gv;
+    }
+    done = n4 * 4;
+  }
+  for (long long i = done + tid; i < n; i += nth) {
+    float pi = p[i], gi = g[i], mi = m[i], vi = v[i];
+    adam_update(pi, gi, mi, vi, clip, step, b1, b2, eps, bc2_sqrt);
+    p[i] = pi; m[i] = mi; v[i] = vi;
     if (write_back_grad) g[i] = gi;
   }
 }
@@ -294,14 +318,22 @@ __global__ void final_sum_kernel(const float* __restrict__ partials, int n, floa
   }
   if (threadIdx.x == 0) *out = static_cast<float>(sm[0]);
 }
-__global__ void multi_sumsq_kernel(const VgAdamTensor* __restrict__ tab, int count, float* out) {
+// Most tensors of a parameter list are tiny (72 of the 109 tensors of the v2 generator hold < 64 K elements): with a fixed
+// thread -> element map block 0 would walk the head of every one of them, one DRAM round trip after the other, while the
+// other blocks idle through the list.  Tensor t is therefore started at block (t * 37) mod gridDim.x: the heads are spread
+// over the grid (a fixed map: the per-block partial sums below stay deterministic and identical on every replica).
+__device__ __forceinline__ long long rotated_tid(int t, int rotate) {
+  const unsigned b = rotate ? (blockIdx.x + gridDim.x - (static_cast<unsigned>(t) * 37u) % gridDim.x) % gridDim.x : blockIdx.x;
+  return static_cast<long long>(b) * blockDim.x + threadIdx.x;
+}
+__global__ void multi_sumsq_kernel(const VgAdamTensor* __restrict__ tab, int count, float* out, int rotate) {
   float acc = 0.f;
-  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
   for (int t = 0; t < count; ++t) {
     const float* g = tab[t].g;
     const long long n = tab[t].n;
     if (g == nullptr) continue;
+    const long long tid = rotated_tid(t, rotate);
     if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
       const long long n4 = n / 4;
       const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -319,18 +351,18 @@ __global__ void multi_sumsq_kernel(const VgAdamTensor* __restrict__ tab, int cou
 }
 __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int count, float lr, float b1, float b2,
                                   float eps, const float* __restrict__ state, const float* __restrict__ gnorm_sq,
-                                  float max_norm, int write_back_grad) {
+                                  float max_norm, int write_back_grad, int rotate) {
   float clip = 1.f;
   if (gnorm_sq != nullptr && max_norm > 0.f) clip = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
   const float step = (lr < 0.f ? state[3] : lr) / state[1];      // lr < 0: the rate lives in the device state block
   const float bc2_sqrt = state[2];
-  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
   for (int t = 0; t < count; ++t) {
     float* p = tab[t].p; float* g = tab[t].g; float* m = tab[t].m; float* v = tab[t].v;
     __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(tab[t].shadow);
     const long long n = tab[t].n;
     if (g == nullptr) continue;
+    const long long tid = rotated_tid(t, rotate);
     long long done = 0;
     if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
           reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(sh) & 7) == 0) {
@@ -373,6 +405,11 @@ __global__ void multi_adam_kernel(const VgAdamTensor* __restrict__ tab, int coun
 
 using namespace vg;
 #define ST static_cast<cudaStream_t>(stream_)
+// development knob: VG_ADAM_ROTATE=0 restores the fixed thread -> element map of the multi-tensor kernels (rotated_tid)
+static int adam_rotate() {
+  static const int on = getenv("VG_ADAM_ROTATE") ? atoi(getenv("VG_ADAM_ROTATE")) : 1;
+  return on;
+}
 
 extern "C" int vg_reparam_kl_fwd(const float* heads, const float* bias_mu, const float* bias_lv, const float* eps, int b,
                                  int z, float* mu, float* logvar, float* zout, float* kl_out, void* stream_) {
@@ -488,7 +525,7 @@ extern "C" int vg_multi_sumsq(const VgAdamTensor* table, int count, float* out, 
                               void* stream_) {
   const int grid = std::min(num_sms() * 4, scratch_len);
   VG_CHECK(grid >= 1, -1, "vg_multi_sumsq: scratch must hold at least one float");
-  multi_sumsq_kernel<<<grid, 256, 0, ST>>>(table, count, scratch);
+  multi_sumsq_kernel<<<grid, 256, 0, ST>>>(table, count, scratch, adam_rotate());
   VG_LAUNCH_OK();
   final_sum_kernel<<<1, 256, 0, ST>>>(scratch, grid, out);
   VG_LAUNCH_OK();
@@ -498,7 +535,7 @@ extern "C" int vg_multi_adam(const VgAdamTensor* table, int count, float lr, flo
                              const float* state, const float* gnorm_sq, float max_norm, int write_back_grad,
                              void* stream_) {
   multi_adam_kernel<<<num_sms() * 4, 256, 0, ST>>>(table, count, lr, beta1, beta2, eps, state, gnorm_sq, max_norm,
-                                                   write_back_grad);
+                                                   write_back_grad, adam_rotate());
   VG_LAUNCH_OK();
   return 0;
 }
